@@ -1,0 +1,114 @@
+/*
+ * rbnics_b200.h -- C ABI of the B200-native greedy-sweep engine (drop-in boundary).
+ *
+ * Plain pointers and sizes only; the caller (the Python online backend `rbnics_b200`, via ctypes) owns every
+ * host buffer, the library owns all device memory inside the handle.  One handle per GPU / process, not
+ * thread-safe per handle (the reference is single-threaded per MPI rank).  Every function returns 0 on
+ * success and a negative RB_ERR_* code otherwise; rb_last_error(ctx) then holds a message (the reference
+ * raises Python exceptions at the same places; a singular reduced matrix raises numpy.linalg.LinAlgError in
+ * rbnics/backends/online/numpy/linear_solver.py:29-31 and is RB_ERR_SINGULAR here).
+ *
+ * All matrices are FP64, row-major, dense.
+ */
+#ifndef RBNICS_B200_H
+#define RBNICS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rb_ctx rb_ctx;
+
+#define RB_OK 0
+#define RB_ERR_CUDA (-1)
+#define RB_ERR_ARG (-2)
+#define RB_ERR_STATE (-3)
+#define RB_ERR_SINGULAR (-4)
+#define RB_ERR_UNSUPPORTED (-5)
+
+/* Error-estimator normalisations.
+ * RB_EST_SQRT_EPS2_OVER_BETA : sqrt(|eps2|)/beta   rbnics/problems/elliptic/elliptic_rb_reduced_problem.py:35-40
+ * RB_EST_SQRT_OF_EPS2_OVER_BETA : sqrt(|eps2|/beta) rbnics/problems/elliptic/elliptic_coercive_compliant_rb_reduced_problem.py:22-27 */
+#define RB_EST_SQRT_EPS2_OVER_BETA 0
+#define RB_EST_SQRT_OF_EPS2_OVER_BETA 1
+
+/* ---- handle ---------------------------------------------------------------------------------------------------- */
+int rb_ctx_create(int device, rb_ctx** out);
+void rb_ctx_destroy(rb_ctx* ctx);
+const char* rb_last_error(const rb_ctx* ctx);
+/* "major.minor" of the device the handle is bound to, and SM count (for bench bookkeeping). */
+int rb_device_info(const rb_ctx* ctx, int* cc_major, int* cc_minor, int* sm_count);
+
+/* ---- reduced system: replaces sum(product(theta, operator[term][:N,:N])) + LinearSolver -------------------------
+ * rbnics/problems/elliptic/elliptic_reduced_problem.py:19-28 (matrix_eval / vector_eval),
+ * rbnics/backends/online/basic/product.py:22-33 (order-1 product), rbnics/backends/online/basic/linear_solver.py:56-71
+ * + wrapping/DirichletBC.py:37-98 (lifting rows), rbnics/backends/online/numpy/linear_solver.py:29-31 (dgesv).
+ *
+ *   lhs(mu) = sum_{q<Ql} Theta[q]      * A[q]   (A: Ql x N x N)
+ *   rhs(mu) = sum_{q<Qr} Theta[Ql + q] * F[q]   (F: Qr x N)
+ *   rows bc_rows[i] (i < n_bc): lhs[row,:] = 0, lhs[row,row] = 1, rhs[row] = ThetaBC[i]
+ * Multi-term / block problems (Stokes a, b, bt; f, g) pass every term's block-embedded N x N matrix as one A[q].
+ * N == 0 is legal (first greedy sweep: empty solution).                                                        */
+int rb_set_system(rb_ctx* ctx, int N, int Ql, int Qr, const double* A, const double* F, int n_bc, const int* bc_rows);
+
+/* ---- estimator: replaces get_residual_norm_squared / estimate_error ---------------------------------------------
+ * rbnics/problems/elliptic/elliptic_rb_reduced_problem.py:55-64 (3 terms), rbnics/problems/stokes/
+ * stokes_rb_reduced_problem.py:35-83 (9 terms), rbnics/backends/online/basic/product.py:34-46 (order-2 product).
+ *
+ * Every such residual norm is one quadratic form  eps2(mu) = z^T G z  with z the concatenation of nblk blocks
+ *   z_b = scale_b * V[src_b : src_b + len_b],   V = [ u(0..N-1) | Theta[v_theta_off .. +v_theta_len) | 1.0 ],
+ *   scale_b = Theta[blk_scale_col[b]]   (blk_scale_col[b] < 0  ->  scale_b = 1)
+ * and G the dense (Kz x Kz, Kz = sum len_b) matrix of Riesz Gram blocks (need not be symmetric: only its symmetric
+ * part contributes and the kernel uses G + G^T).  Elliptic: blocks b < Qa = (scale theta_a[b], src 0, len N) and one
+ * block (scale 1, src N, len Qf) with v_theta = theta_f;  G = [[Gaa, Gaf], [Gaf^T, Gff]].                           */
+int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col, const int* blk_src_off, const int* blk_len,
+                     int v_theta_off, int v_theta_len, const double* G);
+
+/* ---- training set: replaces ParameterSpaceSubset + compute_theta / get_stability_factor_lower_bound --------------
+ * rbnics/sampling/parameter_space_subset.py:52-77.  Theta: B x (Ql+Qr) (theta of every lhs then rhs term, already
+ * evaluated for every mu of this rank's shard), ThetaBC: B x n_bc or NULL, beta: B.
+ * The local row i has global training-set index  index_offset + i*index_stride  (cyclic sharding of the reference:
+ * offset = rank, stride = size, parameter_space_subset.py:57).  Copies host -> device.                            */
+int rb_set_training_set(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta, int n_bc, const double* ThetaBC,
+                        const double* beta, int64_t index_offset, int64_t index_stride);
+
+/* ---- the sweep: replaces training_set.max(solve_and_estimate_error) ----------------------------------------------
+ * rbnics/reduction_methods/base/rb_reduction.py:160-185.  Runs assembly + LU solve + estimator + arg-max over the
+ * resident training set.  max_idx is the GLOBAL index, ties -> lowest index, NaN wins (numpy.argmax,
+ * parameter_space_subset.py:67,75).  delta_out (B) / u_out (B x N) / eps2_out (B) may be NULL.
+ * Returns RB_ERR_SINGULAR if any estimator is non-finite (outputs are still written).                            */
+int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_val, int64_t* max_idx,
+                      double* delta_out, double* u_out, double* eps2_out);
+/* Same, from host buffers in one call (host->device copies inside): the end-to-end entry. */
+int rb_sweep(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta, int n_bc, const double* ThetaBC,
+             const double* beta, int64_t index_offset, int64_t index_stride, int estimator_kind,
+             double* max_val, int64_t* max_idx, double* delta_out, double* u_out, double* eps2_out);
+/* Device pointer to the 16-byte {double max_val; int64 max_idx} result of the last sweep (for a NCCL all-gather
+ * issued by the host layer without a host round trip), and to the per-parameter estimators. */
+int rb_result_device_ptrs(rb_ctx* ctx, void** maxloc16, double** delta);
+/* Kernel-only timings (ms, CUDA events on the handle's stream) of the last sweep:
+ * [0]=assembly GEMM, [1]=LU solve, [2]=estimator GEMM, [3]=finalize+argmax, [4]=total; launches counted. */
+int rb_last_timings(rb_ctx* ctx, float* ms5, int* n_launches);
+
+/* Pinned host memory helpers for the end-to-end path. */
+void* rb_host_alloc(int64_t bytes);
+void rb_host_free(void* p);
+
+/* ---- offline basis linear algebra -------------------------------------------------------------------------------
+ * C = S^T X S2: rbnics/backends/basic/transpose.py:304-313 (POD correlation), :441-468 (Z^T A_q Z), :365-400 (Z^T f).
+ * S: Nh x Ns, S2: Nh x Ns2 row-major (dof-major: row = dof, column = snapshot), X: CSR (Nh x Nh) or indptr == NULL
+ * for the identity.  C: Ns x Ns2 row-major.  If S2 == NULL, S2 = S.  Rows [row_begin, row_end) of X/S are this
+ * rank's dof partition (the partial result is all-reduced by the host layer); pass 0, Nh for a single GPU.       */
+int rb_gram(rb_ctx* ctx, int64_t Nh, int Ns, int Ns2, const double* S, const double* S2, const int64_t* indptr,
+            const int32_t* indices, const double* data, int64_t row_begin, int64_t row_end, double* C);
+/* Batched projection of Q operators sharing one basis: out[q] = Z^T A_q Z (Q x N x N); CSR arrays concatenated,
+ * indptr_all has Q*(Nh+1) entries each starting at 0 relative to its own nnz_off[q].                              */
+int rb_project(rb_ctx* ctx, int64_t Nh, int N, int Q, const double* Z, const int64_t* indptr_all,
+               const int32_t* indices_all, const double* data_all, const int64_t* nnz_off, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,151 @@
+// rb_common.cuh -- shared declarations of the B200 greedy-sweep engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/rbnics_b200.h"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tunables (see DESIGN.md "Kernels")
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int EST_BM = 128;           // parameters (rows of Z) per CTA
+constexpr int EST_BN = 64;            // columns of G' per column tile
+constexpr int EST_CONSUMER_WARPS = 8; // 4 (m) x 2 (n), warp tile 32 x 32
+constexpr int EST_THREADS = (EST_CONSUMER_WARPS + 1) * 32;  // + 1 bulk-copy producer warp
+constexpr int EST_KSTEP_DOUBLES = 4 * EST_BN;               // one k4-step of one column tile, fragment order
+constexpr int EST_STAGE_KSTEPS = 8;                         // 16 KB per stage
+constexpr int EST_NSTAGE = 5;
+
+constexpr int ASM_BM = 128;  // parameters per CTA of the assembly GEMM
+constexpr int ASM_BE = 64;   // matrix entries per CTA
+
+constexpr int LU_MAX_NP_REG = 104;  // largest padded N served by the register-resident LU
+constexpr int LU_MAX_NP = 160;      // largest padded N served at all (shared-memory fallback)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Handle
+// ---------------------------------------------------------------------------------------------------------------------
+struct rb_ctx {
+  int device = 0;
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // reduced system
+  bool have_system = false;
+  int N = 0, NP = 0, Ql = 0, Qr = 0, QlP = 0, n_bc = 0;
+  int E = 0, EP = 0;          // NP*NP and its padding to ASM_BE
+  double* dAq = nullptr;      // [QlP][EP] : A_q transposed/padded: entry (i,j) at j*NP+i
+  double* dF = nullptr;       // [Qr][NP]
+  int* dBcRows = nullptr;     // [n_bc]
+
+  // estimator
+  bool have_est = false;
+  int nblk = 0, Kz = 0, Kp = 0, KS = 0, n_ctile = 0, v_off = 0, v_len = 0, LV = 0, LVS = 0;
+  std::vector<int> h_blk_scale, h_blk_src, h_blk_len, h_blk_ks_begin, h_tile_ks0, h_tile_b0;
+  std::vector<long long> h_tile_off;
+  double* dGp = nullptr;            // packed lower-triangular G' in fragment order
+  long long gp_doubles = 0;
+  long long* dTileOff = nullptr;    // [n_ctile]
+  int* dTileKs0 = nullptr;          // [n_ctile]
+  int* dTileB0 = nullptr;           // [n_ctile] block containing the tile's first k-step
+  int* dBlkKsBegin = nullptr;       // [nblk+1]
+  int* dBlkScale = nullptr;         // [nblk]
+  int* dBlkSrc = nullptr;           // [nblk]
+  int* dColScale = nullptr;         // [n_ctile*EST_BN]
+  int* dColSrc = nullptr;           // [n_ctile*EST_BN]
+
+  // training set
+  bool have_train = false;
+  int64_t B = 0, Bcap = 0;
+  int QT = 0, n_bc_train = 0;
+  int64_t idx_off = 0, idx_stride = 1;
+  double *dTheta = nullptr, *dThetaBC = nullptr, *dBeta = nullptr;
+
+  // work buffers
+  double* dAb = nullptr; int64_t ab_cap = 0;       // assembled matrices of one chunk [chunk][EP]
+  double* dU = nullptr; int64_t u_cap = 0; int ldu = 0;
+  double* dPart = nullptr; int64_t part_cap = 0;   // [nsplit][B]
+  double* dDelta = nullptr; double* dEps2 = nullptr; int64_t delta_cap = 0;
+  double* dBlkVal = nullptr; long long* dBlkIdx = nullptr; int blk_cap = 0;
+  void* dResult = nullptr;           // {double val; int64 idx; int64 n_nonfinite}
+  int* dSplitBegin = nullptr; int split_cap = 0;
+
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float last_ms[5] = {0, 0, 0, 0, 0};
+  int last_launches = 0;
+};
+
+#define RB_CUDA(call)                                                                                       \
+  do {                                                                                                      \
+    cudaError_t e__ = (call);                                                                               \
+    if (e__ != cudaSuccess) {                                                                               \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" +              \
+                 std::to_string(__LINE__) + ")";                                                            \
+      return RB_ERR_CUDA;                                                                                   \
+    }                                                                                                       \
+  } while (0)
+
+#define RB_FAIL(code, msg) \
+  do {                     \
+    ctx->err = (msg);      \
+    return (code);         \
+  } while (0)
+
+// LU launcher (rb_lu.cu): factor + solve `count` systems assembled in Ab ([count][EP], column-major NP x NP each).
+// Theta rows start at theta (already offset to the chunk), U at u.
+int rb_launch_lu(rb_ctx* ctx, int64_t count, const double* Ab, const double* theta, const double* thetaBC, double* u);
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk asynchronous copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// numpy.argmax ordering: NaN beats everything, then larger value, then lower index.
+__device__ __forceinline__ bool argmax_better(double av, long long ai, double bv, long long bi) {
+  bool an = (av != av), bn = (bv != bv);
+  if (an != bn) return an;
+  if (!an && av != bv) return av > bv;
+  return ai < bi;
+}
+#endif

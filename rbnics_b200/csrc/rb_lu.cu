@@ -1,0 +1,157 @@
+// rb_lu.cu -- dispatcher of the batched LU solve + shared-memory fallback for NP > LU_MAX_NP_REG.
+#include "rb_lu_kernel.cuh"
+
+int rb_lu_launch_unit0(int NP, const LuArgs& args, cudaStream_t stream);
+int rb_lu_launch_unit1(int NP, const LuArgs& args, cudaStream_t stream);
+int rb_lu_launch_unit2(int NP, const LuArgs& args, cudaStream_t stream);
+int rb_lu_launch_unit3(int NP, const LuArgs& args, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fallback: matrix in shared memory ([NP][NP+1], odd pitch), one CTA of 128 threads per system, explicit row swaps.
+// Same arithmetic (idamax pivot, reciprocal-scaled multipliers, rank-1 updates); used only for NP > 104.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rb_lu_smem_kernel(LuArgs args, int NP) {
+  extern __shared__ __align__(16) unsigned char lu_smem_raw[];
+  const int P = NP + 1;
+  double* A = reinterpret_cast<double*>(lu_smem_raw);  // [NP][P]
+  double* bs = A + (size_t)NP * P;                     // [NP]
+  double* xs = bs + NP;                                // [NP]
+  __shared__ unsigned long long wkey[4];
+  __shared__ int wrow[4];
+  const long long sys = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int N = args.N;
+  const double* Ab = args.Ab + sys * (long long)args.EP;
+  for (int e = tid; e < NP * NP; e += 128) {
+    const int j = e / NP, i = e % NP;
+    A[i * P + j] = Ab[e];
+  }
+  const double* th = args.theta + sys * (long long)args.QT + args.Ql;
+  for (int i = tid; i < NP; i += 128) {
+    double b = 0.0;
+    if (i < N)
+      for (int q = 0; q < args.Qr; ++q) b = fma(th[q], args.F[q * NP + i], b);
+    bs[i] = b;
+  }
+  __syncthreads();
+  for (int i = tid; i < NP; i += 128) {
+    bool unit_row = (i >= N);
+    for (int t = 0; t < args.n_bc; ++t)
+      if (args.bc_rows[t] == i) {
+        unit_row = true;
+        bs[i] = args.thetaBC[sys * (long long)args.n_bc + t];
+      }
+    if (unit_row)
+      for (int j = 0; j < NP; ++j) A[i * P + j] = (j == i) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int k = 0; k < NP; ++k) {
+    // pivot search over rows k..NP-1 (lowest row on ties)
+    unsigned long long key = 0ull;
+    int row = 0x7fffffff;
+    for (int r = k + tid; r < NP; r += 128) {
+      const unsigned long long kr = (unsigned long long)__double_as_longlong(fabs(A[r * P + k])) + 1ull;
+      if (kr > key) {
+        key = kr;
+        row = r;
+      }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, off);
+      const int r2 = __shfl_xor_sync(0xffffffffu, row, off);
+      if (k2 > key || (k2 == key && r2 < row)) {
+        key = k2;
+        row = r2;
+      }
+    }
+    if (lane == 0) {
+      wkey[w] = key;
+      wrow[w] = row;
+    }
+    __syncthreads();
+    key = wkey[0];
+    row = wrow[0];
+    for (int w2 = 1; w2 < 4; ++w2)
+      if (wkey[w2] > key || (wkey[w2] == key && wrow[w2] < row)) {
+        key = wkey[w2];
+        row = wrow[w2];
+      }
+    if (row != k) {
+      for (int j = tid; j < NP; j += 128) {
+        const double t0 = A[k * P + j];
+        A[k * P + j] = A[row * P + j];
+        A[row * P + j] = t0;
+      }
+      if (tid == 0) {
+        const double t0 = bs[k];
+        bs[k] = bs[row];
+        bs[row] = t0;
+      }
+    }
+    __syncthreads();
+    const double rinv = 1.0 / A[k * P + k];
+    const double bk = bs[k];
+    for (int r = k + 1 + tid; r < NP; r += 128) {
+      const double l = A[r * P + k] * rinv;
+      for (int j = k + 1; j < NP; ++j) A[r * P + j] = fma(-l, A[k * P + j], A[r * P + j]);
+      bs[r] = fma(-l, bk, bs[r]);
+    }
+    __syncthreads();
+  }
+  if (w == 0) {
+    for (int k = NP - 1; k >= 0; --k) {
+      double xk = 0.0;
+      if (lane == 0) {
+        xk = bs[k] / A[k * P + k];
+        xs[k] = xk;
+      }
+      xk = __shfl_sync(0xffffffffu, xk, 0);
+      for (int r = lane; r < k; r += 32) bs[r] = fma(-A[r * P + k], xk, bs[r]);
+      __syncwarp();
+    }
+    for (int r = lane; r < N; r += 32) args.U[sys * (long long)args.ldu + r] = xs[r];
+  }
+}
+
+int rb_launch_lu(rb_ctx* ctx, int64_t count, const double* Ab, const double* theta, const double* thetaBC, double* u) {
+  LuArgs a;
+  a.Ab = Ab;
+  a.theta = theta;
+  a.thetaBC = thetaBC;
+  a.F = ctx->dF;
+  a.bc_rows = ctx->dBcRows;
+  a.U = u;
+  a.count = count;
+  a.N = ctx->N;
+  a.EP = ctx->EP;
+  a.QT = ctx->QT;
+  a.Ql = ctx->Ql;
+  a.Qr = ctx->Qr;
+  a.n_bc = ctx->n_bc;
+  a.ldu = ctx->ldu;
+  const int NP = ctx->NP;
+  int rc;
+  if (NP <= 52)
+    rc = rb_lu_launch_unit0(NP, a, ctx->stream);
+  else if (NP <= 80)
+    rc = rb_lu_launch_unit1(NP, a, ctx->stream);
+  else if (NP <= 96)
+    rc = rb_lu_launch_unit2(NP, a, ctx->stream);
+  else if (NP <= LU_MAX_NP_REG)
+    rc = rb_lu_launch_unit3(NP, a, ctx->stream);
+  else {
+    const size_t bytes = ((size_t)NP * (NP + 1) + 2 * (size_t)NP) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(rb_lu_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("rb_lu_smem_kernel smem attribute: ") + cudaGetErrorString(e);
+      return RB_ERR_CUDA;
+    }
+    rb_lu_smem_kernel<<<(unsigned)count, 128, bytes, ctx->stream>>>(a, NP);
+    rc = (int)cudaGetLastError();
+  }
+  if (rc != 0) {
+    ctx->err = std::string("LU launch failed: ") + (rc == -1000 ? "no instantiation for this NP" : cudaGetErrorString((cudaError_t)rc));
+    return RB_ERR_CUDA;
+  }
+  return RB_OK;
+}

@@ -1,0 +1,896 @@
+// rb_sweep.cu -- the greedy sweep on one B200: affine assembly GEMM, estimator GEMM (z^T G z), finalize + arg-max,
+// operator packing and the C ABI around them.  Reference call stack being replaced: SURVEY.md 3.1 / 8a rows A1-A11.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "rb_common.cuh"
+
+// =====================================================================================================================
+// Packing kernels (run once per greedy iteration, when the reduced operators change)
+// =====================================================================================================================
+
+// A (Ql x N x N row-major)  ->  Aq [QlP][EP] with entry (i,j) at j*NP+i, zero padded.
+__global__ void rb_pack_system_kernel(const double* __restrict__ A, double* __restrict__ Aq, int N, int NP, int Ql,
+                                      int QlP, int EP) {
+  const long long total = (long long)QlP * EP;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(t / EP), e = (int)(t % EP);
+    const int j = e / NP, i = e % NP;
+    double v = 0.0;
+    if (q < Ql && e < NP * NP && i < N && j < N) v = A[((long long)q * N + i) * N + j];
+    Aq[t] = v;
+  }
+}
+
+// Dense G (Kz x Kz) -> G' = tril(G + G^T) with the diagonal counted once, in padded index space, cut into column
+// tiles of EST_BN and k4-steps, each k-step stored in DMMA B-fragment order:
+//   [wn (2)][pair (2)][lane (32)][e (2)]  <-  G'[k = 4*ks + lane%4][c = c0 + wn*32 + (2*pair+e)*8 + lane/4]
+__global__ void rb_pack_estimator_kernel(const double* __restrict__ G, double* __restrict__ Gp,
+                                         const long long* __restrict__ tile_off, const int* __restrict__ tile_ks0,
+                                         const int* __restrict__ pad2unpad, int Kz, int KS, int n_ctile) {
+  const int ct = blockIdx.y;
+  const int ks0 = tile_ks0[ct];
+  const long long n = (long long)(KS - ks0) * EST_KSTEP_DOUBLES;
+  double* dst = Gp + tile_off[ct];
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int ks = ks0 + (int)(t / EST_KSTEP_DOUBLES);
+    const int r = (int)(t % EST_KSTEP_DOUBLES);
+    const int wn = r >> 7, pair = (r >> 6) & 1, lane = (r >> 1) & 31, e = r & 1;
+    const int kp = 4 * ks + (lane & 3);
+    const int cp = ct * EST_BN + wn * 32 + (2 * pair + e) * 8 + (lane >> 2);
+    const int k = pad2unpad[kp];
+    const int c = pad2unpad[cp];
+    double v = 0.0;
+    if (k >= 0 && c >= 0 && kp >= cp) {
+      v = (kp == cp) ? G[(long long)k * Kz + c] : (G[(long long)k * Kz + c] + G[(long long)c * Kz + k]);
+    }
+    dst[t] = v;
+  }
+}
+
+// =====================================================================================================================
+// K_asm: Ab[p][e] = sum_q Theta[p][q] * Aq[q][e]   (DMMA GEMM, M = parameters, N = matrix entries, K = Ql)
+// product order-1 of rbnics/backends/online/basic/product.py:22-33 for a whole chunk of parameters.
+// =====================================================================================================================
+struct AsmArgs {
+  const double* theta;  // [count][QT] (lhs thetas are the first Ql columns)
+  const double* Aq;     // [QlP][EP]
+  double* Ab;           // [count][EP]
+  long long count;
+  int QT, Ql, QlP, EP;
+};
+
+__global__ void __launch_bounds__(256) rb_assemble_kernel(AsmArgs a) {
+  extern __shared__ __align__(16) double asm_smem[];
+  const int TS = a.QlP + ((a.QlP % 8 == 4) ? 0 : 4);  // theta tile pitch == 4 (mod 8): conflict-free A fragments
+  constexpr int BS = ASM_BE + 4;                       // Aq tile pitch == 4 (mod 16): conflict-free B fragments
+  double* ths = asm_smem;                              // [ASM_BM][TS]
+  double* bsm = asm_smem + ASM_BM * TS;                // [QlP][BS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;
+  const long long p0 = (long long)blockIdx.y * ASM_BM;
+  const int e0 = blockIdx.x * ASM_BE;
+
+  for (int t = tid; t < ASM_BM * a.QlP; t += 256) {
+    const int r = t / a.QlP, q = t % a.QlP;
+    const long long p = p0 + r;
+    ths[r * TS + q] = (p < a.count && q < a.Ql) ? __ldg(a.theta + p * a.QT + q) : 0.0;
+  }
+  for (int t = tid; t < a.QlP * (ASM_BE / 2); t += 256) {
+    const int q = t / (ASM_BE / 2), c2 = t % (ASM_BE / 2);
+    const double2 v = *reinterpret_cast<const double2*>(a.Aq + (long long)q * a.EP + e0 + 2 * c2);
+    *reinterpret_cast<double2*>(bsm + q * BS + 2 * c2) = v;
+  }
+  __syncthreads();
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+  const int ar = wm * 32 + (lane >> 2), ak = lane & 3;
+  const int bc = wn * 32 + (lane >> 2);
+  for (int ks = 0; ks < a.QlP / 4; ++ks) {
+    double af[4], bf[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) af[mt] = ths[(ar + mt * 8) * TS + 4 * ks + ak];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) bf[nt] = bsm[(4 * ks + ak) * BS + bc + nt * 8];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const long long p = p0 + wm * 32 + mt * 8 + (lane >> 2);
+    if (p < a.count) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int e = e0 + wn * 32 + nt * 8 + (lane & 3) * 2;
+        __stcs(reinterpret_cast<double2*>(a.Ab + p * a.EP + e), make_double2(acc[mt][nt][0], acc[mt][nt][1]));
+      }
+    }
+  }
+}
+
+// =====================================================================================================================
+// K_est: eps2 partial[split][p] = sum over the split's column tiles of (Z G')[p, c] * z[p, c]
+// order-2 products of rbnics/backends/online/basic/product.py:34-46 + the quadratic forms of
+// rbnics/problems/elliptic/elliptic_rb_reduced_problem.py:55-64, for EST_BM parameters per CTA.
+// =====================================================================================================================
+struct EstArgs {
+  const double* Gp;
+  const long long* tile_off;
+  const int* tile_ks0;
+  const int* tile_b0;
+  const int* blk_ks_begin;
+  const int* blk_scale;
+  const int* blk_src;
+  const int* col_scale;
+  const int* col_src;
+  const int* split_begin;  // [nsplit+1] column-tile boundaries
+  const double* U;         // [B][ldu]
+  const double* theta;     // [B][QT]
+  double* partial;         // [nsplit][B]
+  long long B;
+  int nblk, KS, N, ldu, QT, v_off, v_len, LVS, nsplit;
+};
+
+__global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a) {
+  extern __shared__ __align__(128) unsigned char est_smem_raw[];
+  constexpr int STAGE_DOUBLES = EST_STAGE_KSTEPS * EST_KSTEP_DOUBLES;
+  double* Gs = reinterpret_cast<double*>(est_smem_raw);                 // [NSTAGE][STAGE_DOUBLES]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(Gs + EST_NSTAGE * STAGE_DOUBLES);
+  uint64_t* empty_bar = full_bar + EST_NSTAGE;
+  double* red = reinterpret_cast<double*>(empty_bar + EST_NSTAGE);     // [EST_BM]
+  double* Vs = red + EST_BM;                                            // [EST_BM][LVS]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int split = blockIdx.x % a.nsplit;
+  const long long rb = blockIdx.x / a.nsplit;
+  const long long p0 = rb * EST_BM;
+  const int ct_begin = a.split_begin[split], ct_end = a.split_begin[split + 1];
+  const int LVS = a.LVS;
+
+  // V tile: [u | theta[v_off : v_off+v_len] | 1 | 0 ...]
+  for (int t = tid; t < EST_BM * LVS; t += EST_THREADS) {
+    const int r = t / LVS, c = t % LVS;
+    const long long p = p0 + r;
+    double v = 0.0;
+    if (p < a.B) {
+      if (c < a.N)
+        v = a.U[p * a.ldu + c];
+      else if (c < a.N + a.v_len)
+        v = a.theta[p * a.QT + a.v_off + (c - a.N)];
+      else if (c == a.N + a.v_len)
+        v = 1.0;
+    }
+    Vs[t] = v;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < EST_NSTAGE; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, EST_CONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == EST_CONSUMER_WARPS) {
+    // ---------------- producer: stream G' stages with 1-D bulk copies ----------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ct = ct_begin; ct < ct_end; ++ct) {
+        const int nks = a.KS - a.tile_ks0[ct];
+        const double* src = a.Gp + a.tile_off[ct];
+        for (int k = 0; k < nks; k += EST_STAGE_KSTEPS) {
+          const int n = min(EST_STAGE_KSTEPS, nks - k);
+          mbar_wait(empty_bar + stage, phase ^ 1u);
+          const uint32_t bytes = (uint32_t)n * EST_KSTEP_DOUBLES * 8u;
+          mbar_arrive_expect_tx(full_bar + stage, bytes);
+          bulk_g2s(Gs + stage * STAGE_DOUBLES, src + (long long)k * EST_KSTEP_DOUBLES, bytes, full_bar + stage);
+          if (++stage == EST_NSTAGE) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers: 8 warps, 4 (m) x 2 (n), warp tile 32 x 32 ----------------
+  const int wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, q4 = lane & 3;
+  const int r0 = wm * 32 + g;  // + mt*8
+  long long prow[4];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) prow[mt] = min(p0 + r0 + mt * 8, a.B - 1);
+  double rowacc[4] = {0.0, 0.0, 0.0, 0.0};
+  int stage = 0;
+  uint32_t phase = 0;
+
+  for (int ct = ct_begin; ct < ct_end; ++ct) {
+    double Y[4][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) Y[mt][nt][0] = Y[mt][nt][1] = 0.0;
+
+    int ks = a.tile_ks0[ct];
+    int kin = 0;                                   // k-step within the current stage
+    int nin = min(EST_STAGE_KSTEPS, a.KS - ks);    // k-steps held by the current stage
+    bool waited = false;
+    for (int b = a.tile_b0[ct]; b < a.nblk; ++b) {
+      const int kend = a.blk_ks_begin[b + 1];
+      const int sc = a.blk_scale[b];
+      int src = a.blk_src[b] + 4 * (ks - a.blk_ks_begin[b]) + q4;
+      double th[4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) th[mt] = (sc < 0) ? 1.0 : __ldg(a.theta + prow[mt] * a.QT + sc);
+      double T[4][4][2];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) T[mt][nt][0] = T[mt][nt][1] = 0.0;
+
+      for (; ks < kend; ++ks) {
+        if (!waited) {
+          mbar_wait(full_bar + stage, phase);
+          waited = true;
+        }
+        const double* bp = Gs + stage * STAGE_DOUBLES + kin * EST_KSTEP_DOUBLES + wn * 128 + lane * 2;
+        const double2 b01 = *reinterpret_cast<const double2*>(bp);
+        const double2 b23 = *reinterpret_cast<const double2*>(bp + 64);
+        double af[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) af[mt] = Vs[(r0 + mt * 8) * LVS + src];
+        src += 4;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          dmma884(T[mt][0][0], T[mt][0][1], af[mt], b01.x);
+          dmma884(T[mt][1][0], T[mt][1][1], af[mt], b01.y);
+          dmma884(T[mt][2][0], T[mt][2][1], af[mt], b23.x);
+          dmma884(T[mt][3][0], T[mt][3][1], af[mt], b23.y);
+        }
+        if (++kin == nin) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_bar + stage);
+          if (++stage == EST_NSTAGE) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          kin = 0;
+          nin = min(EST_STAGE_KSTEPS, a.KS - (ks + 1));
+          waited = false;
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          Y[mt][nt][0] = fma(th[mt], T[mt][nt][0], Y[mt][nt][0]);
+          Y[mt][nt][1] = fma(th[mt], T[mt][nt][1], Y[mt][nt][1]);
+        }
+    }
+
+    // epilogue of the column tile: rowacc[p] += sum_c Y[p,c] * z[p,c]
+    const int cbase = ct * EST_BN + wn * 32 + q4 * 2;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = cbase + nt * 8 + e;
+        const int csc = __ldg(a.col_scale + c);
+        const int csr = __ldg(a.col_src + c);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          const double thc = (csc < 0) ? 1.0 : __ldg(a.theta + prow[mt] * a.QT + csc);
+          const double zc = thc * Vs[(r0 + mt * 8) * LVS + csr];
+          rowacc[mt] = fma(Y[mt][nt][e], zc, rowacc[mt]);
+        }
+      }
+    }
+  }
+
+  // reduce over the quad (columns) and over the two n-warps
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    rowacc[mt] += __shfl_xor_sync(0xffffffffu, rowacc[mt], 1);
+    rowacc[mt] += __shfl_xor_sync(0xffffffffu, rowacc[mt], 2);
+  }
+  if (wn == 1 && q4 == 0) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) red[r0 + mt * 8] = rowacc[mt];
+  }
+  asm volatile("bar.sync 1, %0;" ::"r"(EST_CONSUMER_WARPS * 32) : "memory");
+  if (wn == 0 && q4 == 0) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const long long p = p0 + r0 + mt * 8;
+      if (p < a.B) a.partial[(long long)split * a.B + p] = rowacc[mt] + red[r0 + mt * 8];
+    }
+  }
+}
+
+// =====================================================================================================================
+// K_fin: eps2 = sum of split partials (fixed order), Delta, per-block arg-max; then one block reduces the blocks.
+// rbnics/problems/elliptic/elliptic_rb_reduced_problem.py:35-40 and parameter_space_subset.py:67,75.
+// =====================================================================================================================
+struct MaxLoc {
+  double val;
+  long long idx;
+  long long n_nonfinite;
+};
+
+__device__ __forceinline__ void block_argmax(double& v, long long& ix, long long& nf) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  __shared__ long long sn[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int off = 16; off > 0; off >>= 1) {
+    const double v2 = __shfl_xor_sync(0xffffffffu, v, off);
+    const long long i2 = __shfl_xor_sync(0xffffffffu, ix, off);
+    nf += __shfl_xor_sync(0xffffffffu, nf, off);
+    if (argmax_better(v2, i2, v, ix)) {
+      v = v2;
+      ix = i2;
+    }
+  }
+  if (lane == 0) {
+    sv[warp] = v;
+    si[warp] = ix;
+    sn[warp] = nf;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < nw ? sv[lane] : -INFINITY;
+    ix = lane < nw ? si[lane] : 0x7fffffffffffffffLL;
+    nf = lane < nw ? sn[lane] : 0;
+    for (int off = 16; off > 0; off >>= 1) {
+      const double v2 = __shfl_xor_sync(0xffffffffu, v, off);
+      const long long i2 = __shfl_xor_sync(0xffffffffu, ix, off);
+      nf += __shfl_xor_sync(0xffffffffu, nf, off);
+      if (argmax_better(v2, i2, v, ix)) {
+        v = v2;
+        ix = i2;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) rb_finalize_kernel(const double* __restrict__ partial, int nsplit,
+                                                          const double* __restrict__ beta, long long B, int kind,
+                                                          long long idx_off, long long idx_stride,
+                                                          double* __restrict__ delta, double* __restrict__ eps2_out,
+                                                          double* __restrict__ blk_val, long long* __restrict__ blk_idx,
+                                                          long long* __restrict__ blk_nf) {
+  double best = -INFINITY;
+  long long besti = 0x7fffffffffffffffLL, nf = 0;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < B; p += (long long)gridDim.x * blockDim.x) {
+    double e = 0.0;
+    for (int s = 0; s < nsplit; ++s) e += partial[(long long)s * B + p];
+    const double bt = beta[p];
+    const double d = (kind == RB_EST_SQRT_EPS2_OVER_BETA) ? sqrt(fabs(e)) / bt : sqrt(fabs(e) / bt);
+    delta[p] = d;
+    eps2_out[p] = e;
+    if (!isfinite(d)) ++nf;
+    const long long gi = idx_off + p * idx_stride;
+    if (argmax_better(d, gi, best, besti)) {
+      best = d;
+      besti = gi;
+    }
+  }
+  block_argmax(best, besti, nf);
+  if (threadIdx.x == 0) {
+    blk_val[blockIdx.x] = best;
+    blk_idx[blockIdx.x] = besti;
+    blk_nf[blockIdx.x] = nf;
+  }
+}
+
+__global__ void __launch_bounds__(256) rb_argmax_final_kernel(const double* __restrict__ blk_val,
+                                                              const long long* __restrict__ blk_idx,
+                                                              const long long* __restrict__ blk_nf, int nblocks,
+                                                              MaxLoc* __restrict__ out) {
+  double best = -INFINITY;
+  long long besti = 0x7fffffffffffffffLL, nf = 0;
+  for (int t = threadIdx.x; t < nblocks; t += blockDim.x) {
+    nf += blk_nf[t];
+    if (argmax_better(blk_val[t], blk_idx[t], best, besti)) {
+      best = blk_val[t];
+      besti = blk_idx[t];
+    }
+  }
+  block_argmax(best, besti, nf);
+  if (threadIdx.x == 0) {
+    out->val = best;
+    out->idx = besti;
+    out->n_nonfinite = nf;
+  }
+}
+
+// =====================================================================================================================
+// Host side
+// =====================================================================================================================
+static int roundup(int x, int m) { return (x + m - 1) / m * m; }
+
+template <typename T>
+static int dev_realloc(rb_ctx* ctx, T** p, size_t count) {
+  if (*p) {
+    RB_CUDA(cudaFree(*p));
+    *p = nullptr;
+  }
+  if (count) RB_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+  return RB_OK;
+}
+
+extern "C" int rb_ctx_create(int device, rb_ctx** out) {
+  if (!out) return RB_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return RB_ERR_CUDA;
+  rb_ctx* ctx = new rb_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    return RB_ERR_CUDA;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  if (prop.major != 10) {  // sm_100a only: no fallback path exists
+    delete ctx;
+    return RB_ERR_UNSUPPORTED;
+  }
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return RB_ERR_CUDA;
+  }
+  for (int i = 0; i < 6; ++i) cudaEventCreate(&ctx->ev[i]);
+  if (cudaMalloc(&ctx->dResult, sizeof(MaxLoc)) != cudaSuccess) {
+    delete ctx;
+    return RB_ERR_CUDA;
+  }
+  *out = ctx;
+  return RB_OK;
+}
+
+extern "C" void rb_ctx_destroy(rb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  void* ptrs[] = {ctx->dAq,       ctx->dF,       ctx->dBcRows,  ctx->dGp,      ctx->dTileOff, ctx->dTileKs0,
+                  ctx->dTileB0,   ctx->dBlkKsBegin, ctx->dBlkScale, ctx->dBlkSrc, ctx->dColScale, ctx->dColSrc,
+                  ctx->dTheta,    ctx->dThetaBC, ctx->dBeta,    ctx->dAb,      ctx->dU,       ctx->dPart,
+                  ctx->dDelta,    ctx->dEps2,    ctx->dBlkVal,  ctx->dBlkIdx,  ctx->dResult,  ctx->dSplitBegin};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (int i = 0; i < 6; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* rb_last_error(const rb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null handle"; }
+
+extern "C" int rb_device_info(const rb_ctx* ctx, int* cc_major, int* cc_minor, int* sm_count) {
+  if (!ctx) return RB_ERR_ARG;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (sm_count) *sm_count = ctx->sm_count;
+  return RB_OK;
+}
+
+extern "C" void* rb_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (bytes <= 0 || cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void rb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+extern "C" int rb_set_system(rb_ctx* ctx, int N, int Ql, int Qr, const double* A, const double* F, int n_bc,
+                             const int* bc_rows) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (N < 0 || Ql < 0 || Qr < 0 || n_bc < 0 || n_bc > N) RB_FAIL(RB_ERR_ARG, "rb_set_system: negative size or n_bc > N");
+  if (N > 0 && (Ql == 0 || !A || (Qr > 0 && !F))) RB_FAIL(RB_ERR_ARG, "rb_set_system: N > 0 needs A (and F when Qr > 0)");
+  if (n_bc > 0 && !bc_rows) RB_FAIL(RB_ERR_ARG, "rb_set_system: bc_rows is NULL");
+  for (int t = 0; t < n_bc; ++t)
+    if (bc_rows[t] < 0 || bc_rows[t] >= N) RB_FAIL(RB_ERR_ARG, "rb_set_system: bc row out of range");
+  const int NP = roundup(N, 4);
+  if (NP > LU_MAX_NP) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_set_system: N exceeds the supported maximum (160)");
+  ctx->N = N;
+  ctx->NP = NP;
+  ctx->Ql = Ql;
+  ctx->Qr = Qr;
+  ctx->QlP = std::max(4, roundup(Ql, 4));
+  ctx->n_bc = n_bc;
+  ctx->E = NP * NP;
+  ctx->EP = roundup(std::max(ctx->E, 1), ASM_BE);
+  ctx->ldu = std::max(N, 1);
+  ctx->have_system = false;
+  if (N > 0) {
+    if (int rc = dev_realloc(ctx, &ctx->dAq, (size_t)ctx->QlP * ctx->EP)) return rc;
+    if (int rc = dev_realloc(ctx, &ctx->dF, (size_t)std::max(Qr, 1) * NP)) return rc;
+    if (int rc = dev_realloc(ctx, &ctx->dBcRows, (size_t)std::max(n_bc, 1))) return rc;
+    double* dA = nullptr;
+    RB_CUDA(cudaMalloc(&dA, (size_t)Ql * N * N * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(dA, A, (size_t)Ql * N * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+      rb_pack_system_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dA, ctx->dAq, N, NP, Ql, ctx->QlP, ctx->EP);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dA);
+    if (e != cudaSuccess) RB_FAIL(RB_ERR_CUDA, std::string("rb_set_system: ") + cudaGetErrorString(e));
+    std::vector<double> Fp((size_t)std::max(Qr, 1) * NP, 0.0);
+    for (int q = 0; q < Qr; ++q)
+      for (int i = 0; i < N; ++i) Fp[(size_t)q * NP + i] = F[(size_t)q * N + i];
+    RB_CUDA(cudaMemcpy(ctx->dF, Fp.data(), Fp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (n_bc) RB_CUDA(cudaMemcpy(ctx->dBcRows, bc_rows, n_bc * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  ctx->have_system = true;
+  ctx->have_est = false;  // the estimator layout depends on N
+  return RB_OK;
+}
+
+extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col, const int* blk_src_off,
+                                const int* blk_len, int v_theta_off, int v_theta_len, const double* G) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->have_system) RB_FAIL(RB_ERR_STATE, "rb_set_estimator: call rb_set_system first");
+  if (nblk <= 0 || !blk_scale_col || !blk_src_off || !blk_len || !G) RB_FAIL(RB_ERR_ARG, "rb_set_estimator: bad arguments");
+  const int QT = ctx->Ql + ctx->Qr;
+  if (v_theta_off < 0 || v_theta_len < 0 || v_theta_off + v_theta_len > QT)
+    RB_FAIL(RB_ERR_ARG, "rb_set_estimator: v_theta range outside [0, Ql+Qr)");
+  const int LV = ctx->N + v_theta_len + 1;
+  int Kz = 0, Kp = 0;
+  std::vector<int> ks_begin(nblk + 1, 0);
+  for (int b = 0; b < nblk; ++b) {
+    if (blk_len[b] <= 0) RB_FAIL(RB_ERR_ARG, "rb_set_estimator: block length must be positive");
+    if (blk_src_off[b] < 0 || blk_src_off[b] + blk_len[b] > LV) RB_FAIL(RB_ERR_ARG, "rb_set_estimator: block source outside V");
+    if (blk_scale_col[b] >= QT) RB_FAIL(RB_ERR_ARG, "rb_set_estimator: scale column outside theta");
+    Kz += blk_len[b];
+    Kp += roundup(blk_len[b], 4);
+    ks_begin[b + 1] = Kp / 4;
+  }
+  const int KS = Kp / 4;
+  const int n_ctile = (Kp + EST_BN - 1) / EST_BN;
+  const int Cp = n_ctile * EST_BN;
+  // padded index -> unpadded index (or -1), per-column scale / source tables
+  std::vector<int> pad2unpad(std::max(Cp, Kp), -1), col_scale(Cp, -1), col_src(Cp, 0);
+  int zero_src = LV;  // V[LV...] is zero filled
+  {
+    int kp = 0, kz = 0;
+    for (int b = 0; b < nblk; ++b) {
+      const int lp = roundup(blk_len[b], 4);
+      for (int t = 0; t < lp; ++t) {
+        if (t < blk_len[b]) {
+          pad2unpad[kp + t] = kz + t;
+          col_scale[kp + t] = blk_scale_col[b] < 0 ? -1 : blk_scale_col[b];
+          col_src[kp + t] = blk_src_off[b] + t;
+        } else {
+          col_src[kp + t] = zero_src;
+        }
+      }
+      kp += lp;
+      kz += blk_len[b];
+    }
+    for (int c = kp; c < Cp; ++c) col_src[c] = zero_src;
+  }
+  // V tile pitch: >= LV + 4 (A fragments of a padded block may read 3 entries past it; one zero slot) and == 4 mod 8
+  int LVS = LV + 4;
+  while (LVS % 8 != 4) ++LVS;
+  std::vector<long long> tile_off(n_ctile);
+  std::vector<int> tile_ks0(n_ctile), tile_b0(n_ctile);
+  long long off = 0;
+  for (int ct = 0; ct < n_ctile; ++ct) {
+    const int ks0 = std::min(ct * EST_BN / 4, KS);
+    tile_ks0[ct] = ks0;
+    tile_off[ct] = off;
+    off += (long long)(KS - ks0) * EST_KSTEP_DOUBLES;
+    int b0 = 0;
+    while (b0 + 1 < nblk && ks_begin[b0 + 1] <= ks0) ++b0;
+    tile_b0[ct] = b0;
+  }
+  const size_t smem = (size_t)EST_NSTAGE * EST_STAGE_KSTEPS * EST_KSTEP_DOUBLES * 8 + 2 * EST_NSTAGE * 8 +
+                      EST_BM * 8 + (size_t)EST_BM * LVS * 8;
+  if (smem > 227 * 1024) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_set_estimator: N + v_theta_len too large for the estimator tile");
+
+  ctx->nblk = nblk;
+  ctx->Kz = Kz;
+  ctx->Kp = Kp;
+  ctx->KS = KS;
+  ctx->n_ctile = n_ctile;
+  ctx->v_off = v_theta_off;
+  ctx->v_len = v_theta_len;
+  ctx->LV = LV;
+  ctx->LVS = LVS;
+  ctx->h_blk_ks_begin = ks_begin;
+  ctx->h_tile_ks0 = tile_ks0;
+  ctx->gp_doubles = off;
+  ctx->have_est = false;
+
+  if (int rc = dev_realloc(ctx, &ctx->dGp, (size_t)std::max<long long>(off, 1))) return rc;
+  if (int rc = dev_realloc(ctx, &ctx->dTileOff, (size_t)n_ctile)) return rc;
+  if (int rc = dev_realloc(ctx, &ctx->dTileKs0, (size_t)n_ctile)) return rc;
+  if (int rc = dev_realloc(ctx, &ctx->dTileB0, (size_t)n_ctile)) return rc;
+  if (int rc = dev_realloc(ctx, &ctx->dBlkKsBegin, (size_t)nblk + 1)) return rc;
+  if (int rc = dev_realloc(ctx, &ctx->dBlkScale, (size_t)nblk)) return rc;
+  if (int rc = dev_realloc(ctx, &ctx->dBlkSrc, (size_t)nblk)) return rc;
+  if (int rc = dev_realloc(ctx, &ctx->dColScale, (size_t)Cp)) return rc;
+  if (int rc = dev_realloc(ctx, &ctx->dColSrc, (size_t)Cp)) return rc;
+  std::vector<int> scale_norm(nblk);
+  for (int b = 0; b < nblk; ++b) scale_norm[b] = blk_scale_col[b] < 0 ? -1 : blk_scale_col[b];
+  RB_CUDA(cudaMemcpy(ctx->dTileOff, tile_off.data(), n_ctile * sizeof(long long), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(ctx->dTileKs0, tile_ks0.data(), n_ctile * sizeof(int), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(ctx->dTileB0, tile_b0.data(), n_ctile * sizeof(int), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(ctx->dBlkKsBegin, ks_begin.data(), (nblk + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(ctx->dBlkScale, scale_norm.data(), nblk * sizeof(int), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(ctx->dBlkSrc, blk_src_off, nblk * sizeof(int), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(ctx->dColScale, col_scale.data(), Cp * sizeof(int), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(ctx->dColSrc, col_src.data(), Cp * sizeof(int), cudaMemcpyHostToDevice));
+
+  // dense G -> device -> packed G'
+  double* dG = nullptr;
+  int* dP2U = nullptr;
+  RB_CUDA(cudaMalloc(&dG, (size_t)Kz * Kz * sizeof(double)));
+  cudaError_t e = cudaMalloc(&dP2U, pad2unpad.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dG, G, (size_t)Kz * Kz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(dP2U, pad2unpad.data(), pad2unpad.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    dim3 grid(std::max(1, std::min(64, (KS * EST_KSTEP_DOUBLES + 255) / 256)), n_ctile);
+    rb_pack_estimator_kernel<<<grid, 256, 0, ctx->stream>>>(dG, ctx->dGp, ctx->dTileOff, ctx->dTileKs0, dP2U, Kz, KS,
+                                                           n_ctile);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dG);
+  if (dP2U) cudaFree(dP2U);
+  if (e != cudaSuccess) RB_FAIL(RB_ERR_CUDA, std::string("rb_set_estimator: ") + cudaGetErrorString(e));
+  RB_CUDA(cudaFuncSetAttribute(rb_estimator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctx->have_est = true;
+  return RB_OK;
+}
+
+extern "C" int rb_set_training_set(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta, int n_bc,
+                                   const double* ThetaBC, const double* beta, int64_t index_offset,
+                                   int64_t index_stride) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (B <= 0 || n_theta <= 0 || !Theta || !beta || n_bc < 0 || (n_bc > 0 && !ThetaBC) || index_stride <= 0)
+    RB_FAIL(RB_ERR_ARG, "rb_set_training_set: bad arguments");
+  if (B > ctx->Bcap || n_theta != ctx->QT || n_bc != ctx->n_bc_train) {
+    if (int rc = dev_realloc(ctx, &ctx->dTheta, (size_t)B * n_theta)) return rc;
+    if (int rc = dev_realloc(ctx, &ctx->dThetaBC, (size_t)B * std::max(n_bc, 1))) return rc;
+    if (int rc = dev_realloc(ctx, &ctx->dBeta, (size_t)B)) return rc;
+    ctx->Bcap = B;
+  }
+  ctx->B = B;
+  ctx->QT = n_theta;
+  ctx->n_bc_train = n_bc;
+  ctx->idx_off = index_offset;
+  ctx->idx_stride = index_stride;
+  RB_CUDA(cudaMemcpyAsync(ctx->dTheta, Theta, (size_t)B * n_theta * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (n_bc)
+    RB_CUDA(cudaMemcpyAsync(ctx->dThetaBC, ThetaBC, (size_t)B * n_bc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  RB_CUDA(cudaMemcpyAsync(ctx->dBeta, beta, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  RB_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->have_train = true;
+  return RB_OK;
+}
+
+// choose the number of column splits so that units = row-blocks x splits fill the SMs evenly
+static int choose_nsplit(long long nrb, int sms, int n_ctile) {
+  int best = 1;
+  double best_cost = 1e300;
+  for (int s = 1; s <= 16 && s <= n_ctile; ++s) {
+    const long long units = nrb * s;
+    const long long waves = (units + sms - 1) / sms;
+    const double cost = (double)waves / s * (1.0 + 0.004 * (s - 1));
+    if (cost < best_cost - 1e-12) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return best;
+}
+
+extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_val, int64_t* max_idx, double* delta_out,
+                                 double* u_out, double* eps2_out) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->have_system || !ctx->have_est || !ctx->have_train)
+    RB_FAIL(RB_ERR_STATE, "rb_sweep: system, estimator and training set must all be set");
+  if (ctx->QT != ctx->Ql + ctx->Qr) RB_FAIL(RB_ERR_ARG, "rb_sweep: training set theta width != Ql + Qr");
+  if (ctx->n_bc_train != ctx->n_bc) RB_FAIL(RB_ERR_ARG, "rb_sweep: training set n_bc != system n_bc");
+  if (estimator_kind != RB_EST_SQRT_EPS2_OVER_BETA && estimator_kind != RB_EST_SQRT_OF_EPS2_OVER_BETA)
+    RB_FAIL(RB_ERR_ARG, "rb_sweep: unknown estimator kind");
+  const long long B = ctx->B;
+  const int N = ctx->N;
+  cudaStream_t st = ctx->stream;
+  int launches = 0;
+
+  // ---- work buffers
+  const long long nrb = (B + EST_BM - 1) / EST_BM;
+  const int nsplit = choose_nsplit(nrb, ctx->sm_count, ctx->n_ctile);
+  if ((long long)B * ctx->ldu > ctx->u_cap) {
+    if (int rc = dev_realloc(ctx, &ctx->dU, (size_t)B * ctx->ldu)) return rc;
+    ctx->u_cap = (long long)B * ctx->ldu;
+  }
+  if ((long long)nsplit * B > ctx->part_cap) {
+    if (int rc = dev_realloc(ctx, &ctx->dPart, (size_t)nsplit * B)) return rc;
+    ctx->part_cap = (long long)nsplit * B;
+  }
+  if (B > ctx->delta_cap) {
+    if (int rc = dev_realloc(ctx, &ctx->dDelta, (size_t)B)) return rc;
+    if (int rc = dev_realloc(ctx, &ctx->dEps2, (size_t)B)) return rc;
+    ctx->delta_cap = B;
+  }
+  const int fin_blocks = (int)std::min<long long>((B + 255) / 256, ctx->sm_count * 8);
+  if (fin_blocks > ctx->blk_cap) {
+    if (int rc = dev_realloc(ctx, &ctx->dBlkVal, (size_t)fin_blocks)) return rc;
+    if (int rc = dev_realloc(ctx, &ctx->dBlkIdx, (size_t)fin_blocks * 2)) return rc;
+    ctx->blk_cap = fin_blocks;
+  }
+  if (nsplit + 1 > ctx->split_cap) {
+    if (int rc = dev_realloc(ctx, &ctx->dSplitBegin, (size_t)nsplit + 1)) return rc;
+    ctx->split_cap = nsplit + 1;
+  }
+  {
+    // balance the splits by triangular area: tile ct costs (KS - ks0[ct]) k-steps
+    std::vector<int> sb(nsplit + 1, ctx->n_ctile);
+    long long total = 0;
+    for (int ct = 0; ct < ctx->n_ctile; ++ct) total += ctx->KS - ctx->h_tile_ks0[ct];
+    long long accum = 0;
+    int s = 0;
+    sb[0] = 0;
+    for (int ct = 0; ct < ctx->n_ctile && s + 1 < nsplit; ++ct) {
+      accum += ctx->KS - ctx->h_tile_ks0[ct];
+      if (accum * nsplit >= total * (s + 1)) sb[++s] = ct + 1;
+    }
+    for (int t = s + 1; t <= nsplit; ++t) sb[t] = ctx->n_ctile;
+    RB_CUDA(cudaMemcpyAsync(ctx->dSplitBegin, sb.data(), (nsplit + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaStreamSynchronize(st));  // sb is a stack vector
+  }
+
+  RB_CUDA(cudaEventRecord(ctx->ev[0], st));
+  float ms_asm = 0.f, ms_lu = 0.f;
+  if (N > 0) {
+    // chunked assembly + LU; scratch = chunk x EP doubles
+    const long long chunk = std::min<long long>(B, (long long)ctx->sm_count * ASM_BM);
+    if (chunk * ctx->EP > ctx->ab_cap) {
+      if (int rc = dev_realloc(ctx, &ctx->dAb, (size_t)chunk * ctx->EP)) return rc;
+      ctx->ab_cap = chunk * ctx->EP;
+    }
+    const int TS = ctx->QlP + ((ctx->QlP % 8 == 4) ? 0 : 4);
+    const size_t asm_smem = ((size_t)ASM_BM * TS + (size_t)ctx->QlP * (ASM_BE + 4)) * sizeof(double);
+    if (asm_smem > 227 * 1024) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_sweep: too many lhs terms for the assembly tile");
+    RB_CUDA(cudaFuncSetAttribute(rb_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_smem));
+    for (long long c0 = 0; c0 < B; c0 += chunk) {
+      const long long n = std::min(chunk, B - c0);
+      AsmArgs aa;
+      aa.theta = ctx->dTheta + c0 * ctx->QT;
+      aa.Aq = ctx->dAq;
+      aa.Ab = ctx->dAb;
+      aa.count = n;
+      aa.QT = ctx->QT;
+      aa.Ql = ctx->Ql;
+      aa.QlP = ctx->QlP;
+      aa.EP = ctx->EP;
+      dim3 grid(ctx->EP / ASM_BE, (unsigned)((n + ASM_BM - 1) / ASM_BM));
+      rb_assemble_kernel<<<grid, 256, asm_smem, st>>>(aa);
+      RB_CUDA(cudaGetLastError());
+      ++launches;
+      if (int rc = rb_launch_lu(ctx, n, ctx->dAb, ctx->dTheta + c0 * ctx->QT,
+                                ctx->n_bc ? ctx->dThetaBC + c0 * ctx->n_bc : nullptr, ctx->dU + c0 * ctx->ldu))
+        return rc;
+      ++launches;
+    }
+  }
+  RB_CUDA(cudaEventRecord(ctx->ev[1], st));
+  {
+    EstArgs ea;
+    ea.Gp = ctx->dGp;
+    ea.tile_off = ctx->dTileOff;
+    ea.tile_ks0 = ctx->dTileKs0;
+    ea.tile_b0 = ctx->dTileB0;
+    ea.blk_ks_begin = ctx->dBlkKsBegin;
+    ea.blk_scale = ctx->dBlkScale;
+    ea.blk_src = ctx->dBlkSrc;
+    ea.col_scale = ctx->dColScale;
+    ea.col_src = ctx->dColSrc;
+    ea.split_begin = ctx->dSplitBegin;
+    ea.U = ctx->dU;
+    ea.theta = ctx->dTheta;
+    ea.partial = ctx->dPart;
+    ea.B = B;
+    ea.nblk = ctx->nblk;
+    ea.KS = ctx->KS;
+    ea.N = N;
+    ea.ldu = ctx->ldu;
+    ea.QT = ctx->QT;
+    ea.v_off = ctx->v_off;
+    ea.v_len = ctx->v_len;
+    ea.LVS = ctx->LVS;
+    ea.nsplit = nsplit;
+    const size_t smem = (size_t)EST_NSTAGE * EST_STAGE_KSTEPS * EST_KSTEP_DOUBLES * 8 + 2 * EST_NSTAGE * 8 +
+                        EST_BM * 8 + (size_t)EST_BM * ctx->LVS * 8;
+    rb_estimator_kernel<<<(unsigned)(nrb * nsplit), EST_THREADS, smem, st>>>(ea);
+    RB_CUDA(cudaGetLastError());
+    ++launches;
+  }
+  RB_CUDA(cudaEventRecord(ctx->ev[2], st));
+  {
+    long long* blk_nf = ctx->dBlkIdx + fin_blocks;
+    rb_finalize_kernel<<<fin_blocks, 256, 0, st>>>(ctx->dPart, nsplit, ctx->dBeta, B, estimator_kind, ctx->idx_off,
+                                                   ctx->idx_stride, ctx->dDelta, ctx->dEps2, ctx->dBlkVal,
+                                                   ctx->dBlkIdx, blk_nf);
+    RB_CUDA(cudaGetLastError());
+    rb_argmax_final_kernel<<<1, 256, 0, st>>>(ctx->dBlkVal, ctx->dBlkIdx, blk_nf, fin_blocks, (MaxLoc*)ctx->dResult);
+    RB_CUDA(cudaGetLastError());
+    launches += 2;
+  }
+  RB_CUDA(cudaEventRecord(ctx->ev[3], st));
+  MaxLoc res;
+  RB_CUDA(cudaMemcpyAsync(&res, ctx->dResult, sizeof(MaxLoc), cudaMemcpyDeviceToHost, st));
+  if (delta_out) RB_CUDA(cudaMemcpyAsync(delta_out, ctx->dDelta, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (eps2_out) RB_CUDA(cudaMemcpyAsync(eps2_out, ctx->dEps2, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (u_out && N > 0) RB_CUDA(cudaMemcpyAsync(u_out, ctx->dU, (size_t)B * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  (void)ms_asm;
+  (void)ms_lu;
+  float t01 = 0, t12 = 0, t23 = 0, t03 = 0;
+  cudaEventElapsedTime(&t01, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&t12, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&t23, ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&t03, ctx->ev[0], ctx->ev[3]);
+  ctx->last_ms[0] = t01;  // assembly + LU (interleaved per chunk)
+  ctx->last_ms[1] = 0.f;
+  ctx->last_ms[2] = t12;
+  ctx->last_ms[3] = t23;
+  ctx->last_ms[4] = t03;
+  ctx->last_launches = launches;
+  if (max_val) *max_val = res.val;
+  if (max_idx) *max_idx = res.idx;
+  if (res.n_nonfinite > 0) {
+    ctx->err = "rb_sweep: " + std::to_string(res.n_nonfinite) +
+               " non-finite error estimators (singular reduced matrix or beta == 0); numpy.linalg.solve would raise "
+               "LinAlgError";
+    return RB_ERR_SINGULAR;
+  }
+  return RB_OK;
+}
+
+extern "C" int rb_sweep(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta, int n_bc, const double* ThetaBC,
+                        const double* beta, int64_t index_offset, int64_t index_stride, int estimator_kind,
+                        double* max_val, int64_t* max_idx, double* delta_out, double* u_out, double* eps2_out) {
+  if (int rc = rb_set_training_set(ctx, B, n_theta, Theta, n_bc, ThetaBC, beta, index_offset, index_stride)) return rc;
+  return rb_sweep_resident(ctx, estimator_kind, max_val, max_idx, delta_out, u_out, eps2_out);
+}
+
+extern "C" int rb_result_device_ptrs(rb_ctx* ctx, void** maxloc16, double** delta) {
+  if (!ctx) return RB_ERR_ARG;
+  if (maxloc16) *maxloc16 = ctx->dResult;
+  if (delta) *delta = ctx->dDelta;
+  return RB_OK;
+}
+
+extern "C" int rb_last_timings(rb_ctx* ctx, float* ms5, int* n_launches) {
+  if (!ctx) return RB_ERR_ARG;
+  if (ms5) memcpy(ms5, ctx->last_ms, sizeof(ctx->last_ms));
+  if (n_launches) *n_launches = ctx->last_launches;
+  return RB_OK;
+}

@@ -1,0 +1,197 @@
+"""SweepEngine: one handle of the CUDA library = one GPU.  Thin, typed wrapper over the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        assert a.shape == tuple(shape), f"expected shape {shape}, got {a.shape}"
+    return a
+
+
+class SweepEngine:
+    """Greedy sweep over a training set on one B200 (include/rbnics_b200.h)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = L.load()
+        h = C.c_void_p()
+        rc = self._lib.rb_ctx_create(int(device), C.byref(h))
+        if rc != L.RB_OK:
+            raise L.B200LibraryError(
+                f"rb_ctx_create(device={device}) failed with code {rc}: no sm_100 GPU visible? "
+                "(rbnics_b200 has no CPU fallback)")
+        self._h = h
+        self.device = device
+        self.N = self.Ql = self.Qr = 0
+        self.B = 0
+
+    # -- plumbing ----------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == L.RB_OK:
+            return
+        msg = self._lib.rb_last_error(self._h).decode()
+        if rc == L.RB_ERR_SINGULAR:
+            raise L.SingularReducedMatrixError(msg)
+        if rc == L.RB_ERR_ARG:
+            raise ValueError(msg)
+        raise L.B200LibraryError(f"[{rc}] {msg}")
+
+    def device_info(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._check(self._lib.rb_device_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"cc": (a.value, b.value), "sm_count": c.value}
+
+    # -- operators ---------------------------------------------------------------------------------------------
+    def set_system(self, A, F, bc_rows=None):
+        """A: (Ql, N, N), F: (Qr, N); bc_rows: indices of the lifting rows."""
+        A = np.asarray(A, dtype=np.float64)
+        F = np.asarray(F, dtype=np.float64)
+        if A.ndim != 3 or A.shape[1] != A.shape[2]:
+            raise ValueError("A must be (Ql, N, N)")
+        Ql, N = A.shape[0], A.shape[1]
+        if F.ndim != 2 or (N > 0 and F.shape[1] != N):
+            raise ValueError("F must be (Qr, N)")
+        Qr = F.shape[0]
+        A = np.ascontiguousarray(A)
+        F = np.ascontiguousarray(F)
+        bc = np.ascontiguousarray(bc_rows if bc_rows is not None else [], dtype=np.int32)
+        self._check(self._lib.rb_set_system(self._h, N, Ql, Qr, L.dptr(A), L.dptr(F), int(bc.size),
+                                            bc.ctypes.data_as(L.c_int_p)))
+        self.N, self.Ql, self.Qr, self.n_bc = N, Ql, Qr, int(bc.size)
+
+    def set_estimator(self, blk_scale_col, blk_src_off, blk_len, v_theta_off, v_theta_len, G):
+        sc = np.ascontiguousarray(blk_scale_col, dtype=np.int32)
+        so = np.ascontiguousarray(blk_src_off, dtype=np.int32)
+        ln = np.ascontiguousarray(blk_len, dtype=np.int32)
+        Kz = int(ln.sum())
+        G = _f64(G, (Kz, Kz))
+        self._check(self._lib.rb_set_estimator(self._h, int(sc.size), sc.ctypes.data_as(L.c_int_p),
+                                               so.ctypes.data_as(L.c_int_p), ln.ctypes.data_as(L.c_int_p),
+                                               int(v_theta_off), int(v_theta_len), L.dptr(G)))
+
+    def set_elliptic_estimator(self, Gff, Gaf, Gaa):
+        """Residual-norm estimator of rbnics/problems/elliptic/elliptic_rb_reduced_problem.py:55-64.
+
+        Gff: (Qf, Qf), Gaf: (Qa, Qf, N), Gaa: (Qa, Qa, N, N).  z = [theta_a (x) u ; theta_f],
+        G = [[Gaa, Gaf], [Gaf^T, Gff]]  so that z^T G z = aa + 2 af + ff."""
+        G, desc = elliptic_quadratic_form(Gff, Gaf, Gaa, self.Ql, self.Qr, self.N)
+        self.set_estimator(*desc, G)
+
+    # -- training set + sweep ----------------------------------------------------------------------------------
+    def set_training_set(self, Theta, beta, ThetaBC=None, index_offset=0, index_stride=1):
+        Theta = _f64(Theta)
+        beta = _f64(beta)
+        B, QT = Theta.shape
+        assert beta.shape == (B,)
+        nbc = 0
+        if ThetaBC is not None:
+            ThetaBC = _f64(ThetaBC)
+            nbc = ThetaBC.shape[1]
+        self._check(self._lib.rb_set_training_set(self._h, B, QT, L.dptr(Theta), nbc, L.dptr(ThetaBC), L.dptr(beta),
+                                                  int(index_offset), int(index_stride)))
+        self.B = B
+
+    def sweep_resident(self, kind=L.RB_EST_SQRT_EPS2_OVER_BETA, want_delta=False, want_u=False, want_eps2=False,
+                       raise_on_singular=True):
+        mv, mi = C.c_double(), C.c_int64()
+        delta = np.empty(self.B) if want_delta else None
+        u = np.empty((self.B, self.N)) if want_u else None
+        eps2 = np.empty(self.B) if want_eps2 else None
+        rc = self._lib.rb_sweep_resident(self._h, int(kind), C.byref(mv), C.byref(mi), L.dptr(delta), L.dptr(u),
+                                         L.dptr(eps2))
+        if rc != L.RB_ERR_SINGULAR or raise_on_singular:
+            self._check(rc)
+        return {"max": mv.value, "argmax": mi.value, "delta": delta, "u": u, "eps2": eps2}
+
+    def sweep(self, Theta, beta, ThetaBC=None, kind=L.RB_EST_SQRT_EPS2_OVER_BETA, index_offset=0, index_stride=1,
+              want_delta=False, want_u=False, want_eps2=False):
+        """End-to-end entry: host buffers in, (max, argmax) out, copies inside."""
+        Theta = _f64(Theta)
+        beta = _f64(beta)
+        B, QT = Theta.shape
+        nbc = 0
+        if ThetaBC is not None:
+            ThetaBC = _f64(ThetaBC)
+            nbc = ThetaBC.shape[1]
+        mv, mi = C.c_double(), C.c_int64()
+        delta = np.empty(B) if want_delta else None
+        u = np.empty((B, self.N)) if want_u else None
+        eps2 = np.empty(B) if want_eps2 else None
+        self.B = B
+        self._check(self._lib.rb_sweep(self._h, B, QT, L.dptr(Theta), nbc, L.dptr(ThetaBC), L.dptr(beta),
+                                       int(index_offset), int(index_stride), int(kind), C.byref(mv), C.byref(mi),
+                                       L.dptr(delta), L.dptr(u), L.dptr(eps2)))
+        return {"max": mv.value, "argmax": mi.value, "delta": delta, "u": u, "eps2": eps2}
+
+    def last_timings(self):
+        ms = (C.c_float * 5)()
+        n = C.c_int()
+        self._check(self._lib.rb_last_timings(self._h, ms, C.byref(n)))
+        return {"assemble_lu_ms": ms[0], "estimator_ms": ms[2], "finalize_ms": ms[3], "total_ms": ms[4],
+                "launches": n.value}
+
+    def result_device_ptrs(self):
+        p = C.c_void_p()
+        d = L.c_double_p()
+        self._check(self._lib.rb_result_device_ptrs(self._h, C.byref(p), C.byref(d)))
+        return p.value, C.cast(d, C.c_void_p).value
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by page-locked host memory (cudaMallocHost) for the end-to-end path."""
+    lib = L.load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib.rb_host_alloc(max(n, 8))
+    if not p:
+        raise L.B200LibraryError("rb_host_alloc failed")
+    buf = (C.c_char * max(n, 8)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    # keep the allocation alive with the array; freed explicitly by pinned_free
+    arr.flags.writeable = True
+    return arr, p
+
+
+def pinned_free(p):
+    L.load().rb_host_free(C.c_void_p(p))
+
+
+def elliptic_quadratic_form(Gff, Gaf, Gaa, Qa, Qf, N):
+    """Pack (Gff, Gaf, Gaa) into the dense quadratic form + block descriptors of rb_set_estimator.
+
+    Returns (G, (blk_scale_col, blk_src_off, blk_len, v_theta_off, v_theta_len)).
+    Theta columns are [theta_a (Qa) | theta_f (Qf)]; V = [u (N) | theta_f (Qf) | 1]."""
+    Gff = np.asarray(Gff, dtype=np.float64).reshape(Qf, Qf)
+    if N > 0:
+        Gaf = np.asarray(Gaf, dtype=np.float64).reshape(Qa, Qf, N)
+        Gaa = np.asarray(Gaa, dtype=np.float64).reshape(Qa, Qa, N, N)
+        Ka = Qa * N
+        G = np.empty((Ka + Qf, Ka + Qf))
+        G[:Ka, :Ka] = Gaa.transpose(0, 2, 1, 3).reshape(Ka, Ka)
+        Gaf2 = Gaf.transpose(0, 2, 1).reshape(Ka, Qf)
+        G[:Ka, Ka:] = Gaf2
+        G[Ka:, :Ka] = Gaf2.T
+        G[Ka:, Ka:] = Gff
+        scale = list(range(Qa)) + [-1]
+        src = [0] * Qa + [N]
+        length = [N] * Qa + [Qf]
+    else:
+        G = Gff.copy()
+        scale, src, length = [-1], [0], [Qf]
+    return G, (scale, src, length, Qa, Qf)

@@ -1,0 +1,115 @@
+"""GPU parity of the greedy sweep (assembly + LU solve + estimator + arg-max) against the CPU oracle.
+
+Tolerances (north_star): reduced solutions and estimators within 1e-10 relative in FP64; identical arg-max index."""
+import numpy as np
+import pytest
+
+from oracle import rb_oracle as O
+from rbnics_b200 import synthetic
+from rbnics_b200._lib import RB_EST_SQRT_EPS2_OVER_BETA, RB_EST_SQRT_OF_EPS2_OVER_BETA
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def _run(engine, prob, Theta, beta, ThetaBC=None, bc_rows=None, kind=RB_EST_SQRT_EPS2_OVER_BETA):
+    engine.set_system(prob["A"], prob["F"], bc_rows=bc_rows)
+    engine.set_elliptic_estimator(prob["Gff"], prob["Gaf"], prob["Gaa"])
+    engine.set_training_set(Theta, beta, ThetaBC)
+    return engine.sweep_resident(kind=kind, want_delta=True, want_u=True, want_eps2=True)
+
+
+def _check(res, ref, N):
+    d_ref, U_ref, i_ref, v_ref, e_ref = ref
+    if N > 0:
+        err_u = np.max(np.abs(res["u"] - U_ref), axis=1) / np.max(np.abs(U_ref), axis=1)
+        assert err_u.max() <= RTOL, f"u rel err {err_u.max():.3e}"
+    err_e = np.abs(res["eps2"] - e_ref) / np.abs(e_ref)
+    assert err_e.max() <= RTOL, f"eps2 rel err {err_e.max():.3e}"
+    err_d = np.abs(res["delta"] - d_ref) / np.abs(d_ref)
+    assert err_d.max() <= RTOL, f"delta rel err {err_d.max():.3e}"
+    assert res["argmax"] == i_ref
+    assert abs(res["max"] - v_ref) <= RTOL * abs(v_ref)
+
+
+@pytest.mark.parametrize("N,Qa,Qf,B", [(4, 2, 1, 100), (16, 6, 6, 10), (32, 10, 10, 10), (20, 3, 2, 777),
+                                        (33, 5, 3, 300), (64, 9, 3, 500), (100, 50, 10, 384)])
+def test_sweep_matches_batched_oracle(engine, N, Qa, Qf, B):
+    prob = synthetic.elliptic_reduced_problem(N, Qa, Qf, seed=N + Qa, riesz_rank=64)
+    Theta, beta, _ = synthetic.training_set(B, Qa, Qf, seed=B)
+    res = _run(engine, prob, Theta, beta)
+    ref = O.sweep_batched(Theta[:, :Qa], Theta[:, Qa:], beta, prob["A"], prob["F"], prob["Gff"], prob["Gaf"],
+                          prob["Gaa"], return_eps2=True)
+    _check(res, ref, N)
+
+
+@pytest.mark.parametrize("N,Qa,Qf,B", [(4, 2, 1, 100), (16, 6, 6, 10), (25, 4, 3, 40)])
+def test_sweep_matches_reference_loop_oracle(engine, N, Qa, Qf, B):
+    """Against the loop-faithful restatement (sequential sum_q, row-major (i,j) loops, numpy.linalg.solve)."""
+    prob = synthetic.elliptic_reduced_problem(N, Qa, Qf, seed=7, riesz_rank=48)
+    Theta, beta, _ = synthetic.training_set(B, Qa, Qf, seed=11)
+    res = _run(engine, prob, Theta, beta, kind=RB_EST_SQRT_OF_EPS2_OVER_BETA)
+    A_q = [prob["A"][q] for q in range(Qa)]
+    f_q = [prob["F"][q] for q in range(Qf)]
+    G_ff = [[prob["Gff"][i, j] for j in range(Qf)] for i in range(Qf)]
+    G_af = [[prob["Gaf"][i, j] for j in range(Qf)] for i in range(Qa)]
+    G_aa = [[prob["Gaa"][i, j] for j in range(Qa)] for i in range(Qa)]
+    ref = O.sweep_loop(Theta[:, :Qa], Theta[:, Qa:], beta, A_q, f_q, G_ff, G_af, G_aa, N,
+                       kind="sqrt_of_eps2_over_beta", return_eps2=True)
+    _check(res, ref, N)
+
+
+def test_sweep_N0_first_greedy_iteration(engine):
+    """N == 0: empty solution, estimator = sqrt(|thf^T Gff thf|)/beta (parametrized_reduced_differential_problem.py:328-333)."""
+    Qa, Qf, B = 3, 4, 1000
+    prob = synthetic.elliptic_reduced_problem(0, Qa, Qf, seed=3, riesz_rank=16)
+    Theta, beta, _ = synthetic.training_set(B, Qa, Qf, seed=5)
+    res = _run(engine, prob, Theta, beta)
+    ref = O.sweep_batched(Theta[:, :Qa], Theta[:, Qa:], beta, prob["A"], prob["F"], prob["Gff"], prob["Gaf"],
+                          prob["Gaa"], return_eps2=True)
+    _check(res, ref, 0)
+
+
+def test_sweep_with_lifting_rows(engine):
+    """N_bc > 0: rows i < N_bc become identity rows with rhs theta_bc (DirichletBC.py:41-56)."""
+    N, Qa, Qf, B, nbc = 12, 3, 2, 200, 2
+    prob = synthetic.elliptic_reduced_problem(N, Qa, Qf, seed=2, riesz_rank=32)
+    Theta, beta, ThetaBC = synthetic.training_set(B, Qa, Qf, seed=9, n_bc=nbc)
+    res = _run(engine, prob, Theta, beta, ThetaBC=ThetaBC, bc_rows=list(range(nbc)))
+    ref = O.sweep_batched(Theta[:, :Qa], Theta[:, Qa:], beta, prob["A"], prob["F"], prob["Gff"], prob["Gaf"],
+                          prob["Gaa"], Theta_bc=ThetaBC, return_eps2=True)
+    _check(res, ref, N)
+
+
+def test_argmax_ties_take_lowest_index(engine):
+    """Duplicate parameters -> equal estimators -> numpy.argmax returns the first (parameter_space_subset.py:67)."""
+    N, Qa, Qf = 8, 2, 2
+    prob = synthetic.elliptic_reduced_problem(N, Qa, Qf, seed=4, riesz_rank=32)
+    Theta, beta, _ = synthetic.training_set(50, Qa, Qf, seed=1)
+    Theta = np.concatenate([Theta, Theta, Theta])
+    beta = np.concatenate([beta, beta, beta])
+    res = _run(engine, prob, Theta, beta)
+    ref = O.sweep_batched(Theta[:, :Qa], Theta[:, Qa:], beta, prob["A"], prob["F"], prob["Gff"], prob["Gaf"],
+                          prob["Gaa"])
+    assert res["argmax"] == ref[2] < 50
+    d = res["delta"]
+    assert np.array_equal(d[:50], d[50:100]) and np.array_equal(d[:50], d[100:])
+
+
+def test_global_index_mapping_cyclic_shard(engine):
+    """index_offset/stride reproduce the reference's cyclic shard range(rank, len, size) (parameter_space_subset.py:57)."""
+    N, Qa, Qf, B = 8, 2, 2, 101
+    prob = synthetic.elliptic_reduced_problem(N, Qa, Qf, seed=4, riesz_rank=32)
+    Theta, beta, _ = synthetic.training_set(B, Qa, Qf, seed=1)
+    engine.set_system(prob["A"], prob["F"])
+    engine.set_elliptic_estimator(prob["Gff"], prob["Gaf"], prob["Gaa"])
+    full = O.sweep_batched(Theta[:, :Qa], Theta[:, Qa:], beta, prob["A"], prob["F"], prob["Gff"], prob["Gaf"], prob["Gaa"])
+    best = (-1.0, -1)
+    for rank in range(3):
+        sl = slice(rank, B, 3)
+        engine.set_training_set(Theta[sl], beta[sl], index_offset=rank, index_stride=3)
+        r = engine.sweep_resident()
+        if r["max"] > best[0] or (r["max"] == best[0] and r["argmax"] < best[1]):
+            best = (r["max"], r["argmax"])
+    assert best[1] == full[2]
