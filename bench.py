@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- greedy-sweep parameters/second at N=100, Q_a=50, Q_f=10 over a 10^6-parameter training set.
+
+    python bench.py --gpus N --steps K --warmup W            # the B200 arm (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm on the host cores
+
+A "step" is one full greedy sweep (assembly + LU solve + error estimator + arg-max) over the whole training set
+(BASELINE.json configs[2]); at N > 1 the SAME 10^6 parameters are sharded cyclically over the ranks (the reference's
+own data-parallel strategy, rbnics/sampling/parameter_space_subset.py:56-73) => strong scaling.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_RB, Q_A, Q_F = 100, 50, 10
+NTRAIN = 1_000_000
+METRIC = "greedy_sweep_params_per_sec"
+UNIT = "params/s"
+
+
+def flops_per_param(N, Qa, Qf):
+    """Algorithmic FP64 flops of one parameter (DESIGN.md 'Algorithmic work')."""
+    asm = 2 * Qa * N * N + 2 * Qf * N
+    lu = (2 * N ** 3) // 3 + 2 * N * N
+    Kz = Qa * N + Qf
+    est_ref = 2 * Qf * Qf + 2 * Qa * Qf * N + 2 * N + 2 * Qa * Qa * N * N + 2 * N * N + 2 * N  # reference formulation
+    est_sym = Kz * (Kz + 1) + 3 * Kz  # executed: z^T tril(G+G^T) z, z built on the fly, row dot
+    return {"assembly": asm, "lu": lu, "estimator_reference": est_ref, "estimator_sym": est_sym,
+            "F_alg": asm + lu + est_ref, "F_sym": asm + lu + est_sym}
+
+
+def fp64_peak_tflops():
+    """FP64 roofline denominator: MEASURED_PEAKS.json has no FP64 entry, so the DMMA peak measured on this pool
+    by tools/fp64_peak.cu (profiles/FP64_PEAK.json) is used; say which."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mp = json.load(f)
+        for k in ("fp64_tflops", "fp64_dmma_tflops"):
+            if k in mp:
+                return float(mp[k]), "MEASURED_PEAKS.json:" + k
+    except Exception:
+        pass
+    with open(os.path.join(ROOT, "profiles", "FP64_PEAK.json")) as f:
+        p = json.load(f)
+    return float(p["fp64_dmma_tflops"]), "profiles/FP64_PEAK.json (DMMA.8x8x4 peak measured with tools/fp64_peak.cu; MEASURED_PEAKS.json has no FP64 entry)"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference's algorithm; the only place bench.py touches oracle/)
+# ----------------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One emulated MPI rank of the reference: cyclic shard of the sample, per-parameter loop, local arg-max."""
+    rank, size, n_sample, seed_prob, seed_train = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import rb_oracle as O
+    from rbnics_b200 import synthetic
+    prob = synthetic.elliptic_reduced_problem(N_RB, Q_A, Q_F, seed=seed_prob)
+    Theta, beta, _ = synthetic.training_set(n_sample, Q_A, Q_F, seed=seed_train)
+    A_q = [prob["A"][q] for q in range(Q_A)]
+    f_q = [prob["F"][q] for q in range(Q_F)]
+    G_ff = [[prob["Gff"][i, j] for j in range(Q_F)] for i in range(Q_F)]
+    G_af = [[prob["Gaf"][i, j] for j in range(Q_F)] for i in range(Q_A)]
+    G_aa = [[prob["Gaa"][i, j] for j in range(Q_A)] for i in range(Q_A)]
+    idx = list(range(rank, n_sample, size))
+    t0 = time.perf_counter()
+    d, _, i, v = O.sweep_loop(Theta[idx, :Q_A], Theta[idx, Q_A:], beta[idx], A_q, f_q, G_ff, G_af, G_aa, N_RB)
+    return time.perf_counter() - t0, len(idx), float(v), idx[i]
+
+
+def cpu_reference_loop(n_per_core, cores):
+    """R2 of BASELINE.md: the reference's per-parameter loop under its own cyclic MPI sharding, emulated with one
+    process per core (mpi4py is not installed).  Returns params/s."""
+    import multiprocessing as mp
+    n_sample = n_per_core * cores
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        out = pool.map(_cpu_worker, [(r, cores, n_sample, 0, 1) for r in range(cores)])
+    tmax = max(o[0] for o in out)
+    return n_sample / tmax, n_sample, tmax
+
+
+def cpu_vectorized(n_sample, prob):
+    """R3 of BASELINE.md: chunked einsum / batched numpy.linalg.solve with all BLAS threads."""
+    from oracle import rb_oracle as O
+    from rbnics_b200 import synthetic
+    Theta, beta, _ = synthetic.training_set(n_sample, Q_A, Q_F, seed=1)
+    t0 = time.perf_counter()
+    O.sweep_batched(Theta[:, :Q_A], Theta[:, Q_A:], beta, prob["A"], prob["F"], prob["Gff"], prob["Gaf"], prob["Gaa"],
+                    chunk=2048)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    per_core = max(20, int(args.cpu_params_per_core))
+    vals = []
+    for _ in range(max(1, args.warmup)):  # warm-up: page in numpy/BLAS in the workers' image
+        cpu_reference_loop(4, cores)
+        break
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, n_sample, tmax = cpu_reference_loop(per_core, cores)
+        vals.append(v)
+    wall = time.perf_counter() - t_all
+    value = statistics.median(vals)
+    from rbnics_b200 import synthetic
+    prob = synthetic.elliptic_reduced_problem(N_RB, Q_A, Q_F, seed=0)
+    vec, vec_dt = cpu_vectorized(4096 * 4, prob)
+    fl = flops_per_param(N_RB, Q_A, Q_F)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * NTRAIN / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic affine elliptic reduced system N=100 Qa=50 Qf=10, training set 10^6 "
+                               "(BASELINE.json configs[2])", "N": N_RB, "Qa": Q_A, "Qf": Q_F, "ntrain": NTRAIN},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_sample} parameters per step ({per_core} per core, cyclic shards, one process "
+                                   f"per core emulating the reference's mpirun), extrapolated linearly to 10^6; "
+                                   f"loop-faithful numpy port of the per-parameter path (oracle/rb_oracle.py sweep_loop)"},
+        "cpu_vectorized": {"value": vec, "unit": UNIT, "cores": cores,
+                           "sample": f"{4096 * 4} parameters, chunked einsum + batched numpy.linalg.solve"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gflops_fp64_F_alg": fl["F_alg"] * value * 1e-9,
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.tmp.read().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            load = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+            out = {"sm_mhz": statistics.median(load), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                   "samples": len(sm), "power_w_max": max(power)}
+        try:
+            os.unlink(self.tmp.name)
+        except Exception:
+            pass
+        return out
+
+
+def run_b200_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    ntrain = args.ntrain
+
+    # ---- CPU baseline first (rank 0, N=1 only), before any CUDA context exists in this process
+    cpu_baseline = None
+    cpu_vec = None
+    cores = host_cores()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, n_sample, tmax = cpu_reference_loop(max(20, int(args.cpu_params_per_core)), cores)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{n_sample} parameters ({n_sample // cores} per core, cyclic shards over {cores} "
+                                  f"processes emulating the reference's mpirun; {tmax:.1f} s), extrapolated linearly; "
+                                  "loop-faithful numpy port of the per-parameter path (oracle/rb_oracle.py sweep_loop)"}
+
+    from rbnics_b200 import synthetic
+    from rbnics_b200.engine import SweepEngine, pinned_empty, pinned_free
+    from rbnics_b200.sweep import DistributedMaxLoc
+
+    prob = synthetic.elliptic_reduced_problem(N_RB, Q_A, Q_F, seed=0)
+    if cpu_baseline is not None:
+        vec, vec_dt = cpu_vectorized(8192, prob)
+        cpu_vec = {"value": vec, "unit": UNIT, "cores": cores,
+                   "sample": f"8192 parameters ({vec_dt:.1f} s), chunked einsum + batched numpy.linalg.solve, all BLAS threads"}
+
+    dist = DistributedMaxLoc(local_rank) if world > 1 else None
+    eng = SweepEngine(local_rank)
+    eng.set_system(prob["A"], prob["F"])
+    eng.set_elliptic_estimator(prob["Gff"], prob["Gaf"], prob["Gaa"])
+
+    # this rank's cyclic shard of the SAME global training set (identical seed on every rank)
+    n_local = len(range(rank, ntrain, world))
+    Theta_p, hT = pinned_empty((n_local, Q_A + Q_F))
+    beta_p, hB = pinned_empty((n_local,))
+    chunk = 100_000
+    rng_done = 0
+    # generate the global set in chunks and keep rows rank::world (bitwise identical across ranks)
+    g = np.random.default_rng(1)
+    lo = 0
+    while rng_done < ntrain:
+        n = min(chunk, ntrain - rng_done)
+        ta = g.uniform(0.1, 10.0, size=(n, Q_A))
+        tf = g.uniform(-1.0, 1.0, size=(n, Q_F))
+        first = (rank - rng_done) % world
+        rows = slice(first, n, world)
+        k = len(range(first, n, world))
+        Theta_p[lo:lo + k, :Q_A] = ta[rows]
+        Theta_p[lo:lo + k, Q_A:] = tf[rows]
+        lo += k
+        rng_done += n
+    beta_p[:] = Theta_p[:, :Q_A].min(axis=1)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def step_resident():
+        r = eng.sweep_resident()
+        if dist is not None:
+            return dist.maxloc(r["max"], r["argmax"])
+        return r["max"], r["argmax"]
+
+    def step_e2e():
+        r = eng.sweep(Theta_p, beta_p, index_offset=rank, index_stride=world)
+        if dist is not None:
+            return dist.maxloc(r["max"], r["argmax"])
+        return r["max"], r["argmax"]
+
+    # ---- device-resident timing
+    eng.set_training_set(Theta_p, beta_p, index_offset=rank, index_stride=world)
+    for _ in range(args.warmup):
+        res = step_resident()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    est_ms, tot_ms, launches = [], [], 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step_resident()
+        tm = eng.last_timings()
+        est_ms.append(tm["estimator_ms"])
+        tot_ms.append(tm["total_ms"])
+        launches += tm["launches"]
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    if dist is not None:
+        dt = dist.max_float(dt)
+        launches = int(dist.sum_float(float(launches)))
+    ms_per_step = 1e3 * dt / args.steps
+    value = ntrain / (dt / args.steps)
+
+    # ---- end-to-end timing: pinned host buffers in, (max, argmax) out, copies inside
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_e2e = step_e2e()
+    barrier()
+    dt2 = time.perf_counter() - t0
+    if dist is not None:
+        dt2 = dist.max_float(dt2)
+    e2e_value = ntrain / (dt2 / args.steps)
+    h2d = (n_local * (Q_A + Q_F) + n_local) * 8 * world
+    d2h = 24 * world
+
+    if rank == 0:
+        fl = flops_per_param(N_RB, Q_A, Q_F)
+        peak, peak_src = fp64_peak_tflops()
+        est_launch_ms = statistics.mean(est_ms)
+        achieved = fl["estimator_sym"] * n_local / (est_launch_ms * 1e-3) * 1e-12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "estimator_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic affine elliptic reduced system N=100 Qa=50 Qf=10, training set "
+                                   f"{ntrain} parameters sharded cyclically over {world} GPU(s) (BASELINE.json configs[2])",
+                       "N": N_RB, "Qa": Q_A, "Qf": Q_F, "ntrain": ntrain, "parallelism": f"dp{world} (training-set shards)",
+                       "l2": "no flush needed: per-step inputs (Theta 480 MB, assembled-matrix scratch 1.5 GB, "
+                             "packed G' 101 MB) exceed the 126 MB L2",
+                       "timing": "perf_counter around K blocking sweeps bracketed by barrier+stream sync, max over ranks; "
+                                 "kernel times from CUDA events on the engine's stream"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "rb_estimator_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "launch_ms": est_launch_ms,
+                         "algorithmic_flops_per_param": fl["estimator_sym"], "params_per_launch": n_local},
+            "sweep": {"F_sym_flops_per_param": fl["F_sym"], "F_alg_flops_per_param": fl["F_alg"],
+                      "fp64_tflops_F_sym": fl["F_sym"] * value * 1e-12, "frac_of_peak_F_sym": fl["F_sym"] * value * 1e-12 / (peak * world),
+                      "kernel_ms_mean": {"assemble_lu": statistics.mean(tot_ms) - est_launch_ms, "estimator": est_launch_ms},
+                      "argmax": int(res[1]), "max": float(res[0]), "argmax_e2e": int(res_e2e[1])},
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+            line["cpu_vectorized"] = cpu_vec
+        print(json.dumps(line), flush=True)
+    pinned_free(hT)
+    pinned_free(hB)
+    eng.close()
+    if dist is not None:
+        dist.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ntrain", type=int, default=NTRAIN)
+    ap.add_argument("--cpu-params-per-core", type=int, default=400,
+                    help="sample size per host core of the CPU reference loop (~34 ms per parameter)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

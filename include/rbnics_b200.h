@@ -108,6 +108,17 @@ int rb_gram(rb_ctx* ctx, int64_t Nh, int Ns, int Ns2, const double* S, const dou
 int rb_project(rb_ctx* ctx, int64_t Nh, int N, int Q, const double* Z, const int64_t* indptr_all,
                const int32_t* indices_all, const double* data_all, const int64_t* nnz_off, double* out);
 
+/* Z = S V : S Nh x Ns, V Ns x n, Z Nh x n (row-major).  Mode construction b_n = S * eigenvector_n of the POD
+ * (rbnics/backends/basic/proper_orthogonal_decomposition_base.py:77-79, dolfin/wrapping/functions_list_mul.py:10-36)
+ * and reconstruction Z u_N (basis_functions_matrix_mul.py:10-46).                                                 */
+int rb_lincomb(rb_ctx* ctx, int64_t Nh, int Ns, int n, const double* S, const double* V, double* Z);
+/* One single-pass modified Gram-Schmidt step in the X inner product (identity if indptr == NULL):
+ *   for k < n: z -= (z^T X b_k) b_k ;  norm = sqrt(z^T X z) ;  if norm != 0: z /= norm
+ * rbnics/backends/basic/gram_schmidt.py:22-36, dolfin/wrapping/gram_schmidt_projection_step.py:8-11.
+ * Zb: Nh x n row-major (may be NULL when n == 0); z: Nh, updated in place; *norm_out = the norm before scaling.  */
+int rb_gram_schmidt(rb_ctx* ctx, int64_t Nh, int n, const double* Zb, const int64_t* indptr, const int32_t* indices,
+                    const double* data, double* z, double* norm_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,9 @@ SIGNATURES = {
     "rb_host_free": (None, [C.c_void_p]),
     "rb_gram": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, c_double_p, c_double_p, c_int64_p, c_int32_p,
                           c_double_p, C.c_int64, C.c_int64, c_double_p]),
+    "rb_lincomb": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]),
+    "rb_gram_schmidt": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_double_p, c_int64_p, c_int32_p, c_double_p,
+                                  c_double_p, c_double_p]),
     "rb_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, c_double_p, c_int64_p, c_int32_p, c_double_p,
                              c_int64_p, c_double_p]),
 }

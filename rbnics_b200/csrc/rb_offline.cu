@@ -1,14 +1,514 @@
-// rb_offline.cu -- offline basis linear algebra (Gram S^T X S2, Galerkin projections).  Placeholder until the kernels
-// land: returns RB_ERR_UNSUPPORTED (fails loudly; no CPU fallback).
+// rb_offline.cu -- offline basis linear algebra on one B200: C = S^T (X S2) for the POD correlation matrix
+// (rbnics/backends/basic/transpose.py:304-313 called from proper_orthogonal_decomposition_base.py:44-47), the
+// Galerkin projections Z^T A_q Z / Z^T f_q (transpose.py:441-468, 365-400; parametrized_reduced_differential_
+// problem.py:727-790) and the Riesz Gram blocks R_q^T X R_q' (rb_reduced_problem.py:238-258).
+//
+// The reference does Ns sparse mat-vecs and Ns^2 PETSc VecDot calls (each an MPI all-reduce).  Here:
+//   K_spmm : Y = X S2        CSR x dense (dof-major, so every non-zero reads one contiguous row of S2)   -- HBM bound
+//   K_tsmm : C += S^T Y      tall-skinny FP64 GEMM on DMMA.8x8x4, split over dof rows, cp.async double buffering
+//   K_red  : fixed-order sum of the split partials (deterministic)
+// Rows [row_begin, row_end) select this rank's dof partition; the host layer all-reduces the Ns x Ns2 partials.
+#include <algorithm>
+
 #include "rb_common.cuh"
 
-extern "C" int rb_gram(rb_ctx* ctx, int64_t, int, int, const double*, const double*, const int64_t*, const int32_t*,
-                       const double*, int64_t, int64_t, double*) {
-  if (!ctx) return RB_ERR_ARG;
-  RB_FAIL(RB_ERR_UNSUPPORTED, "rb_gram: not implemented yet");
+constexpr int TS_TM = 64, TS_TN = 64, TS_KC = 32, TS_THREADS = 128, TS_STAGES = 3;
+constexpr int TS_PITCH = TS_TM + 4;  // == 4 (mod 16): conflict-free DMMA fragment loads
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Y[r, :] = sum_k data[k] * S2[indices[k], :]  for r in [row_begin, row_end); one warp per (row, 128-column chunk)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rb_spmm_kernel(const long long* __restrict__ indptr,
+                                                      const int* __restrict__ indices,
+                                                      const double* __restrict__ data, const double* __restrict__ S2,
+                                                      int ld2, int ns2, double* __restrict__ Y, int ldy,
+                                                      long long row_begin, long long row_end) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int nchunk = (ns2 + 127) / 128;
+  const long long r = row_begin + warp / nchunk;
+  const int c0 = (int)(warp % nchunk) * 128;
+  if (r >= row_end) return;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const long long k0 = indptr[r], k1 = indptr[r + 1];
+  for (long long k = k0; k < k1; ++k) {
+    const double v = __ldg(data + k);
+    const double* row = S2 + (long long)__ldg(indices + k) * ld2 + c0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int c = lane + 32 * t;
+      if (c0 + c < ns2) acc[t] = fma(v, __ldg(row + c), acc[t]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int c = lane + 32 * t;
+    if (c0 + c < ns2) Y[r * ldy + c0 + c] = acc[t];
+  }
 }
-extern "C" int rb_project(rb_ctx* ctx, int64_t, int, int, const double*, const int64_t*, const int32_t*, const double*,
-                          const int64_t*, double*) {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Partial C tile (64 x 64) over a contiguous range of dof rows: ws[split][i][j] = sum_r S[r][i] * Y[r][j]
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, bool valid) {
+  const uint32_t d = smem_u32(dst);
+  const int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(TS_THREADS) rb_tsmm_kernel(const double* __restrict__ S, int lds, int ns,
+                                                             const double* __restrict__ Y, int ldy, int ns2,
+                                                             long long row_begin, long long row_end,
+                                                             long long rows_per_split, double* __restrict__ ws,
+                                                             int ldw) {
+  extern __shared__ __align__(16) double ts_smem[];
+  double* As = ts_smem;                                   // [STAGES][KC][PITCH]  (rows of S, columns i0..i0+63)
+  double* Bs = ts_smem + TS_STAGES * TS_KC * TS_PITCH;    // [STAGES][KC][PITCH]  (rows of Y, columns j0..j0+63)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 1, wn = warp >> 1;
+  const int i0 = blockIdx.x * TS_TM, j0 = blockIdx.y * TS_TN;
+  const int split = blockIdx.z;
+  const long long rs = row_begin + split * rows_per_split;
+  const long long re = min(row_end, rs + rows_per_split);
+  const int nchunks = (int)((re - rs + TS_KC - 1) / TS_KC);
+
+  auto load_stage = [&](int stage, int chunk) {
+    const long long r0 = rs + (long long)chunk * TS_KC;
+    double* as = As + stage * TS_KC * TS_PITCH;
+    double* bs = Bs + stage * TS_KC * TS_PITCH;
+    for (int t = tid; t < TS_KC * TS_TM; t += TS_THREADS) {
+      const int rr = t / TS_TM, cc = t % TS_TM;
+      const long long r = r0 + rr;
+      const bool rv = r < re;
+      const bool va = rv && (i0 + cc < ns);
+      const bool vb = rv && (j0 + cc < ns2);
+      cp_async8(as + rr * TS_PITCH + cc, va ? (S + r * lds + i0 + cc) : S, va);
+      cp_async8(bs + rr * TS_PITCH + cc, vb ? (Y + r * ldy + j0 + cc) : Y, vb);
+    }
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+  for (int s = 0; s < TS_STAGES - 1; ++s) {
+    if (s < nchunks) load_stage(s, s);
+    cp_async_commit();
+  }
+  const int g = lane >> 2, q4 = lane & 3;
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<TS_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = c + TS_STAGES - 1;
+      if (nxt < nchunks) load_stage(nxt % TS_STAGES, nxt);
+      cp_async_commit();
+    }
+    const double* as = As + (c % TS_STAGES) * TS_KC * TS_PITCH;
+    const double* bs = Bs + (c % TS_STAGES) * TS_KC * TS_PITCH;
+#pragma unroll
+    for (int ks = 0; ks < TS_KC / 4; ++ks) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) af[mt] = as[(4 * ks + q4) * TS_PITCH + wm * 32 + mt * 8 + g];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) bf[nt] = bs[(4 * ks + q4) * TS_PITCH + wn * 32 + nt * 8 + g];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    }
+  }
+  cp_async_wait<0>();
+  double* w = ws + (long long)split * ldw * ldw;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const int i = i0 + wm * 32 + mt * 8 + g;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int j = j0 + wn * 32 + nt * 8 + q4 * 2;
+      *reinterpret_cast<double2*>(w + (long long)i * ldw + j) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+    }
+  }
+}
+
+__global__ void rb_split_reduce_kernel(const double* __restrict__ ws, int ldw, int nsplit, int ns, int ns2,
+                                       double* __restrict__ C) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ns * ns2) return;
+  const int i = t / ns2, j = t % ns2;
+  double s = 0.0;
+  for (int k = 0; k < nsplit; ++k) s += ws[(long long)k * ldw * ldw + (long long)i * ldw + j];
+  C[t] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Host
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+  template <typename T>
+  T* as() {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+// C (host, ns x ns2) = S^T (X S2) over rows [rb, re); all operands already on the device.
+int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, const double* dS2,
+                const long long* dIndptr, const int* dIndices, const double* dData, long long rb, long long re,
+                double* C_host, float* ms_spmm, float* ms_tsmm) {
+  cudaStream_t st = ctx->stream;
+  DevBuf Ybuf, ws, dC;
+  const double* dY = dS2;
+  if (dIndptr) {
+    RB_CUDA(Ybuf.alloc((size_t)Nh * ns2 * sizeof(double)));
+    const int nchunk = (ns2 + 127) / 128;
+    const long long warps = (re - rb) * nchunk;
+    const long long blocks = (warps * 32 + 255) / 256;
+    RB_CUDA(cudaEventRecord(ctx->ev[4], st));
+    if (blocks > 0) {
+      rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIndptr, dIndices, dData, dS2, ns2, ns2, Ybuf.as<double>(), ns2,
+                                                      rb, re);
+      RB_CUDA(cudaGetLastError());
+    }
+    dY = Ybuf.as<double>();
+  } else {
+    RB_CUDA(cudaEventRecord(ctx->ev[4], st));
+  }
+  RB_CUDA(cudaEventRecord(ctx->ev[5], st));
+  const int ti = (ns + TS_TM - 1) / TS_TM, tj = (ns2 + TS_TN - 1) / TS_TN;
+  const int ldw = std::max(ti * TS_TM, tj * TS_TN);
+  const long long rows = std::max<long long>(re - rb, 0);
+  // enough splits for ~3 waves of 148 SMs x 3 resident CTAs, at least TS_KC*8 rows each
+  long long nsplit = std::max<long long>(1, (long long)ctx->sm_count * 9 / (ti * tj));
+  nsplit = std::min(nsplit, std::max<long long>(1, rows / (TS_KC * 8)));
+  nsplit = std::min<long long>(nsplit, 65535);
+  long long rps = (rows + nsplit - 1) / nsplit;
+  rps = (rps + TS_KC - 1) / TS_KC * TS_KC;
+  if (rps == 0) rps = TS_KC;
+  nsplit = std::max<long long>(1, (rows + rps - 1) / rps);
+  RB_CUDA(ws.alloc((size_t)nsplit * ldw * ldw * sizeof(double)));
+  RB_CUDA(dC.alloc((size_t)ns * ns2 * sizeof(double)));
+  const size_t smem = (size_t)2 * TS_STAGES * TS_KC * TS_PITCH * sizeof(double);
+  RB_CUDA(cudaFuncSetAttribute(rb_tsmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ti, tj, (unsigned)nsplit);
+  rb_tsmm_kernel<<<grid, TS_THREADS, smem, st>>>(dS, ns, ns, dY, ns2, ns2, rb, re, rps, ws.as<double>(), ldw);
+  RB_CUDA(cudaGetLastError());
+  rb_split_reduce_kernel<<<(ns * ns2 + 255) / 256, 256, 0, st>>>(ws.as<double>(), ldw, (int)nsplit, ns, ns2,
+                                                                 dC.as<double>());
+  RB_CUDA(cudaGetLastError());
+  RB_CUDA(cudaEventRecord(ctx->ev[0], st));
+  RB_CUDA(cudaMemcpyAsync(C_host, dC.p, (size_t)ns * ns2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  float a = 0, b = 0;
+  cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]);
+  cudaEventElapsedTime(&b, ctx->ev[5], ctx->ev[0]);
+  if (ms_spmm) *ms_spmm = a;
+  if (ms_tsmm) *ms_tsmm = b;
+  ctx->last_ms[0] = a;
+  ctx->last_ms[1] = b;
+  ctx->last_ms[4] = a + b;
+  ctx->last_launches = (dIndptr ? 1 : 0) + 2;
+  return RB_OK;
+}
+}  // namespace
+
+extern "C" int rb_gram(rb_ctx* ctx, int64_t Nh, int Ns, int Ns2, const double* S, const double* S2,
+                       const int64_t* indptr, const int32_t* indices, const double* data, int64_t row_begin,
+                       int64_t row_end, double* C) {
   if (!ctx) return RB_ERR_ARG;
-  RB_FAIL(RB_ERR_UNSUPPORTED, "rb_project: not implemented yet");
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (Nh <= 0 || Ns <= 0 || !S || !C || row_begin < 0 || row_end > Nh || row_begin > row_end)
+    RB_FAIL(RB_ERR_ARG, "rb_gram: bad arguments");
+  if (indptr && (!indices || !data)) RB_FAIL(RB_ERR_ARG, "rb_gram: CSR arrays incomplete");
+  if (!S2) Ns2 = Ns;
+  if (Ns2 <= 0) RB_FAIL(RB_ERR_ARG, "rb_gram: Ns2 must be positive");
+  cudaStream_t st = ctx->stream;
+  DevBuf dS, dS2, dIp, dIx, dDt;
+  RB_CUDA(dS.alloc((size_t)Nh * Ns * sizeof(double)));
+  RB_CUDA(cudaMemcpyAsync(dS.p, S, (size_t)Nh * Ns * sizeof(double), cudaMemcpyHostToDevice, st));
+  const double* pS2 = dS.as<double>();
+  if (S2) {
+    RB_CUDA(dS2.alloc((size_t)Nh * Ns2 * sizeof(double)));
+    RB_CUDA(cudaMemcpyAsync(dS2.p, S2, (size_t)Nh * Ns2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    pS2 = dS2.as<double>();
+  }
+  if (indptr) {
+    const long long nnz = indptr[Nh];
+    RB_CUDA(dIp.alloc((size_t)(Nh + 1) * sizeof(long long)));
+    RB_CUDA(dIx.alloc((size_t)nnz * sizeof(int)));
+    RB_CUDA(dDt.alloc((size_t)nnz * sizeof(double)));
+    RB_CUDA(cudaMemcpyAsync(dIp.p, indptr, (size_t)(Nh + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaMemcpyAsync(dIx.p, indices, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaMemcpyAsync(dDt.p, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  return gram_device(ctx, Nh, Ns, Ns2, dS.as<double>(), pS2, indptr ? dIp.as<long long>() : nullptr,
+                     indptr ? dIx.as<int>() : nullptr, indptr ? dDt.as<double>() : nullptr, row_begin, row_end, C,
+                     nullptr, nullptr);
+}
+
+extern "C" int rb_project(rb_ctx* ctx, int64_t Nh, int N, int Q, const double* Z, const int64_t* indptr_all,
+                          const int32_t* indices_all, const double* data_all, const int64_t* nnz_off, double* out) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (Nh <= 0 || N <= 0 || Q <= 0 || !Z || !indptr_all || !indices_all || !data_all || !nnz_off || !out)
+    RB_FAIL(RB_ERR_ARG, "rb_project: bad arguments");
+  cudaStream_t st = ctx->stream;
+  DevBuf dZ, dIp, dIx, dDt;
+  RB_CUDA(dZ.alloc((size_t)Nh * N * sizeof(double)));
+  RB_CUDA(cudaMemcpyAsync(dZ.p, Z, (size_t)Nh * N * sizeof(double), cudaMemcpyHostToDevice, st));
+  const long long nnz_total = nnz_off[Q];
+  RB_CUDA(dIp.alloc((size_t)Q * (Nh + 1) * sizeof(long long)));
+  RB_CUDA(dIx.alloc((size_t)nnz_total * sizeof(int)));
+  RB_CUDA(dDt.alloc((size_t)nnz_total * sizeof(double)));
+  RB_CUDA(cudaMemcpyAsync(dIp.p, indptr_all, (size_t)Q * (Nh + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaMemcpyAsync(dIx.p, indices_all, (size_t)nnz_total * sizeof(int), cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaMemcpyAsync(dDt.p, data_all, (size_t)nnz_total * sizeof(double), cudaMemcpyHostToDevice, st));
+  float tot_a = 0, tot_b = 0;
+  for (int q = 0; q < Q; ++q) {
+    float a = 0, b = 0;
+    if (int rc = gram_device(ctx, Nh, N, N, dZ.as<double>(), dZ.as<double>(), dIp.as<long long>() + (size_t)q * (Nh + 1),
+                             dIx.as<int>() + nnz_off[q], dDt.as<double>() + nnz_off[q], 0, Nh,
+                             out + (size_t)q * N * N, &a, &b))
+      return rc;
+    tot_a += a;
+    tot_b += b;
+  }
+  ctx->last_ms[0] = tot_a;
+  ctx->last_ms[1] = tot_b;
+  ctx->last_ms[4] = tot_a + tot_b;
+  ctx->last_launches = 3 * Q;
+  return RB_OK;
+}
+
+// =====================================================================================================================
+// Z = S V  (tall GEMM, M = Nh): 128 rows x 64 columns per CTA, K chunks of 32, cp.async double buffering, DMMA
+// =====================================================================================================================
+constexpr int LC_BM = 128, LC_BN = 64, LC_KC = 32, LC_THREADS = 256;
+constexpr int LC_APITCH = LC_KC + 4;  // == 4 (mod 8)
+constexpr int LC_BPITCH = LC_BN + 4;  // == 4 (mod 16)
+
+__global__ void __launch_bounds__(LC_THREADS) rb_lincomb_kernel(const double* __restrict__ S, int ns,
+                                                                const double* __restrict__ V, int n,
+                                                                double* __restrict__ Z, long long Nh) {
+  extern __shared__ __align__(16) double lc_smem[];
+  double(*As)[LC_BM * LC_APITCH] = reinterpret_cast<double(*)[LC_BM * LC_APITCH]>(lc_smem);
+  double(*Bs)[LC_KC * LC_BPITCH] = reinterpret_cast<double(*)[LC_KC * LC_BPITCH]>(lc_smem + 2 * LC_BM * LC_APITCH);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2, g = lane >> 2, q4 = lane & 3;
+  const long long r0 = (long long)blockIdx.x * LC_BM;
+  const int n0 = blockIdx.y * LC_BN;
+  const int nchunks = (ns + LC_KC - 1) / LC_KC;
+  auto load_stage = [&](int stage, int chunk) {
+    const int k0 = chunk * LC_KC;
+    for (int t = tid; t < LC_BM * LC_KC; t += LC_THREADS) {
+      const int rr = t / LC_KC, kk = t % LC_KC;
+      const bool v = (r0 + rr < Nh) && (k0 + kk < ns);
+      cp_async8(&As[stage][rr * LC_APITCH + kk], v ? (S + (r0 + rr) * ns + k0 + kk) : S, v);
+    }
+    for (int t = tid; t < LC_KC * LC_BN; t += LC_THREADS) {
+      const int kk = t / LC_BN, cc = t % LC_BN;
+      const bool v = (k0 + kk < ns) && (n0 + cc < n);
+      cp_async8(&Bs[stage][kk * LC_BPITCH + cc], v ? (V + (long long)(k0 + kk) * n + n0 + cc) : V, v);
+    }
+  };
+  double acc[4][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  load_stage(0, 0);
+  cp_async_commit();
+  for (int c = 0; c < nchunks; ++c) {
+    if (c + 1 < nchunks) load_stage((c + 1) & 1, c + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const double* as = As[c & 1];
+    const double* bs = Bs[c & 1];
+#pragma unroll
+    for (int ks = 0; ks < LC_KC / 4; ++ks) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) af[mt] = as[(wm * 32 + mt * 8 + g) * LC_APITCH + 4 * ks + q4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) bf[nt] = bs[(4 * ks + q4) * LC_BPITCH + wn * 32 + nt * 8 + g];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const long long r = r0 + wm * 32 + mt * 8 + g;
+    if (r >= Nh) continue;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int c = n0 + wn * 32 + nt * 8 + q4 * 2;
+      if (c < n) Z[r * n + c] = acc[mt][nt][0];
+      if (c + 1 < n) Z[r * n + c + 1] = acc[mt][nt][1];
+    }
+  }
+}
+
+extern "C" int rb_lincomb(rb_ctx* ctx, int64_t Nh, int Ns, int n, const double* S, const double* V, double* Z) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (Nh <= 0 || Ns <= 0 || n <= 0 || !S || !V || !Z) RB_FAIL(RB_ERR_ARG, "rb_lincomb: bad arguments");
+  cudaStream_t st = ctx->stream;
+  DevBuf dS, dV, dZ;
+  RB_CUDA(dS.alloc((size_t)Nh * Ns * sizeof(double)));
+  RB_CUDA(dV.alloc((size_t)Ns * n * sizeof(double)));
+  RB_CUDA(dZ.alloc((size_t)Nh * n * sizeof(double)));
+  RB_CUDA(cudaMemcpyAsync(dS.p, S, (size_t)Nh * Ns * sizeof(double), cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaMemcpyAsync(dV.p, V, (size_t)Ns * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  dim3 grid((unsigned)((Nh + LC_BM - 1) / LC_BM), (n + LC_BN - 1) / LC_BN);
+  RB_CUDA(cudaEventRecord(ctx->ev[4], st));
+  const size_t lc_smem_bytes = (size_t)(2 * LC_BM * LC_APITCH + 2 * LC_KC * LC_BPITCH) * sizeof(double);
+  RB_CUDA(cudaFuncSetAttribute(rb_lincomb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc_smem_bytes));
+  rb_lincomb_kernel<<<grid, LC_THREADS, lc_smem_bytes, st>>>(dS.as<double>(), Ns, dV.as<double>(), n, dZ.as<double>(), Nh);
+  RB_CUDA(cudaGetLastError());
+  RB_CUDA(cudaEventRecord(ctx->ev[5], st));
+  RB_CUDA(cudaMemcpyAsync(Z, dZ.p, (size_t)Nh * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  float a = 0;
+  cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]);
+  ctx->last_ms[0] = a;
+  ctx->last_ms[4] = a;
+  ctx->last_launches = 1;
+  return RB_OK;
+}
+
+// =====================================================================================================================
+// Gram-Schmidt step: sequential dot + axpy over the basis columns (deterministic two-stage dots)
+// =====================================================================================================================
+constexpr int GS_BLOCKS = 592, GS_THREADS = 256;
+
+__global__ void __launch_bounds__(GS_THREADS) rb_dot_partial_kernel(const double* __restrict__ x, int incx,
+                                                                    const double* __restrict__ y, int incy,
+                                                                    long long n, double* __restrict__ partial) {
+  __shared__ double sh[GS_THREADS / 32];
+  double s = 0.0;
+  for (long long i = blockIdx.x * (long long)GS_THREADS + threadIdx.x; i < n; i += (long long)GS_BLOCKS * GS_THREADS)
+    s = fma(x[i * incx], y[i * incy], s);
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < GS_THREADS / 32; ++w) t += sh[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__device__ __forceinline__ double gs_sum_partials(const double* partial) {
+  // every block sums the same partials in the same order -> identical, deterministic scalar
+  __shared__ double tot;
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < GS_BLOCKS; ++b) t += partial[b];
+    tot = t;
+  }
+  __syncthreads();
+  return tot;
+}
+
+// z -= d * b  with d = sum(partial)
+__global__ void __launch_bounds__(GS_THREADS) rb_axpy_kernel(const double* __restrict__ partial,
+                                                             const double* __restrict__ b, int incb,
+                                                             double* __restrict__ z, long long n) {
+  const double d = gs_sum_partials(partial);
+  for (long long i = blockIdx.x * (long long)GS_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * GS_THREADS)
+    z[i] = fma(-d, b[i * incb], z[i]);
+}
+
+// z /= sqrt(sum(partial)) unless that is zero; writes the norm
+__global__ void __launch_bounds__(GS_THREADS) rb_normalize_kernel(const double* __restrict__ partial,
+                                                                  double* __restrict__ z, long long n,
+                                                                  double* __restrict__ norm_out) {
+  const double nrm = sqrt(gs_sum_partials(partial));
+  if (blockIdx.x == 0 && threadIdx.x == 0) *norm_out = nrm;
+  if (nrm != 0.0) {
+    for (long long i = blockIdx.x * (long long)GS_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * GS_THREADS)
+      z[i] = z[i] / nrm;
+  }
+}
+
+extern "C" int rb_gram_schmidt(rb_ctx* ctx, int64_t Nh, int n, const double* Zb, const int64_t* indptr,
+                               const int32_t* indices, const double* data, double* z, double* norm_out) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (Nh <= 0 || n < 0 || (n > 0 && !Zb) || !z) RB_FAIL(RB_ERR_ARG, "rb_gram_schmidt: bad arguments");
+  if (indptr && (!indices || !data)) RB_FAIL(RB_ERR_ARG, "rb_gram_schmidt: CSR arrays incomplete");
+  cudaStream_t st = ctx->stream;
+  DevBuf dZ, dXZ, dz, dXz, dIp, dIx, dDt, dPart, dNorm;
+  RB_CUDA(dz.alloc((size_t)Nh * sizeof(double)));
+  RB_CUDA(dPart.alloc(GS_BLOCKS * sizeof(double)));
+  RB_CUDA(dNorm.alloc(sizeof(double)));
+  RB_CUDA(cudaMemcpyAsync(dz.p, z, (size_t)Nh * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (n > 0) {
+    RB_CUDA(dZ.alloc((size_t)Nh * n * sizeof(double)));
+    RB_CUDA(cudaMemcpyAsync(dZ.p, Zb, (size_t)Nh * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  if (indptr) {
+    const long long nnz = indptr[Nh];
+    RB_CUDA(dIp.alloc((size_t)(Nh + 1) * sizeof(long long)));
+    RB_CUDA(dIx.alloc((size_t)nnz * sizeof(int)));
+    RB_CUDA(dDt.alloc((size_t)nnz * sizeof(double)));
+    RB_CUDA(cudaMemcpyAsync(dIp.p, indptr, (size_t)(Nh + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaMemcpyAsync(dIx.p, indices, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, st));
+    RB_CUDA(cudaMemcpyAsync(dDt.p, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  int launches = 0;
+  const double* dXZp = dZ.as<double>();
+  if (indptr && n > 0) {
+    RB_CUDA(dXZ.alloc((size_t)Nh * n * sizeof(double)));
+    const int nchunk = (n + 127) / 128;
+    const long long blocks = (Nh * nchunk * 32 + 255) / 256;
+    rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIp.as<long long>(), dIx.as<int>(), dDt.as<double>(),
+                                                    dZ.as<double>(), n, n, dXZ.as<double>(), n, 0, Nh);
+    RB_CUDA(cudaGetLastError());
+    dXZp = dXZ.as<double>();
+    ++launches;
+  }
+  for (int k = 0; k < n; ++k) {
+    rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dz.as<double>(), 1, dXZp + k, n, Nh, dPart.as<double>());
+    rb_axpy_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dPart.as<double>(), dZ.as<double>() + k, n, dz.as<double>(), Nh);
+    launches += 2;
+  }
+  RB_CUDA(cudaGetLastError());
+  const double* dXzp = dz.as<double>();
+  if (indptr) {
+    RB_CUDA(dXz.alloc((size_t)Nh * sizeof(double)));
+    const long long blocks = (Nh * 32 + 255) / 256;
+    rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIp.as<long long>(), dIx.as<int>(), dDt.as<double>(),
+                                                    dz.as<double>(), 1, 1, dXz.as<double>(), 1, 0, Nh);
+    dXzp = dXz.as<double>();
+    ++launches;
+  }
+  rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dz.as<double>(), 1, dXzp, 1, Nh, dPart.as<double>());
+  rb_normalize_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dPart.as<double>(), dz.as<double>(), Nh, dNorm.as<double>());
+  launches += 2;
+  RB_CUDA(cudaGetLastError());
+  double nrm = 0.0;
+  RB_CUDA(cudaMemcpyAsync(z, dz.p, (size_t)Nh * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaMemcpyAsync(&nrm, dNorm.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  if (norm_out) *norm_out = nrm;
+  ctx->last_launches = launches;
+  return RB_OK;
 }

@@ -1,0 +1,125 @@
+"""Reduced-basis greedy offline loop driven by the batched B200 sweep.
+
+Host-side mirror of ``RBReduction._offline / greedy / _greedy / update_basis_matrix``
+(rbnics/reduction_methods/base/rb_reduction.py:79-185) and of the reduced-problem pieces it calls:
+``build_reduced_operators`` (rbnics/problems/base/parametrized_reduced_differential_problem.py:447-479,727-790) and
+``build_error_estimation_operators`` (rbnics/problems/base/rb_reduced_problem.py:142-263).  Same method names, same
+bookkeeping (``greedy_selected_parameters``, ``greedy_error_estimators``, stop on ``N >= Nmax`` or relative estimator
+``< tol``); the per-parameter closure is replaced by ONE batched sweep per iteration.
+
+The truth problem (high-fidelity solves, Riesz solves) is the reference's job and stays on the host: it is passed in
+as an object with
+
+    operators_a : list of scipy.sparse matrices A_q           operators_f : list of Nh-vectors f_q
+    inner_product : scipy.sparse X                             solve(mu) -> Nh-vector (truth solution)
+    riesz_solve(rhs) -> X^-1 rhs (homogeneous Dirichlet)       compute_theta(term, mus) -> (B x Q) array, vectorised
+    get_stability_factor_lower_bound(mus) -> (B,) array
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+from . import offline
+from .sweep import TrainingSetSweep
+
+
+class ReducedBasisGreedy:
+    def __init__(self, engine, truth_problem, training_set, Nmax, tol, estimator_kind=L.RB_EST_SQRT_EPS2_OVER_BETA,
+                 dist=None, verbose=False):
+        self.engine = engine
+        self.truth_problem = truth_problem
+        self.training_set = [tuple(mu) for mu in training_set]
+        self.Nmax = Nmax
+        self.tol = tol
+        self.kind = estimator_kind
+        self.dist = dist
+        self.verbose = verbose
+        tp = truth_problem
+        self.Qa, self.Qf = len(tp.operators_a), len(tp.operators_f)
+        self.Nh = tp.operators_f[0].shape[0]
+        # theta / beta for the whole training set, once (they do not change during the greedy loop)
+        mus = np.asarray(self.training_set, dtype=np.float64)
+        Theta = np.concatenate([tp.compute_theta("a", mus), tp.compute_theta("f", mus)], axis=1)
+        beta = tp.get_stability_factor_lower_bound(mus)
+        self._sweep = TrainingSetSweep(engine, Theta, beta, dist=dist)
+        # reduced problem state
+        self.N = 0
+        self.basis_functions = np.zeros((self.Nh, 0))
+        self.operator_a = np.zeros((self.Qa, 0, 0))
+        self.operator_f = np.zeros((self.Qf, 0))
+        self.riesz_f = None                      # Nh x Qf
+        self.riesz_a = [np.zeros((self.Nh, 0)) for _ in range(self.Qa)]   # Nh x N each
+        self.G = None
+        self.GS = offline.GramSchmidt(engine, tp.inner_product)
+        self.greedy_selected_parameters = []
+        self.greedy_selected_indices = []
+        self.greedy_error_estimators = []
+        self.mu = None
+
+    # -- reduced_problem.build_reduced_operators() ---------------------------------------------------------------
+    def build_reduced_operators(self):
+        if self.N == 0:
+            self.operator_a = np.zeros((self.Qa, 0, 0))
+            self.operator_f = np.zeros((self.Qf, 0))
+        else:
+            Z = self.basis_functions
+            self.operator_a = offline.project_matrices(self.engine, Z, self.truth_problem.operators_a)
+            self.operator_f = offline.project_vectors(self.engine, Z, self.truth_problem.operators_f)
+        self.engine.set_system(self.operator_a, self.operator_f)
+
+    # -- reduced_problem.build_error_estimation_operators() ------------------------------------------------------
+    def build_error_estimation_operators(self):
+        tp = self.truth_problem
+        if self.riesz_f is None:   # does not depend on N: computed once (rb_reduced_problem.py:156-163)
+            self.riesz_f = np.stack([tp.riesz_solve(f) for f in tp.operators_f], axis=1)
+        for q in range(self.Qa):   # Riesz representers of -A_q z_n for the new basis functions (:183-195)
+            have = self.riesz_a[q].shape[1]
+            new = [tp.riesz_solve(-(tp.operators_a[q] @ self.basis_functions[:, n])) for n in range(have, self.N)]
+            if new:
+                self.riesz_a[q] = np.concatenate([self.riesz_a[q], np.stack(new, axis=1)], axis=1)
+        # all Riesz Gram blocks at once: S = [R_1 | ... | R_Qa | r_f],  G = S^T X S  in z-order [(q, n) ... | f]
+        S = np.concatenate(self.riesz_a + [self.riesz_f], axis=1)
+        self.G = offline.gram(self.engine, S, tp.inner_product, dist=self.dist)
+        N, Qa, Qf = self.N, self.Qa, self.Qf
+        if N > 0:
+            scale = list(range(Qa)) + [-1]
+            src = [0] * Qa + [N]
+            length = [N] * Qa + [Qf]
+        else:
+            scale, src, length = [-1], [0], [Qf]
+        self.engine.set_estimator(scale, src, length, Qa, Qf, self.G)
+
+    # -- RBReduction.greedy / _greedy ----------------------------------------------------------------------------
+    def _greedy(self):
+        return self._sweep.max(kind=self.kind)
+
+    def greedy(self):
+        (error_estimator_max, error_estimator_argmax) = self._greedy()
+        self.mu = self.training_set[error_estimator_argmax]
+        self.greedy_selected_parameters.append(self.mu)
+        self.greedy_selected_indices.append(int(error_estimator_argmax))
+        self.greedy_error_estimators.append(error_estimator_max)
+        return (error_estimator_max, error_estimator_max / self.greedy_error_estimators[0])
+
+    def update_basis_matrix(self, snapshot):
+        new_basis_function = self.GS.apply(snapshot, self.basis_functions)
+        self.basis_functions = np.concatenate([self.basis_functions, new_basis_function[:, None]], axis=1)
+        self.N += 1
+
+    # -- RBReduction._offline ------------------------------------------------------------------------------------
+    def offline(self):
+        self.build_reduced_operators()
+        self.build_error_estimation_operators()
+        (absolute, relative) = self.greedy()
+        if self.verbose:
+            print("initial maximum absolute error estimator over training set =", absolute)
+        while self.N < self.Nmax and relative >= self.tol:
+            snapshot = self.truth_problem.solve(self.mu)
+            self.update_basis_matrix(snapshot)
+            self.build_reduced_operators()
+            self.build_error_estimation_operators()
+            (absolute, relative) = self.greedy()
+            if self.verbose:
+                print("N =", self.N, "max estimator", absolute, "relative", relative)
+        return self

@@ -1,0 +1,187 @@
+"""Offline basis linear algebra on the B200: POD correlation (Gram) matrix, Galerkin projections, POD, Gram-Schmidt.
+
+Mirrors (same operation names / argument meaning):
+  transpose(S) * X * S            rbnics/backends/basic/transpose.py:304-313      -> :func:`gram`
+  transpose(Z) * A_q * Z, Z^T f   rbnics/backends/basic/transpose.py:441-468,365-400 -> :func:`project_matrices`, :func:`project_vectors`
+  S * eigenvector                 rbnics/backends/dolfin/wrapping/functions_list_mul.py:10-36 -> :func:`lincomb`
+  ProperOrthogonalDecomposition   rbnics/backends/basic/proper_orthogonal_decomposition_base.py:39-92 -> :class:`ProperOrthogonalDecomposition`
+  GramSchmidt                     rbnics/backends/basic/gram_schmidt.py:22-36     -> :class:`GramSchmidt`
+
+Snapshots / basis functions are dof-major dense arrays (Nh x Ns, one column per function); inner-product and
+operator matrices are scipy.sparse CSR.  Multi-GPU: the dof rows are partitioned contiguously over the ranks, every
+rank computes a full-size partial and one SUM all-reduce (NCCL) replaces the reference's Ns^2 scalar VecDot
+all-reduces.  The eigen-decomposition of the small Ns x Ns matrix stays on the host
+(scipy.linalg.eigh, exactly the reference's call, rbnics/backends/online/numpy/eigen_solver.py:36-56): replicas only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from math import sqrt
+
+import numpy as np
+import scipy.linalg
+
+from . import _lib as L
+
+
+def _csr_arrays(X):
+    X = X.tocsr()
+    X.sort_indices()
+    return (np.ascontiguousarray(X.indptr, dtype=np.int64), np.ascontiguousarray(X.indices, dtype=np.int32),
+            np.ascontiguousarray(X.data, dtype=np.float64))
+
+
+def row_range(Nh, rank, size):
+    """Contiguous dof-row partition of rank ``rank`` out of ``size`` (PETSc-style ownership ranges)."""
+    per = (Nh + size - 1) // size
+    return min(Nh, rank * per), min(Nh, (rank + 1) * per)
+
+
+def _dist_range(Nh, dist):
+    if dist is None or dist.size == 1:
+        return 0, Nh
+    return row_range(Nh, dist.rank, dist.size)
+
+
+def gram(engine, S, X=None, S2=None, dist=None):
+    """C[i, j] = s_i . (X s2_j)  (Ns x Ns2)."""
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    Nh, Ns = S.shape
+    S2c = None
+    Ns2 = Ns
+    if S2 is not None:
+        S2c = np.ascontiguousarray(S2, dtype=np.float64)
+        assert S2c.shape[0] == Nh
+        Ns2 = S2c.shape[1]
+    Cm = np.empty((Ns, Ns2))
+    rb, re = _dist_range(Nh, dist)
+    if X is not None:
+        assert X.shape == (Nh, Nh)
+        ip, ix, dt = _csr_arrays(X)
+        args = (ip.ctypes.data_as(L.c_int64_p), ix.ctypes.data_as(L.c_int32_p), L.dptr(dt))
+    else:
+        args = (None, None, None)
+    engine._check(engine._lib.rb_gram(engine._h, Nh, Ns, Ns2, L.dptr(S), L.dptr(S2c), *args, rb, re, L.dptr(Cm)))
+    if dist is not None and dist.size > 1:
+        dist.allreduce_sum_(Cm)
+    return Cm
+
+
+def project_matrices(engine, Z, operators, dist=None):
+    """[Z^T A_q Z for q]  -> (Q, N, N).  Single GPU: one batched call; multi GPU: per-operator partial Grams."""
+    Z = np.ascontiguousarray(Z, dtype=np.float64)
+    Nh, N = Z.shape
+    Q = len(operators)
+    if dist is not None and dist.size > 1:
+        return np.stack([gram(engine, Z, A, dist=dist) for A in operators])
+    ips, ixs, dts, off = [], [], [], [0]
+    for A in operators:
+        ip, ix, dt = _csr_arrays(A)
+        ips.append(ip)
+        ixs.append(ix)
+        dts.append(dt)
+        off.append(off[-1] + len(dt))
+    ip = np.concatenate(ips)
+    ix = np.concatenate(ixs) if off[-1] else np.zeros(1, dtype=np.int32)
+    dt = np.concatenate(dts) if off[-1] else np.zeros(1)
+    off = np.asarray(off, dtype=np.int64)
+    out = np.empty((Q, N, N))
+    engine._check(engine._lib.rb_project(engine._h, Nh, N, Q, L.dptr(Z), ip.ctypes.data_as(L.c_int64_p),
+                                         ix.ctypes.data_as(L.c_int32_p), L.dptr(dt), off.ctypes.data_as(L.c_int64_p),
+                                         L.dptr(out)))
+    return out
+
+
+def project_vectors(engine, Z, vectors, dist=None):
+    """[Z^T f_q for q] -> (Q, N): one Gram with S2 = [f_1 ... f_Q]."""
+    Fm = np.ascontiguousarray(np.stack([np.asarray(f, dtype=np.float64) for f in vectors], axis=1))
+    return gram(engine, Z, None, Fm, dist=dist).T.copy()
+
+
+def lincomb(engine, S, V):
+    """Z = S V  (functions_list_mul_online_matrix / _vector)."""
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    Nh, Ns = S.shape
+    assert V.shape[0] == Ns
+    n = V.shape[1]
+    Z = np.empty((Nh, n))
+    engine._check(engine._lib.rb_lincomb(engine._h, Nh, Ns, n, L.dptr(S), L.dptr(V), L.dptr(Z)))
+    return Z
+
+
+class ProperOrthogonalDecomposition:
+    """POD by the method of snapshots; same interface as the reference's backend class
+    (rbnics/backends/abstract/proper_orthogonal_decomposition.py:11-44)."""
+
+    def __init__(self, engine, inner_product=None, dist=None):
+        self.engine = engine
+        self.inner_product = inner_product
+        self.dist = dist
+        self.clear()
+
+    def clear(self):
+        self._snapshots = []
+        self.eigenvalues = []
+        self.retained_energy = []
+
+    def store_snapshot(self, snapshot, weight=None):
+        s = np.asarray(snapshot, dtype=np.float64)
+        self._snapshots.append(s if weight is None else s * weight)
+
+    def snapshots_matrix(self):
+        return np.ascontiguousarray(np.stack(self._snapshots, axis=1))
+
+    def apply(self, Nmax, tol):
+        """-> (eigenvalues[:N], eigenvectors, basis (Nh x N), N)."""
+        S = self.snapshots_matrix()
+        X = self.inner_product
+        correlation = gram(self.engine, S, X, dist=self.dist)
+        eigs, eigv = scipy.linalg.eigh(correlation)          # online/numpy/eigen_solver.py:39
+        idx = eigs.argsort()[::-1]                           # "largest real" (:44-46)
+        eigs, eigv = eigs[idx], eigv[:, idx]
+        Neigs = S.shape[1]
+        Nmax = min(Nmax, Neigs)
+        self.eigenvalues = [float(e) for e in eigs]
+        abs_e = np.abs(eigs)
+        total = abs_e.sum()
+        self.retained_energy = list(np.cumsum(abs_e) / total) if total > 0.0 else [1.0] * Neigs
+        N = 0
+        for n in range(Nmax):
+            N = n + 1
+            if tol > 0.0 and self.retained_energy[n] > 1.0 - tol:
+                break
+        V = np.ascontiguousarray(eigv[:, :N])
+        Z = lincomb(self.engine, S, V)
+        # norm_b = sqrt(b^T X b) from the modes themselves (proper_orthogonal_decomposition_base.py:80-87)
+        norms2 = np.diag(gram(self.engine, Z, X, dist=self.dist))
+        scale = np.array([1.0 / sqrt(v) if v > 0.0 else 1.0 for v in norms2])
+        Z = lincomb(self.engine, S, V * scale[None, :])
+        return self.eigenvalues[:N], [eigv[:, n].copy() for n in range(N)], Z, N
+
+
+class GramSchmidt:
+    """Single-pass modified Gram-Schmidt in the X inner product (rbnics/backends/basic/gram_schmidt.py:22-36)."""
+
+    def __init__(self, engine, inner_product):
+        self.engine = engine
+        self.inner_product = inner_product
+        self._csr = _csr_arrays(inner_product) if inner_product is not None else None
+
+    def apply(self, new_basis_function, basis_functions):
+        z = np.ascontiguousarray(new_basis_function, dtype=np.float64).copy()
+        Nh = z.shape[0]
+        if basis_functions is None:
+            Zb = np.zeros((Nh, 0))
+        else:
+            Zb = np.ascontiguousarray(basis_functions, dtype=np.float64)
+        n = Zb.shape[1]
+        if self._csr is not None:
+            ip, ix, dt = self._csr
+            args = (ip.ctypes.data_as(L.c_int64_p), ix.ctypes.data_as(L.c_int32_p), L.dptr(dt))
+        else:
+            args = (None, None, None)
+        norm = C.c_double()
+        self.engine._check(self.engine._lib.rb_gram_schmidt(self.engine._h, Nh, n, L.dptr(Zb) if n else None, *args,
+                                                            L.dptr(z), C.byref(norm)))
+        return z

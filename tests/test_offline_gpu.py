@@ -1,0 +1,130 @@
+"""GPU parity of the offline basis linear algebra (Gram, projections, POD, Gram-Schmidt) against the CPU oracle.
+
+Tolerances: Gram / projection entries within 1e-10 relative to max|C| (parity defined on the same CSR
+matrix + dense vectors); POD eigenvalues within 1e-10 * lambda_max (north_star)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import rb_oracle as O
+from rbnics_b200 import offline
+from truth_problems import ThermalBlock
+
+pytestmark = pytest.mark.gpu
+
+
+def _lap2d(n):
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(n, n))
+    I = sp.identity(n)
+    return (sp.kron(T, I) + sp.kron(I, T) + 0.5 * sp.identity(n * n)).tocsr()
+
+
+@pytest.mark.parametrize("n,Ns", [(9, 1), (20, 7), (31, 61), (40, 64), (33, 130), (50, 200)])
+def test_gram_matches_loop_oracle(engine, n, Ns):
+    rng = np.random.default_rng(n + Ns)
+    X = _lap2d(n)
+    S = rng.standard_normal((n * n, Ns))
+    C = offline.gram(engine, S, X)
+    ref = O.gram_loop(S, X) if Ns <= 64 else O.gram_blas(S, X)
+    assert np.max(np.abs(C - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
+def test_gram_identity_inner_product_and_rectangular(engine):
+    rng = np.random.default_rng(5)
+    S = rng.standard_normal((1000, 13))
+    S2 = rng.standard_normal((1000, 70))
+    C = offline.gram(engine, S, None, S2)
+    ref = S.T @ S2
+    assert C.shape == (13, 70)
+    assert np.max(np.abs(C - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
+def test_gram_reference_distribution(engine):
+    """Heavy-tailed signed inputs of the reference's own performance tests (test_numpy_utils.py:58-59)."""
+    rng = np.random.default_rng(0)
+    X = _lap2d(16)
+    S = O.reference_rand(rng, 256, 10)
+    C = offline.gram(engine, S, X)
+    ref = O.gram_loop(S, X)
+    assert np.max(np.abs(C - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
+def test_gram_row_partition_sums_to_full(engine):
+    """dof-row partition: the per-rank partials add up to the full Gram matrix."""
+    import ctypes as C
+    from rbnics_b200 import _lib as L
+    rng = np.random.default_rng(2)
+    n = 30
+    X = _lap2d(n)
+    S = np.ascontiguousarray(rng.standard_normal((n * n, 20)))
+    ip, ix, dt = offline._csr_arrays(X)
+    total = np.zeros((20, 20))
+    for rank in range(3):
+        rb, re = offline.row_range(n * n, rank, 3)
+        part = np.empty((20, 20))
+        engine._check(engine._lib.rb_gram(engine._h, n * n, 20, 20, L.dptr(S), None, ip.ctypes.data_as(L.c_int64_p),
+                                          ix.ctypes.data_as(L.c_int32_p), L.dptr(dt), rb, re, L.dptr(part)))
+        total += part
+    ref = O.gram_blas(S, X)
+    assert np.max(np.abs(total - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
+def test_projection_of_operators_and_vectors(engine):
+    tp = ThermalBlock(n=14, nblocks=3, nloads=2)
+    rng = np.random.default_rng(1)
+    Z = rng.standard_normal((tp.Nh, 9))
+    A_N = offline.project_matrices(engine, Z, tp.operators_a)
+    f_N = offline.project_vectors(engine, Z, tp.operators_f)
+    A_ref, f_ref = O.build_reduced_operators(Z, tp.operators_a, tp.operators_f)
+    for q in range(3):
+        assert np.max(np.abs(A_N[q] - O.gram_loop(Z, tp.operators_a[q]))) <= 1e-10 * np.max(np.abs(A_ref[q]))
+    for q in range(2):
+        assert np.max(np.abs(f_N[q] - O.project_vector_loop(Z, tp.operators_f[q]))) <= 1e-10 * np.max(np.abs(f_ref[q]))
+
+
+def test_lincomb(engine):
+    rng = np.random.default_rng(3)
+    S = rng.standard_normal((777, 45))
+    V = rng.standard_normal((45, 70))
+    Z = offline.lincomb(engine, S, V)
+    ref = S @ V
+    assert np.max(np.abs(Z - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
+def test_gram_schmidt_step(engine):
+    tp = ThermalBlock(n=12, nblocks=2)
+    X = tp.inner_product
+    rng = np.random.default_rng(4)
+    Z = np.zeros((tp.Nh, 0))
+    gs = offline.GramSchmidt(engine, X)
+    for k in range(6):
+        snap = rng.standard_normal(tp.Nh)
+        z_gpu = gs.apply(snap, Z)
+        z_ref = O.gram_schmidt(snap, Z, X)
+        assert np.max(np.abs(z_gpu - z_ref)) <= 1e-10 * np.max(np.abs(z_ref))
+        Z = np.concatenate([Z, z_ref[:, None]], axis=1)
+    # X-orthonormal basis
+    assert np.max(np.abs(O.gram_blas(Z, X) - np.eye(6))) < 1e-10
+
+
+def test_pod_eigenvalues_and_modes(engine):
+    tp = ThermalBlock(n=16, nblocks=3, nloads=1)
+    X = tp.inner_product
+    mus = tp.sample_training_set(30, seed=3)
+    snaps = [tp.solve(mu) for mu in mus]
+    pod = offline.ProperOrthogonalDecomposition(engine, X)
+    for s in snaps:
+        pod.store_snapshot(s)
+    eigs, vecs, Z, N = pod.apply(10, 1e-9)
+    S = np.stack(snaps, axis=1)
+    eigs_ref, vecs_ref, Z_ref, N_ref, _ = O.pod(S, X, 10, 1e-9)
+    assert N == N_ref
+    lam_max = abs(eigs_ref[0])
+    assert np.max(np.abs(np.array(eigs) - eigs_ref)) <= 1e-10 * lam_max
+    # modes agree up to sign wherever the eigenvalue is well separated from round-off
+    for n in range(N):
+        if eigs_ref[n] > 1e-8 * lam_max:
+            s = np.sign(np.dot(Z[:, n], X @ Z_ref[:, n]))
+            assert np.max(np.abs(s * Z[:, n] - Z_ref[:, n])) <= 1e-6 * np.max(np.abs(Z_ref[:, n]))
+    G = O.gram_blas(Z, X)
+    assert np.max(np.abs(np.diag(G) - 1.0)) < 1e-10
