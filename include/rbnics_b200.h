@@ -92,6 +92,24 @@ int rb_result_device_ptrs(rb_ctx* ctx, void** maxloc16, double** delta);
  * [0]=assembly GEMM, [1]=LU solve, [2]=estimator GEMM, [3]=finalize+argmax, [4]=total; launches counted. */
 int rb_last_timings(rb_ctx* ctx, float* ms5, int* n_launches);
 
+/* ---- single-parameter entries: the per-mu API of the reference's online backend ---------------------------------
+ * out = sum_q c[q] * ops[q]  for one parameter, in the reference's order AND rounding (multiply, then add, no FMA;
+ * the first term always, later terms skipped when c[q] == 0): rbnics/backends/online/basic/product.py:22-33.
+ * ops: Q x numel.  Bit-identical to the numpy backend.                                                          */
+int rb_affine_combine(rb_ctx* ctx, int Q, int64_t numel, const double* coeffs, const double* ops, double* out);
+/* out = sum_{i,j} th1[i] * ops[i][j] * th2[j], row-major (i, j) order, ((th1*op)*th2) rounding, skipping terms with a
+ * zero theta except (0,0): rbnics/backends/online/basic/product.py:34-46.  ops: Q1 x Q2 x numel.                 */
+int rb_affine_combine2(rb_ctx* ctx, int Q1, int Q2, int64_t numel, const double* th1, const double* th2,
+                       const double* ops, double* out);
+/* x = lhs^-1 rhs for ONE dense N x N system after applying the lifting rows (lhs[row,:] = e_row, rhs[row] = bc_vals):
+ * LinearSolver.solve(), rbnics/backends/online/numpy/linear_solver.py:29-33 + online/basic/linear_solver.py:56-71.
+ * RB_ERR_SINGULAR if the solution is not finite.                                                                  */
+int rb_solve_dense(rb_ctx* ctx, int N, const double* lhs, const double* rhs, int n_bc, const int* bc_rows,
+                   const double* bc_vals, double* x);
+/* *out = u^T (M v), M: m x n row-major (M == NULL: u^T v with m == n): transpose(u)*M*v / transpose(u)*v,
+ * rbnics/backends/basic/transpose.py:126-237.                                                                     */
+int rb_bilinear(rb_ctx* ctx, int m, int n, const double* u, const double* M, const double* v, double* out);
+
 /* Pinned host memory helpers for the end-to-end path. */
 void* rb_host_alloc(int64_t bytes);
 void rb_host_free(void* p);

@@ -40,6 +40,12 @@ SIGNATURES = {
                            C.c_int64, C.c_int, c_double_p, c_int64_p, c_double_p, c_double_p, c_double_p]),
     "rb_result_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(c_double_p)]),
     "rb_last_timings": (C.c_int, [C.c_void_p, c_float_p, c_int_p]),
+    "rb_affine_combine": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_double_p, c_double_p, c_double_p]),
+    "rb_affine_combine2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, c_double_p, c_double_p, c_double_p,
+                                     c_double_p]),
+    "rb_solve_dense": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_int, c_int_p, c_double_p,
+                                 c_double_p]),
+    "rb_bilinear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "rb_host_alloc": (C.c_void_p, [C.c_int64]),
     "rb_host_free": (None, [C.c_void_p]),
     "rb_gram": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, c_double_p, c_double_p, c_int64_p, c_int32_p,

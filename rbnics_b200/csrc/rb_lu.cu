@@ -113,23 +113,7 @@ __global__ void __launch_bounds__(128) rb_lu_smem_kernel(LuArgs args, int NP) {
   }
 }
 
-int rb_launch_lu(rb_ctx* ctx, int64_t count, const double* Ab, const double* theta, const double* thetaBC, double* u) {
-  LuArgs a;
-  a.Ab = Ab;
-  a.theta = theta;
-  a.thetaBC = thetaBC;
-  a.F = ctx->dF;
-  a.bc_rows = ctx->dBcRows;
-  a.U = u;
-  a.count = count;
-  a.N = ctx->N;
-  a.EP = ctx->EP;
-  a.QT = ctx->QT;
-  a.Ql = ctx->Ql;
-  a.Qr = ctx->Qr;
-  a.n_bc = ctx->n_bc;
-  a.ldu = ctx->ldu;
-  const int NP = ctx->NP;
+int rb_launch_lu_args(rb_ctx* ctx, const LuArgs& a, int NP) {
   int rc;
   if (NP <= 52)
     rc = rb_lu_launch_unit0(NP, a, ctx->stream);
@@ -146,12 +130,32 @@ int rb_launch_lu(rb_ctx* ctx, int64_t count, const double* Ab, const double* the
       ctx->err = std::string("rb_lu_smem_kernel smem attribute: ") + cudaGetErrorString(e);
       return RB_ERR_CUDA;
     }
-    rb_lu_smem_kernel<<<(unsigned)count, 128, bytes, ctx->stream>>>(a, NP);
+    rb_lu_smem_kernel<<<(unsigned)a.count, 128, bytes, ctx->stream>>>(a, NP);
     rc = (int)cudaGetLastError();
   }
   if (rc != 0) {
-    ctx->err = std::string("LU launch failed: ") + (rc == -1000 ? "no instantiation for this NP" : cudaGetErrorString((cudaError_t)rc));
+    ctx->err = std::string("LU launch failed: ") +
+               (rc == -1000 ? "no instantiation for this NP" : cudaGetErrorString((cudaError_t)rc));
     return RB_ERR_CUDA;
   }
   return RB_OK;
+}
+
+int rb_launch_lu(rb_ctx* ctx, int64_t count, const double* Ab, const double* theta, const double* thetaBC, double* u) {
+  LuArgs a;
+  a.Ab = Ab;
+  a.theta = theta;
+  a.thetaBC = thetaBC;
+  a.F = ctx->dF;
+  a.bc_rows = ctx->dBcRows;
+  a.U = u;
+  a.count = count;
+  a.N = ctx->N;
+  a.EP = ctx->EP;
+  a.QT = ctx->QT;
+  a.Ql = ctx->Ql;
+  a.Qr = ctx->Qr;
+  a.n_bc = ctx->n_bc;
+  a.ldu = ctx->ldu;
+  return rb_launch_lu_args(ctx, a, ctx->NP);
 }

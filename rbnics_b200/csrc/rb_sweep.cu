@@ -139,17 +139,58 @@ struct EstArgs {
   const double* theta;     // [B][QT]
   double* partial;         // [nsplit][B]
   long long B;
-  int nblk, KS, N, ldu, QT, v_off, v_len, LVS, nsplit;
+  int nblk, KS, N, ldu, QT, v_off, v_len, LVS, nsplit, n_ctile, stage_ksteps;
 };
+
+// shared-memory footprint of rb_estimator_kernel (host + device agree through this one function)
+__host__ __device__ inline size_t est_smem_bytes(int stage_ksteps, int LVS, int nblk, int n_ctile) {
+  size_t b = (size_t)EST_NSTAGE * stage_ksteps * EST_KSTEP_DOUBLES * 8;  // G' stages
+  b += (size_t)EST_NSTAGE * 8;                                            // full barriers
+  b += (size_t)EST_BM * 8;                                                // cross-warp reduction
+  b += (size_t)EST_BM * LVS * 8;                                          // V tile
+  b += (size_t)n_ctile * 8;                                               // tile offsets
+  b += (size_t)(2 * n_ctile + 3 * nblk + 1 + EST_NSTAGE) * 4;             // int tables + release counters
+  return b + 16;
+}
+
+// Fragments of one k-step: B from the staged G' (fragment order, conflict-free LDS.128), A from the V tile.
+struct EstFrag {
+  double2 b01, b23;
+  double a[4];
+};
+
+__device__ __forceinline__ void est_load_frag(EstFrag& f, const double* gs, const double* vp, int LVS) {
+  f.b01 = *reinterpret_cast<const double2*>(gs);
+  f.b23 = *reinterpret_cast<const double2*>(gs + 64);
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) f.a[mt] = vp[mt * 8 * LVS];
+}
+
+__device__ __forceinline__ void est_mma(double (&T)[4][4][2], const EstFrag& f) {
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    dmma884(T[mt][0][0], T[mt][0][1], f.a[mt], f.b01.x);
+    dmma884(T[mt][1][0], T[mt][1][1], f.a[mt], f.b01.y);
+    dmma884(T[mt][2][0], T[mt][2][1], f.a[mt], f.b23.x);
+    dmma884(T[mt][3][0], T[mt][3][1], f.a[mt], f.b23.y);
+  }
+}
 
 __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a) {
   extern __shared__ __align__(128) unsigned char est_smem_raw[];
-  constexpr int STAGE_DOUBLES = EST_STAGE_KSTEPS * EST_KSTEP_DOUBLES;
-  double* Gs = reinterpret_cast<double*>(est_smem_raw);                 // [NSTAGE][STAGE_DOUBLES]
+  const int SK = a.stage_ksteps;
+  const int STAGE_DOUBLES = SK * EST_KSTEP_DOUBLES;
+  double* Gs = reinterpret_cast<double*>(est_smem_raw);                     // [NSTAGE][STAGE_DOUBLES]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(Gs + EST_NSTAGE * STAGE_DOUBLES);
-  uint64_t* empty_bar = full_bar + EST_NSTAGE;
-  double* red = reinterpret_cast<double*>(empty_bar + EST_NSTAGE);     // [EST_BM]
-  double* Vs = red + EST_BM;                                            // [EST_BM][LVS]
+  double* red = reinterpret_cast<double*>(full_bar + EST_NSTAGE);          // [EST_BM]
+  double* Vs = red + EST_BM;                                                // [EST_BM][LVS]
+  long long* s_tile_off = reinterpret_cast<long long*>(Vs + EST_BM * a.LVS);  // [n_ctile]
+  int* s_tile_ks0 = reinterpret_cast<int*>(s_tile_off + a.n_ctile);         // [n_ctile]
+  int* s_tile_b0 = s_tile_ks0 + a.n_ctile;                                  // [n_ctile]
+  int* s_ks_begin = s_tile_b0 + a.n_ctile;                                  // [nblk+1]
+  int* s_scale = s_ks_begin + (a.nblk + 1);                                 // [nblk]
+  int* s_src = s_scale + a.nblk;                                            // [nblk]
+  int* s_cnt = s_src + a.nblk;                                              // [NSTAGE] release counters
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int split = blockIdx.x % a.nsplit;
@@ -173,112 +214,166 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a)
     }
     Vs[t] = v;
   }
+  for (int t = tid; t < a.n_ctile; t += EST_THREADS) {
+    s_tile_off[t] = a.tile_off[t];
+    s_tile_ks0[t] = a.tile_ks0[t];
+    s_tile_b0[t] = a.tile_b0[t];
+  }
+  for (int t = tid; t <= a.nblk; t += EST_THREADS) {
+    s_ks_begin[t] = a.blk_ks_begin[t];
+    if (t < a.nblk) {
+      s_scale[t] = a.blk_scale[t];
+      s_src[t] = a.blk_src[t];
+    }
+  }
   if (tid == 0) {
     for (int s = 0; s < EST_NSTAGE; ++s) {
       mbar_init(full_bar + s, 1);
-      mbar_init(empty_bar + s, EST_CONSUMER_WARPS);
+      s_cnt[s] = 0;
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp == EST_CONSUMER_WARPS) {
-    // ---------------- producer: stream G' stages with 1-D bulk copies ----------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int ct = ct_begin; ct < ct_end; ++ct) {
-        const int nks = a.KS - a.tile_ks0[ct];
-        const double* src = a.Gp + a.tile_off[ct];
-        for (int k = 0; k < nks; k += EST_STAGE_KSTEPS) {
-          const int n = min(EST_STAGE_KSTEPS, nks - k);
-          mbar_wait(empty_bar + stage, phase ^ 1u);
-          const uint32_t bytes = (uint32_t)n * EST_KSTEP_DOUBLES * 8u;
-          mbar_arrive_expect_tx(full_bar + stage, bytes);
-          bulk_g2s(Gs + stage * STAGE_DOUBLES, src + (long long)k * EST_KSTEP_DOUBLES, bytes, full_bar + stage);
-          if (++stage == EST_NSTAGE) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-      }
+  // ---- G' stream: 1-D bulk copies (TMA engine).  Cursor = next stage to issue; every warp advances it identically,
+  // the warp that is LAST to release a stage slot issues the refill of that slot (no dedicated producer warp).
+  int pct = ct_begin, pk = 0;
+  auto issue_stage = [&](int slot) {  // called by exactly one thread per stage
+    const int nks = a.KS - s_tile_ks0[pct];
+    const int n = min(SK, nks - pk);
+    const uint32_t bytes = (uint32_t)n * EST_KSTEP_DOUBLES * 8u;
+    mbar_arrive_expect_tx(full_bar + slot, bytes);
+    bulk_g2s(Gs + slot * STAGE_DOUBLES, a.Gp + s_tile_off[pct] + (long long)pk * EST_KSTEP_DOUBLES, bytes,
+             full_bar + slot);
+  };
+  auto advance_cursor = [&]() {
+    pk += SK;
+    if (pk >= a.KS - s_tile_ks0[pct]) {
+      ++pct;
+      pk = 0;
     }
-    return;
+  };
+  for (int s = 0; s < EST_NSTAGE; ++s) {
+    if (pct < ct_end) {
+      if (tid == 0) issue_stage(s);
+      advance_cursor();
+    }
   }
 
-  // ---------------- consumers: 8 warps, 4 (m) x 2 (n), warp tile 32 x 32 ----------------
   const int wm = warp & 3, wn = warp >> 2;
   const int g = lane >> 2, q4 = lane & 3;
   const int r0 = wm * 32 + g;  // + mt*8
+  const double* vrow = Vs + r0 * LVS + q4;
+  const double* gsw = Gs + wn * 128 + lane * 2;
+  const double* th_base = a.theta;
   long long prow[4];
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) prow[mt] = min(p0 + r0 + mt * 8, a.B - 1);
+  for (int mt = 0; mt < 4; ++mt) prow[mt] = min(p0 + r0 + mt * 8, a.B - 1) * a.QT;
   double rowacc[4] = {0.0, 0.0, 0.0, 0.0};
   int stage = 0;
   uint32_t phase = 0;
 
   for (int ct = ct_begin; ct < ct_end; ++ct) {
-    double Y[4][4][2];
+    double Y[4][4][2], T[4][4][2];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) Y[mt][nt][0] = Y[mt][nt][1] = 0.0;
+      for (int nt = 0; nt < 4; ++nt) Y[mt][nt][0] = Y[mt][nt][1] = T[mt][nt][0] = T[mt][nt][1] = 0.0;
 
-    int ks = a.tile_ks0[ct];
-    int kin = 0;                                   // k-step within the current stage
-    int nin = min(EST_STAGE_KSTEPS, a.KS - ks);    // k-steps held by the current stage
-    bool waited = false;
-    for (int b = a.tile_b0[ct]; b < a.nblk; ++b) {
-      const int kend = a.blk_ks_begin[b + 1];
-      const int sc = a.blk_scale[b];
-      int src = a.blk_src[b] + 4 * (ks - a.blk_ks_begin[b]) + q4;
-      double th[4];
+    int ks = s_tile_ks0[ct];
+    int b = s_tile_b0[ct];
+    int kend = s_ks_begin[b + 1];
+    const int src = s_src[b] + 4 * (ks - s_ks_begin[b]);
+    int kin = 0;                   // k-step within the current stage
+    int nin = min(SK, a.KS - ks);  // k-steps held by the current stage
+    double th[4], thn[4];
+    {
+      const int sc = s_scale[b];
+      const int scn = (b + 1 < a.nblk) ? s_scale[b + 1] : -1;
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) th[mt] = (sc < 0) ? 1.0 : __ldg(a.theta + prow[mt] * a.QT + sc);
-      double T[4][4][2];
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) T[mt][nt][0] = T[mt][nt][1] = 0.0;
+      for (int mt = 0; mt < 4; ++mt) {
+        th[mt] = (sc < 0) ? 1.0 : __ldg(th_base + prow[mt] + sc);
+        thn[mt] = (scn < 0) ? 1.0 : __ldg(th_base + prow[mt] + scn);
+      }
+    }
+    mbar_wait(full_bar + stage, phase);
+    const double* gp = gsw + stage * STAGE_DOUBLES;   // this warp's B fragments of the current k-step
+    const double* vp = vrow + src;                    // this thread's A fragments of the current k-step
+    EstFrag f0, f1;
+    est_load_frag(f0, gp, vp, LVS);
 
-      for (; ks < kend; ++ks) {
-        if (!waited) {
-          mbar_wait(full_bar + stage, phase);
-          waited = true;
+    // The k loop is cut into segments that end at the next stage or block boundary, so that the steady-state body is
+    // 16 DMMAs + the fragment loads of the next k-step and nothing else (two warps per SM sub-partition then run in
+    // anti-phase: one issues DMMAs while the other does its loads / boundary bookkeeping).
+    while (true) {
+      const int nseg = min(kend - ks, nin - kin);
+      int i = nseg;
+      while (i > 2) {  // steady state, two k-steps per trip (ping-pong fragment buffers)
+        est_mma(T, f0);
+        est_load_frag(f1, gp + EST_KSTEP_DOUBLES, vp + 4, LVS);
+        est_mma(T, f1);
+        gp += 2 * EST_KSTEP_DOUBLES;
+        vp += 8;
+        est_load_frag(f0, gp, vp, LVS);
+        i -= 2;
+      }
+      if (i == 2) {
+        est_mma(T, f0);
+        gp += EST_KSTEP_DOUBLES;
+        vp += 4;
+        est_load_frag(f0, gp, vp, LVS);
+      }
+      est_mma(T, f0);  // last k-step of the segment; its successor is loaded after the boundary bookkeeping
+      ks += nseg;
+      kin += nseg;
+      gp += EST_KSTEP_DOUBLES;
+      vp += 4;
+      const bool tile_done = (ks == a.KS);
+      if (kin == nin) {  // stage consumed: release it; the last warp to do so refills the slot
+        __syncwarp();
+        if (lane == 0) {
+          const int old = atomicAdd(&s_cnt[stage], 1);
+          if (old == EST_WARPS - 1) {
+            s_cnt[stage] = 0;
+            if (pct < ct_end) issue_stage(stage);
+          }
         }
-        const double* bp = Gs + stage * STAGE_DOUBLES + kin * EST_KSTEP_DOUBLES + wn * 128 + lane * 2;
-        const double2 b01 = *reinterpret_cast<const double2*>(bp);
-        const double2 b23 = *reinterpret_cast<const double2*>(bp + 64);
-        double af[4];
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) af[mt] = Vs[(r0 + mt * 8) * LVS + src];
-        src += 4;
+        if (pct < ct_end) advance_cursor();
+        if (++stage == EST_NSTAGE) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        kin = 0;
+        nin = min(SK, a.KS - ks);
+        gp = gsw + stage * STAGE_DOUBLES;
+        if (!tile_done) mbar_wait(full_bar + stage, phase);
+      }
+      const bool blk_done = (ks == kend);
+      if (blk_done && !tile_done) {
+        ++b;
+        kend = s_ks_begin[b + 1];
+        vp = vrow + s_src[b];
+      }
+      if (!tile_done) est_load_frag(f0, gp, vp, LVS);
+      if (blk_done) {  // fold the finished block: Y += theta_b * T
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
-          dmma884(T[mt][0][0], T[mt][0][1], af[mt], b01.x);
-          dmma884(T[mt][1][0], T[mt][1][1], af[mt], b01.y);
-          dmma884(T[mt][2][0], T[mt][2][1], af[mt], b23.x);
-          dmma884(T[mt][3][0], T[mt][3][1], af[mt], b23.y);
-        }
-        if (++kin == nin) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty_bar + stage);
-          if (++stage == EST_NSTAGE) {
-            stage = 0;
-            phase ^= 1u;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            Y[mt][nt][0] = fma(th[mt], T[mt][nt][0], Y[mt][nt][0]);
+            Y[mt][nt][1] = fma(th[mt], T[mt][nt][1], Y[mt][nt][1]);
+            T[mt][nt][0] = 0.0;
+            T[mt][nt][1] = 0.0;
           }
-          kin = 0;
-          nin = min(EST_STAGE_KSTEPS, a.KS - (ks + 1));
-          waited = false;
+          th[mt] = thn[mt];
+        }
+        if (!tile_done) {
+          const int scn = (b + 1 < a.nblk) ? s_scale[b + 1] : -1;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) thn[mt] = (scn < 0) ? 1.0 : __ldg(th_base + prow[mt] + scn);
         }
       }
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          Y[mt][nt][0] = fma(th[mt], T[mt][nt][0], Y[mt][nt][0]);
-          Y[mt][nt][1] = fma(th[mt], T[mt][nt][1], Y[mt][nt][1]);
-        }
+      if (tile_done) break;
     }
 
     // epilogue of the column tile: rowacc[p] += sum_c Y[p,c] * z[p,c]
@@ -292,7 +387,7 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a)
         const int csr = __ldg(a.col_src + c);
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
-          const double thc = (csc < 0) ? 1.0 : __ldg(a.theta + prow[mt] * a.QT + csc);
+          const double thc = (csc < 0) ? 1.0 : __ldg(th_base + prow[mt] + csc);
           const double zc = thc * Vs[(r0 + mt * 8) * LVS + csr];
           rowacc[mt] = fma(Y[mt][nt][e], zc, rowacc[mt]);
         }
@@ -310,7 +405,7 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a)
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) red[r0 + mt * 8] = rowacc[mt];
   }
-  asm volatile("bar.sync 1, %0;" ::"r"(EST_CONSUMER_WARPS * 32) : "memory");
+  __syncthreads();
   if (wn == 0 && q4 == 0) {
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
@@ -604,8 +699,10 @@ extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col,
     while (b0 + 1 < nblk && ks_begin[b0 + 1] <= ks0) ++b0;
     tile_b0[ct] = b0;
   }
-  const size_t smem = (size_t)EST_NSTAGE * EST_STAGE_KSTEPS * EST_KSTEP_DOUBLES * 8 + 2 * EST_NSTAGE * 8 +
-                      EST_BM * 8 + (size_t)EST_BM * LVS * 8;
+  if (nblk > EST_MAX_BLOCKS) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_set_estimator: too many z blocks");
+  int stage_ksteps = 16;
+  while (stage_ksteps > 2 && est_smem_bytes(stage_ksteps, LVS, nblk, n_ctile) > 227 * 1024) stage_ksteps /= 2;
+  const size_t smem = est_smem_bytes(stage_ksteps, LVS, nblk, n_ctile);
   if (smem > 227 * 1024) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_set_estimator: N + v_theta_len too large for the estimator tile");
 
   ctx->nblk = nblk;
@@ -617,6 +714,7 @@ extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col,
   ctx->v_len = v_theta_len;
   ctx->LV = LV;
   ctx->LVS = LVS;
+  ctx->stage_ksteps = stage_ksteps;
   ctx->h_blk_ks_begin = ks_begin;
   ctx->h_tile_ks0 = tile_ks0;
   ctx->gp_doubles = off;
@@ -826,8 +924,9 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     ea.v_len = ctx->v_len;
     ea.LVS = ctx->LVS;
     ea.nsplit = nsplit;
-    const size_t smem = (size_t)EST_NSTAGE * EST_STAGE_KSTEPS * EST_KSTEP_DOUBLES * 8 + 2 * EST_NSTAGE * 8 +
-                        EST_BM * 8 + (size_t)EST_BM * ctx->LVS * 8;
+    ea.n_ctile = ctx->n_ctile;
+    ea.stage_ksteps = ctx->stage_ksteps;
+    const size_t smem = est_smem_bytes(ctx->stage_ksteps, ctx->LVS, ctx->nblk, ctx->n_ctile);
     rb_estimator_kernel<<<(unsigned)(nrb * nsplit), EST_THREADS, smem, st>>>(ea);
     RB_CUDA(cudaGetLastError());
     ++launches;
