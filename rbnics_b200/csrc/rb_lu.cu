@@ -1,10 +1,13 @@
 // rb_lu.cu -- dispatcher of the batched LU solve + shared-memory fallback for NP > LU_MAX_NP_REG.
+#include <stdlib.h>
+
 #include "rb_lu_kernel.cuh"
 
 int rb_lu_launch_unit0(int NP, const LuArgs& args, cudaStream_t stream);
 int rb_lu_launch_unit1(int NP, const LuArgs& args, cudaStream_t stream);
 int rb_lu_launch_unit2(int NP, const LuArgs& args, cudaStream_t stream);
 int rb_lu_launch_unit3(int NP, const LuArgs& args, cudaStream_t stream);
+int rb_lu_dmma_dispatch(int N, const LuArgs& args, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Fallback: matrix in shared memory ([NP][NP+1], odd pitch), one CTA of 128 threads per system, explicit row swaps.
@@ -115,7 +118,10 @@ __global__ void __launch_bounds__(128) rb_lu_smem_kernel(LuArgs args, int NP) {
 
 int rb_launch_lu_args(rb_ctx* ctx, const LuArgs& a, int NP) {
   int rc;
-  if (NP <= 52)
+  static const bool force_rowreg = getenv("RB_LU_ROWREG") != nullptr;  // A/B switch for profiling the older kernel
+  if (NP > 32 && NP <= LU_MAX_NP_REG && !force_rowreg)
+    rc = rb_lu_dmma_dispatch(a.N, a, ctx->stream);
+  else if (NP <= 52)
     rc = rb_lu_launch_unit0(NP, a, ctx->stream);
   else if (NP <= 80)
     rc = rb_lu_launch_unit1(NP, a, ctx->stream);
