@@ -17,6 +17,20 @@
 #pragma once
 #include "rb_lu_kernel.cuh"
 
+#ifdef LUD_TIMING
+__device__ unsigned long long lud_timing[32];
+#define LUD_TDECL long long lud_t_last = clock64();
+#define LUD_T(i)                                                             \
+  if (lane == 0) {                                                           \
+    const long long now__ = clock64();                                       \
+    atomicAdd(&lud_timing[i], (unsigned long long)(now__ - lud_t_last));     \
+    lud_t_last = now__;                                                      \
+  }
+#else
+#define LUD_TDECL
+#define LUD_T(i)
+#endif
+
 constexpr int LUD_PP = 12;  // pitch of the panel / multiplier buffers (doubles): conflict-free A fragments, 16 B rows
 
 template <int NT, int NC>
@@ -28,22 +42,101 @@ struct LudCfg {
   static constexpr int SPC = WS >= 4 ? 1 : 4 / WS;
   static constexpr int THREADS = WS * 32 * SPC;
   static constexpr int P_OFF = 0;                                // [NP8][PP]
-  static constexpr int L_OFF = P_OFF + NP8 * LUD_PP;             // [NP8][PP]  negated multipliers
-  static constexpr int U_OFF = L_OFF + NP8 * LUD_PP;             // [NP8][UP]  U rows in pivot order (+ rhs column N)
+  static constexpr int L_OFF = P_OFF;                            // [NP8][PP]  negated multipliers; ALIASES the panel buffer:
+                                                                 // B reads the whole panel into registers before it writes nL, and the tile warps
+                                                                 // only store the next panel after their last read of nL (barrier LUD_BAR_C2)
+  static constexpr int U_OFF = P_OFF + NP8 * LUD_PP;             // [NP8][UP]  U rows in pivot order (+ rhs column N)
   static constexpr int R_OFF = U_OFF + NP8 * UP;                 // [NP8] reciprocal pivots
-  static constexpr int UB_OFF = R_OFF + NP8;                     // [8] pivot-row broadcast
-  static constexpr int PIV_OFF = UB_OFF + 8;                     // [NP8] ints (NP8/2 doubles)
+  static constexpr int UB_OFF = R_OFF + NP8;                     // [2][32][10] candidate rows of the panel warp's lanes
+  static constexpr int PIV_OFF = UB_OFF + 2 * 32 * 10;                     // [NP8] ints (NP8/2 doubles)
   static constexpr int DOUBLES = PIV_OFF + NP8 / 2 + 2;
   static constexpr int BYTES_PER_SYS = ((DOUBLES * 8 + 15) / 16) * 16;
   static constexpr int BYTES = BYTES_PER_SYS * SPC;
 };
 
+// branch-free select (the compiler turns "cond ? a : b" on a lane-varying condition into divergent branches here)
+__device__ __forceinline__ double lud_selp(double a, double b, int x, int y) {  // x == y ? a : b
+  double r;
+  asm("{\n .reg .pred p;\n setp.eq.s32 p, %3, %4;\n selp.f64 %0, %1, %2, p;\n}" : "=d"(r) : "d"(a), "d"(b), "r"(x), "r"(y));
+  return r;
+}
+
+// One pivot step T of phase B as a template: a "#pragma unroll" of the t loop is not honoured for a body of this size
+// (the front end then indexes pv[j][t] dynamically through select ladders, ~10x more instructions per step).
+template <int T>
+__device__ __forceinline__ void lud_pivot_step(double (&pv)[4][8], int (&tst)[4], unsigned& dmask, int* pivrow,
+                                               double* rinvs, double* ubuf, int p, int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int t = T;
+  // local best among this lane's live rows (strict >: the lower row of the lane wins ties)
+  unsigned long long key = 0ull;
+  int jb = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned long long kj =
+        ((dmask >> j) & 1u) ? 0ull : ((unsigned long long)__double_as_longlong(fabs(pv[j][t])) + 1ull);
+    if (kj > key) {
+      key = kj;
+      jb = j;
+    }
+  }
+  // arg-max of the 64-bit key over the warp, lowest row index on ties (idamax): REDUX.MAX on the high word, then
+  // REDUX.MAX on {low word without its 7 lowest bits, 127 - row}.  Candidates that differ only below 2^-45 relative
+  // are treated as equal (any of them is an equally good pivot).
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mhi = __reduce_max_sync(FULL, hi);
+  // the lane's candidate row (columns >= t), selected branch-free; every lane stages it (and a speculative
+  // reciprocal) in its shared-memory slot while the reductions are in flight; the winner's slot is then read by all
+  // lanes (one __syncwarp per step)
+  double sel[8];
+#pragma unroll
+  for (int c = t; c < 8; ++c) {
+    double v = pv[0][c];
+    v = lud_selp(pv[1][c], v, jb, 1);
+    v = lud_selp(pv[2][c], v, jb, 2);
+    v = lud_selp(pv[3][c], v, jb, 3);
+    sel[c] = v;
+  }
+  const double myrinv = 1.0 / sel[t];
+  double* slot = ubuf + ((t & 1) * 32 + lane) * 10;
+#pragma unroll
+  for (int c = t + 1; c < 8; ++c) slot[c] = sel[c];
+  slot[8] = myrinv;
+  const int myrow = jb * 32 + lane;
+  const unsigned k2 = (hi == mhi && key != 0ull) ? ((lo & ~127u) | (unsigned)(127 - myrow)) : 0u;
+  const unsigned m2 = __reduce_max_sync(FULL, k2);
+  const int prow = 127 - (int)(m2 & 127u);
+  const int ol = prow & 31;
+  if ((lane == ol) && (k2 == m2)) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j == jb) tst[j] = t;
+    dmask |= 1u << jb;
+    pivrow[8 * p + t] = prow;
+    rinvs[8 * p + t] = myrinv;
+  }
+  __syncwarp();
+  const double* wslot = ubuf + ((t & 1) * 32 + ol) * 10;
+  const double rinv = wslot[8];
+  double u[8];
+#pragma unroll
+  for (int c = t + 1; c < 8; ++c) u[c] = wslot[c];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (!((dmask >> j) & 1u)) {
+      const double l = pv[j][t] * rinv;
+      pv[j][t] = l;
+#pragma unroll
+      for (int c = t + 1; c < 8; ++c) pv[j][c] = fma(-l, u[c], pv[j][c]);
+    }
+  }
+}
+
 // Phase B.  Returns the updated per-lane mask of used rows (bit j = row lane+32j).
-__device__ __forceinline__ unsigned lud_panel_factor(double* __restrict__ P, double* __restrict__ nL,
+__device__ __forceinline__ unsigned lud_panel_factor(double* P, double* nL,
                                                   double* __restrict__ Uf, int* __restrict__ pivrow,
                                                   double* __restrict__ rinvs, double* __restrict__ ubuf, int p, int N,
                                                   int NP8, int UP, unsigned dmask, int lane) {
-  constexpr unsigned FULL = 0xffffffffu;
   const unsigned dmask_in = dmask;
   double pv[4][8];
   int tst[4];
@@ -66,65 +159,14 @@ __device__ __forceinline__ unsigned lud_panel_factor(double* __restrict__ P, dou
     }
   }
   const int nst = min(8, N - 8 * p);
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    if (t < nst) {
-      // local best among this lane's live rows (strict >: the lower row of the lane wins ties)
-      unsigned long long key = 0ull;
-      int jb = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned long long kj =
-            ((dmask >> j) & 1u) ? 0ull : ((unsigned long long)__double_as_longlong(fabs(pv[j][t])) + 1ull);
-        if (kj > key) {
-          key = kj;
-          jb = j;
-        }
-      }
-      double sel[8];  // the lane's candidate row; the winner's copy is the pivot row
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        double v = pv[0][c];
-        v = (jb == 1) ? pv[1][c] : v;
-        v = (jb == 2) ? pv[2][c] : v;
-        v = (jb == 3) ? pv[3][c] : v;
-        sel[c] = v;
-      }
-      const double myrinv = 1.0 / sel[t];  // speculative: overlaps the reductions, only the winner's is used
-      // arg-max of the 64-bit key over the warp, lowest row index on ties (idamax): REDUX.MAX on the high word, then
-      // REDUX.MAX on {low word without its 7 lowest bits, 127 - row}.  Candidates that differ only below 2^-45
-      // relative are treated as equal (any of them is an equally good pivot).
-      const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-      const unsigned mhi = __reduce_max_sync(FULL, hi);
-      const int myrow = jb * 32 + lane;
-      const unsigned k2 = (hi == mhi && key != 0ull) ? ((lo & ~127u) | (unsigned)(127 - myrow)) : 0u;
-      const unsigned m2 = __reduce_max_sync(FULL, k2);
-      const int prow = 127 - (int)(m2 & 127u);
-      const int ol = prow & 31;
-      const bool iown = (lane == ol) && (k2 == m2);
-      if (iown) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j == jb) tst[j] = t;
-        dmask |= 1u << jb;
-        pivrow[8 * p + t] = prow;
-        rinvs[8 * p + t] = myrinv;
-      }
-      const double rinv = __shfl_sync(FULL, myrinv, ol);
-      double u[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) u[c] = (c > t) ? __shfl_sync(FULL, sel[c], ol) : 0.0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (!((dmask >> j) & 1u)) {
-          const double l = pv[j][t] * rinv;
-          pv[j][t] = l;
-#pragma unroll
-          for (int c = t + 1; c < 8; ++c) pv[j][c] = fma(-l, u[c], pv[j][c]);
-        }
-      }
-    }
-  }
+  lud_pivot_step<0>(pv, tst, dmask, pivrow, rinvs, ubuf, p, lane);
+  if (nst > 1) lud_pivot_step<1>(pv, tst, dmask, pivrow, rinvs, ubuf, p, lane);
+  if (nst > 2) lud_pivot_step<2>(pv, tst, dmask, pivrow, rinvs, ubuf, p, lane);
+  if (nst > 3) lud_pivot_step<3>(pv, tst, dmask, pivrow, rinvs, ubuf, p, lane);
+  if (nst > 4) lud_pivot_step<4>(pv, tst, dmask, pivrow, rinvs, ubuf, p, lane);
+  if (nst > 5) lud_pivot_step<5>(pv, tst, dmask, pivrow, rinvs, ubuf, p, lane);
+  if (nst > 6) lud_pivot_step<6>(pv, tst, dmask, pivrow, rinvs, ubuf, p, lane);
+  if (nst > 7) lud_pivot_step<7>(pv, tst, dmask, pivrow, rinvs, ubuf, p, lane);
   // negated multipliers of every row for phases C2 / D, and the diagonal block of U
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -192,30 +234,16 @@ __global__ void __launch_bounds__(LudCfg<NT, NC>::THREADS, 2) rb_lu_dmma_kernel(
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (lane + 32 * j >= N) dmask |= 1u << j;
+    LUD_TDECL
     for (int p = 0; p < npan; ++p) {
       lud_bar_sync(LUD_BAR_P, NTH);
+      LUD_T(0)
       dmask = lud_panel_factor(P, nL, Uf, pivrow, rinvs, ubuf, p, N, NP8, UP, dmask, lane);
+      LUD_T(1)
       lud_bar_arrive(LUD_BAR_B, NTH);
-      if (p + 1 < NC) {
-        lud_bar_sync(LUD_BAR_C, NTH);
-        // C2: unit-lower 8x8 solve on the gathered rows, one lane per trailing column
-        for (int col = 8 * (p + 1) + lane; col < 8 * NC; col += 32) {
-          double x[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) x[t] = Uf[(8 * p + t) * UP + col];
-#pragma unroll
-          for (int t = 1; t < 8; ++t) {
-            const double* nlrow = nL + pivrow[8 * p + t] * LUD_PP;
-#pragma unroll
-            for (int s = 0; s < t; ++s) x[t] = fma(nlrow[s], x[s], x[t]);
-          }
-#pragma unroll
-          for (int t = 1; t < 8; ++t) Uf[(8 * p + t) * UP + col] = x[t];
-        }
-        lud_bar_arrive(LUD_BAR_C2, NTH);
-      }
     }
     lud_bar_sync(LUD_BAR_END, NTH);
+    LUD_T(2)
     // back-substitution U x = y; lane owns rows lane, lane+32, ...; y is column N of the U store
     constexpr int R = (NP8 + 31) / 32;
     double acc[R], ri[R], xo[R];
@@ -246,10 +274,12 @@ __global__ void __launch_bounds__(LudCfg<NT, NC>::THREADS, 2) rb_lu_dmma_kernel(
       const int row = r * 32 + lane;
       if (row < N) u[row] = xo[r];
     }
+    LUD_T(3)
     return;
   }
 
   // =================== tile warps: phases A, C and D ===================
+  LUD_TDECL
   const int g = lane >> 2, q4 = lane & 3;
   const int NPc = (N + 3) / 4 * 4;  // leading dimension of the assembled matrices (column-major)
   const int tr0 = 2 * w, tr1 = 2 * w + 1;
@@ -315,9 +345,11 @@ __global__ void __launch_bounds__(LudCfg<NT, NC>::THREADS, 2) rb_lu_dmma_kernel(
   };
 
   store_panel(0);
+  if (w == 0) { LUD_T(10) }
   lud_bar_arrive(LUD_BAR_P, NTH);
   for (int p = 0; p < npan; ++p) {
     lud_bar_sync(LUD_BAR_B, NTH);  // panel p factored: pivot rows, multipliers, diagonal block of U
+    if (w == 0) { LUD_T(11) }
     if (p + 1 < NC) {
       // ---- C: gather the trailing part of the 8 pivot rows (pivot order) from registers
 #pragma unroll
@@ -344,8 +376,25 @@ __global__ void __launch_bounds__(LudCfg<NT, NC>::THREADS, 2) rb_lu_dmma_kernel(
         a10 = nL[(8 * tr1 + g) * LUD_PP + q4];
         a11 = nL[(8 * tr1 + g) * LUD_PP + 4 + q4];
       }
-      lud_bar_arrive(LUD_BAR_C, NTH);
-      lud_bar_sync(LUD_BAR_C2, NTH);  // final U rows of panel p
+      lud_bar_sync(LUD_BAR_C, W * 32);  // tile warps only: the gathered rows are complete
+      if (w == 0) { LUD_T(12) }
+      // ---- C2: unit-lower 8x8 solve on the gathered rows, one thread per trailing column
+      for (int col = 8 * (p + 1) + tid; col < 8 * NC; col += W * 32) {
+        double x[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) x[t] = Uf[(8 * p + t) * UP + col];
+#pragma unroll
+        for (int t = 1; t < 8; ++t) {
+          const double* nlrow = nL + pivrow[8 * p + t] * LUD_PP;
+#pragma unroll
+          for (int s = 0; s < t; ++s) x[t] = fma(nlrow[s], x[s], x[t]);
+        }
+#pragma unroll
+        for (int t = 1; t < 8; ++t) Uf[(8 * p + t) * UP + col] = x[t];
+      }
+      if (w == 0) { LUD_T(13) }
+      lud_bar_sync(LUD_BAR_C2, W * 32);  // tile warps only: final U rows of panel p
+      if (w == 0) { LUD_T(14) }
       // ---- D: rank-8 update of the register tiles right of the panel (2 DMMA per tile); the next panel's tile
       // column goes first and is handed to the panel warp at once (look-ahead: phase B(p+1) overlaps the rest of D(p))
       const double* ub0 = Uf + (8 * p + q4) * UP + g;
@@ -364,6 +413,7 @@ __global__ void __launch_bounds__(LudCfg<NT, NC>::THREADS, 2) rb_lu_dmma_kernel(
       }
       if (p + 1 < npan) {
         store_panel(p + 1);
+        if (w == 0) { LUD_T(15) }
         lud_bar_arrive(LUD_BAR_P, NTH);
       }
 #pragma unroll
@@ -381,6 +431,7 @@ __global__ void __launch_bounds__(LudCfg<NT, NC>::THREADS, 2) rb_lu_dmma_kernel(
     }
   }
   lud_bar_arrive(LUD_BAR_END, NTH);
+  if (w == 0) { LUD_T(16) }
 }
 
 template <int NT, int NC>
