@@ -1,0 +1,319 @@
+"""Per-parameter online backend on the B200: host-side mirror of ``rbnics/backends/online/numpy`` for the calls on the
+greedy-sweep path, same names and argument meaning:
+
+    AffineExpansionStorage   rbnics/backends/online/basic/affine_expansion_storage.py:22-54,329-349
+    product / sum            rbnics/backends/online/basic/product.py:22-46, sum.py:8-9, numpy/product.py:23-25
+    LinearSolver             rbnics/backends/online/basic/linear_solver.py:19-71, numpy/linear_solver.py:25-33
+    transpose                rbnics/backends/basic/transpose.py:126-237 (vector^T * matrix * vector, vector^T * vector)
+    Matrix / Vector / Function   rbnics/backends/online/numpy/{matrix,vector,function}.py
+
+Every arithmetic call goes through the C ABI (``rb_affine_combine[2]``, ``rb_solve_dense``, ``rb_bilinear``) into
+CUDA; there is no numpy fallback.  The affine sums keep the reference's order AND rounding (multiply then add, zero
+thetas skipped except the first term), so they are bit-identical to the numpy backend.  The greedy loop itself does
+not use these one-at-a-time calls: it uses the batched sweep (``rbnics_b200.sweep``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from numbers import Number
+
+import numpy as np
+
+from . import _lib as L
+
+_engine = None
+
+
+def set_engine(engine):
+    """Engine (= GPU) used by the class-based API below."""
+    global _engine
+    _engine = engine
+
+
+def get_engine():
+    global _engine
+    if _engine is None:
+        from .engine import SweepEngine
+        _engine = SweepEngine(0)  # raises without a B200: no CPU fallback
+    return _engine
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# functional layer (explicit engine)
+# ----------------------------------------------------------------------------------------------------------------------
+def affine_combine(engine, thetas, ops):
+    """sum_q thetas[q] * ops[q] in the reference's order and rounding.  ops: (Q, ...) -> (...)."""
+    ops = np.ascontiguousarray(ops, dtype=np.float64)
+    th = np.ascontiguousarray(thetas, dtype=np.float64)
+    Q = ops.shape[0]
+    if th.shape != (Q,):
+        raise ValueError("thetas and operators have different lengths")
+    out = np.empty(ops.shape[1:])
+    engine._check(engine._lib.rb_affine_combine(engine._h, Q, out.size, L.dptr(th), L.dptr(ops), L.dptr(out)))
+    return out
+
+
+def affine_combine2(engine, thetas, thetas2, ops):
+    """sum_ij thetas[i] * ops[i, j] * thetas2[j], row-major (i, j) order.  ops: (Q1, Q2, ...) -> (...)."""
+    ops = np.ascontiguousarray(ops, dtype=np.float64)
+    t1 = np.ascontiguousarray(thetas, dtype=np.float64)
+    t2 = np.ascontiguousarray(thetas2, dtype=np.float64)
+    Q1, Q2 = ops.shape[0], ops.shape[1]
+    if t1.shape != (Q1,) or t2.shape != (Q2,):
+        raise ValueError("thetas and operators have different lengths")
+    out = np.empty(ops.shape[2:])
+    engine._check(engine._lib.rb_affine_combine2(engine._h, Q1, Q2, out.size, L.dptr(t1), L.dptr(t2), L.dptr(ops),
+                                                 L.dptr(out)))
+    return out
+
+
+def solve_dense(engine, lhs, rhs, bc_rows=None, bc_vals=None):
+    """x = lhs^-1 rhs after the lifting rows (LinearSolver.solve)."""
+    lhs = np.ascontiguousarray(lhs, dtype=np.float64)
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    N = rhs.shape[0]
+    if lhs.shape != (N, N):
+        raise ValueError("lhs must be N x N and rhs N")
+    rows = np.ascontiguousarray(bc_rows if bc_rows is not None else [], dtype=np.int32)
+    vals = np.ascontiguousarray(bc_vals if bc_vals is not None else [], dtype=np.float64)
+    if rows.shape != vals.shape:
+        raise ValueError("bc_rows and bc_vals have different lengths")
+    x = np.empty(N)
+    engine._check(engine._lib.rb_solve_dense(engine._h, N, L.dptr(lhs), L.dptr(rhs), int(rows.size),
+                                             rows.ctypes.data_as(L.c_int_p), L.dptr(vals), L.dptr(x)))
+    return x
+
+
+def bilinear(engine, u, M, v):
+    """u^T M v (M is None: u^T v)."""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    if M is not None:
+        M = np.ascontiguousarray(M, dtype=np.float64)
+        if M.shape != (u.shape[0], v.shape[0]):
+            raise ValueError("transpose(u)*M*v: inconsistent shapes")
+    elif u.shape != v.shape:
+        raise ValueError("transpose(u)*v: inconsistent shapes")
+    out = C.c_double()
+    engine._check(engine._lib.rb_bilinear(engine._h, u.shape[0], v.shape[0], L.dptr(u), L.dptr(M), L.dptr(v),
+                                          C.byref(out)))
+    return out.value
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Matrix / Vector / Function (thin ndarray subclasses; the reference's wrappers forward arithmetic to ndarray too,
+# rbnics/backends/online/basic/matrix.py:216-235)
+# ----------------------------------------------------------------------------------------------------------------------
+class _MatrixType(np.ndarray):
+    @property
+    def M(self):
+        return self.shape[0]
+
+    @property
+    def N(self):
+        return self.shape[1]
+
+
+class _VectorType(np.ndarray):
+    @property
+    def N(self):
+        return self.shape[0]
+
+
+class _FunctionType:
+    def __init__(self, vec):
+        self._v = vec
+
+    def vector(self):
+        return self._v
+
+    @property
+    def N(self):
+        return self._v.shape[0]
+
+
+def Matrix(M, N=None):
+    """Matrix(M, N) -> zero matrix; Matrix(ndarray) wraps (copy)."""
+    if isinstance(M, np.ndarray):
+        return np.array(M, dtype=np.float64).view(_MatrixType)
+    return np.zeros((M, N)).view(_MatrixType)
+
+
+def Vector(N):
+    if isinstance(N, np.ndarray):
+        return np.array(N, dtype=np.float64).view(_VectorType)
+    return np.zeros(N).view(_VectorType)
+
+
+def Function(N):
+    if isinstance(N, _FunctionType):
+        return _FunctionType(N._v.copy())
+    return _FunctionType(Vector(N))
+
+
+Matrix.Type = lambda: _MatrixType
+Vector.Type = lambda: _VectorType
+Function.Type = lambda: _FunctionType
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# AffineExpansionStorage
+# ----------------------------------------------------------------------------------------------------------------------
+class AffineExpansionStorage:
+    """Order-1 (Q,) or order-2 (Q1, Q2) storage of reduced operators: matrices, vectors or scalars.
+
+    ``AffineExpansionStorage(Q)`` / ``(Q1, Q2)`` creates empty storage filled by ``storage[q] = item``;
+    ``AffineExpansionStorage((op_0, op_1, ...))`` wraps a tuple.  ``storage[:N, :N]`` / ``storage[:N]`` slices
+    every item (affine_expansion_storage.py:329-349); slices are cached like the reference's precomputed slices."""
+
+    def __init__(self, arg1, arg2=None):
+        if isinstance(arg1, (tuple, list)):
+            self._content = np.empty((len(arg1),), dtype=object)
+            for i, a in enumerate(arg1):
+                self[i] = a
+        elif arg2 is None:
+            self._content = np.empty((int(arg1),), dtype=object)
+        else:
+            self._content = np.empty((int(arg1), int(arg2)), dtype=object)
+        self._slices = {}
+        self._stacked = None
+
+    def order(self):
+        return self._content.ndim
+
+    def __len__(self):
+        assert self.order() == 1
+        return self._content.shape[0]
+
+    @property
+    def shape(self):
+        return self._content.shape
+
+    def __setitem__(self, key, item):
+        if isinstance(item, Number):
+            item = float(item)
+        else:
+            item = np.ascontiguousarray(item, dtype=np.float64)
+        self._content[key] = item
+        self._slices = {}
+        self._stacked = None
+
+    def __getitem__(self, key):
+        if isinstance(key, (int, np.integer)) or (isinstance(key, tuple) and all(isinstance(k, (int, np.integer)) for k in key)):
+            return self._content[key]
+        ck = repr(key)
+        if ck not in self._slices:
+            out = AffineExpansionStorage.__new__(AffineExpansionStorage)
+            out._content = np.empty(self._content.shape, dtype=object)
+            for idx in np.ndindex(self._content.shape):
+                it = self._content[idx]
+                out._content[idx] = it if isinstance(it, float) else np.ascontiguousarray(it[key])
+            out._slices = {}
+            out._stacked = None
+            self._slices[ck] = out
+        return self._slices[ck]
+
+    def stacked(self):
+        """Contiguous (Q, ...) / (Q1, Q2, ...) FP64 tensor of all items: what the C ABI takes."""
+        if self._stacked is None:
+            first = self._content.flat[0]
+            shp = () if isinstance(first, float) else first.shape
+            out = np.empty(self._content.shape + shp)
+            for idx in np.ndindex(self._content.shape):
+                out[idx] = self._content[idx]
+            self._stacked = out
+        return self._stacked
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# product / sum
+# ----------------------------------------------------------------------------------------------------------------------
+class ProductOutput:
+    def __init__(self, sum_product_return_value):
+        self.sum_product_return_value = sum_product_return_value
+
+
+def product(thetas, operators, thetas2=None):
+    """``sum(product(thetas, operators[, thetas2]))`` assembles the affine expansion (the product carries out both,
+    as in the reference)."""
+    eng = get_engine()
+    ops = operators.stacked()
+    if operators.order() == 1:
+        assert thetas2 is None
+        assert len(thetas) == len(operators)
+        out = affine_combine(eng, thetas, ops)
+    else:
+        assert thetas2 is not None
+        assert (len(thetas), len(thetas2)) == operators.shape
+        out = affine_combine2(eng, thetas, thetas2, ops if ops.ndim > 2 else ops[..., None])
+        if ops.ndim == 2:
+            out = float(out[0])
+    if isinstance(out, np.ndarray):
+        if out.ndim == 2:
+            out = out.view(_MatrixType)
+        elif out.ndim == 1:
+            out = out.view(_VectorType)
+        else:
+            out = float(out)
+    return ProductOutput(out)
+
+
+def sum(product_output):  # noqa: A001  (the reference shadows the builtin in the same way)
+    return product_output.sum_product_return_value
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# transpose
+# ----------------------------------------------------------------------------------------------------------------------
+class _Transposed:
+    def __init__(self, u, M=None):
+        self._u = u.vector() if isinstance(u, _FunctionType) else u
+        self._M = M
+
+    def __mul__(self, other):
+        if isinstance(other, _FunctionType):
+            other = other.vector()
+        other = np.asarray(other)
+        if self._M is None and other.ndim == 2:
+            assert other.shape[0] == self._u.shape[0]
+            return _Transposed(self._u, other)
+        return bilinear(get_engine(), self._u, self._M, other)
+
+
+def transpose(arg):
+    return _Transposed(arg)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# LinearSolver
+# ----------------------------------------------------------------------------------------------------------------------
+class LinearSolver:
+    """``LinearSolver(lhs, solution, rhs, bcs=None)`` or ``LinearSolver(problem_wrapper, solution)`` with a wrapper
+    exposing ``matrix_eval() / vector_eval() / bc_eval() / monitor(solution)``
+    (rbnics/backends/abstract/linear_solver.py:29-44).  ``bcs`` is a tuple of theta_bc values: rows i < len(bcs) become
+    identity rows with rhs ``bcs[i]`` (rbnics/backends/online/basic/wrapping/DirichletBC.py:37-56)."""
+
+    def __init__(self, lhs, solution, rhs=None, bcs=None):
+        if rhs is None and hasattr(lhs, "matrix_eval"):
+            wrapper = lhs
+            lhs, rhs, bcs = wrapper.matrix_eval(), wrapper.vector_eval(), wrapper.bc_eval()
+            self.monitor = getattr(wrapper, "monitor", None)
+        else:
+            self.monitor = None
+        self.lhs, self.rhs, self.solution = lhs, rhs, solution
+        if bcs is not None and not isinstance(bcs, tuple):
+            raise TypeError("bcs must be a tuple of theta values or None")
+        self.bcs = bcs
+
+    def set_parameters(self, parameters):
+        assert len(parameters) == 0, "the B200 linear solver does not accept parameters"
+
+    def solve(self):
+        rows = list(range(len(self.bcs))) if self.bcs else None
+        x = solve_dense(get_engine(), self.lhs, self.rhs, rows, self.bcs if self.bcs else None)
+        self.solution.vector()[:] = x
+        if self.monitor is not None:
+            self.monitor(self.solution)
+
+
+__all__ = ["AffineExpansionStorage", "Function", "LinearSolver", "Matrix", "product", "sum", "transpose", "Vector"]

@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""Generate golden vectors by EXECUTING THE REFERENCE'S OWN FUNCTION BODIES for the hot path.
+
+The reference (RBniCS) cannot be imported as a package in the build container (multipledispatch, mpi4py, dolfin are
+absent), so this script loads the individual source files that hold the arithmetic of the path from
+``/root/reference`` and executes them with the missing infrastructure stubbed out:
+
+  * ``rbnics.utils.decorators.overload`` -> a tiny isinstance-based dispatcher (the reference's is multipledispatch)
+  * ``mpi4py.MPI.COMM_WORLD``            -> an in-process fake communicator (threads + barrier) for 1..4 "ranks"
+  * online Matrix / Vector wrappers      -> plain numpy arrays (the wrappers forward ``*``/``+=`` to
+                                            ``ndarray.__rmul__/__iadd__``, rbnics/backends/online/basic/matrix.py:216-235)
+
+Executed reference code (unmodified source text, read at run time):
+  rbnics/backends/online/basic/product.py            (order-1 / order-2 affine products: the loops and zero skipping)
+  rbnics/backends/online/basic/sum.py
+  rbnics/backends/online/basic/wrapping/DirichletBC.py (lifting rows)
+  rbnics/problems/elliptic/elliptic_rb_reduced_problem.py      get_residual_norm_squared / estimate_error (source of
+  rbnics/problems/elliptic/elliptic_coercive_compliant_rb_reduced_problem.py   the two methods, run on a stub ``self``)
+  rbnics/sampling/parameter_space_subset.py          ParameterSpaceSubset.max (loop, cyclic shard, numpy.argmax)
+  rbnics/utils/mpi/parallel_max.py                   (max-loc over ranks)
+``numpy.linalg.solve`` is the reference's linear solver itself (rbnics/backends/online/numpy/linear_solver.py:29-31).
+
+Output: tests/golden/reference_sweep_*.npz -- inputs and outputs; committed.  Run:  python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import ast
+import inspect
+import os
+import sys
+import textwrap
+import threading
+import types
+from math import sqrt
+from numbers import Number
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# stubs
+# ----------------------------------------------------------------------------------------------------------------------
+class _TupleOfNumbers(tuple):
+    pass
+
+
+ThetaType = (tuple,)
+DictOfThetaType = (dict,)
+
+
+def _matches(arg, spec):
+    if spec is None:
+        return arg is None
+    if isinstance(spec, tuple):
+        return any(_matches(arg, s) for s in spec)
+    if spec is object:
+        return True
+    return isinstance(arg, spec)
+
+
+_REGISTRY = {}
+
+
+def overload(*types_or_fn):
+    """isinstance-based stand-in for rbnics.utils.decorators.overload (both ``@overload(T1, T2)`` and bare
+    ``@overload`` with annotations)."""
+
+    def register(fn, types):
+        key = (fn.__module__, fn.__qualname__)
+        entries = _REGISTRY.setdefault(key, [])
+        entries.append((types, fn))
+        is_method = "." in fn.__qualname__ and "<locals>" not in fn.__qualname__.split(".")[-2:]
+
+        def dispatcher(*args, **kwargs):
+            call_args = args[1:] if _looks_like_method(fn) else args
+            for tys, f in entries:
+                padded = list(call_args) + [None] * (len(tys) - len(call_args))
+                if len(call_args) <= len(tys) and all(_matches(a, t) for a, t in zip(padded, tys)):
+                    return f(*args, **kwargs)
+            raise TypeError("no overload of %s for %r" % (fn.__qualname__, [type(a) for a in call_args]))
+
+        dispatcher.__name__ = fn.__name__
+        dispatcher.__qualname__ = fn.__qualname__
+        return dispatcher
+
+    if len(types_or_fn) == 1 and inspect.isfunction(types_or_fn[0]):
+        fn = types_or_fn[0]
+        params = list(inspect.signature(fn).parameters.values())
+        if _looks_like_method(fn):
+            params = params[1:]
+        tys = tuple(object if p.annotation is inspect.Parameter.empty else p.annotation for p in params)
+        return register(fn, tys)
+    return lambda fn: register(fn, tuple(types_or_fn))
+
+
+def _looks_like_method(fn):
+    params = list(inspect.signature(fn).parameters)
+    return bool(params) and params[0] == "self"
+
+
+class Storage:
+    """numpy-object-array stand-in for OnlineAffineExpansionStorage (order 1 or 2, int / slice indexing)."""
+
+    def __init__(self, content):
+        self._content = np.empty(np.shape(content)[:self._order_of(content)], dtype=object)
+        if self._content.ndim == 1:
+            for i, c in enumerate(content):
+                self._content[i] = c
+        else:
+            for i, row in enumerate(content):
+                for j, c in enumerate(row):
+                    self._content[i, j] = c
+
+    @staticmethod
+    def _order_of(content):
+        first = content[0]
+        if isinstance(first, (list, tuple)):
+            return 2
+        return 1
+
+    def order(self):
+        return self._content.ndim
+
+    def __len__(self):
+        assert self.order() == 1
+        return self._content.shape[0]
+
+    def __getitem__(self, key):
+        if isinstance(key, int) or (isinstance(key, tuple) and all(isinstance(k, int) for k in key)):
+            return self._content[key]
+        # slicing of every item (affine_expansion_storage.py:329-349)
+        out = Storage.__new__(Storage)
+        out._content = np.empty(self._content.shape, dtype=object)
+        for idx in np.ndindex(self._content.shape):
+            item = self._content[idx]
+            out._content[idx] = item if isinstance(item, Number) else np.array(item[key])
+        return out
+
+
+class NonAffineStorage:
+    pass
+
+
+class Solution(np.ndarray):
+    """reduced solution vector with the ``N`` attribute the estimator reads (``self._solution.N``)."""
+
+    @property
+    def N(self):
+        return self.shape[0]
+
+
+class Transpose:
+    """transpose(u) * M * v == dot(u, M @ v); transpose(u) * w == dot(u, w)
+    (rbnics/backends/basic/transpose.py:126-237 with the numpy wrapping functions vector_mul.py / matrix.py:31-41)."""
+
+    def __init__(self, u, M=None):
+        self.u, self.M = np.asarray(u), M
+
+    def __mul__(self, other):
+        other = np.asarray(other)
+        if self.M is not None:
+            return float(np.dot(self.u, self.M @ other))
+        if other.ndim == 2:
+            return Transpose(self.u, other)
+        return float(np.dot(self.u, other))
+
+
+def transpose(u):
+    return Transpose(u)
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def _exec_reference_file(relpath, modname):
+    src = open(os.path.join(REF, relpath)).read()
+    mod = types.ModuleType(modname)
+    mod.__file__ = os.path.join(REF, relpath)
+    sys.modules[modname] = mod
+    exec(compile(src, mod.__file__, "exec"), mod.__dict__)
+    return mod
+
+
+def _method_source(relpath, name):
+    """Source text of a method of the reference, de-indented to a plain function."""
+    src = open(os.path.join(REF, relpath)).read()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            lines = src.splitlines()[node.lineno - 1:node.end_lineno]
+            return textwrap.dedent("\n".join(lines))
+    raise KeyError(name)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fake MPI (threads) for parallel_max / ParameterSpaceSubset.max
+# ----------------------------------------------------------------------------------------------------------------------
+class FakeComm:
+    def __init__(self, rank, size, shared):
+        self.rank, self.size, self._s = rank, size, shared
+
+    def _exchange(self, value):
+        s = self._s
+        s["slots"][self.rank] = value
+        s["barrier"].wait()
+        vals = list(s["slots"])
+        s["barrier"].wait()
+        return vals
+
+    def allreduce(self, value, op=None):
+        vals = self._exchange(value)
+        assert op == "MAX"
+        return max(vals)
+
+    def bcast(self, value, root=0):
+        return self._exchange(value)[root]
+
+
+def run_ranks(size, fn):
+    shared = {"slots": [None] * size, "barrier": threading.Barrier(size)}
+    out = [None] * size
+
+    def work(r):
+        out[r] = fn(FakeComm(r, size, shared))
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(size)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def load_reference():
+    ndarray = np.ndarray
+
+    class _TypeHolder:
+        def __init__(self, t):
+            self._t = t
+
+        def Type(self):
+            return self._t
+
+    backend = types.SimpleNamespace(AffineExpansionStorage=Storage, NonAffineExpansionStorage=NonAffineStorage,
+                                    Matrix=_TypeHolder(ndarray), Vector=_TypeHolder(ndarray),
+                                    Function=_TypeHolder(ndarray))
+    _module("rbnics")
+    _module("rbnics.backends")
+    _module("rbnics.backends.abstract", ParametrizedTensorFactory=type("PTF", (), {}))
+    _module("rbnics.backends.basic")
+    _module("rbnics.backends.basic.wrapping", DelayedTranspose=type("DelayedTranspose", (), {}))
+    _module("rbnics.utils")
+    _module("rbnics.utils.decorators", overload=overload, ThetaType=ThetaType, DictOfThetaType=DictOfThetaType)
+    _module("rbnics.utils.io", ComponentNameToBasisComponentIndexDict=dict, OnlineSizeDict=dict,
+            ExportableList=type("ExportableList", (), {"__init__": lambda self, kind: setattr(self, "_list", []),
+                                                       "__len__": lambda self: len(self._list)}))
+    MPI = _module("mpi4py.MPI", COMM_WORLD=FakeComm(0, 1, {"slots": [None], "barrier": threading.Barrier(1)}),
+                  MAX="MAX")
+    _module("mpi4py", MPI=MPI)
+    prod_mod = _exec_reference_file("rbnics/backends/online/basic/product.py", "ref_product")
+    sum_mod = _exec_reference_file("rbnics/backends/online/basic/sum.py", "ref_sum")
+    bc_mod = _exec_reference_file("rbnics/backends/online/basic/wrapping/DirichletBC.py", "ref_dirichlet")
+    pmax_mod = _exec_reference_file("rbnics/utils/mpi/parallel_max.py", "ref_parallel_max")
+    _module("rbnics.utils.mpi", parallel_io=lambda f, comm=None: f(), parallel_max=pmax_mod.parallel_max)
+    _module("rbnics.sampling")
+    _module("rbnics.sampling.distributions", CompositeDistribution=object, UniformDistribution=object)
+    pss_mod = _exec_reference_file("rbnics/sampling/parameter_space_subset.py", "ref_pss")
+
+    wrapping = types.SimpleNamespace(DelayedTransposeWithArithmetic=type("DTWA", (), {}))
+    product_base, ProductOutput = prod_mod.product(backend, wrapping)
+
+    def product(thetas, operators, thetas2=None):  # rbnics/backends/online/numpy/product.py:23-25
+        return product_base(thetas, operators, thetas2)
+
+    ns = {"product": product, "sum": sum_mod.sum, "transpose": transpose, "sqrt": sqrt, "isclose": np.isclose,
+          "abs": abs}
+    exec(_method_source("rbnics/problems/elliptic/elliptic_rb_reduced_problem.py", "get_residual_norm_squared"), ns)
+    exec(_method_source("rbnics/problems/elliptic/elliptic_rb_reduced_problem.py", "estimate_error"), ns)
+    estimate_error_plain = ns["estimate_error"]
+    exec(_method_source("rbnics/problems/elliptic/elliptic_coercive_compliant_rb_reduced_problem.py",
+                        "estimate_error"), ns)
+    estimate_error_compliant = ns["estimate_error"]
+    exec(_method_source("rbnics/problems/elliptic/elliptic_reduced_problem.py", "matrix_eval"), ns)
+    exec(_method_source("rbnics/problems/elliptic/elliptic_reduced_problem.py", "vector_eval"), ns)
+    return types.SimpleNamespace(product=product, sum=sum_mod.sum, DirichletBC=bc_mod.DirichletBC,
+                                 parallel_max=pmax_mod.parallel_max, ParameterSpaceSubset=pss_mod.ParameterSpaceSubset,
+                                 get_residual_norm_squared=ns["get_residual_norm_squared"],
+                                 estimate_error_plain=estimate_error_plain,
+                                 estimate_error_compliant=estimate_error_compliant, matrix_eval=ns["matrix_eval"],
+                                 vector_eval=ns["vector_eval"])
+
+
+def ref_rand(rng, *shape):
+    """tests/performance/backends/online/numpy/test_numpy_utils.py:58-59 on a seeded Generator."""
+    return (-1.0) ** rng.integers(0, 2, size=shape) * rng.random(shape) / (1e-3 + rng.random(shape))
+
+
+class FakeReducedProblem:
+    """the attributes the reference's solve / estimator methods read from ``self``"""
+
+    def __init__(self, ref, A, F, Gff, Gaf, Gaa, n_bc):
+        Qa, Qf = A.shape[0], F.shape[0]
+        self.operator = {"a": Storage([A[q] for q in range(Qa)]), "f": Storage([F[q] for q in range(Qf)])}
+        self.error_estimation_operator = {
+            ("f", "f"): Storage([[float(Gff[i, j]) for j in range(Qf)] for i in range(Qf)]),
+            ("a", "f"): Storage([[Gaf[i, j] for j in range(Qf)] for i in range(Qa)]),
+            ("a", "a"): Storage([[Gaa[i, j] for j in range(Qa)] for i in range(Qa)])}
+        self.n_bc = n_bc
+        self.ref = ref
+        self.truth_problem = self
+        self.problem = self
+        self.N = A.shape[1]
+
+    def set(self, theta_a, theta_f, beta, theta_bc):
+        self._ta, self._tf, self._beta, self._tbc = theta_a, theta_f, beta, theta_bc
+
+    def compute_theta(self, term):
+        return {"a": self._ta, "f": self._tf}[term]
+
+    def get_stability_factor_lower_bound(self):
+        return self._beta
+
+    def get_residual_norm_squared(self):
+        return self.ref.get_residual_norm_squared(self)
+
+    def solve(self):
+        """LinearSolver(problem_wrapper, solution): online/basic/linear_solver.py:29-35,56-59 + numpy solve"""
+        N = self.N
+        lhs = np.array(self.ref.matrix_eval(self))
+        rhs = np.array(self.ref.vector_eval(self))
+        if self._tbc is not None:
+            bcs = self.ref.DirichletBC(self._tbc)
+            bcs.apply_to_vector(rhs)
+            bcs.apply_to_matrix(lhs)
+        u = np.linalg.solve(lhs, rhs) if N > 0 else np.zeros(0)
+        self._solution = u.view(Solution)
+        return u
+
+
+def make_case(ref, name, N, Qa, Qf, B, seed, n_bc=0, well_conditioned=True, ranks=(1, 2, 3)):
+    rng = np.random.default_rng(seed)
+    if well_conditioned:
+        A = np.stack([(lambda Bq: Bq @ Bq.T / N + np.eye(N))(rng.standard_normal((N, N))) for _ in range(Qa)])
+        F = rng.standard_normal((Qf, N))
+        R = rng.standard_normal((3 * (Qa * N + Qf) // 2 + 8, Qa * N + Qf))
+        G = R.T @ R / R.shape[0]
+        Ka = Qa * N
+        Gaa = G[:Ka, :Ka].reshape(Qa, N, Qa, N).transpose(0, 2, 1, 3).copy()
+        Gaf = G[:Ka, Ka:].reshape(Qa, N, Qf).transpose(0, 2, 1).copy()
+        Gff = G[Ka:, Ka:].copy()
+        Theta_a = rng.uniform(0.1, 10.0, size=(B, Qa))
+        Theta_f = rng.uniform(-1.0, 1.0, size=(B, Qf))
+    else:  # the reference tests' heavy-tailed signed distribution (products only; not used for solves)
+        A = ref_rand(rng, Qa, N, N)
+        F = ref_rand(rng, Qf, N)
+        Gaa, Gaf, Gff = ref_rand(rng, Qa, Qa, N, N), ref_rand(rng, Qa, Qf, N), ref_rand(rng, Qf, Qf)
+        Theta_a, Theta_f = ref_rand(rng, B, Qa), ref_rand(rng, B, Qf)
+    Theta_a[B // 2, Qa - 1] = 0.0  # exercises the zero-theta skipping of product.py:32,45
+    beta = np.abs(Theta_a).min(axis=1) + 0.05
+    Theta_bc = rng.uniform(-1.0, 1.0, size=(B, n_bc)) if n_bc else None
+
+    prob = FakeReducedProblem(ref, A, F, Gff, Gaf, Gaa, n_bc)
+    U = np.zeros((B, N))
+    lhs_all = np.zeros((B, N, N))
+    eps2 = np.zeros(B)
+    d_plain = np.zeros(B)
+    d_compl = np.zeros(B)
+    for p in range(B):
+        ta = tuple(float(x) for x in Theta_a[p])
+        tf = tuple(float(x) for x in Theta_f[p])
+        tbc = None if Theta_bc is None else tuple(float(x) for x in Theta_bc[p])
+        prob.set(ta, tf, float(beta[p]), tbc)
+        lhs_all[p] = np.array(ref.matrix_eval(prob))
+        if well_conditioned:
+            U[p] = prob.solve()
+        else:
+            prob._solution = ref_rand(rng, N).view(Solution)
+            U[p] = prob._solution
+        eps2[p] = ref.get_residual_norm_squared(prob)
+        if well_conditioned:
+            d_plain[p] = ref.estimate_error_plain(prob)
+            d_compl[p] = ref.estimate_error_compliant(prob)
+
+    out = dict(A=A, F=F, Gff=Gff, Gaf=Gaf, Gaa=Gaa, Theta_a=Theta_a, Theta_f=Theta_f, beta=beta, U=U, lhs=lhs_all,
+               eps2=eps2, delta_plain=d_plain, delta_compliant=d_compl, n_bc=np.int64(n_bc),
+               well_conditioned=np.bool_(well_conditioned))
+    if Theta_bc is not None:
+        out["Theta_bc"] = Theta_bc
+    if well_conditioned:
+        # ParameterSpaceSubset.max on the precomputed estimators: serial and distributed (cyclic shards + parallel_max)
+        values = d_plain.copy()
+        values[B // 3] = values.max()            # an exact tie between two parameters
+        tie_lo = int(min(B // 3, int(np.argmax(d_plain))))
+        pss = ref.ParameterSpaceSubset()
+        pss._list = [(float(i),) for i in range(B)]
+        pss.serialize_maximum_computations()
+        v, i = pss.max(lambda mu: values[int(mu[0])])
+        out["max_values"] = values
+        out["max_serial"] = np.array([v, i])
+        assert int(i) == tie_lo
+        for size in ranks:
+            def rank_fn(comm, size=size):
+                s = ref.ParameterSpaceSubset()
+                s._list = [(float(k),) for k in range(B)]
+                s.mpi_comm = comm
+                return s.max(lambda mu: values[int(mu[0])])
+            res = run_ranks(size, rank_fn)
+            assert all(r == res[0] for r in res)
+            out[f"max_mpi_{size}"] = np.array([res[0][0], res[0][1]])
+    np.savez_compressed(os.path.join(HERE, f"reference_sweep_{name}.npz"), **out)
+    print(name, "N", N, "Qa", Qa, "Qf", Qf, "B", B, "eps2[0]", eps2[0], "max_serial", out.get("max_serial"))
+
+
+def main():
+    ref = load_reference()
+    make_case(ref, "tutorial01", N=4, Qa=2, Qf=1, B=100, seed=1)
+    make_case(ref, "n16q6", N=16, Qa=6, Qf=6, B=40, seed=2)
+    make_case(ref, "n32q10_bc", N=32, Qa=10, Qf=10, B=24, seed=3, n_bc=2)
+    make_case(ref, "n40q7", N=40, Qa=7, Qf=3, B=16, seed=4)
+    make_case(ref, "heavytail_n16", N=16, Qa=6, Qf=10, B=10, seed=5, well_conditioned=False)
+
+
+if __name__ == "__main__":
+    main()
