@@ -362,3 +362,49 @@ def build_error_estimation_operators(Z, X, A_ops, f_ops, solve_X):
     G_af = [[R_a[i].T @ (X @ r_f[j]) for j in range(Qf)] for i in range(Qa)]
     G_aa = [[gram_blas(R_a[i], X, R_a[j]) for j in range(Qa)] for i in range(Qa)]
     return G_ff, G_af, G_aa, r_f, R_a
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Stokes (saddle point, components u, s, p): multi-term assembly and the 9-term residual norm
+# ----------------------------------------------------------------------------------------------------------------------
+
+def reduced_solve_stokes(theta, op, N, theta_bc=None):
+    """lhs = sum_a + sum_b + sum_bt, rhs = sum_f + sum_g, each an order-1 product; then the lifting rows and dgesv.
+
+    theta / op: dicts over the terms "a", "b", "bt", "f", "g" (op[term] = list of N x N matrices / N-vectors).
+    rbnics/problems/stokes/stokes_reduced_problem.py:38-53 (matrix_eval / vector_eval)."""
+    assembled = {}
+    for term in ("a", "b", "bt"):
+        assembled[term] = product_order1(theta[term], [A[:N, :N] for A in op[term]])
+    lhs = np.array(assembled["a"] + assembled["b"] + assembled["bt"], dtype=np.float64)
+    for term in ("f", "g"):
+        assembled[term] = product_order1(theta[term], [f[:N] for f in op[term]])
+    rhs = np.array(assembled["f"] + assembled["g"], dtype=np.float64)
+    apply_dirichlet_rows(lhs, rhs, theta_bc)
+    return np.linalg.solve(lhs, rhs)
+
+
+STOKES_ERROR_ESTIMATION_TERMS = [("f", "f"), ("g", "g"), ("a", "f"), ("bt", "f"), ("b", "g"),
+                                 ("a", "a"), ("a", "bt"), ("bt", "bt"), ("b", "b")]
+
+
+def residual_norm_squared_stokes(u, theta, E, N):
+    """The 9 term pairs of rbnics/problems/stokes/stokes_rb_reduced_problem.py:53-83, in the reference's order.
+
+    E[(t1, t2)][i][j]: scalar (f,f / g,g), N-vector (x,f / x,g) or N x N matrix."""
+    def o2(t1, t2, slicer):
+        return product_order2(theta[t1], [[slicer(x) for x in row] for row in E[t1, t2]], theta[t2])
+
+    sc = lambda x: x            # noqa: E731
+    vec = lambda x: x[:N]       # noqa: E731
+    mat = lambda x: x[:N, :N]   # noqa: E731
+    return float(
+        o2("f", "f", sc)
+        + o2("g", "g", sc)
+        + 2.0 * np.dot(u, o2("a", "f", vec))
+        + 2.0 * np.dot(u, o2("bt", "f", vec))
+        + 2.0 * np.dot(u, o2("b", "g", vec))
+        + np.dot(u, o2("a", "a", mat) @ u)
+        + 2.0 * np.dot(u, o2("a", "bt", mat) @ u)
+        + np.dot(u, o2("bt", "bt", mat) @ u)
+        + np.dot(u, o2("b", "b", mat) @ u))

@@ -67,6 +67,7 @@ struct rb_ctx {
   // work buffers
   double* dAb = nullptr; int64_t ab_cap = 0;       // assembled matrices of one chunk [chunk][EP]
   double* dU = nullptr; int64_t u_cap = 0; int ldu = 0;
+  double* dLuScratch = nullptr; long long lu_scratch_cap = 0;  // L records + packed U of the left-looking LU
   double* dPart = nullptr; int64_t part_cap = 0;   // [nsplit][B]
   double* dDelta = nullptr; double* dEps2 = nullptr; int64_t delta_cap = 0;
   double* dBlkVal = nullptr; long long* dBlkIdx = nullptr; int blk_cap = 0;

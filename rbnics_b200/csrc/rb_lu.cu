@@ -8,6 +8,25 @@ int rb_lu_launch_unit1(int NP, const LuArgs& args, cudaStream_t stream);
 int rb_lu_launch_unit2(int NP, const LuArgs& args, cudaStream_t stream);
 int rb_lu_launch_unit3(int NP, const LuArgs& args, cudaStream_t stream);
 int rb_lu_dmma_dispatch(int N, const LuArgs& args, cudaStream_t stream);
+int rb_lu_stream_launch(const LuArgs& args, double* Awork, cudaStream_t stream);
+int rb_lu_warp_launch(const LuArgs& args, double* Awork, cudaStream_t stream);
+int rb_lu_left_launch(const LuArgs& args, double* scratch, cudaStream_t stream);
+long long rb_lu_left_scratch_doubles(int N);
+
+// Which kernel serves 32 < N (A/B switch for profiling): "left" (default; one warp per system, left-looking, L records
+// streamed from L2), "warp" (one warp per system, right-looking in global memory), "stream" (thread per row,
+// right-looking in global memory), "dmma" (register-resident, 2 systems per SM), "rowreg" (oldest).
+int rb_lu_variant() {
+  static const int v = [] {
+    const char* e = getenv("RB_LU_KERNEL");
+    if (e && e[0] == 'd') return 1;
+    if (e && e[0] == 'r') return 2;
+    if (e && e[0] == 's') return 3;
+    if (e && e[0] == 'w') return 4;
+    return 0;
+  }();
+  return v;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Fallback: matrix in shared memory ([NP][NP+1], odd pitch), one CTA of 128 threads per system, explicit row swaps.
@@ -118,8 +137,27 @@ __global__ void __launch_bounds__(128) rb_lu_smem_kernel(LuArgs args, int NP) {
 
 int rb_launch_lu_args(rb_ctx* ctx, const LuArgs& a, int NP) {
   int rc;
-  static const bool force_rowreg = getenv("RB_LU_ROWREG") != nullptr;  // A/B switch for profiling the older kernel
-  if (NP > 32 && NP <= LU_MAX_NP_REG && !force_rowreg)
+  const int variant = rb_lu_variant();
+  const bool force_rowreg = variant == 2;  // A/B switches for profiling the older kernels
+  if (NP > 32 && a.N <= 128 && variant == 0) {
+    const long long need = a.count * rb_lu_left_scratch_doubles(a.N);
+    if (need > ctx->lu_scratch_cap) {
+      if (ctx->dLuScratch) cudaFree(ctx->dLuScratch);
+      ctx->dLuScratch = nullptr;
+      ctx->lu_scratch_cap = 0;
+      cudaError_t e = cudaMalloc((void**)&ctx->dLuScratch, (size_t)need * sizeof(double));
+      if (e != cudaSuccess) {
+        ctx->err = std::string("LU scratch allocation: ") + cudaGetErrorString(e);
+        return RB_ERR_CUDA;
+      }
+      ctx->lu_scratch_cap = need;
+    }
+    rc = rb_lu_left_launch(a, ctx->dLuScratch, ctx->stream);
+  } else if (NP > 32 && a.N <= 128 && variant == 4)
+    rc = rb_lu_warp_launch(a, const_cast<double*>(a.Ab), ctx->stream);
+  else if (NP > 32 && a.N <= 128 && variant == 3)
+    rc = rb_lu_stream_launch(a, const_cast<double*>(a.Ab), ctx->stream);
+  else if (NP > 32 && NP <= LU_MAX_NP_REG && !force_rowreg)
     rc = rb_lu_dmma_dispatch(a.N, a, ctx->stream);
   else if (NP <= 52)
     rc = rb_lu_launch_unit0(NP, a, ctx->stream);

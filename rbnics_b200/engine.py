@@ -94,6 +94,14 @@ class SweepEngine:
         G, desc = elliptic_quadratic_form(Gff, Gaf, Gaa, self.Ql, self.Qr, self.N)
         self.set_estimator(*desc, G)
 
+    def set_stokes_estimator(self, E, Q):
+        """Residual-norm estimator of rbnics/problems/stokes/stokes_rb_reduced_problem.py:53-83 (9 term pairs).
+
+        The system must have been set with lhs terms ordered [a | b | bt] and rhs terms [f | g];
+        Q = {"a": Qa, "b": Qb, "bt": Qbt, "f": Qf, "g": Qg}; E[(t1, t2)] stacked arrays (Q1, Q2[, N[, N]])."""
+        G, desc = stokes_quadratic_form(E, Q, self.N)
+        self.set_estimator(*desc, G)
+
     # -- training set + sweep ----------------------------------------------------------------------------------
     def set_training_set(self, Theta, beta, ThetaBC=None, index_offset=0, index_stride=1):
         Theta = _f64(Theta)
@@ -195,3 +203,67 @@ def elliptic_quadratic_form(Gff, Gaf, Gaa, Qa, Qf, N):
         G = Gff.copy()
         scale, src, length = [-1], [0], [Qf]
     return G, (scale, src, length, Qa, Qf)
+
+
+STOKES_TERM_PAIRS = (("f", "f"), ("g", "g"), ("a", "f"), ("bt", "f"), ("b", "g"),
+                     ("a", "a"), ("a", "bt"), ("bt", "bt"), ("b", "b"))
+
+
+def stokes_quadratic_form(E, Q, N):
+    """Pack the 9 Stokes error-estimation storages into ONE quadratic form z^T G z (rb_set_estimator).
+
+    Theta columns: [a | b | bt | f | g];  V = [u (N) | theta_f | theta_g | 1];
+    z = [theta_a (x) u ; theta_b (x) u ; theta_bt (x) u ; theta_f ; theta_g].  Cross pairs (t1 != t2) are placed in
+    both triangles so that z^T G z carries the reference's factor 2; pairs the reference skips ("useless Riesz
+    products", stokes_rb_reduced_problem.py:27-32) are zero blocks."""
+    Qa, Qb, Qbt, Qf, Qg = Q["a"], Q["b"], Q["bt"], Q["f"], Q["g"]
+    col = {"a": 0, "b": Qa, "bt": Qa + Qb, "f": Qa + Qb + Qbt, "g": Qa + Qb + Qbt + Qf}
+    # z offsets
+    zoff, o = {}, 0
+    for t in ("a", "b", "bt"):
+        zoff[t] = o
+        o += Q[t] * N
+    zoff["f"] = o
+    o += Qf
+    zoff["g"] = o
+    o += Qg
+    Kz = o
+    G = np.zeros((Kz, Kz))
+
+    def zslice(t):
+        n = Q[t] * N if t in ("a", "b", "bt") else Q[t]
+        return slice(zoff[t], zoff[t] + n)
+
+    for (t1, t2) in STOKES_TERM_PAIRS:
+        blk = np.asarray(E[t1, t2], dtype=np.float64)
+        q1, q2 = Q[t1], Q[t2]
+        op1, op2 = t1 in ("a", "b", "bt"), t2 in ("a", "b", "bt")
+        if op1 and op2:
+            M = blk.reshape(q1, q2, N, N).transpose(0, 2, 1, 3).reshape(q1 * N, q2 * N)
+        elif op1:
+            M = blk.reshape(q1, q2, N).transpose(0, 2, 1).reshape(q1 * N, q2)
+        else:
+            M = blk.reshape(q1, q2)
+        if N == 0 and (op1 or op2):
+            continue
+        G[zslice(t1), zslice(t2)] += M
+        if t1 != t2:
+            G[zslice(t2), zslice(t1)] += M.T
+    scale, src, length = [], [], []
+    if N > 0:
+        for t in ("a", "b", "bt"):
+            for q in range(Q[t]):
+                scale.append(col[t] + q)
+                src.append(0)
+                length.append(N)
+    else:  # empty solution: only the (f,f) and (g,g) terms remain
+        G = G[zoff["f"]:, zoff["f"]:].copy()
+    if Qf:
+        scale.append(-1)
+        src.append(N)
+        length.append(Qf)
+    if Qg:
+        scale.append(-1)
+        src.append(N + Qf)
+        length.append(Qg)
+    return G, (scale, src, length, col["f"], Qf + Qg)

@@ -288,7 +288,15 @@ def load_reference():
     estimate_error_compliant = ns["estimate_error"]
     exec(_method_source("rbnics/problems/elliptic/elliptic_reduced_problem.py", "matrix_eval"), ns)
     exec(_method_source("rbnics/problems/elliptic/elliptic_reduced_problem.py", "vector_eval"), ns)
-    return types.SimpleNamespace(product=product, sum=sum_mod.sum, DirichletBC=bc_mod.DirichletBC,
+    sns = dict(ns)
+    exec(_method_source("rbnics/problems/stokes/stokes_rb_reduced_problem.py", "get_residual_norm_squared"), sns)
+    exec(_method_source("rbnics/problems/stokes/stokes_rb_reduced_problem.py", "estimate_error"), sns)
+    exec(_method_source("rbnics/problems/stokes/stokes_reduced_problem.py", "matrix_eval"), sns)
+    exec(_method_source("rbnics/problems/stokes/stokes_reduced_problem.py", "vector_eval"), sns)
+    stokes = types.SimpleNamespace(get_residual_norm_squared=sns["get_residual_norm_squared"],
+                                   estimate_error=sns["estimate_error"], matrix_eval=sns["matrix_eval"],
+                                   vector_eval=sns["vector_eval"])
+    return types.SimpleNamespace(stokes=stokes, product=product, sum=sum_mod.sum, DirichletBC=bc_mod.DirichletBC,
                                  parallel_max=pmax_mod.parallel_max, ParameterSpaceSubset=pss_mod.ParameterSpaceSubset,
                                  get_residual_norm_squared=ns["get_residual_norm_squared"],
                                  estimate_error_plain=estimate_error_plain,
@@ -417,6 +425,121 @@ def make_case(ref, name, N, Qa, Qf, B, seed, n_bc=0, well_conditioned=True, rank
     print(name, "N", N, "Qa", Qa, "Qf", Qf, "B", B, "eps2[0]", eps2[0], "max_serial", out.get("max_serial"))
 
 
+class FakeStokesReducedProblem:
+    """attributes read by the reference's Stokes matrix_eval / vector_eval / get_residual_norm_squared"""
+    PAIRS = [("f", "f"), ("g", "g"), ("a", "f"), ("bt", "f"), ("b", "g"), ("a", "a"), ("a", "bt"), ("bt", "bt"),
+             ("b", "b")]
+
+    def __init__(self, ref, op, E, N):
+        self.ref = ref
+        self.operator = {t: Storage([op[t][q] for q in range(op[t].shape[0])]) for t in op}
+        self.error_estimation_operator = {}
+        for (t1, t2) in self.PAIRS:
+            blk = E[t1, t2]
+            if blk.ndim == 2:
+                content = [[float(blk[i, j]) for j in range(blk.shape[1])] for i in range(blk.shape[0])]
+            else:
+                content = [[blk[i, j] for j in range(blk.shape[1])] for i in range(blk.shape[0])]
+            self.error_estimation_operator[t1, t2] = Storage(content)
+        self.N = N
+        self.problem = self
+        self.truth_problem = self
+
+    def set(self, theta, beta, theta_bc):
+        self._theta, self._beta, self._tbc = theta, beta, theta_bc
+
+    def compute_theta(self, term):
+        return self._theta[term]
+
+    def get_stability_factor_lower_bound(self):
+        return self._beta
+
+    def get_residual_norm_squared(self):
+        return self.ref.stokes.get_residual_norm_squared(self)
+
+    def solve(self):
+        lhs = np.array(self.ref.stokes.matrix_eval(self))
+        rhs = np.array(self.ref.stokes.vector_eval(self))
+        if self._tbc is not None:
+            bcs = self.ref.DirichletBC(self._tbc)
+            bcs.apply_to_vector(rhs)
+            bcs.apply_to_matrix(lhs)
+        u = np.linalg.solve(lhs, rhs)
+        self._solution = u.view(Solution)
+        return u
+
+
+def make_stokes_case(ref, name, n, Q, B, seed, n_bc=0):
+    """Saddle-point reduced system with components (u, s, p) of n basis functions each (N = 3n): a on the velocity
+    block, bt = [0 B^T; 0 0], b = [0 0; B 0] -> indefinite matrix (pivoting matters); the Riesz Gram blocks come from
+    velocity-space representers (a, bt, f) and pressure-space representers (b, g), so the pairs the reference skips
+    are exactly zero and eps2 >= 0."""
+    rng = np.random.default_rng(seed)
+    nv, N = 2 * n, 3 * n
+    op = {}
+    op["a"] = np.zeros((Q["a"], N, N))
+    for q in range(Q["a"]):
+        Bq = rng.standard_normal((nv, nv))
+        op["a"][q, :nv, :nv] = Bq @ Bq.T / nv + np.eye(nv)
+    op["b"] = np.zeros((Q["b"], N, N))
+    op["bt"] = np.zeros((Q["bt"], N, N))
+    for q in range(Q["b"]):
+        op["b"][q, nv:, :nv] = rng.standard_normal((n, nv))
+    for q in range(Q["bt"]):
+        op["bt"][q, :nv, nv:] = op["b"][q % Q["b"], nv:, :nv].T
+    op["f"] = np.zeros((Q["f"], N))
+    op["f"][:, :nv] = rng.standard_normal((Q["f"], nv))
+    op["g"] = np.zeros((Q["g"], N))
+    op["g"][:, nv:] = rng.standard_normal((Q["g"], n))
+    # Riesz factors: velocity space (a, bt, f) and pressure space (b, g)
+    Kv = Q["a"] * N + Q["bt"] * N + Q["f"]
+    Kp = Q["b"] * N + Q["g"]
+    Rv = rng.standard_normal((Kv + 7, Kv))
+    Rp = rng.standard_normal((Kp + 5, Kp))
+    Gv = Rv.T @ Rv / Rv.shape[0]
+    Gp = Rp.T @ Rp / Rp.shape[0]
+    offv = {"a": 0, "bt": Q["a"] * N, "f": Q["a"] * N + Q["bt"] * N}
+    offp = {"b": 0, "g": Q["b"] * N}
+
+    def block(Gm, off, t1, t2):
+        n1 = Q[t1] * N if t1 in ("a", "b", "bt") else Q[t1]
+        n2 = Q[t2] * N if t2 in ("a", "b", "bt") else Q[t2]
+        M = Gm[off[t1]:off[t1] + n1, off[t2]:off[t2] + n2]
+        o1, o2 = t1 in ("a", "b", "bt"), t2 in ("a", "b", "bt")
+        if o1 and o2:
+            return M.reshape(Q[t1], N, Q[t2], N).transpose(0, 2, 1, 3).copy()
+        if o1:
+            return M.reshape(Q[t1], N, Q[t2]).transpose(0, 2, 1).copy()
+        return M.copy()
+
+    E = {}
+    for (t1, t2) in FakeStokesReducedProblem.PAIRS:
+        E[t1, t2] = block(Gv, offv, t1, t2) if t1 in offv else block(Gp, offp, t1, t2)
+    theta = {t: rng.uniform(0.5, 2.0, size=(B, Q[t])) for t in ("a", "b", "bt")}
+    theta["f"] = rng.uniform(-1.0, 1.0, size=(B, Q["f"]))
+    theta["g"] = rng.uniform(-1.0, 1.0, size=(B, Q["g"]))
+    theta["a"][B // 2, Q["a"] - 1] = 0.0
+    beta = np.ones(B)                                      # tutorials/12_stokes: beta == 1
+    Theta_bc = rng.uniform(-1.0, 1.0, size=(B, n_bc)) if n_bc else None
+    prob = FakeStokesReducedProblem(ref, op, E, N)
+    U, eps2, delta = np.zeros((B, N)), np.zeros(B), np.zeros(B)
+    for p in range(B):
+        th = {t: tuple(float(x) for x in theta[t][p]) for t in theta}
+        tbc = None if Theta_bc is None else tuple(float(x) for x in Theta_bc[p])
+        prob.set(th, float(beta[p]), tbc)
+        U[p] = prob.solve()
+        eps2[p] = ref.stokes.get_residual_norm_squared(prob)
+        delta[p] = ref.stokes.estimate_error(prob)
+    out = {"op_" + t: op[t] for t in op}
+    out.update({"E_%s_%s" % k: v for k, v in E.items()})
+    out.update({"theta_" + t: theta[t] for t in theta})
+    out.update(beta=beta, U=U, eps2=eps2, delta=delta, n_bc=np.int64(n_bc), n=np.int64(n))
+    if Theta_bc is not None:
+        out["Theta_bc"] = Theta_bc
+    np.savez_compressed(os.path.join(HERE, f"reference_stokes_{name}.npz"), **out)
+    print("stokes", name, "N", N, "B", B, "eps2[0]", eps2[0], "argmax", int(np.argmax(delta)))
+
+
 def main():
     ref = load_reference()
     make_case(ref, "tutorial01", N=4, Qa=2, Qf=1, B=100, seed=1)
@@ -424,6 +547,8 @@ def main():
     make_case(ref, "n32q10_bc", N=32, Qa=10, Qf=10, B=24, seed=3, n_bc=2)
     make_case(ref, "n40q7", N=40, Qa=7, Qf=3, B=16, seed=4)
     make_case(ref, "heavytail_n16", N=16, Qa=6, Qf=10, B=10, seed=5, well_conditioned=False)
+    make_stokes_case(ref, "n5", n=5, Q={"a": 3, "b": 2, "bt": 2, "f": 2, "g": 1}, B=24, seed=6)
+    make_stokes_case(ref, "n12_bc", n=12, Q={"a": 4, "b": 3, "bt": 3, "f": 3, "g": 2}, B=16, seed=7, n_bc=1)
 
 
 if __name__ == "__main__":
