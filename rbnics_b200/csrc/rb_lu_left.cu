@@ -9,10 +9,11 @@
 // every panel (latency-bound read-modify-write, rb_lu_warp.cu).  Left-looking, panel p (8 columns) is read ONCE from
 // the assembled matrix into DMMA accumulator tiles that stay in registers while the records of the finished panels
 // q < p stream by:
-//     record q = { negated multipliers of panel q in DMMA A-fragment order, its 8x8 unit-lower block, its pivot rows }
+//     record q = { negated multipliers of panel q in DMMA A-fragment order, inverse of its 8x8 unit-lower block,
+//                  its pivot rows, mask of tile rows with non-zero multipliers }
 // written once, read-only afterwards, contiguous (7.2 KB at N = 100) -> prefetched with cp.async into a 2-stage
 // shared-memory ring.  Per record:  X = the panel rows pivoted in q (final since the records >= q have zero
-// multipliers for them), U_qp = L_qq^-1 X (8 lanes, one column each), C -= L_q U_qp (2 DMMA.8x8x4 per live tile row).
+// multipliers for them), U_qp = L_qq^-1 X (2 DMMA.8x8x4), C -= L_q U_qp (2 DMMA.8x8x4 per live tile row).
 // Then the panel is transposed through shared memory to one row set per lane and factored exactly like
 // rb_lu_warp.cu / rb_lu_dmma.cuh (REDUX.MAX arg-max, idamax tie rule, implicit pivoting, rhs carried along).
 // U is stored in 8x8 blocks, block column p contiguous, so the back-substitution reads coalesced rows.
@@ -25,7 +26,8 @@ template <int NT>
 struct LlCfg {
   static constexpr int NP8 = 8 * NT;
   static constexpr int R = (NP8 + 31) / 32;        // pivot indices / rows per lane
-  static constexpr int REC = NT * 64 + 64 + 8;     // doubles per record: nLf | Lpp | pivrow (8 ints) + pad
+  static constexpr int REC = 64 + 8 + NT * 64;     // doubles per record: L_qq^-1 | pivrow[8], live mask | packed nLf
+  static constexpr int SLOT = REC < 640 ? 640 : REC;  // ring slot (doubles): slot 0 also hosts the 640 candidate doubles
   static constexpr int PP = 10;                    // pitch of the transpose buffer
   static constexpr int UBLK = NT * (NT + 1) / 2;   // 8x8 blocks of the packed upper-triangular U store
   // scratch doubles per system beyond the assembled matrix: records of all panels + packed U
@@ -41,7 +43,7 @@ template <int NT>
 struct LlSmem {
   using C = LlCfg<NT>;
   union {
-    double ring[2][C::REC];     // prefetched records
+    double ring[2][C::SLOT];    // prefetched records / staged panel of A / staged block column of U
     double cand[2][32][10];     // pivot candidate slots of phase F (the ring is idle then)
   };
   union {
@@ -52,6 +54,7 @@ struct LlSmem {
   double ys[C::NP8];            // rhs in pivot order -> solution
   double rinvs[C::NP8];         // reciprocal pivots
   int pivrow[C::NP8];           // pivot order -> row
+  int recsz[NT];                // 16-byte chunks of record q (header + live tile rows)
 };
 
 __device__ __forceinline__ double ll_selp(double a, double b, int x, int y) {  // x == y ? a : b, branch-free
@@ -180,31 +183,49 @@ __global__ void __launch_bounds__(32, 8) rb_lu_left_kernel(LuArgs args, double* 
   }
 
   const int npan = (N + 7) / 8;
+  // 16-byte chunk copiers (cp.async, one commit group per call site)
+  auto issue_chunks = [&](double* dst, const double* src, int n16, int maxtrips) {
+    for (int k = 0; k < maxtrips; ++k) {
+      const int i = lane + 32 * k;
+      if (i < n16) ll_cp_async16(dst + 2 * i, src + 2 * i);
+    }
+  };
+  auto issue_record = [&](int q, int slot) {
+    issue_chunks(sm.ring[slot], Lrec + (long long)q * C::REC, sm.recsz[q], (C::REC / 2 + 31) / 32);
+  };
+  auto issue_apanel = [&](int pn) {  // 8 columns of the assembled matrix are contiguous: -> ring slot 1
+    issue_chunks(sm.ring[1], A + (long long)(8 * pn) * NP, min(8, N - 8 * pn) * NP / 2, NT + 1);
+  };
+  issue_apanel(0);
+  ll_cp_commit();
+
   for (int p = 0; p < npan; ++p) {
     const int c0 = 8 * p;
     const int nst = min(8, N - c0);
-    // ---- prefetch the first record(s), then load the panel of the assembled matrix into accumulator tiles
-    auto issue_record = [&](int q, int slot) {
-      const double* src = Lrec + (long long)q * C::REC;
-      for (int i = lane; i < C::REC / 2; i += 32) ll_cp_async16(&sm.ring[slot][2 * i], src + 2 * i);
-    };
+    // ---- first record on its way, then the staged panel of the assembled matrix into accumulator tiles
     if (p > 0) issue_record(0, 0);
     ll_cp_commit();
+    ll_cp_wait<1>();  // the panel (older group) has landed
+    __syncwarp();
     double c[NT][2];
+    {
+      const double* As = sm.ring[1];
 #pragma unroll
-    for (int tr = 0; tr < NT; ++tr) {
-      const int row = 8 * tr + g;
+      for (int tr = 0; tr < NT; ++tr) {
+        const int row = 8 * tr + g;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int col = c0 + 2 * q4 + e;
-        double v = 0.0;
-        if (row < N && col < N) {
-          v = __ldcs(A + (long long)col * NP + row);
-          if ((bc_frag >> tr) & 1u) v = (col == row) ? 1.0 : 0.0;
+        for (int e = 0; e < 2; ++e) {
+          const int cl = 2 * q4 + e;
+          double v = 0.0;
+          if (row < N && cl < nst) {
+            v = As[cl * NP + row];
+            if ((bc_frag >> tr) & 1u) v = (c0 + cl == row) ? 1.0 : 0.0;
+          }
+          c[tr][e] = v;
         }
-        c[tr][e] = v;
       }
     }
+    __syncwarp();  // ring slot 1 is free for record 1
     // ---- apply the records q < p
     for (int q = 0; q < p; ++q) {
       if (q + 1 < p) issue_record(q + 1, (q + 1) & 1);
@@ -216,35 +237,30 @@ __global__ void __launch_bounds__(32, 8) rb_lu_left_kernel(LuArgs args, double* 
       ll_cp_wait<1>();
       __syncwarp();
       const double* rq = sm.ring[q & 1];
-      const double* Lpp = rq + NT * 64;
-      const int* prq = reinterpret_cast<const int*>(rq + NT * 64 + 64);
-      if (lane < 8) {  // lane = column of the panel: U_qp[:, lane] = L_qq^-1 X[:, lane]
-        double x[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) x[t] = sm.P[prq[t]][lane];
-#pragma unroll
-        for (int t = 1; t < 8; ++t) {
-          double acc = x[t];
-#pragma unroll
-          for (int s = 0; s < t; ++s) acc = fma(Lpp[t * 8 + s], x[s], acc);
-          x[t] = acc;
-        }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) sm.Ub[t][lane] = x[t];
+      const int* prq = reinterpret_cast<const int*>(rq + 64);
+      {  // U_qp = L_qq^-1 X on the tensor pipe (the inverse of the 8x8 unit-lower block travels in the record)
+        const double la0 = rq[lane], la1 = rq[32 + lane];
+        const double xb0 = sm.P[prq[q4]][g], xb1 = sm.P[prq[4 + q4]][g];
+        double u0 = 0.0, u1 = 0.0;
+        dmma884(u0, u1, la0, xb0);
+        dmma884(u0, u1, la1, xb1);
+        *reinterpret_cast<double2*>(&sm.Ub[g][2 * q4]) = make_double2(u0, u1);
       }
       __syncwarp();
-      {  // U block (q, p) -> packed store (2 doubles per lane, coalesced)
+      {  // U block (q, p) -> packed store (2 doubles per lane, coalesced; read once, at the very end)
         const double2 v = *reinterpret_cast<const double2*>(&sm.Ub[0][0] + 2 * lane);
-        __stcg(reinterpret_cast<double2*>(Ust + ((long long)(p * (p + 1) / 2 + q)) * 64 + 2 * lane), v);
+        __stcs(reinterpret_cast<double2*>(Ust + ((long long)(p * (p + 1) / 2 + q)) * 64 + 2 * lane), v);
       }
       const double b0 = sm.Ub[q4][g], b1 = sm.Ub[4 + q4][g];
-      const unsigned live_q = *reinterpret_cast<const unsigned*>(prq + 8);  // tile rows with non-zero multipliers
+      const unsigned live_q = (unsigned)prq[8];  // tile rows with non-zero multipliers (packed in this order)
+      const double* af = rq + 72 + lane;
 #pragma unroll
       for (int tr = 0; tr < NT; ++tr) {
         if ((live_q >> tr) & 1u) {  // uniform
-          const double a0 = rq[tr * 64 + lane], a1 = rq[tr * 64 + 32 + lane];
+          const double a0 = af[0], a1 = af[32];
           dmma884(c[tr][0], c[tr][1], a0, b0);
           dmma884(c[tr][0], c[tr][1], a1, b1);
+          af += 64;
         }
       }
       __syncwarp();  // all lanes are done with this ring slot, P and Ub
@@ -272,6 +288,9 @@ __global__ void __launch_bounds__(32, 8) rb_lu_left_kernel(LuArgs args, double* 
       }
     }
     __syncwarp();
+    // the next panel of the assembled matrix streams into ring slot 1 while this one is factored (slot 0 = cand)
+    if (p + 1 < npan) issue_apanel(p + 1);
+    ll_cp_commit();
     ll_pivot_step<0>(pv, b, tst, dmask, sm.pivrow, sm.rinvs, sm.cand, c0, lane);
     if (nst > 1) ll_pivot_step<1>(pv, b, tst, dmask, sm.pivrow, sm.rinvs, sm.cand, c0, lane);
     if (nst > 2) ll_pivot_step<2>(pv, b, tst, dmask, sm.pivrow, sm.rinvs, sm.cand, c0, lane);
@@ -285,18 +304,30 @@ __global__ void __launch_bounds__(32, 8) rb_lu_left_kernel(LuArgs args, double* 
     // ---- publish: rhs and diagonal U block of the new pivots; the record of this panel
     const bool last = (p + 1 == npan);
     double* rec = sm.rec;  // aliases P (dead now)
+    // tile rows that held a live row BEFORE this panel have (possibly) non-zero multipliers: only those are stored
+    unsigned live_tr = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned bal = __ballot_sync(FULL, !((dmask_in >> j) & 1u));
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq)
+        if ((bal >> (8 * qq)) & 0xffu) live_tr |= 1u << (4 * j + qq);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int row = lane + 32 * j;
       if (row < C::NP8) {
         const bool dead = (dmask_in >> j) & 1u;
-        if (!last) {
-          const int tr = row >> 3, gg = row & 7;
+        const int tr = row >> 3, gg = row & 7;
+        if (!last && ((live_tr >> tr) & 1u)) {
+          double* dstf = rec + 72 + 64 * __popc(live_tr & ((1u << tr) - 1u)) + gg * 4;
+          double nl[8];
 #pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            const bool is_mult = !dead && (tst[j] < 0 || s < tst[j]);
-            rec[tr * 64 + (s >> 2) * 32 + gg * 4 + (s & 3)] = is_mult ? -pv[j][s] : 0.0;
-          }
+          for (int s = 0; s < 8; ++s) nl[s] = (!dead && (tst[j] < 0 || s < tst[j])) ? -pv[j][s] : 0.0;
+          *reinterpret_cast<double2*>(dstf) = make_double2(nl[0], nl[1]);
+          *reinterpret_cast<double2*>(dstf + 2) = make_double2(nl[2], nl[3]);
+          *reinterpret_cast<double2*>(dstf + 32) = make_double2(nl[4], nl[5]);
+          *reinterpret_cast<double2*>(dstf + 34) = make_double2(nl[6], nl[7]);
         }
         if (tst[j] >= 0) {
           const int tt = tst[j];
@@ -304,58 +335,66 @@ __global__ void __launch_bounds__(32, 8) rb_lu_left_kernel(LuArgs args, double* 
           double* ud = Ust + ((long long)(p * (p + 1) / 2 + p)) * 64 + tt * 8;
 #pragma unroll
           for (int s = 0; s < 8; ++s) {
-            if (!last && s < tt) rec[NT * 64 + tt * 8 + s] = -pv[j][s];
-            if (s > tt && s < nst) __stcg(ud + s, pv[j][s]);
+            if (!last && s < tt) sm.Ub[tt][s] = -pv[j][s];
+            if (s > tt && s < nst) __stcs(ud + s, pv[j][s]);
           }
         }
       }
     }
     if (!last) {
-      // tile rows that still hold a live row BEFORE this panel have (possibly) non-zero multipliers
-      unsigned live_tr = 0u;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned bal = __ballot_sync(FULL, !((dmask_in >> j) & 1u));
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq)
-          if ((bal >> (8 * qq)) & 0xffu) live_tr |= 1u << (4 * j + qq);
-      }
-      int* pri = reinterpret_cast<int*>(rec + NT * 64 + 64);
+      const int nlive = __popc(live_tr);
+      int* pri = reinterpret_cast<int*>(rec + 64);
       if (lane < 8) pri[lane] = sm.pivrow[c0 + lane];
       if (lane == 8) pri[8] = (int)live_tr;
+      if (lane == 9) sm.recsz[p] = (72 + 64 * nlive) / 2;
+      __syncwarp();
+      if (lane < 8) {  // column `lane` of L_qq^-1 (unit lower; Ub holds the negated multipliers), A-fragment order
+        double x[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          double acc = (t == lane) ? 1.0 : 0.0;
+#pragma unroll
+          for (int s2 = 0; s2 < t; ++s2)
+            if (s2 >= lane) acc = fma(sm.Ub[t][s2], x[s2], acc);
+          x[t] = (t >= lane) ? acc : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) rec[(lane >> 2) * 32 + t * 4 + (lane & 3)] = x[t];
+      }
       __syncwarp();
       double* dst = Lrec + (long long)p * C::REC;
-      for (int i = lane; i < C::REC / 2; i += 32)
+      const int n16 = (72 + 64 * nlive) / 2;
+      for (int i = lane; i < n16; i += 32)
         __stcg(reinterpret_cast<double2*>(dst) + i, *reinterpret_cast<const double2*>(rec + 2 * i));
     }
     __syncwarp();
   }
 
   // ---- back-substitution U x = y by panels in reverse; ys is overwritten with the solution.
-  // Block column p of the packed U store is contiguous: rows of pivots k < 8p at (p(p+1)/2) * 64 + k * 8.
+  // Block column p of the packed U store is contiguous ((p + 1) blocks: rows of the pivots k < 8p, then the diagonal
+  // block) and is staged one panel ahead in the (now idle) ring.
+  auto issue_ucol = [&](int pc) {
+    issue_chunks(sm.ring[pc & 1], Ust + ((long long)(pc * (pc + 1) / 2)) * 64, (pc + 1) * 32, NT);
+  };
+  ll_cp_wait<0>();
+  __syncwarp();
+  issue_ucol(npan - 1);
+  ll_cp_commit();
   for (int p = npan - 1; p >= 0; --p) {
     const int c0 = 8 * p;
     const int nst = min(8, N - c0);
-    const double* colp = Ust + ((long long)(p * (p + 1) / 2)) * 64;
-    double uv[C::R][8];
-#pragma unroll
-    for (int r = 0; r < C::R; ++r) {
-      const int k = lane + 32 * r;
-#pragma unroll
-      for (int s = 0; s < 8; s += 2) {
-        double2 v = make_double2(0.0, 0.0);
-        if (k < c0) v = __ldcg(reinterpret_cast<const double2*>(colp + (long long)k * 8 + s));
-        uv[r][s] = v.x;
-        uv[r][s + 1] = v.y;
-      }
-    }
+    if (p > 0) issue_ucol(p - 1);
+    ll_cp_commit();
+    ll_cp_wait<1>();
+    __syncwarp();
+    const double* colp = sm.ring[p & 1];
     {  // 8x8 upper-triangular solve: lane t < nst owns pivot c0 + t
       const bool act = lane < nst;
       double y = act ? sm.ys[c0 + lane] : 0.0;
       const double ri = act ? sm.rinvs[c0 + lane] : 0.0;
       double ud[8];
 #pragma unroll
-      for (int s = 1; s < 8; ++s) ud[s] = (act && s > lane && s < nst) ? __ldcg(colp + (long long)(c0 + lane) * 8 + s) : 0.0;
+      for (int s = 1; s < 8; ++s) ud[s] = (act && s > lane && s < nst) ? colp[(c0 + lane) * 8 + s] : 0.0;
       double xo = 0.0;
 #pragma unroll
       for (int t = 7; t >= 0; --t) {
@@ -368,19 +407,26 @@ __global__ void __launch_bounds__(32, 8) rb_lu_left_kernel(LuArgs args, double* 
       if (act) sm.ys[c0 + lane] = xo;
     }
     __syncwarp();
+    double xs8[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) xs8[s] = (s < nst) ? sm.ys[c0 + s] : 0.0;
 #pragma unroll
     for (int r = 0; r < C::R; ++r) {
       const int k = lane + 32 * r;
       if (k < c0) {
         double acc = sm.ys[k];
 #pragma unroll
-        for (int s = 0; s < 8; ++s)
-          if (s < nst) acc = fma(-uv[r][s], sm.ys[c0 + s], acc);
+        for (int s = 0; s < 8; s += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(colp + k * 8 + s);
+          acc = fma(-v.x, xs8[s], acc);
+          acc = fma(-v.y, xs8[s + 1], acc);
+        }
         sm.ys[k] = acc;
       }
     }
     __syncwarp();
   }
+  ll_cp_wait<0>();
   double* u = args.U + sys * (long long)args.ldu;
 #pragma unroll
   for (int r = 0; r < C::R; ++r) {
@@ -389,9 +435,27 @@ __global__ void __launch_bounds__(32, 8) rb_lu_left_kernel(LuArgs args, double* 
   }
 }
 
+// Systems in flight per SM (A/B knob): occupancy is capped by padding with unused dynamic shared memory.
+static int ll_target_occupancy() {
+  static const int occ = [] {
+    const char* e = getenv("RB_LL_OCC");
+    const int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
+  }();
+  return occ;
+}
+
 template <int NT>
 static int ll_launch(const LuArgs& args, double* scratch, cudaStream_t stream) {
-  rb_lu_left_kernel<NT><<<(unsigned)args.count, 32, 0, stream>>>(args, scratch);
+  const int occ = ll_target_occupancy();
+  long long pad = 0;
+  if (occ < 8) {
+    pad = (227 * 1024) / occ - 1024 - (long long)sizeof(LlSmem<NT>);
+    pad = pad < 0 ? 0 : pad / 128 * 128;
+    cudaError_t e = cudaFuncSetAttribute(rb_lu_left_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+    if (e != cudaSuccess) return (int)e;
+  }
+  rb_lu_left_kernel<NT><<<(unsigned)args.count, 32, (size_t)pad, stream>>>(args, scratch);
   return (int)cudaGetLastError();
 }
 
