@@ -8,21 +8,18 @@ int rb_lu_launch_unit1(int NP, const LuArgs& args, cudaStream_t stream);
 int rb_lu_launch_unit2(int NP, const LuArgs& args, cudaStream_t stream);
 int rb_lu_launch_unit3(int NP, const LuArgs& args, cudaStream_t stream);
 int rb_lu_dmma_dispatch(int N, const LuArgs& args, cudaStream_t stream);
-int rb_lu_stream_launch(const LuArgs& args, double* Awork, cudaStream_t stream);
-int rb_lu_warp_launch(const LuArgs& args, double* Awork, cudaStream_t stream);
 int rb_lu_left_launch(const LuArgs& args, double* scratch, cudaStream_t stream);
 long long rb_lu_left_scratch_doubles(int N);
 
 // Which kernel serves 32 < N (A/B switch for profiling): "left" (default; one warp per system, left-looking, L records
-// streamed from L2), "warp" (one warp per system, right-looking in global memory), "stream" (thread per row,
-// right-looking in global memory), "dmma" (register-resident, 2 systems per SM), "rowreg" (oldest).
+// streamed from L2, 8 systems per SM), "dmma" (register-resident, 2 systems per SM), "rowreg" (row per thread).
+// Two right-looking variants that kept the trailing matrix in global memory (thread-per-row and warp-per-system with
+// DMMA updates) were measured at the same 0.27 us/system as "dmma" (read-modify-write latency through L2) and removed.
 int rb_lu_variant() {
   static const int v = [] {
     const char* e = getenv("RB_LU_KERNEL");
     if (e && e[0] == 'd') return 1;
     if (e && e[0] == 'r') return 2;
-    if (e && e[0] == 's') return 3;
-    if (e && e[0] == 'w') return 4;
     return 0;
   }();
   return v;
@@ -153,11 +150,7 @@ int rb_launch_lu_args(rb_ctx* ctx, const LuArgs& a, int NP) {
       ctx->lu_scratch_cap = need;
     }
     rc = rb_lu_left_launch(a, ctx->dLuScratch, ctx->stream);
-  } else if (NP > 32 && a.N <= 128 && variant == 4)
-    rc = rb_lu_warp_launch(a, const_cast<double*>(a.Ab), ctx->stream);
-  else if (NP > 32 && a.N <= 128 && variant == 3)
-    rc = rb_lu_stream_launch(a, const_cast<double*>(a.Ab), ctx->stream);
-  else if (NP > 32 && NP <= LU_MAX_NP_REG && !force_rowreg)
+  } else if (NP > 32 && NP <= LU_MAX_NP_REG && !force_rowreg)
     rc = rb_lu_dmma_dispatch(a.N, a, ctx->stream);
   else if (NP <= 52)
     rc = rb_lu_launch_unit0(NP, a, ctx->stream);

@@ -6,7 +6,7 @@
 //
 // Why left-looking: the pivot chain of a system is sequential, so an SM must interleave many systems, and then the
 // matrices cannot live on chip.  A right-looking update reads AND writes the trailing matrix in global memory after
-// every panel (latency-bound read-modify-write, rb_lu_warp.cu).  Left-looking, panel p (8 columns) is read ONCE from
+// every panel (latency-bound read-modify-write; measured, then dropped).  Left-looking, panel p (8 columns) is read ONCE from
 // the assembled matrix into DMMA accumulator tiles that stay in registers while the records of the finished panels
 // q < p stream by:
 //     record q = { negated multipliers of panel q in DMMA A-fragment order, inverse of its 8x8 unit-lower block,
@@ -15,7 +15,7 @@
 // shared-memory ring.  Per record:  X = the panel rows pivoted in q (final since the records >= q have zero
 // multipliers for them), U_qp = L_qq^-1 X (2 DMMA.8x8x4), C -= L_q U_qp (2 DMMA.8x8x4 per live tile row).
 // Then the panel is transposed through shared memory to one row set per lane and factored exactly like
-// rb_lu_warp.cu / rb_lu_dmma.cuh (REDUX.MAX arg-max, idamax tie rule, implicit pivoting, rhs carried along).
+// rb_lu_dmma.cuh (REDUX.MAX arg-max, idamax tie rule, implicit pivoting, rhs carried along).
 // U is stored in 8x8 blocks, block column p contiguous, so the back-substitution reads coalesced rows.
 // CTA = one warp; no block-level barrier; ~26 KB of shared memory -> 8 systems per SM.
 #include <stdlib.h>
@@ -28,7 +28,7 @@ struct LlCfg {
   static constexpr int R = (NP8 + 31) / 32;        // pivot indices / rows per lane
   static constexpr int REC = 64 + 8 + NT * 64;     // doubles per record: L_qq^-1 | pivrow[8], live mask | packed nLf
   static constexpr int SLOT = REC < 640 ? 640 : REC;  // ring slot (doubles): slot 0 also hosts the 640 candidate doubles
-  static constexpr int PP = 10;                    // pitch of the transpose buffer
+  static constexpr int PP = 8;                     // pitch of the transpose buffer (dump: conflict-free STS.128)
   static constexpr int UBLK = NT * (NT + 1) / 2;   // 8x8 blocks of the packed upper-triangular U store
   // scratch doubles per system beyond the assembled matrix: records of all panels + packed U
   static constexpr long long SCRATCH = (long long)NT * REC + (long long)UBLK * 64;
@@ -71,7 +71,7 @@ __device__ __forceinline__ void ll_cp_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// One pivot step T of phase F (a template: the register indices must be static).  Same arithmetic as rb_lu_warp.cu.
+// One pivot step T of phase F (a template: the register indices must be static).  Same arithmetic as lud_pivot_step of rb_lu_dmma.cuh, plus the rhs entry.
 template <int T>
 __device__ __forceinline__ void ll_pivot_step(double (&pv)[4][8], double (&b)[4], int (&tst)[4], unsigned& dmask,
                                               int* pivrow, double* rinvs, double (*cand)[32][10], int c0, int lane) {
@@ -238,20 +238,27 @@ __global__ void __launch_bounds__(32, 8) rb_lu_left_kernel(LuArgs args, double* 
       __syncwarp();
       const double* rq = sm.ring[q & 1];
       const int* prq = reinterpret_cast<const int*>(rq + 64);
-      {  // U_qp = L_qq^-1 X on the tensor pipe (the inverse of the 8x8 unit-lower block travels in the record)
+      // U_qp = L_qq^-1 X on the tensor pipe (the inverse of the 8x8 unit-lower block travels in the record)
+      double u0 = 0.0, u1 = 0.0;
+      {
         const double la0 = rq[lane], la1 = rq[32 + lane];
         const double xb0 = sm.P[prq[q4]][g], xb1 = sm.P[prq[4 + q4]][g];
-        double u0 = 0.0, u1 = 0.0;
         dmma884(u0, u1, la0, xb0);
         dmma884(u0, u1, la1, xb1);
-        *reinterpret_cast<double2*>(&sm.Ub[g][2 * q4]) = make_double2(u0, u1);
       }
-      __syncwarp();
-      {  // U block (q, p) -> packed store (2 doubles per lane, coalesced; read once, at the very end)
-        const double2 v = *reinterpret_cast<const double2*>(&sm.Ub[0][0] + 2 * lane);
-        __stcs(reinterpret_cast<double2*>(Ust + ((long long)(p * (p + 1) / 2 + q)) * 64 + 2 * lane), v);
+      // U block (q, p) -> packed store straight from the accumulator layout (row g, columns 2q4, 2q4+1: 16 B per
+      // lane, 512 B contiguous per warp; read once, at the very end)
+      __stcs(reinterpret_cast<double2*>(Ust + ((long long)(p * (p + 1) / 2 + q)) * 64 + 8 * g + 2 * q4),
+             make_double2(u0, u1));
+      // accumulator layout -> B-fragment layout by shuffles: b0 = U[q4][g], b1 = U[4 + q4][g]
+      double b0, b1;
+      {
+        const int src0 = q4 * 4 + (g >> 1), src1 = (4 + q4) * 4 + (g >> 1);
+        const double e0 = __shfl_sync(FULL, u0, src0), o0 = __shfl_sync(FULL, u1, src0);
+        const double e1 = __shfl_sync(FULL, u0, src1), o1 = __shfl_sync(FULL, u1, src1);
+        b0 = (g & 1) ? o0 : e0;
+        b1 = (g & 1) ? o1 : e1;
       }
-      const double b0 = sm.Ub[q4][g], b1 = sm.Ub[4 + q4][g];
       const unsigned live_q = (unsigned)prq[8];  // tile rows with non-zero multipliers (packed in this order)
       const double* af = rq + 72 + lane;
 #pragma unroll
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(32, 8) rb_lu_left_kernel(LuArgs args, double* 
           af += 64;
         }
       }
-      __syncwarp();  // all lanes are done with this ring slot, P and Ub
+      __syncwarp();  // all lanes are done with this ring slot and P
     }
     ll_cp_wait<0>();
     // ---- transpose into phase F: lane owns rows lane+32j
@@ -439,8 +446,8 @@ __global__ void __launch_bounds__(32, 8) rb_lu_left_kernel(LuArgs args, double* 
 static int ll_target_occupancy() {
   static const int occ = [] {
     const char* e = getenv("RB_LL_OCC");
-    const int v = e ? atoi(e) : 8;
-    return v < 1 ? 1 : (v > 8 ? 8 : v);
+    const int v = e ? atoi(e) : 9;
+    return v < 1 ? 1 : (v > 9 ? 9 : v);
   }();
   return occ;
 }
@@ -449,7 +456,7 @@ template <int NT>
 static int ll_launch(const LuArgs& args, double* scratch, cudaStream_t stream) {
   const int occ = ll_target_occupancy();
   long long pad = 0;
-  if (occ < 8) {
+  if (occ < 9) {
     pad = (227 * 1024) / occ - 1024 - (long long)sizeof(LlSmem<NT>);
     pad = pad < 0 ? 0 : pad / 128 * 128;
     cudaError_t e = cudaFuncSetAttribute(rb_lu_left_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);

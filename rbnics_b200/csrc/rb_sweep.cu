@@ -515,8 +515,6 @@ __global__ void __launch_bounds__(256) rb_argmax_final_kernel(const double* __re
 // =====================================================================================================================
 // Host side
 // =====================================================================================================================
-int rb_lu_variant();
-int rb_lu_stream_occupancy();
 static int roundup(int x, int m) { return (x + m - 1) / m * m; }
 
 template <typename T>
@@ -871,14 +869,8 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
   float ms_asm = 0.f, ms_lu = 0.f;
   if (N > 0) {
     // chunked assembly + LU; scratch = chunk x EP doubles
-    // The L2-streamed LU works in place on the scratch, which must stay L2-resident: one wave of 8 systems per SM
-    // (95 MB at N = 100).  The register-resident kernels take big chunks instead.
     long long chunk = (long long)ctx->sm_count * ASM_BM;
-    if (ctx->NP > 32 && N <= 128 && rb_lu_variant() == 3) {
-      static const long long env_chunk = getenv("RB_LU_CHUNK") ? atoll(getenv("RB_LU_CHUNK")) : 0;
-      chunk = env_chunk > 0 ? env_chunk : (long long)ctx->sm_count * rb_lu_stream_occupancy();
-    }
-    if (getenv("RB_LU_CHUNK") && rb_lu_variant() != 3) chunk = atoll(getenv("RB_LU_CHUNK"));
+    if (getenv("RB_LU_CHUNK")) chunk = atoll(getenv("RB_LU_CHUNK"));
     chunk = std::min<long long>(B, chunk);
     if (chunk * ctx->EP > ctx->ab_cap) {
       if (int rc = dev_realloc(ctx, &ctx->dAb, (size_t)chunk * ctx->EP)) return rc;
