@@ -205,3 +205,77 @@ def test_cuda_per_parameter_online_api_matches_reference_golden(engine, case):
                 + 2.0 * (online.transpose(u) * online.sum(online.product(ta, e_af[:N], tf)))
                 + online.transpose(u) * online.sum(online.product(ta, e_aa[:N, :N], ta)) * u)
         assert abs(eps2 - g["eps2"][p]) <= RTOL * abs(g["eps2"][p])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Stokes (BASELINE.json configs[4]): block saddle-point system, 9 estimator term pairs
+# (rbnics/problems/stokes/stokes_reduced_problem.py:38-53, stokes_rb_reduced_problem.py:35-83)
+# ----------------------------------------------------------------------------------------------------------------------
+STOKES_CASES = sorted(os.path.basename(p)[len("reference_stokes_"):-len(".npz")]
+                      for p in glob.glob(os.path.join(HERE, "golden", "reference_stokes_*.npz")))
+STOKES_PAIRS = [("f", "f"), ("g", "g"), ("a", "f"), ("bt", "f"), ("b", "g"), ("a", "a"), ("a", "bt"), ("bt", "bt"),
+                ("b", "b")]
+
+
+def _load_stokes(case):
+    g = dict(np.load(os.path.join(HERE, "golden", f"reference_stokes_{case}.npz")))
+    op = {t: g["op_" + t] for t in ("a", "b", "bt", "f", "g")}
+    E = {(t1, t2): g[f"E_{t1}_{t2}"] for (t1, t2) in STOKES_PAIRS}
+    theta = {t: g["theta_" + t] for t in ("a", "b", "bt", "f", "g")}
+    return g, op, E, theta
+
+
+def test_stokes_fixtures_present():
+    assert {"n5", "n12_bc"} <= set(STOKES_CASES)
+
+
+@pytest.mark.parametrize("case", STOKES_CASES)
+def test_oracle_stokes_is_bit_identical_to_reference(case):
+    g, op, E, theta = _load_stokes(case)
+    N = op["a"].shape[1]
+    Eo = {k: ([[float(v[i, j]) for j in range(v.shape[1])] for i in range(v.shape[0])] if v.ndim == 2 else
+              [[v[i, j] for j in range(v.shape[1])] for i in range(v.shape[0])]) for k, v in E.items()}
+    opl = {t: [op[t][q] for q in range(op[t].shape[0])] for t in op}
+    for p in range(g["U"].shape[0]):
+        th = {t: tuple(float(x) for x in theta[t][p]) for t in theta}
+        tbc = tuple(float(x) for x in g["Theta_bc"][p]) if int(g["n_bc"]) else None
+        u = O.reduced_solve_stokes(th, opl, N, tbc)
+        assert np.array_equal(u, g["U"][p])
+        assert O.residual_norm_squared_stokes(u, th, Eo, N) == g["eps2"][p]
+
+
+@pytest.mark.parametrize("case", STOKES_CASES)
+def test_stokes_quadratic_form_packing_matches_reference(case):
+    """z^T G z with the packed G of engine.stokes_quadratic_form == the reference's 9-term eps2 (CPU, numpy only)."""
+    from rbnics_b200.engine import stokes_quadratic_form
+    g, op, E, theta = _load_stokes(case)
+    N = op["a"].shape[1]
+    Q = {t: op[t].shape[0] for t in op}
+    G, (scale, src, length, v_off, v_len) = stokes_quadratic_form(E, Q, N)
+    for p in range(g["U"].shape[0]):
+        Theta = np.concatenate([theta[t][p] for t in ("a", "b", "bt", "f", "g")])
+        V = np.concatenate([g["U"][p], Theta[v_off:v_off + v_len], [1.0]])
+        z = np.concatenate([(Theta[sc] if sc >= 0 else 1.0) * V[so:so + ln] for sc, so, ln in zip(scale, src, length)])
+        assert abs(z @ G @ z - g["eps2"][p]) <= 1e-12 * abs(g["eps2"][p])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", STOKES_CASES)
+def test_cuda_stokes_sweep_matches_reference_golden(engine, case):
+    from rbnics_b200._lib import RB_EST_SQRT_OF_EPS2_OVER_BETA
+    g, op, E, theta = _load_stokes(case)
+    N = op["a"].shape[1]
+    Q = {t: op[t].shape[0] for t in op}
+    nbc = int(g["n_bc"])
+    A = np.concatenate([op["a"], op["b"], op["bt"]])            # every lhs term block-embedded in N x N
+    F = np.concatenate([op["f"], op["g"]])
+    Theta = np.concatenate([theta[t] for t in ("a", "b", "bt", "f", "g")], axis=1)
+    engine.set_system(A, F, bc_rows=list(range(nbc)) if nbc else None)
+    engine.set_stokes_estimator(E, Q)
+    engine.set_training_set(Theta, g["beta"], g.get("Theta_bc"))
+    r = engine.sweep_resident(kind=RB_EST_SQRT_OF_EPS2_OVER_BETA, want_delta=True, want_u=True, want_eps2=True)
+    err_u = np.max(np.abs(r["u"] - g["U"]), axis=1) / np.max(np.abs(g["U"]), axis=1)
+    assert err_u.max() <= RTOL
+    assert np.max(np.abs(r["eps2"] - g["eps2"]) / np.abs(g["eps2"])) <= RTOL
+    assert np.max(np.abs(r["delta"] - g["delta"]) / g["delta"]) <= RTOL
+    assert r["argmax"] == int(np.argmax(g["delta"]))
