@@ -146,7 +146,7 @@ struct EstArgs {
 __host__ __device__ inline size_t est_smem_bytes(int stage_ksteps, int LVS, int nblk, int n_ctile) {
   size_t b = (size_t)EST_NSTAGE * stage_ksteps * EST_KSTEP_DOUBLES * 8;  // G' stages
   b += (size_t)EST_NSTAGE * 8;                                            // full barriers
-  b += (size_t)EST_BM * 8;                                                // cross-warp reduction
+  b += (size_t)3 * EST_BM * 8;                                            // cross-warp reduction
   b += (size_t)EST_BM * LVS * 8;                                          // V tile
   b += (size_t)n_ctile * 8;                                               // tile offsets
   b += (size_t)(2 * n_ctile + 3 * nblk + 1 + EST_NSTAGE) * 4;             // int tables + release counters
@@ -154,36 +154,45 @@ __host__ __device__ inline size_t est_smem_bytes(int stage_ksteps, int LVS, int 
 }
 
 // Fragments of one k-step: B from the staged G' (fragment order, conflict-free LDS.128), A from the V tile.
+template <int NTN>
 struct EstFrag {
-  double2 b01, b23;
+  double2 b[NTN / 2];
   double a[4];
 };
 
-__device__ __forceinline__ void est_load_frag(EstFrag& f, const double* gs, const double* vp, int LVS) {
-  f.b01 = *reinterpret_cast<const double2*>(gs);
-  f.b23 = *reinterpret_cast<const double2*>(gs + 64);
+template <int NTN>
+__device__ __forceinline__ void est_load_frag(EstFrag<NTN>& f, const double* gs, const double* vp, int LVS) {
+#pragma unroll
+  for (int h = 0; h < NTN / 2; ++h) f.b[h] = *reinterpret_cast<const double2*>(gs + 64 * h);
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) f.a[mt] = vp[mt * 8 * LVS];
 }
 
-__device__ __forceinline__ void est_mma(double (&T)[4][4][2], const EstFrag& f) {
+template <int NTN>
+__device__ __forceinline__ void est_mma(double (&T)[4][NTN][2], const EstFrag<NTN>& f) {
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
-    dmma884(T[mt][0][0], T[mt][0][1], f.a[mt], f.b01.x);
-    dmma884(T[mt][1][0], T[mt][1][1], f.a[mt], f.b01.y);
-    dmma884(T[mt][2][0], T[mt][2][1], f.a[mt], f.b23.x);
-    dmma884(T[mt][3][0], T[mt][3][1], f.a[mt], f.b23.y);
+#pragma unroll
+    for (int h = 0; h < NTN / 2; ++h) {
+      dmma884(T[mt][2 * h][0], T[mt][2 * h][1], f.a[mt], f.b[h].x);
+      dmma884(T[mt][2 * h + 1][0], T[mt][2 * h + 1][1], f.a[mt], f.b[h].y);
+    }
   }
 }
 
-__global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a) {
+// NTN = 8-column tiles per warp: 4 -> 8 warps (4 m x 2 n, warp tile 32 x 32), 2 -> 16 warps (4 m x 4 n, 32 x 16).
+template <int NTN>
+__global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(EstArgs a) {
+  constexpr int WN = 8 / NTN;              // warps along n
+  constexpr int NWARPS = 4 * WN;
+  constexpr int NTHREADS = 32 * NWARPS;
   extern __shared__ __align__(128) unsigned char est_smem_raw[];
   const int SK = a.stage_ksteps;
   const int STAGE_DOUBLES = SK * EST_KSTEP_DOUBLES;
   double* Gs = reinterpret_cast<double*>(est_smem_raw);                     // [NSTAGE][STAGE_DOUBLES]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(Gs + EST_NSTAGE * STAGE_DOUBLES);
-  double* red = reinterpret_cast<double*>(full_bar + EST_NSTAGE);          // [EST_BM]
-  double* Vs = red + EST_BM;                                                // [EST_BM][LVS]
+  double* red = reinterpret_cast<double*>(full_bar + EST_NSTAGE);          // [3][EST_BM]
+  double* Vs = red + 3 * EST_BM;                                            // [EST_BM][LVS]
   long long* s_tile_off = reinterpret_cast<long long*>(Vs + EST_BM * a.LVS);  // [n_ctile]
   int* s_tile_ks0 = reinterpret_cast<int*>(s_tile_off + a.n_ctile);         // [n_ctile]
   int* s_tile_b0 = s_tile_ks0 + a.n_ctile;                                  // [n_ctile]
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a)
   const int LVS = a.LVS;
 
   // V tile: [u | theta[v_off : v_off+v_len] | 1 | 0 ...]
-  for (int t = tid; t < EST_BM * LVS; t += EST_THREADS) {
+  for (int t = tid; t < EST_BM * LVS; t += NTHREADS) {
     const int r = t / LVS, c = t % LVS;
     const long long p = p0 + r;
     double v = 0.0;
@@ -214,12 +223,12 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a)
     }
     Vs[t] = v;
   }
-  for (int t = tid; t < a.n_ctile; t += EST_THREADS) {
+  for (int t = tid; t < a.n_ctile; t += NTHREADS) {
     s_tile_off[t] = a.tile_off[t];
     s_tile_ks0[t] = a.tile_ks0[t];
     s_tile_b0[t] = a.tile_b0[t];
   }
-  for (int t = tid; t <= a.nblk; t += EST_THREADS) {
+  for (int t = tid; t <= a.nblk; t += NTHREADS) {
     s_ks_begin[t] = a.blk_ks_begin[t];
     if (t < a.nblk) {
       s_scale[t] = a.blk_scale[t];
@@ -260,11 +269,11 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a)
     }
   }
 
-  const int wm = warp & 3, wn = warp >> 2;
+  const int wm = warp & 3, wn = warp >> 2;  // wn < WN
   const int g = lane >> 2, q4 = lane & 3;
   const int r0 = wm * 32 + g;  // + mt*8
   const double* vrow = Vs + r0 * LVS + q4;
-  const double* gsw = Gs + wn * 128 + lane * 2;
+  const double* gsw = Gs + wn * (32 * NTN) + lane * 2;
   const double* th_base = a.theta;
   long long prow[4];
 #pragma unroll
@@ -274,11 +283,11 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a)
   uint32_t phase = 0;
 
   for (int ct = ct_begin; ct < ct_end; ++ct) {
-    double Y[4][4][2], T[4][4][2];
+    double Y[4][NTN][2], T[4][NTN][2];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) Y[mt][nt][0] = Y[mt][nt][1] = T[mt][nt][0] = T[mt][nt][1] = 0.0;
+      for (int nt = 0; nt < NTN; ++nt) Y[mt][nt][0] = Y[mt][nt][1] = T[mt][nt][0] = T[mt][nt][1] = 0.0;
 
     int ks = s_tile_ks0[ct];
     int b = s_tile_b0[ct];
@@ -299,7 +308,7 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a)
     mbar_wait(full_bar + stage, phase);
     const double* gp = gsw + stage * STAGE_DOUBLES;   // this warp's B fragments of the current k-step
     const double* vp = vrow + src;                    // this thread's A fragments of the current k-step
-    EstFrag f0, f1;
+    EstFrag<NTN> f0, f1;
     est_load_frag(f0, gp, vp, LVS);
 
     // The k loop is cut into segments that end at the next stage or block boundary, so that the steady-state body is
@@ -333,7 +342,7 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a)
         __syncwarp();
         if (lane == 0) {
           const int old = atomicAdd(&s_cnt[stage], 1);
-          if (old == EST_WARPS - 1) {
+          if (old == NWARPS - 1) {
             s_cnt[stage] = 0;
             if (pct < ct_end) issue_stage(stage);
           }
@@ -359,7 +368,7 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a)
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
+          for (int nt = 0; nt < NTN; ++nt) {
             Y[mt][nt][0] = fma(th[mt], T[mt][nt][0], Y[mt][nt][0]);
             Y[mt][nt][1] = fma(th[mt], T[mt][nt][1], Y[mt][nt][1]);
             T[mt][nt][0] = 0.0;
@@ -377,9 +386,9 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a)
     }
 
     // epilogue of the column tile: rowacc[p] += sum_c Y[p,c] * z[p,c]
-    const int cbase = ct * EST_BN + wn * 32 + q4 * 2;
+    const int cbase = ct * EST_BN + wn * (8 * NTN) + q4 * 2;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+    for (int nt = 0; nt < NTN; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int c = cbase + nt * 8 + e;
@@ -401,16 +410,19 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_kernel(EstArgs a)
     rowacc[mt] += __shfl_xor_sync(0xffffffffu, rowacc[mt], 1);
     rowacc[mt] += __shfl_xor_sync(0xffffffffu, rowacc[mt], 2);
   }
-  if (wn == 1 && q4 == 0) {
+  if (wn > 0 && q4 == 0) {
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) red[r0 + mt * 8] = rowacc[mt];
+    for (int mt = 0; mt < 4; ++mt) red[(wn - 1) * EST_BM + r0 + mt * 8] = rowacc[mt];
   }
   __syncthreads();
   if (wn == 0 && q4 == 0) {
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
       const long long p = p0 + r0 + mt * 8;
-      if (p < a.B) a.partial[(long long)split * a.B + p] = rowacc[mt] + red[r0 + mt * 8];
+      double e = rowacc[mt];
+#pragma unroll
+      for (int w2 = 0; w2 < WN - 1; ++w2) e += red[w2 * EST_BM + r0 + mt * 8];  // fixed order: deterministic
+      if (p < a.B) a.partial[(long long)split * a.B + p] = e;
     }
   }
 }
@@ -759,7 +771,8 @@ extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col,
   cudaFree(dG);
   if (dP2U) cudaFree(dP2U);
   if (e != cudaSuccess) RB_FAIL(RB_ERR_CUDA, std::string("rb_set_estimator: ") + cudaGetErrorString(e));
-  RB_CUDA(cudaFuncSetAttribute(rb_estimator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RB_CUDA(cudaFuncSetAttribute(rb_estimator_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RB_CUDA(cudaFuncSetAttribute(rb_estimator_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ctx->have_est = true;
   return RB_OK;
 }
@@ -930,7 +943,11 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     ea.n_ctile = ctx->n_ctile;
     ea.stage_ksteps = ctx->stage_ksteps;
     const size_t smem = est_smem_bytes(ctx->stage_ksteps, ctx->LVS, ctx->nblk, ctx->n_ctile);
-    rb_estimator_kernel<<<(unsigned)(nrb * nsplit), EST_THREADS, smem, st>>>(ea);
+    static const bool est16 = getenv("RB_EST_WARPS") && atoi(getenv("RB_EST_WARPS")) == 16;  // A/B switch (default 8)
+    if (est16)
+      rb_estimator_kernel<2><<<(unsigned)(nrb * nsplit), 512, smem, st>>>(ea);
+    else
+      rb_estimator_kernel<4><<<(unsigned)(nrb * nsplit), 256, smem, st>>>(ea);
     RB_CUDA(cudaGetLastError());
     ++launches;
   }
