@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""bench_offline.py -- the offline basis linear algebra at BASELINE.json configs[3] shapes (tutorial 06 scaled to
+10^6 dofs): POD Gram matrix S^T X S, Galerkin projections Z^T A_q Z, mode construction S V and one Gram-Schmidt
+step, each with its kernel time (CUDA events on the engine's stream, rb_last_timings) and the roofline it is bound by
+(SURVEY.md 8d):  SpMM  12*nnz + 16*Nh*Ns bytes (HBM);  tall-skinny Gram 2*Nh*Ns*Ns2 flops / 8*Nh*(Ns+Ns2) bytes.
+
+    python bench_offline.py [--nh 1000000] [--ns 61 400] [--n 20 100]
+
+Prints one JSON line per kernel.  Not the headline metric (bench.py is); this is the measurement of rows B1-B5."""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def lap2d(n):
+    """7-point-like P1 stiffness + mass on an n x n grid (5 nnz per row), the synthetic X of SURVEY.md 8d config 4."""
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(n, n))
+    I = sp.identity(n)
+    return (sp.kron(T, I) + sp.kron(I, T) + 0.5 * sp.identity(n * n)).tocsr()
+
+
+def peaks():
+    hbm, fp64 = 6545.9, 37.15
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    try:
+        fp64 = float(json.load(open(os.path.join(ROOT, "profiles", "FP64_PEAK.json")))["fp64_dmma_tflops"])
+    except Exception:
+        pass
+    return hbm, fp64
+
+
+def timings(eng):
+    ms = (C.c_float * 5)()
+    n = C.c_int()
+    eng._lib.rb_last_timings(eng._h, ms, C.byref(n))
+    return list(ms), n.value
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nh", type=int, default=1_000_000)
+    ap.add_argument("--ns", type=int, nargs="+", default=[61, 400])
+    ap.add_argument("--n", type=int, nargs="+", default=[20, 100])
+    ap.add_argument("--q", type=int, default=3)
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    from rbnics_b200 import offline
+    from rbnics_b200.engine import SweepEngine
+    eng = SweepEngine(0)
+    hbm, fp64 = peaks()
+    side = int(round(args.nh ** 0.5))
+    Nh = side * side
+    X = lap2d(side)
+    nnz = X.nnz
+    rng = np.random.default_rng(0)
+
+    def emit(kernel, shape, ms, bytes_alg, flops_alg, e2e_ms, note=""):
+        gbs = bytes_alg / (ms * 1e-3) * 1e-9 if ms > 0 else 0.0
+        tfs = flops_alg / (ms * 1e-3) * 1e-12 if ms > 0 else 0.0
+        bound = "hbm" if (flops_alg / max(bytes_alg, 1)) < fp64 * 1e12 / (hbm * 1e9) else "tensor"
+        frac = gbs / hbm if bound == "hbm" else tfs / fp64
+        print(json.dumps({"kernel": kernel, "shape": shape, "kernel_ms": ms, "e2e_ms_with_copies": e2e_ms,
+                          "algorithmic_bytes": bytes_alg, "algorithmic_flops": flops_alg, "achieved_GBps": gbs,
+                          "achieved_TFLOPs": tfs, "bound": bound, "peak": hbm if bound == "hbm" else fp64,
+                          "frac": frac, "note": note}), flush=True)
+
+    for Ns in args.ns:
+        S = np.ascontiguousarray(rng.standard_normal((Nh, Ns)))
+        best = None
+        for _ in range(args.reps):
+            t0 = time.perf_counter()
+            offline.gram(eng, S, X)
+            e2e = (time.perf_counter() - t0) * 1e3
+            ms, _ = timings(eng)
+            if best is None or ms[4] < best[0][4]:
+                best = (ms, e2e)
+        ms, e2e = best
+        shape = {"Nh": Nh, "Ns": Ns, "nnz": nnz}
+        emit("rb_spmm_kernel (Y = X S)", shape, ms[0], 12 * nnz + 16 * Nh * Ns, 2 * nnz * Ns, e2e)
+        emit("rb_tsmm_kernel + reduce (C = S^T Y)", shape, ms[1], 16 * Nh * Ns, 2 * Nh * Ns * Ns, e2e,
+             "Y is re-read from HBM (not fused with the SpMM yet)")
+        del S
+    ops = [X, (X + sp.identity(Nh)).tocsr(), (2.0 * X).tocsr()][:args.q]
+    for N in args.n:
+        Z = np.ascontiguousarray(rng.standard_normal((Nh, N)))
+        t0 = time.perf_counter()
+        offline.project_matrices(eng, Z, ops)
+        e2e = (time.perf_counter() - t0) * 1e3
+        ms, _ = timings(eng)
+        shape = {"Nh": Nh, "N": N, "Q": len(ops), "nnz": nnz}
+        emit("rb_project (Q x (SpMM + Z^T Y))", shape, ms[4], len(ops) * (12 * nnz + 16 * Nh * N) + 8 * Nh * N,
+             len(ops) * (2 * nnz * N + 2 * Nh * N * N), e2e)
+        V = np.ascontiguousarray(rng.standard_normal((N, min(N, 20))))
+        t0 = time.perf_counter()
+        offline.lincomb(eng, Z, V)
+        e2e = (time.perf_counter() - t0) * 1e3
+        ms, _ = timings(eng)
+        emit("rb_lincomb_kernel (Z = S V)", {"Nh": Nh, "Ns": N, "n": V.shape[1]}, ms[4],
+             8 * Nh * (N + V.shape[1]), 2 * Nh * N * V.shape[1], e2e)
+        gs = offline.GramSchmidt(eng, X)
+        z = rng.standard_normal(Nh)
+        t0 = time.perf_counter()
+        gs.apply(z, Z)
+        e2e = (time.perf_counter() - t0) * 1e3
+        print(json.dumps({"kernel": "rb_gram_schmidt (MGS step, N dots + axpys)", "shape": {"Nh": Nh, "N": N},
+                          "e2e_ms_with_copies": e2e}), flush=True)
+        del Z
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

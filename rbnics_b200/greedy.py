@@ -25,8 +25,12 @@ from .sweep import TrainingSetSweep
 
 
 class ReducedBasisGreedy:
+    """``incremental=True`` (default) reuses ``A^N_q[:N-1, :N-1]`` and the Riesz Gram blocks of the previous greedy
+    iteration and computes only the new row / column; the reference recomputes every inner
+    product at every iteration (rb_reduction.py:106,112).  ``incremental=False`` is that full recomputation."""
+
     def __init__(self, engine, truth_problem, training_set, Nmax, tol, estimator_kind=L.RB_EST_SQRT_EPS2_OVER_BETA,
-                 dist=None, verbose=False):
+                 dist=None, verbose=False, incremental=True):
         self.engine = engine
         self.truth_problem = truth_problem
         self.training_set = [tuple(mu) for mu in training_set]
@@ -35,6 +39,7 @@ class ReducedBasisGreedy:
         self.kind = estimator_kind
         self.dist = dist
         self.verbose = verbose
+        self.incremental = incremental
         tp = truth_problem
         self.Qa, self.Qf = len(tp.operators_a), len(tp.operators_f)
         self.Nh = tp.operators_f[0].shape[0]
@@ -59,13 +64,30 @@ class ReducedBasisGreedy:
 
     # -- reduced_problem.build_reduced_operators() ---------------------------------------------------------------
     def build_reduced_operators(self):
+        tp = self.truth_problem
         if self.N == 0:
             self.operator_a = np.zeros((self.Qa, 0, 0))
             self.operator_f = np.zeros((self.Qf, 0))
+        elif self.incremental and self.operator_a.shape[1] == self.N - 1:
+            # only the new row and column: A^N[:, N-1] = Z^T (A_q z), A^N[N-1, :] = z^T (A_q Z); Z is unchanged for the
+            # first N-1 functions because the Gram-Schmidt step never modifies earlier basis functions
+            Z = self.basis_functions
+            z = np.ascontiguousarray(Z[:, -1:])
+            N = self.N
+            A_new = np.zeros((self.Qa, N, N))
+            A_new[:, :N - 1, :N - 1] = self.operator_a
+            for q, A in enumerate(tp.operators_a):
+                A_new[q, :, N - 1] = offline.gram(self.engine, Z, A, z, dist=self.dist)[:, 0]
+                A_new[q, N - 1, :] = offline.gram(self.engine, z, A, Z, dist=self.dist)[0, :]
+            self.operator_a = A_new
+            f_new = np.zeros((self.Qf, N))
+            f_new[:, :N - 1] = self.operator_f
+            f_new[:, N - 1] = offline.project_vectors(self.engine, z, tp.operators_f, dist=self.dist)[:, 0]
+            self.operator_f = f_new
         else:
             Z = self.basis_functions
-            self.operator_a = offline.project_matrices(self.engine, Z, self.truth_problem.operators_a)
-            self.operator_f = offline.project_vectors(self.engine, Z, self.truth_problem.operators_f)
+            self.operator_a = offline.project_matrices(self.engine, Z, tp.operators_a)
+            self.operator_f = offline.project_vectors(self.engine, Z, tp.operators_f)
         self.engine.set_system(self.operator_a, self.operator_f)
 
     # -- reduced_problem.build_error_estimation_operators() ------------------------------------------------------
@@ -78,10 +100,21 @@ class ReducedBasisGreedy:
             new = [tp.riesz_solve(-(tp.operators_a[q] @ self.basis_functions[:, n])) for n in range(have, self.N)]
             if new:
                 self.riesz_a[q] = np.concatenate([self.riesz_a[q], np.stack(new, axis=1)], axis=1)
+        N, Qa, Qf = self.N, self.Qa, self.Qf
         # all Riesz Gram blocks at once: S = [R_1 | ... | R_Qa | r_f],  G = S^T X S  in z-order [(q, n) ... | f]
         S = np.concatenate(self.riesz_a + [self.riesz_f], axis=1)
-        self.G = offline.gram(self.engine, S, tp.inner_product, dist=self.dist)
-        N, Qa, Qf = self.N, self.Qa, self.Qf
+        if self.incremental and self.G is not None and N > 0 and self.G.shape[0] == Qa * (N - 1) + Qf:
+            # only the Qa new representers against everything: G_new[(q, N-1), :] = r_{q,N-1}^T X S; X is symmetric
+            old_idx = [q * N + n for q in range(Qa) for n in range(N - 1)] + [Qa * N + j for j in range(Qf)]
+            new_idx = [q * N + (N - 1) for q in range(Qa)]
+            G = np.empty((Qa * N + Qf, Qa * N + Qf))
+            G[np.ix_(old_idx, old_idx)] = self.G
+            rows = offline.gram(self.engine, np.ascontiguousarray(S[:, new_idx]), tp.inner_product, S, dist=self.dist)
+            G[new_idx, :] = rows
+            G[:, new_idx] = rows.T
+            self.G = G
+        else:
+            self.G = offline.gram(self.engine, S, tp.inner_product, dist=self.dist)
         if N > 0:
             scale = list(range(Qa)) + [-1]
             src = [0] * Qa + [N]

@@ -37,3 +37,19 @@ def test_greedy_thermal_block_stress_variant(engine):
     run = ReducedBasisGreedy(engine, tp, train, Nmax=8, tol=1e-4).offline()
     ref = greedy_oracle.greedy_offline(tp, train, Nmax=8, tol=1e-4, vectorised=True)
     _compare(run, ref, 1e-5)
+
+
+def test_incremental_offline_updates_equal_full_recomputation(engine):
+    """reusing A^N[:N-1,:N-1] and the old Riesz Gram blocks gives the same reduced operators, the
+    same estimator operators and the same greedy sequence as recomputing everything (the reference's behaviour)."""
+    tp = ThermalBlock(n=14, nblocks=3, nloads=2)
+    train = tp.sample_training_set(200, seed=2)
+    inc = ReducedBasisGreedy(engine, tp, train, Nmax=6, tol=1e-6, incremental=True).offline()
+    full = ReducedBasisGreedy(engine, tp, train, Nmax=6, tol=1e-6, incremental=False).offline()
+    assert inc.greedy_selected_indices == full.greedy_selected_indices
+    assert inc.N == full.N and inc.N >= 4
+    assert np.max(np.abs(inc.operator_a - full.operator_a)) <= 1e-12 * np.max(np.abs(full.operator_a))
+    assert np.max(np.abs(inc.operator_f - full.operator_f)) <= 1e-12 * np.max(np.abs(full.operator_f))
+    assert np.max(np.abs(inc.G - full.G)) <= 1e-11 * np.max(np.abs(full.G))
+    e1, e2 = np.array(inc.greedy_error_estimators), np.array(full.greedy_error_estimators)
+    assert np.max(np.abs(e1 - e2) / e2) <= 1e-6
