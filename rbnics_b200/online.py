@@ -213,6 +213,78 @@ class AffineExpansionStorage:
             self._slices[ck] = out
         return self._slices[ck]
 
+    # -- on-disk format of the reference (rbnics/backends/online/basic/affine_expansion_storage.py:56-153,155-290;
+    #    rbnics/utils/io/text_io.py:11-44 -> repr()/eval() text files; numpy_io.py:12-40 -> numpy.save):
+    #    <directory>/<filename>/content_item_type.txt, content_item_shape.txt, content_item_<C-order index>.npy
+    #    (.txt for scalars), component_name_to_basis_component_{index,length}.txt
+    def save(self, directory, filename):
+        import os
+        full = os.path.join(str(directory), filename)
+        os.makedirs(full, exist_ok=True)
+        if self._content.size == 0:
+            return
+        first = self._content.flat[0]
+
+        def text(name, value):
+            with open(os.path.join(full, name + ".txt"), "w") as f:
+                f.write(repr(value))
+
+        if first is None:
+            text("content_item_type", "empty")
+            text("content_item_shape", None)
+        elif isinstance(first, float):
+            text("content_item_type", "scalar")
+            text("content_item_shape", None)
+            for k, idx in enumerate(np.ndindex(self._content.shape)):
+                text("content_item_" + str(k), self._content[idx])
+        else:
+            if first.ndim == 2:
+                text("content_item_type", "matrix")
+                text("content_item_shape", (int(first.shape[0]), int(first.shape[1])))
+            else:
+                text("content_item_type", "vector")
+                text("content_item_shape", int(first.shape[0]))
+            for k, idx in enumerate(np.ndindex(self._content.shape)):
+                np.save(os.path.join(full, "content_item_" + str(k) + ".npy"), np.asarray(self._content[idx]),
+                        allow_pickle=True)
+        text("component_name_to_basis_component_index", getattr(self, "_component_name_to_basis_component_index", None))
+        text("component_name_to_basis_component_length", getattr(self, "_component_name_to_basis_component_length", None))
+
+    def load(self, directory, filename, globals=None):
+        """Fill an (empty) storage of the right order/shape from the reference's directory layout.  Returns False if
+        the storage already holds content (the reference avoids loading twice), True otherwise."""
+        import os
+        if any(it is not None for it in self._content.flat):
+            return False
+        full = os.path.join(str(directory), filename)
+        if self._content.size == 0:
+            return True
+
+        def text(name):
+            env = dict(globals or {})
+            env.update({"__builtins__": None})
+            with open(os.path.join(full, name + ".txt")) as f:
+                return eval(f.read(), env, {})
+
+        kind = text("content_item_type")
+        assert kind in ("matrix", "vector", "function", "scalar", "empty"), kind
+        shape = text("content_item_shape")
+        for k, idx in enumerate(np.ndindex(self._content.shape)):
+            if kind == "scalar":
+                self._content[idx] = float(text("content_item_" + str(k)))
+            elif kind == "empty":
+                self._content[idx] = None
+            else:
+                arr = np.load(os.path.join(full, "content_item_" + str(k) + ".npy"), allow_pickle=True)
+                expect = tuple(shape) if kind == "matrix" else (shape,)
+                assert arr.shape == tuple(int(x) for x in expect), (arr.shape, expect)
+                self._content[idx] = np.ascontiguousarray(arr, dtype=np.float64)
+        self._component_name_to_basis_component_index = text("component_name_to_basis_component_index")
+        self._component_name_to_basis_component_length = text("component_name_to_basis_component_length")
+        self._slices = {}
+        self._stacked = None
+        return True
+
     def stacked(self):
         """Contiguous (Q, ...) / (Q1, Q2, ...) FP64 tensor of all items: what the C ABI takes."""
         if self._stacked is None:
