@@ -15,7 +15,7 @@ constexpr int EST_BN = 64;            // columns of G' per column tile
 constexpr int EST_WARPS = 8;          // 4 (m) x 2 (n), warp tile 32 x 32; no producer warp (last-arriving warp refills)
 constexpr int EST_THREADS = EST_WARPS * 32;
 constexpr int EST_KSTEP_DOUBLES = 4 * EST_BN;               // one k4-step of one column tile, fragment order (2 KB)
-constexpr int EST_NSTAGE = 3;                               // stages of `stage_ksteps` k-steps (16 -> 32 KB each)
+constexpr int EST_NSTAGE = 3;                               // maximum number of G' ring stages (barrier storage)
 constexpr int EST_MAX_BLOCKS = 1024;                        // z blocks whose tables are staged in shared memory
 
 constexpr int ASM_BM = 128;  // parameters per CTA of the assembly GEMM
@@ -43,7 +43,7 @@ struct rb_ctx {
 
   // estimator
   bool have_est = false;
-  int nblk = 0, Kz = 0, Kp = 0, KS = 0, n_ctile = 0, v_off = 0, v_len = 0, LV = 0, LVS = 0, stage_ksteps = 16;
+  int nblk = 0, Kz = 0, Kp = 0, KS = 0, n_ctile = 0, v_off = 0, v_len = 0, LV = 0, LVS = 0, stage_ksteps = 16, est_nstage = 3, est_align = 0;
   std::vector<int> h_blk_scale, h_blk_src, h_blk_len, h_blk_ks_begin, h_tile_ks0, h_tile_b0;
   std::vector<long long> h_tile_off;
   double* dGp = nullptr;            // packed lower-triangular G' in fragment order

@@ -140,12 +140,14 @@ struct EstArgs {
   double* partial;         // [nsplit][B]
   long long B;
   int nblk, KS, N, ldu, QT, v_off, v_len, LVS, nsplit, n_ctile, stage_ksteps;
+  int nstage;  // stages of the G' ring (2: stages end at z-block boundaries; 3: fixed-length stages)
+  int align;   // 1: a stage never crosses a z-block boundary (stage and block bookkeeping coincide)
 };
 
 // shared-memory footprint of rb_estimator_kernel (host + device agree through this one function)
-__host__ __device__ inline size_t est_smem_bytes(int stage_ksteps, int LVS, int nblk, int n_ctile) {
-  size_t b = (size_t)EST_NSTAGE * stage_ksteps * EST_KSTEP_DOUBLES * 8;  // G' stages
-  b += (size_t)EST_NSTAGE * 8;                                            // full barriers
+__host__ __device__ inline size_t est_smem_bytes(int nstage, int stage_ksteps, int LVS, int nblk, int n_ctile) {
+  size_t b = (size_t)nstage * stage_ksteps * EST_KSTEP_DOUBLES * 8;       // G' stages
+  b += (size_t)EST_NSTAGE * 8;                                            // full barriers (EST_NSTAGE = maximum)
   b += (size_t)3 * EST_BM * 8;                                            // cross-warp reduction
   b += (size_t)EST_BM * LVS * 8;                                          // V tile
   b += (size_t)n_ctile * 8;                                               // tile offsets
@@ -190,7 +192,8 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
   const int SK = a.stage_ksteps;
   const int STAGE_DOUBLES = SK * EST_KSTEP_DOUBLES;
   double* Gs = reinterpret_cast<double*>(est_smem_raw);                     // [NSTAGE][STAGE_DOUBLES]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(Gs + EST_NSTAGE * STAGE_DOUBLES);
+  const int NSTAGE = a.nstage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(Gs + NSTAGE * STAGE_DOUBLES);
   double* red = reinterpret_cast<double*>(full_bar + EST_NSTAGE);          // [3][EST_BM]
   double* Vs = red + 3 * EST_BM;                                            // [EST_BM][LVS]
   long long* s_tile_off = reinterpret_cast<long long*>(Vs + EST_BM * a.LVS);  // [n_ctile]
@@ -246,23 +249,29 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
 
   // ---- G' stream: 1-D bulk copies (TMA engine).  Cursor = next stage to issue; every warp advances it identically,
   // the warp that is LAST to release a stage slot issues the refill of that slot (no dedicated producer warp).
-  int pct = ct_begin, pk = 0;
+  int pct = ct_begin, pks = s_tile_ks0[min(ct_begin, a.n_ctile - 1)], pb = s_tile_b0[min(ct_begin, a.n_ctile - 1)];
+  auto stage_len = [&]() {  // k-steps of the stage at the cursor
+    const int lim = a.align ? s_ks_begin[pb + 1] : a.KS;
+    return min(SK, lim - pks);
+  };
   auto issue_stage = [&](int slot) {  // called by exactly one thread per stage
-    const int nks = a.KS - s_tile_ks0[pct];
-    const int n = min(SK, nks - pk);
-    const uint32_t bytes = (uint32_t)n * EST_KSTEP_DOUBLES * 8u;
+    const uint32_t bytes = (uint32_t)stage_len() * EST_KSTEP_DOUBLES * 8u;
     mbar_arrive_expect_tx(full_bar + slot, bytes);
-    bulk_g2s(Gs + slot * STAGE_DOUBLES, a.Gp + s_tile_off[pct] + (long long)pk * EST_KSTEP_DOUBLES, bytes,
-             full_bar + slot);
+    bulk_g2s(Gs + slot * STAGE_DOUBLES,
+             a.Gp + s_tile_off[pct] + (long long)(pks - s_tile_ks0[pct]) * EST_KSTEP_DOUBLES, bytes, full_bar + slot);
   };
   auto advance_cursor = [&]() {
-    pk += SK;
-    if (pk >= a.KS - s_tile_ks0[pct]) {
+    pks += stage_len();
+    while (pb + 1 < a.nblk && s_ks_begin[pb + 1] <= pks) ++pb;
+    if (pks >= a.KS) {
       ++pct;
-      pk = 0;
+      if (pct < ct_end) {
+        pks = s_tile_ks0[pct];
+        pb = s_tile_b0[pct];
+      }
     }
   };
-  for (int s = 0; s < EST_NSTAGE; ++s) {
+  for (int s = 0; s < NSTAGE; ++s) {
     if (pct < ct_end) {
       if (tid == 0) issue_stage(s);
       advance_cursor();
@@ -294,7 +303,7 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
     int kend = s_ks_begin[b + 1];
     const int src = s_src[b] + 4 * (ks - s_ks_begin[b]);
     int kin = 0;                   // k-step within the current stage
-    int nin = min(SK, a.KS - ks);  // k-steps held by the current stage
+    int nin = min(SK, (a.align ? kend : a.KS) - ks);  // k-steps held by the current stage
     double th[4], thn[4];
     {
       const int sc = s_scale[b];
@@ -338,6 +347,12 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
       gp += EST_KSTEP_DOUBLES;
       vp += 4;
       const bool tile_done = (ks == a.KS);
+      const bool blk_done = (ks == kend);
+      if (blk_done && !tile_done) {
+        ++b;
+        kend = s_ks_begin[b + 1];
+        vp = vrow + s_src[b];
+      }
       if (kin == nin) {  // stage consumed: release it; the last warp to do so refills the slot
         __syncwarp();
         if (lane == 0) {
@@ -348,20 +363,14 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
           }
         }
         if (pct < ct_end) advance_cursor();
-        if (++stage == EST_NSTAGE) {
+        if (++stage == NSTAGE) {
           stage = 0;
           phase ^= 1u;
         }
         kin = 0;
-        nin = min(SK, a.KS - ks);
+        nin = min(SK, (a.align ? kend : a.KS) - ks);
         gp = gsw + stage * STAGE_DOUBLES;
         if (!tile_done) mbar_wait(full_bar + stage, phase);
-      }
-      const bool blk_done = (ks == kend);
-      if (blk_done && !tile_done) {
-        ++b;
-        kend = s_ks_begin[b + 1];
-        vp = vrow + s_src[b];
       }
       if (!tile_done) est_load_frag(f0, gp, vp, LVS);
       if (blk_done) {  // fold the finished block: Y += theta_b * T
@@ -713,9 +722,16 @@ extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col,
     tile_b0[ct] = b0;
   }
   if (nblk > EST_MAX_BLOCKS) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_set_estimator: too many z blocks");
-  int stage_ksteps = 16;
-  while (stage_ksteps > 2 && est_smem_bytes(stage_ksteps, LVS, nblk, n_ctile) > 227 * 1024) stage_ksteps /= 2;
-  const size_t smem = est_smem_bytes(stage_ksteps, LVS, nblk, n_ctile);
+  // G' ring: by default 2 stages that end at z-block boundaries (stage = block for N <= 128: the stage hand-over and
+  // the block fold then happen at the same k-step); RB_EST_ALIGN=0 selects the older 3 fixed-length stages.
+  static const bool est_align = !(getenv("RB_EST_ALIGN") && atoi(getenv("RB_EST_ALIGN")) == 0);
+  int max_blk_ks = 1;
+  for (int b = 0; b < nblk; ++b) max_blk_ks = std::max(max_blk_ks, ks_begin[b + 1] - ks_begin[b]);
+  const int nstage = est_align ? 2 : 3;
+  int stage_ksteps = est_align ? std::min(32, max_blk_ks) : 16;
+  while (stage_ksteps > 2 && est_smem_bytes(nstage, stage_ksteps, LVS, nblk, n_ctile) > 227 * 1024)
+    stage_ksteps = est_align ? stage_ksteps - 1 : stage_ksteps / 2;
+  const size_t smem = est_smem_bytes(nstage, stage_ksteps, LVS, nblk, n_ctile);
   if (smem > 227 * 1024) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_set_estimator: N + v_theta_len too large for the estimator tile");
 
   ctx->nblk = nblk;
@@ -728,6 +744,8 @@ extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col,
   ctx->LV = LV;
   ctx->LVS = LVS;
   ctx->stage_ksteps = stage_ksteps;
+  ctx->est_nstage = nstage;
+  ctx->est_align = est_align ? 1 : 0;
   ctx->h_blk_ks_begin = ks_begin;
   ctx->h_tile_ks0 = tile_ks0;
   ctx->gp_doubles = off;
@@ -942,7 +960,9 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     ea.nsplit = nsplit;
     ea.n_ctile = ctx->n_ctile;
     ea.stage_ksteps = ctx->stage_ksteps;
-    const size_t smem = est_smem_bytes(ctx->stage_ksteps, ctx->LVS, ctx->nblk, ctx->n_ctile);
+    ea.nstage = ctx->est_nstage;
+    ea.align = ctx->est_align;
+    const size_t smem = est_smem_bytes(ctx->est_nstage, ctx->stage_ksteps, ctx->LVS, ctx->nblk, ctx->n_ctile);
     static const bool est16 = getenv("RB_EST_WARPS") && atoi(getenv("RB_EST_WARPS")) == 16;  // A/B switch (default 8)
     if (est16)
       rb_estimator_kernel<2><<<(unsigned)(nrb * nsplit), 512, smem, st>>>(ea);
