@@ -64,58 +64,78 @@ struct AsmArgs {
   int QT, Ql, QlP, EP;
 };
 
-__global__ void __launch_bounds__(256) rb_assemble_kernel(AsmArgs a) {
+__device__ __forceinline__ void asm_cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+// One CTA = one block of ASM_BM parameters x a strided set of 64-entry tiles: the theta tile is loaded once, the A_q
+// tiles stream through a 2-stage cp.async ring, so global-load latency is off the critical path and the kernel runs
+// at the rate of its 80 KB-per-parameter output.
+__global__ void __launch_bounds__(256, 2) rb_assemble_kernel(AsmArgs a) {
   extern __shared__ __align__(16) double asm_smem[];
   const int TS = a.QlP + ((a.QlP % 8 == 4) ? 0 : 4);  // theta tile pitch == 4 (mod 8): conflict-free A fragments
   constexpr int BS = ASM_BE + 4;                       // Aq tile pitch == 4 (mod 16): conflict-free B fragments
   double* ths = asm_smem;                              // [ASM_BM][TS]
-  double* bsm = asm_smem + ASM_BM * TS;                // [QlP][BS]
+  double* bsm0 = asm_smem + ASM_BM * TS;               // [2][QlP][BS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 3, wn = warp >> 2;
   const long long p0 = (long long)blockIdx.y * ASM_BM;
-  const int e0 = blockIdx.x * ASM_BE;
+  const int ntile = a.EP / ASM_BE;
 
-  for (int t = tid; t < ASM_BM * a.QlP; t += 256) {
-    const int r = t / a.QlP, q = t % a.QlP;
+  auto issue_tile = [&](int t, int slot) {
+    double* bsm = bsm0 + (size_t)slot * a.QlP * BS;
+    const double* src = a.Aq + (long long)t * ASM_BE;
+    for (int i = tid; i < a.QlP * (ASM_BE / 2); i += 256) {
+      const int q = i / (ASM_BE / 2), c2 = i % (ASM_BE / 2);
+      asm_cp_async16(bsm + q * BS + 2 * c2, src + (long long)q * a.EP + 2 * c2);
+    }
+  };
+  int t = blockIdx.x;
+  if (t < ntile) issue_tile(t, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < ASM_BM * a.QlP; i += 256) {
+    const int r = i / a.QlP, q = i % a.QlP;
     const long long p = p0 + r;
     ths[r * TS + q] = (p < a.count && q < a.Ql) ? __ldg(a.theta + p * a.QT + q) : 0.0;
   }
-  for (int t = tid; t < a.QlP * (ASM_BE / 2); t += 256) {
-    const int q = t / (ASM_BE / 2), c2 = t % (ASM_BE / 2);
-    const double2 v = *reinterpret_cast<const double2*>(a.Aq + (long long)q * a.EP + e0 + 2 * c2);
-    *reinterpret_cast<double2*>(bsm + q * BS + 2 * c2) = v;
-  }
-  __syncthreads();
-
-  double acc[4][4][2];
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-
   const int ar = wm * 32 + (lane >> 2), ak = lane & 3;
   const int bc = wn * 32 + (lane >> 2);
-  for (int ks = 0; ks < a.QlP / 4; ++ks) {
-    double af[4], bf[4];
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) af[mt] = ths[(ar + mt * 8) * TS + 4 * ks + ak];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) bf[nt] = bsm[(4 * ks + ak) * BS + bc + nt * 8];
+  int slot = 0;
+  for (; t < ntile; t += gridDim.x, slot ^= 1) {
+    if (t + (int)gridDim.x < ntile) issue_tile(t + gridDim.x, slot ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const double* bsm = bsm0 + (size_t)slot * a.QlP * BS;
+    double acc[4][4][2];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
-  }
+      for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    for (int ks = 0; ks < a.QlP / 4; ++ks) {
+      double af[4], bf[4];
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) {
-    const long long p = p0 + wm * 32 + mt * 8 + (lane >> 2);
-    if (p < a.count) {
+      for (int mt = 0; mt < 4; ++mt) af[mt] = ths[(ar + mt * 8) * TS + 4 * ks + ak];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int e = e0 + wn * 32 + nt * 8 + (lane & 3) * 2;
-        __stcs(reinterpret_cast<double2*>(a.Ab + p * a.EP + e), make_double2(acc[mt][nt][0], acc[mt][nt][1]));
+      for (int nt = 0; nt < 4; ++nt) bf[nt] = bsm[(4 * ks + ak) * BS + bc + nt * 8];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    }
+    const int e0 = t * ASM_BE;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const long long p = p0 + wm * 32 + mt * 8 + (lane >> 2);
+      if (p < a.count) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int e = e0 + wn * 32 + nt * 8 + (lane & 3) * 2;
+          __stcs(reinterpret_cast<double2*>(a.Ab + p * a.EP + e), make_double2(acc[mt][nt][0], acc[mt][nt][1]));
+        }
       }
     }
+    __syncthreads();  // every warp is done with this slot before it is refilled
   }
 }
 
@@ -908,7 +928,7 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
       ctx->ab_cap = chunk * ctx->EP;
     }
     const int TS = ctx->QlP + ((ctx->QlP % 8 == 4) ? 0 : 4);
-    const size_t asm_smem = ((size_t)ASM_BM * TS + (size_t)ctx->QlP * (ASM_BE + 4)) * sizeof(double);
+    const size_t asm_smem = ((size_t)ASM_BM * TS + 2 * (size_t)ctx->QlP * (ASM_BE + 4)) * sizeof(double);
     if (asm_smem > 227 * 1024) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_sweep: too many lhs terms for the assembly tile");
     RB_CUDA(cudaFuncSetAttribute(rb_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_smem));
     for (long long c0 = 0; c0 < B; c0 += chunk) {
@@ -922,7 +942,11 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
       aa.Ql = ctx->Ql;
       aa.QlP = ctx->QlP;
       aa.EP = ctx->EP;
-      dim3 grid(ctx->EP / ASM_BE, (unsigned)((n + ASM_BM - 1) / ASM_BM));
+      // row blocks x entry-tile splits: 2 resident CTAs per SM, ~2 waves
+      const unsigned nrb_asm = (unsigned)((n + ASM_BM - 1) / ASM_BM);
+      unsigned esplit = (unsigned)std::max<long long>(1, (4LL * ctx->sm_count + nrb_asm - 1) / nrb_asm);
+      esplit = std::min<unsigned>(esplit, (unsigned)(ctx->EP / ASM_BE));
+      dim3 grid(esplit, nrb_asm);
       rb_assemble_kernel<<<grid, 256, asm_smem, st>>>(aa);
       RB_CUDA(cudaGetLastError());
       ++launches;
