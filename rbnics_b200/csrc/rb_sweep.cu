@@ -26,29 +26,68 @@ __global__ void rb_pack_system_kernel(const double* __restrict__ A, double* __re
   }
 }
 
-// Dense G (Kz x Kz) -> G' = tril(G + G^T) with the diagonal counted once, in padded index space, cut into column
-// tiles of EST_BN and k4-steps, each k-step stored in DMMA B-fragment order:
-//   [wn (2)][pair (2)][lane (32)][e (2)]  <-  G'[k = 4*ks + lane%4][c = c0 + wn*32 + (2*pair+e)*8 + lane/4]
-__global__ void rb_pack_estimator_kernel(const double* __restrict__ G, double* __restrict__ Gp,
-                                         const long long* __restrict__ tile_off, const int* __restrict__ tile_ks0,
-                                         const int* __restrict__ pad2unpad, int Kz, int KS, int n_ctile) {
-  const int ct = blockIdx.y;
-  const int ks0 = tile_ks0[ct];
-  const long long n = (long long)(KS - ks0) * EST_KSTEP_DOUBLES;
-  double* dst = Gp + tile_off[ct];
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-    const int ks = ks0 + (int)(t / EST_KSTEP_DOUBLES);
+// Dense G (Kz x Kz) -> packed G'.  z^T G z only sees the symmetric part of G, and blocks of z that scale the SAME
+// slice of V (z_b = theta_b v, z_b' = theta_b' v: the Q_a blocks theta^a_q u of the elliptic estimator) make the
+// coefficient of G[(b,n),(b',m)] symmetric in (n, m) as well.  Both symmetries are folded into the lower triangles:
+//   b == b'              : n > m : G[k,c] + G[c,k]          n == m : G[k,c]
+//   b >  b', same slice  : n > m : S(n,m) + S(m,n)          n == m : S(n,n)      S(n,m) = G[(b,n),(b',m)] + G[(b',m),(b,n)]
+//   b >  b', other slice : G[k,c] + G[c,k]
+//   everything else 0.
+// A column tile (64 columns = two 32-column halves) takes the same 32-column range [32r, 32r+32) of TWO blocks of one
+// slice class, so every row block of that class contributes only its rows n >= 32r: the k range of the tile skips 8r
+// k-steps per block.  The stream of a tile is the concatenation of its k-step records; each record is stored in DMMA
+// B-fragment order  [wn (2)][pair (2)][lane (32)][e (2)]  <-  G'[row 4*ks + lane%4][column wn*32 + (2*pair+e)*8 + lane/4].
+struct PackArgs {
+  const double* G;
+  double* Gp;
+  long long total_rec;
+  const int* rec_tile;    // [total_rec] column tile of the record
+  const int* rec_ks;      // [total_rec] k-step (padded row / 4) of the record
+  const int* row_unpad;   // [Kp] padded row -> dense index or -1
+  const int* row_blk;     // [Kp]
+  const int* row_idx;     // [Kp] index within the block
+  const int* col_unpad;   // [n_ctile * 64]
+  const int* col_blk;
+  const int* col_idx;
+  const int* blk_cls;     // [nblk] slice class
+  const int* blk_ubegin;  // [nblk] dense index of the block's first entry
+  int Kz;
+};
+
+__global__ void rb_pack_estimator_kernel(PackArgs a) {
+  const long long total = a.total_rec * EST_KSTEP_DOUBLES;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long rec = t / EST_KSTEP_DOUBLES;
     const int r = (int)(t % EST_KSTEP_DOUBLES);
+    const int ct = a.rec_tile[rec], ks = a.rec_ks[rec];
     const int wn = r >> 7, pair = (r >> 6) & 1, lane = (r >> 1) & 31, e = r & 1;
     const int kp = 4 * ks + (lane & 3);
-    const int cp = ct * EST_BN + wn * 32 + (2 * pair + e) * 8 + (lane >> 2);
-    const int k = pad2unpad[kp];
-    const int c = pad2unpad[cp];
+    const int cpos = ct * EST_BN + wn * 32 + (2 * pair + e) * 8 + (lane >> 2);
+    const long long k = a.row_unpad[kp], c = a.col_unpad[cpos];
     double v = 0.0;
-    if (k >= 0 && c >= 0 && kp >= cp) {
-      v = (kp == cp) ? G[(long long)k * Kz + c] : (G[(long long)k * Kz + c] + G[(long long)c * Kz + k]);
+    if (k >= 0 && c >= 0) {
+      const int b = a.row_blk[kp], n = a.row_idx[kp], bp = a.col_blk[cpos], m = a.col_idx[cpos];
+      const long long Kz = a.Kz;
+      if (b == bp) {
+        if (n > m)
+          v = a.G[k * Kz + c] + a.G[c * Kz + k];
+        else if (n == m)
+          v = a.G[k * Kz + c];
+      } else if (b > bp) {
+        if (a.blk_cls[b] == a.blk_cls[bp]) {
+          if (n >= m) {
+            v = a.G[k * Kz + c] + a.G[c * Kz + k];
+            if (n > m) {
+              const long long k2 = a.blk_ubegin[b] + m, c2 = a.blk_ubegin[bp] + n;
+              v += a.G[k2 * Kz + c2] + a.G[c2 * Kz + k2];
+            }
+          }
+        } else {
+          v = a.G[k * Kz + c] + a.G[c * Kz + k];
+        }
+      }
     }
-    dst[t] = v;
+    a.Gp[t] = v;
   }
 }
 
@@ -147,11 +186,13 @@ __global__ void __launch_bounds__(256, 2) rb_assemble_kernel(AsmArgs a) {
 struct EstArgs {
   const double* Gp;
   const long long* tile_off;
-  const int* tile_ks0;
-  const int* tile_b0;
+  const int* tile_skip;    // k-steps skipped at the start of every row block of the tile's slice class
+  const int* tile_cls;
+  const int* tile_b0;      // first row block of the tile
   const int* blk_ks_begin;
   const int* blk_scale;
   const int* blk_src;
+  const int* blk_cls;
   const int* col_scale;
   const int* col_src;
   const int* split_begin;  // [nsplit+1] column-tile boundaries
@@ -160,8 +201,7 @@ struct EstArgs {
   double* partial;         // [nsplit][B]
   long long B;
   int nblk, KS, N, ldu, QT, v_off, v_len, LVS, nsplit, n_ctile, stage_ksteps;
-  int nstage;  // stages of the G' ring (2: stages end at z-block boundaries; 3: fixed-length stages)
-  int align;   // 1: a stage never crosses a z-block boundary (stage and block bookkeeping coincide)
+  int nstage;  // stages of the G' ring; a stage never crosses a z-block boundary
 };
 
 // shared-memory footprint of rb_estimator_kernel (host + device agree through this one function)
@@ -171,7 +211,7 @@ __host__ __device__ inline size_t est_smem_bytes(int nstage, int stage_ksteps, i
   b += (size_t)3 * EST_BM * 8;                                            // cross-warp reduction
   b += (size_t)EST_BM * LVS * 8;                                          // V tile
   b += (size_t)n_ctile * 8;                                               // tile offsets
-  b += (size_t)(2 * n_ctile + 3 * nblk + 1 + EST_NSTAGE) * 4;             // int tables + release counters
+  b += (size_t)(3 * n_ctile + 4 * nblk + 1 + EST_NSTAGE) * 4;             // int tables + release counters
   return b + 16;
 }
 
@@ -217,12 +257,14 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
   double* red = reinterpret_cast<double*>(full_bar + EST_NSTAGE);          // [3][EST_BM]
   double* Vs = red + 3 * EST_BM;                                            // [EST_BM][LVS]
   long long* s_tile_off = reinterpret_cast<long long*>(Vs + EST_BM * a.LVS);  // [n_ctile]
-  int* s_tile_ks0 = reinterpret_cast<int*>(s_tile_off + a.n_ctile);         // [n_ctile]
-  int* s_tile_b0 = s_tile_ks0 + a.n_ctile;                                  // [n_ctile]
+  int* s_tile_skip = reinterpret_cast<int*>(s_tile_off + a.n_ctile);        // [n_ctile]
+  int* s_tile_cls = s_tile_skip + a.n_ctile;                                // [n_ctile]
+  int* s_tile_b0 = s_tile_cls + a.n_ctile;                                  // [n_ctile]
   int* s_ks_begin = s_tile_b0 + a.n_ctile;                                  // [nblk+1]
   int* s_scale = s_ks_begin + (a.nblk + 1);                                 // [nblk]
   int* s_src = s_scale + a.nblk;                                            // [nblk]
-  int* s_cnt = s_src + a.nblk;                                              // [NSTAGE] release counters
+  int* s_cls = s_src + a.nblk;                                              // [nblk]
+  int* s_cnt = s_cls + a.nblk;                                              // [NSTAGE] release counters
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int split = blockIdx.x % a.nsplit;
@@ -248,7 +290,8 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
   }
   for (int t = tid; t < a.n_ctile; t += NTHREADS) {
     s_tile_off[t] = a.tile_off[t];
-    s_tile_ks0[t] = a.tile_ks0[t];
+    s_tile_skip[t] = a.tile_skip[t];
+    s_tile_cls[t] = a.tile_cls[t];
     s_tile_b0[t] = a.tile_b0[t];
   }
   for (int t = tid; t <= a.nblk; t += NTHREADS) {
@@ -256,6 +299,7 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
     if (t < a.nblk) {
       s_scale[t] = a.blk_scale[t];
       s_src[t] = a.blk_src[t];
+      s_cls[t] = a.blk_cls[t];
     }
   }
   if (tid == 0) {
@@ -269,26 +313,32 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
 
   // ---- G' stream: 1-D bulk copies (TMA engine).  Cursor = next stage to issue; every warp advances it identically,
   // the warp that is LAST to release a stage slot issues the refill of that slot (no dedicated producer warp).
-  int pct = ct_begin, pks = s_tile_ks0[min(ct_begin, a.n_ctile - 1)], pb = s_tile_b0[min(ct_begin, a.n_ctile - 1)];
-  auto stage_len = [&]() {  // k-steps of the stage at the cursor
-    const int lim = a.align ? s_ks_begin[pb + 1] : a.KS;
-    return min(SK, lim - pks);
-  };
+  // cursor: tile pct, row block pb, k-step pks (absolute), element offset poff inside the tile's stream
+  auto blk_first_ks = [&](int ct, int b) { return s_ks_begin[b] + ((s_cls[b] == s_tile_cls[ct]) ? s_tile_skip[ct] : 0); };
+  int pct = ct_begin, pb = 0, pks = 0;
+  long long poff = 0;
+  if (pct < ct_end) {
+    pb = s_tile_b0[pct];
+    pks = blk_first_ks(pct, pb);
+  }
+  auto stage_len = [&]() { return min(SK, s_ks_begin[pb + 1] - pks); };  // k-steps of the stage at the cursor
   auto issue_stage = [&](int slot) {  // called by exactly one thread per stage
     const uint32_t bytes = (uint32_t)stage_len() * EST_KSTEP_DOUBLES * 8u;
     mbar_arrive_expect_tx(full_bar + slot, bytes);
-    bulk_g2s(Gs + slot * STAGE_DOUBLES,
-             a.Gp + s_tile_off[pct] + (long long)(pks - s_tile_ks0[pct]) * EST_KSTEP_DOUBLES, bytes, full_bar + slot);
+    bulk_g2s(Gs + slot * STAGE_DOUBLES, a.Gp + s_tile_off[pct] + poff, bytes, full_bar + slot);
   };
   auto advance_cursor = [&]() {
-    pks += stage_len();
-    while (pb + 1 < a.nblk && s_ks_begin[pb + 1] <= pks) ++pb;
-    if (pks >= a.KS) {
-      ++pct;
-      if (pct < ct_end) {
-        pks = s_tile_ks0[pct];
-        pb = s_tile_b0[pct];
+    const int n = stage_len();
+    pks += n;
+    poff += (long long)n * EST_KSTEP_DOUBLES;
+    if (pks == s_ks_begin[pb + 1]) {
+      ++pb;
+      if (pb == a.nblk) {
+        ++pct;
+        poff = 0;
+        if (pct < ct_end) pb = s_tile_b0[pct];
       }
+      if (pct < ct_end) pks = blk_first_ks(pct, pb);
     }
   };
   for (int s = 0; s < NSTAGE; ++s) {
@@ -318,12 +368,12 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
 #pragma unroll
       for (int nt = 0; nt < NTN; ++nt) Y[mt][nt][0] = Y[mt][nt][1] = T[mt][nt][0] = T[mt][nt][1] = 0.0;
 
-    int ks = s_tile_ks0[ct];
     int b = s_tile_b0[ct];
+    int ks = blk_first_ks(ct, b);
     int kend = s_ks_begin[b + 1];
     const int src = s_src[b] + 4 * (ks - s_ks_begin[b]);
     int kin = 0;                   // k-step within the current stage
-    int nin = min(SK, (a.align ? kend : a.KS) - ks);  // k-steps held by the current stage
+    int nin = min(SK, kend - ks);  // k-steps held by the current stage (a stage never crosses a block boundary)
     double th[4], thn[4];
     {
       const int sc = s_scale[b];
@@ -366,12 +416,13 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
       kin += nseg;
       gp += EST_KSTEP_DOUBLES;
       vp += 4;
-      const bool tile_done = (ks == a.KS);
       const bool blk_done = (ks == kend);
+      const bool tile_done = blk_done && (b + 1 == a.nblk);
       if (blk_done && !tile_done) {
         ++b;
+        ks = blk_first_ks(ct, b);
         kend = s_ks_begin[b + 1];
-        vp = vrow + s_src[b];
+        vp = vrow + s_src[b] + 4 * (ks - s_ks_begin[b]);
       }
       if (kin == nin) {  // stage consumed: release it; the last warp to do so refills the slot
         __syncwarp();
@@ -388,7 +439,7 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
           phase ^= 1u;
         }
         kin = 0;
-        nin = min(SK, (a.align ? kend : a.KS) - ks);
+        nin = min(SK, kend - ks);
         gp = gsw + stage * STAGE_DOUBLES;
         if (!tile_done) mbar_wait(full_bar + stage, phase);
       }
@@ -606,6 +657,7 @@ extern "C" void rb_ctx_destroy(rb_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dAq,       ctx->dF,       ctx->dBcRows,  ctx->dGp,      ctx->dTileOff, ctx->dTileKs0,
                   ctx->dTileB0,   ctx->dBlkKsBegin, ctx->dBlkScale, ctx->dBlkSrc, ctx->dColScale, ctx->dColSrc,
+                  ctx->dTileCls,  ctx->dBlkCls,
                   ctx->dTheta,    ctx->dThetaBC, ctx->dBeta,    ctx->dAb,      ctx->dU,       ctx->dPart,
                   ctx->dDelta,    ctx->dEps2,    ctx->dBlkVal,  ctx->dBlkIdx,  ctx->dResult,  ctx->dSplitBegin,
                   ctx->dLuScratch};
@@ -703,54 +755,112 @@ extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col,
     ks_begin[b + 1] = Kp / 4;
   }
   const int KS = Kp / 4;
-  const int n_ctile = (Kp + EST_BN - 1) / EST_BN;
-  const int Cp = n_ctile * EST_BN;
-  // padded index -> unpadded index (or -1), per-column scale / source tables
-  std::vector<int> pad2unpad(std::max(Cp, Kp), -1), col_scale(Cp, -1), col_src(Cp, 0);
-  int zero_src = LV;  // V[LV...] is zero filled
-  {
-    int kp = 0, kz = 0;
-    for (int b = 0; b < nblk; ++b) {
-      const int lp = roundup(blk_len[b], 4);
-      for (int t = 0; t < lp; ++t) {
-        if (t < blk_len[b]) {
-          pad2unpad[kp + t] = kz + t;
-          col_scale[kp + t] = blk_scale_col[b] < 0 ? -1 : blk_scale_col[b];
-          col_src[kp + t] = blk_src_off[b] + t;
-        } else {
-          col_src[kp + t] = zero_src;
-        }
+  if (nblk > EST_MAX_BLOCKS) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_set_estimator: too many z blocks");
+  // ---- slice classes: blocks that scale the same slice of V are foldable against each other (see the pack kernel)
+  std::vector<int> cls(nblk), ubegin(nblk), scale_norm(nblk);
+  for (int b = 0, u = 0; b < nblk; ++b) {
+    cls[b] = b;
+    for (int b2 = 0; b2 < b; ++b2)
+      if (blk_src_off[b2] == blk_src_off[b] && blk_len[b2] == blk_len[b]) {
+        cls[b] = cls[b2];
+        break;
       }
-      kp += lp;
-      kz += blk_len[b];
-    }
-    for (int c = kp; c < Cp; ++c) col_src[c] = zero_src;
+    ubegin[b] = u;
+    u += blk_len[b];
+    scale_norm[b] = blk_scale_col[b] < 0 ? -1 : blk_scale_col[b];
   }
+  // ---- padded rows
+  std::vector<int> row_unpad(Kp, -1), row_blk(Kp, 0), row_idx(Kp, 0);
+  for (int b = 0; b < nblk; ++b)
+    for (int t = 0; t < roundup(blk_len[b], 4); ++t) {
+      const int kp = 4 * ks_begin[b] + t;
+      row_blk[kp] = b;
+      row_idx[kp] = t;
+      if (t < blk_len[b]) row_unpad[kp] = ubegin[b] + t;
+    }
+  // ---- column tiles: 64 columns = two 32-column halves, each the range [32 r, 32 r + 32) of one block; both blocks
+  // of a tile belong to one class, so the tile's k range skips 8 r k-steps in every row block of that class.  A last
+  // range of <= 8 columns is packed 8 blocks to a tile instead.
+  struct Tile {
+    int b0, skip, cls;
+  };
+  constexpr int RW = 32;
+  const int zero_src = LV;  // V[LV...] is zero filled
+  std::vector<Tile> tiles;
+  std::vector<int> col_unpad, col_blk, col_idx, col_scale, col_src;
+  auto new_tile = [&](int b0, int skip, int c) {
+    tiles.push_back({b0, skip, c});
+    col_unpad.resize(tiles.size() * EST_BN, -1);
+    col_blk.resize(tiles.size() * EST_BN, 0);
+    col_idx.resize(tiles.size() * EST_BN, 0);
+    col_scale.resize(tiles.size() * EST_BN, -1);
+    col_src.resize(tiles.size() * EST_BN, zero_src);
+    return (int)(tiles.size() - 1) * EST_BN;
+  };
+  auto put_cols = [&](int base, int pos, int b, int m0, int w) {
+    for (int j = 0; j < w; ++j) {
+      col_unpad[base + pos + j] = ubegin[b] + m0 + j;
+      col_blk[base + pos + j] = b;
+      col_idx[base + pos + j] = m0 + j;
+      col_scale[base + pos + j] = scale_norm[b];
+      col_src[base + pos + j] = blk_src_off[b] + m0 + j;
+    }
+  };
+  for (int c = 0; c < nblk; ++c) {
+    if (cls[c] != c) continue;
+    std::vector<int> members;
+    for (int b = c; b < nblk; ++b)
+      if (cls[b] == c) members.push_back(b);
+    const int L = blk_len[c];
+    const int nr = (L + RW - 1) / RW;
+    const int last_w = L - RW * (nr - 1);
+    const bool leftover = (nr > 1 && last_w <= 8);
+    const int nfull = leftover ? nr - 1 : nr;
+    for (size_t i = 0; i < members.size(); i += 2) {
+      const int m0 = members[i], m1 = (i + 1 < members.size()) ? members[i + 1] : -1;
+      for (int r = 0; r < nfull; ++r) {
+        const int w = std::min(RW, L - RW * r);
+        const int base = new_tile(m0, (RW * r) / 4, c);
+        put_cols(base, 0, m0, RW * r, w);
+        if (m1 >= 0) put_cols(base, 32, m1, RW * r, w);
+      }
+    }
+    if (leftover)
+      for (size_t i = 0; i < members.size(); i += 8) {
+        const int base = new_tile(members[i], (RW * (nr - 1)) / 4, c);
+        for (size_t j = i; j < std::min(members.size(), i + 8); ++j)
+          put_cols(base, 8 * (int)(j - i), members[j], RW * (nr - 1), last_w);
+      }
+  }
+  const int n_ctile = (int)tiles.size();
+  const int Cp = n_ctile * EST_BN;
+  // ---- records (k-steps) of every tile, in stream order
+  std::vector<long long> tile_off(n_ctile);
+  std::vector<int> tile_b0(n_ctile), tile_skip(n_ctile), tile_cls(n_ctile), tile_cost(n_ctile), rec_tile, rec_ks;
+  for (int ct = 0; ct < n_ctile; ++ct) {
+    tile_off[ct] = (long long)rec_tile.size() * EST_KSTEP_DOUBLES;
+    tile_b0[ct] = tiles[ct].b0;
+    tile_skip[ct] = tiles[ct].skip;
+    tile_cls[ct] = tiles[ct].cls;
+    for (int b = tiles[ct].b0; b < nblk; ++b)
+      for (int ks = ks_begin[b] + (cls[b] == tiles[ct].cls ? tiles[ct].skip : 0); ks < ks_begin[b + 1]; ++ks) {
+        rec_tile.push_back(ct);
+        rec_ks.push_back(ks);
+      }
+    tile_cost[ct] = (int)(rec_tile.size() - tile_off[ct] / EST_KSTEP_DOUBLES);
+  }
+  const long long total_rec = (long long)rec_tile.size();
+  const long long off = total_rec * EST_KSTEP_DOUBLES;
   // V tile pitch: >= LV + 4 (A fragments of a padded block may read 3 entries past it; one zero slot) and == 4 mod 8
   int LVS = LV + 4;
   while (LVS % 8 != 4) ++LVS;
-  std::vector<long long> tile_off(n_ctile);
-  std::vector<int> tile_ks0(n_ctile), tile_b0(n_ctile);
-  long long off = 0;
-  for (int ct = 0; ct < n_ctile; ++ct) {
-    const int ks0 = std::min(ct * EST_BN / 4, KS);
-    tile_ks0[ct] = ks0;
-    tile_off[ct] = off;
-    off += (long long)(KS - ks0) * EST_KSTEP_DOUBLES;
-    int b0 = 0;
-    while (b0 + 1 < nblk && ks_begin[b0 + 1] <= ks0) ++b0;
-    tile_b0[ct] = b0;
-  }
-  if (nblk > EST_MAX_BLOCKS) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_set_estimator: too many z blocks");
-  // G' ring: by default 2 stages that end at z-block boundaries (stage = block for N <= 128: the stage hand-over and
-  // the block fold then happen at the same k-step); RB_EST_ALIGN=0 selects the older 3 fixed-length stages.
-  static const bool est_align = !(getenv("RB_EST_ALIGN") && atoi(getenv("RB_EST_ALIGN")) == 0);
+  // G' ring: 2 stages that end at z-block boundaries (stage = block for N <= 128: the stage hand-over and the block
+  // fold then happen at the same k-step)
   int max_blk_ks = 1;
   for (int b = 0; b < nblk; ++b) max_blk_ks = std::max(max_blk_ks, ks_begin[b + 1] - ks_begin[b]);
-  const int nstage = est_align ? 2 : 3;
-  int stage_ksteps = est_align ? std::min(32, max_blk_ks) : 16;
-  while (stage_ksteps > 2 && est_smem_bytes(nstage, stage_ksteps, LVS, nblk, n_ctile) > 227 * 1024)
-    stage_ksteps = est_align ? stage_ksteps - 1 : stage_ksteps / 2;
+  const int nstage = 2;
+  int stage_ksteps = std::min(32, max_blk_ks);
+  while (stage_ksteps > 2 && est_smem_bytes(nstage, stage_ksteps, LVS, nblk, n_ctile) > 227 * 1024) --stage_ksteps;
   const size_t smem = est_smem_bytes(nstage, stage_ksteps, LVS, nblk, n_ctile);
   if (smem > 227 * 1024) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_set_estimator: N + v_theta_len too large for the estimator tile");
 
@@ -765,49 +875,71 @@ extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col,
   ctx->LVS = LVS;
   ctx->stage_ksteps = stage_ksteps;
   ctx->est_nstage = nstage;
-  ctx->est_align = est_align ? 1 : 0;
   ctx->h_blk_ks_begin = ks_begin;
-  ctx->h_tile_ks0 = tile_ks0;
+  ctx->h_tile_cost = tile_cost;
   ctx->gp_doubles = off;
   ctx->have_est = false;
 
   if (int rc = dev_realloc(ctx, &ctx->dGp, (size_t)std::max<long long>(off, 1))) return rc;
   if (int rc = dev_realloc(ctx, &ctx->dTileOff, (size_t)n_ctile)) return rc;
-  if (int rc = dev_realloc(ctx, &ctx->dTileKs0, (size_t)n_ctile)) return rc;
+  if (int rc = dev_realloc(ctx, &ctx->dTileKs0, (size_t)n_ctile)) return rc;   // tile_skip
+  if (int rc = dev_realloc(ctx, &ctx->dTileCls, (size_t)n_ctile)) return rc;
   if (int rc = dev_realloc(ctx, &ctx->dTileB0, (size_t)n_ctile)) return rc;
   if (int rc = dev_realloc(ctx, &ctx->dBlkKsBegin, (size_t)nblk + 1)) return rc;
   if (int rc = dev_realloc(ctx, &ctx->dBlkScale, (size_t)nblk)) return rc;
   if (int rc = dev_realloc(ctx, &ctx->dBlkSrc, (size_t)nblk)) return rc;
+  if (int rc = dev_realloc(ctx, &ctx->dBlkCls, (size_t)nblk)) return rc;
   if (int rc = dev_realloc(ctx, &ctx->dColScale, (size_t)Cp)) return rc;
   if (int rc = dev_realloc(ctx, &ctx->dColSrc, (size_t)Cp)) return rc;
-  std::vector<int> scale_norm(nblk);
-  for (int b = 0; b < nblk; ++b) scale_norm[b] = blk_scale_col[b] < 0 ? -1 : blk_scale_col[b];
   RB_CUDA(cudaMemcpy(ctx->dTileOff, tile_off.data(), n_ctile * sizeof(long long), cudaMemcpyHostToDevice));
-  RB_CUDA(cudaMemcpy(ctx->dTileKs0, tile_ks0.data(), n_ctile * sizeof(int), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(ctx->dTileKs0, tile_skip.data(), n_ctile * sizeof(int), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(ctx->dTileCls, tile_cls.data(), n_ctile * sizeof(int), cudaMemcpyHostToDevice));
   RB_CUDA(cudaMemcpy(ctx->dTileB0, tile_b0.data(), n_ctile * sizeof(int), cudaMemcpyHostToDevice));
   RB_CUDA(cudaMemcpy(ctx->dBlkKsBegin, ks_begin.data(), (nblk + 1) * sizeof(int), cudaMemcpyHostToDevice));
   RB_CUDA(cudaMemcpy(ctx->dBlkScale, scale_norm.data(), nblk * sizeof(int), cudaMemcpyHostToDevice));
   RB_CUDA(cudaMemcpy(ctx->dBlkSrc, blk_src_off, nblk * sizeof(int), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(ctx->dBlkCls, cls.data(), nblk * sizeof(int), cudaMemcpyHostToDevice));
   RB_CUDA(cudaMemcpy(ctx->dColScale, col_scale.data(), Cp * sizeof(int), cudaMemcpyHostToDevice));
   RB_CUDA(cudaMemcpy(ctx->dColSrc, col_src.data(), Cp * sizeof(int), cudaMemcpyHostToDevice));
 
-  // dense G -> device -> packed G'
+  // dense G + packing tables -> device -> packed G'
   double* dG = nullptr;
-  int* dP2U = nullptr;
+  int* dTab = nullptr;
+  std::vector<int> tab;   // rec_tile | rec_ks | row_unpad | row_blk | row_idx | col_unpad | col_blk | col_idx | ubegin
+  const size_t o_rec_tile = 0, o_rec_ks = o_rec_tile + rec_tile.size(), o_row_unpad = o_rec_ks + rec_ks.size(),
+               o_row_blk = o_row_unpad + Kp, o_row_idx = o_row_blk + Kp, o_col_unpad = o_row_idx + Kp,
+               o_col_blk = o_col_unpad + Cp, o_col_idx = o_col_blk + Cp, o_ubegin = o_col_idx + Cp;
+  tab.reserve(o_ubegin + nblk);
+  for (const std::vector<int>* v : {&rec_tile, &rec_ks, &row_unpad, &row_blk, &row_idx, &col_unpad, &col_blk, &col_idx, &ubegin})
+    tab.insert(tab.end(), v->begin(), v->end());
   RB_CUDA(cudaMalloc(&dG, (size_t)Kz * Kz * sizeof(double)));
-  cudaError_t e = cudaMalloc(&dP2U, pad2unpad.size() * sizeof(int));
+  cudaError_t e = cudaMalloc(&dTab, tab.size() * sizeof(int));
   if (e == cudaSuccess) e = cudaMemcpyAsync(dG, G, (size_t)Kz * Kz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(dP2U, pad2unpad.data(), pad2unpad.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) {
-    dim3 grid(std::max(1, std::min(64, (KS * EST_KSTEP_DOUBLES + 255) / 256)), n_ctile);
-    rb_pack_estimator_kernel<<<grid, 256, 0, ctx->stream>>>(dG, ctx->dGp, ctx->dTileOff, ctx->dTileKs0, dP2U, Kz, KS,
-                                                           n_ctile);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dTab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && total_rec > 0) {
+    PackArgs pa;
+    pa.G = dG;
+    pa.Gp = ctx->dGp;
+    pa.total_rec = total_rec;
+    pa.rec_tile = dTab + o_rec_tile;
+    pa.rec_ks = dTab + o_rec_ks;
+    pa.row_unpad = dTab + o_row_unpad;
+    pa.row_blk = dTab + o_row_blk;
+    pa.row_idx = dTab + o_row_idx;
+    pa.col_unpad = dTab + o_col_unpad;
+    pa.col_blk = dTab + o_col_blk;
+    pa.col_idx = dTab + o_col_idx;
+    pa.blk_cls = ctx->dBlkCls;
+    pa.blk_ubegin = dTab + o_ubegin;
+    pa.Kz = Kz;
+    const long long nthr = total_rec * EST_KSTEP_DOUBLES;
+    const int blocks = (int)std::min<long long>((nthr + 255) / 256, (long long)ctx->sm_count * 16);
+    rb_pack_estimator_kernel<<<blocks, 256, 0, ctx->stream>>>(pa);
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // tab is a local vector
   cudaFree(dG);
-  if (dP2U) cudaFree(dP2U);
+  if (dTab) cudaFree(dTab);
   if (e != cudaSuccess) RB_FAIL(RB_ERR_CUDA, std::string("rb_set_estimator: ") + cudaGetErrorString(e));
   RB_CUDA(cudaFuncSetAttribute(rb_estimator_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RB_CUDA(cudaFuncSetAttribute(rb_estimator_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -900,15 +1032,15 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     ctx->split_cap = nsplit + 1;
   }
   {
-    // balance the splits by triangular area: tile ct costs (KS - ks0[ct]) k-steps
+    // balance the splits by the number of k-step records of their tiles
     std::vector<int> sb(nsplit + 1, ctx->n_ctile);
     long long total = 0;
-    for (int ct = 0; ct < ctx->n_ctile; ++ct) total += ctx->KS - ctx->h_tile_ks0[ct];
+    for (int ct = 0; ct < ctx->n_ctile; ++ct) total += ctx->h_tile_cost[ct];
     long long accum = 0;
     int s = 0;
     sb[0] = 0;
     for (int ct = 0; ct < ctx->n_ctile && s + 1 < nsplit; ++ct) {
-      accum += ctx->KS - ctx->h_tile_ks0[ct];
+      accum += ctx->h_tile_cost[ct];
       if (accum * nsplit >= total * (s + 1)) sb[++s] = ct + 1;
     }
     for (int t = s + 1; t <= nsplit; ++t) sb[t] = ctx->n_ctile;
@@ -961,11 +1093,13 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     EstArgs ea;
     ea.Gp = ctx->dGp;
     ea.tile_off = ctx->dTileOff;
-    ea.tile_ks0 = ctx->dTileKs0;
+    ea.tile_skip = ctx->dTileKs0;
+    ea.tile_cls = ctx->dTileCls;
     ea.tile_b0 = ctx->dTileB0;
     ea.blk_ks_begin = ctx->dBlkKsBegin;
     ea.blk_scale = ctx->dBlkScale;
     ea.blk_src = ctx->dBlkSrc;
+    ea.blk_cls = ctx->dBlkCls;
     ea.col_scale = ctx->dColScale;
     ea.col_src = ctx->dColSrc;
     ea.split_begin = ctx->dSplitBegin;
@@ -985,7 +1119,6 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     ea.n_ctile = ctx->n_ctile;
     ea.stage_ksteps = ctx->stage_ksteps;
     ea.nstage = ctx->est_nstage;
-    ea.align = ctx->est_align;
     const size_t smem = est_smem_bytes(ctx->est_nstage, ctx->stage_ksteps, ctx->LVS, ctx->nblk, ctx->n_ctile);
     static const bool est16 = getenv("RB_EST_WARPS") && atoi(getenv("RB_EST_WARPS")) == 16;  // A/B switch (default 8)
     if (est16)
