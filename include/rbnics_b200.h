@@ -88,6 +88,9 @@ int rb_sweep(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta, int n_bc,
 /* Device pointer to the 16-byte {double max_val; int64 max_idx} result of the last sweep (for a NCCL all-gather
  * issued by the host layer without a host round trip), and to the per-parameter estimators. */
 int rb_result_device_ptrs(rb_ctx* ctx, void** maxloc16, double** delta);
+/* Work of the estimator kernel per parameter as packed by rb_set_estimator: multiply-adds issued on the tensor pipe
+ * (k-step records x 256, zero padding of the triangular tiles included) and number of 64-column tiles. */
+int rb_estimator_work(rb_ctx* ctx, int64_t* issued_macs_per_param, int* n_column_tiles);
 /* Kernel-only timings (ms, CUDA events on the handle's stream) of the last sweep:
  * [0]=assembly GEMM, [1]=LU solve, [2]=estimator GEMM, [3]=finalize+argmax, [4]=total; launches counted. */
 int rb_last_timings(rb_ctx* ctx, float* ms5, int* n_launches);

@@ -40,6 +40,7 @@ SIGNATURES = {
                            C.c_int64, C.c_int, c_double_p, c_int64_p, c_double_p, c_double_p, c_double_p]),
     "rb_result_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(c_double_p)]),
     "rb_last_timings": (C.c_int, [C.c_void_p, c_float_p, c_int_p]),
+    "rb_estimator_work": (C.c_int, [C.c_void_p, c_int64_p, c_int_p]),
     "rb_affine_combine": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_double_p, c_double_p, c_double_p]),
     "rb_affine_combine2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, c_double_p, c_double_p, c_double_p,
                                      c_double_p]),

@@ -784,7 +784,11 @@ extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col,
   struct Tile {
     int b0, skip, cls;
   };
-  constexpr int RW = 32;
+  static const int RW = [] {  // column-range width: 16 by default (4 blocks per tile); 8 / 32 for A/B measurements
+    const int v = getenv("RB_EST_RW") ? atoi(getenv("RB_EST_RW")) : 16;
+    return (v == 8 || v == 32) ? v : 16;
+  }();
+  const size_t GRP = EST_BN / RW;  // blocks per tile
   const int zero_src = LV;  // V[LV...] is zero filled
   std::vector<Tile> tiles;
   std::vector<int> col_unpad, col_blk, col_idx, col_scale, col_src;
@@ -816,13 +820,11 @@ extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col,
     const int last_w = L - RW * (nr - 1);
     const bool leftover = (nr > 1 && last_w <= 8);
     const int nfull = leftover ? nr - 1 : nr;
-    for (size_t i = 0; i < members.size(); i += 2) {
-      const int m0 = members[i], m1 = (i + 1 < members.size()) ? members[i + 1] : -1;
+    for (size_t i = 0; i < members.size(); i += GRP) {
       for (int r = 0; r < nfull; ++r) {
         const int w = std::min(RW, L - RW * r);
-        const int base = new_tile(m0, (RW * r) / 4, c);
-        put_cols(base, 0, m0, RW * r, w);
-        if (m1 >= 0) put_cols(base, 32, m1, RW * r, w);
+        const int base = new_tile(members[i], (RW * r) / 4, c);
+        for (size_t j = i; j < std::min(members.size(), i + GRP); ++j) put_cols(base, RW * (int)(j - i), members[j], RW * r, w);
       }
     }
     if (leftover)
@@ -1181,6 +1183,14 @@ extern "C" int rb_result_device_ptrs(rb_ctx* ctx, void** maxloc16, double** delt
   if (!ctx) return RB_ERR_ARG;
   if (maxloc16) *maxloc16 = ctx->dResult;
   if (delta) *delta = ctx->dDelta;
+  return RB_OK;
+}
+
+extern "C" int rb_estimator_work(rb_ctx* ctx, int64_t* issued_macs_per_param, int* n_column_tiles) {
+  if (!ctx) return RB_ERR_ARG;
+  if (!ctx->have_est) RB_FAIL(RB_ERR_STATE, "rb_estimator_work: no estimator set");
+  if (issued_macs_per_param) *issued_macs_per_param = ctx->gp_doubles;  // one packed double = one multiply-add per row
+  if (n_column_tiles) *n_column_tiles = ctx->n_ctile;
   return RB_OK;
 }
 

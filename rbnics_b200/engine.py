@@ -155,6 +155,12 @@ class SweepEngine:
         return {"assemble_lu_ms": ms[0], "estimator_ms": ms[2], "finalize_ms": ms[3], "total_ms": ms[4],
                 "launches": n.value}
 
+    def estimator_work(self):
+        """Multiply-adds per parameter issued by the estimator kernel (padding included) and its tile count."""
+        m, n = C.c_int64(), C.c_int()
+        self._check(self._lib.rb_estimator_work(self._h, C.byref(m), C.byref(n)))
+        return {"issued_macs_per_param": m.value, "column_tiles": n.value}
+
     def result_device_ptrs(self):
         p = C.c_void_p()
         d = L.c_double_p()
