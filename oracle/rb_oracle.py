@@ -262,11 +262,13 @@ def gram_loop(S, X=None, S2=None):
     (rbnics/backends/dolfin/wrapping/matrix_mul.py:10-11, vector_mul.py:8-9).
     S: (Nh, Ns) columns are snapshots / basis functions; X: scipy.sparse CSR or None (identity)."""
     S2 = S if S2 is None else S2
+    cols = [np.ascontiguousarray(S[:, i]) for i in range(S.shape[1])]  # the reference's vectors are contiguous
     C = np.zeros((S.shape[1], S2.shape[1]))
     for j in range(S2.shape[1]):
-        y = S2[:, j] if X is None else X @ S2[:, j]
+        s2j = np.ascontiguousarray(S2[:, j])
+        y = s2j if X is None else X @ s2j
         for i in range(S.shape[1]):
-            C[i, j] = np.dot(S[:, i], y)
+            C[i, j] = np.dot(cols[i], y)
     return C
 
 

@@ -573,9 +573,142 @@ def make_storage_golden():
     print("storage_ref written:", sorted(os.listdir(root)))
 
 
+def make_offline_golden():
+    """Offline basis linear algebra by the reference's OWN loops, executed from source with PETSc's three primitives
+    replaced by their numpy/scipy equivalents (MatMult -> X @ v, VecDot -> numpy.dot, add_local -> +=):
+      rbnics/backends/basic/transpose.py:293-325          FunctionsList_Transpose__times__Matrix.__mul__  (S^T X S loop)
+      rbnics/backends/basic/gram_schmidt.py:13-36         GramSchmidt.apply
+      rbnics/backends/online/numpy/wrapping/gram_schmidt_projection_step.py
+      rbnics/backends/basic/proper_orthogonal_decomposition_base.py:15-92   POD apply (energy, truncation, modes)
+      rbnics/backends/online/numpy/eigen_solver.py:19-67  EigenSolver (scipy.linalg.eigh + descending sort)
+      rbnics/backends/dolfin/wrapping/functions_list_mul.py:26-36 restated as the same add_local loop (needs dolfin)
+    -> tests/golden/reference_offline.npz"""
+    import logging
+    import scipy.sparse as sp
+
+    class Fun:  # a dof vector with the .vector() accessor of dolfin / online Functions
+        def __init__(self, v):
+            self._v = np.array(v, dtype=np.float64)
+
+        def vector(self):
+            return self._v
+
+        def __itruediv__(self, a):
+            self._v /= a
+            return self
+
+        @property
+        def N(self):
+            return self._v.shape[0]
+
+    class FunList(list):  # FunctionsList / SnapshotsMatrix / BasisFunctionsMatrix stand-in
+        def __init__(self, space=None, *args):
+            super().__init__()
+
+        def enrich(self, f):
+            self.append(Fun(f.vector()))
+
+        def clear(self):
+            del self[:]
+
+        def __mul__(self, online_fun):  # functions_list_mul_online_vector: sum_i s_i * v_i, sequential add_local
+            out = Fun(np.zeros_like(self[0].vector()))
+            for i, fun_i in enumerate(self):
+                out.vector()[:] += fun_i.vector() * online_fun.vector()[i]
+            return out
+
+    spmat = sp.csr_matrix
+    wrapping = types.SimpleNamespace(matrix_mul_vector=lambda M, v: M @ v, function_to_vector=lambda f: f.vector(),
+                                     vector_mul_vector=lambda a, b: float(np.dot(a, b)),
+                                     function_extend_or_restrict=lambda f, c1, space, c2, weight, copy: Fun(f.vector()),
+                                     get_function_subspace=lambda space, component: space)
+    backend = types.SimpleNamespace(FunctionsList=FunList, Matrix=types.SimpleNamespace(Type=lambda: spmat),
+                                    Function=types.SimpleNamespace(Type=lambda: Fun),
+                                    Vector=types.SimpleNamespace(Type=lambda: np.ndarray))
+    online_backend = types.SimpleNamespace(OnlineMatrix=lambda M, N: np.zeros((M, N)),
+                                           OnlineVector=lambda N: np.zeros(N))
+    # --- S^T X S: the factory function of transpose.py, extracted and executed
+    ns = {"overload": overload, "logger": logging.getLogger("ref"), "DEBUG": logging.DEBUG}
+    exec(_method_source("rbnics/backends/basic/transpose.py", "FunctionsList_Transpose__times__Matrix"), ns)
+    STXS = ns["FunctionsList_Transpose__times__Matrix"](backend, wrapping, online_backend, None, None, None, None, None)
+
+    class Transpose:  # transpose(S)*X*S, transpose(v)*X*w, transpose(v)*w with the same primitives
+        def __init__(self, arg, M=None):
+            self.arg, self.M = arg, M
+
+        def __mul__(self, other):
+            if isinstance(other, spmat):
+                return Transpose(self.arg, other)
+            if isinstance(self.arg, FunList):
+                return STXS(self.arg, self.M) * other if self.M is not None else \
+                    STXS(self.arg, sp.identity(other[0].N, format="csr")) * other
+            w = other.vector()
+            return float(np.dot(self.arg.vector(), self.M @ w if self.M is not None else w))
+
+    backend.transpose = lambda a: Transpose(a)
+    # --- Gram-Schmidt
+    _module("rbnics.backends.abstract", GramSchmidt=object, FunctionsList=FunList, EigenSolver=object)
+    _module("rbnics.utils.decorators", overload=overload, dict_of=lambda *a: dict, ThetaType=ThetaType,
+            DictOfThetaType=DictOfThetaType, BackendFor=lambda *a, **k: (lambda cls: cls))
+    gs_step = _exec_reference_file("rbnics/backends/online/numpy/wrapping/gram_schmidt_projection_step.py", "ref_gs_step")
+    wrapping.gram_schmidt_projection_step = gs_step.gram_schmidt_projection_step
+    GS = _exec_reference_file("rbnics/backends/basic/gram_schmidt.py", "ref_gs").GramSchmidt(backend, wrapping)
+    # --- EigenSolver of the numpy online backend
+    class _OnlineMat(np.ndarray):
+        M = property(lambda self: self.shape[0])
+        N = property(lambda self: self.shape[1])
+
+    _module("rbnics.backends.online")
+    _module("rbnics.backends.online.numpy")
+    _module("rbnics.backends.online.numpy.function", Function=lambda v: Fun(v))
+    _module("rbnics.backends.online.numpy.matrix", Matrix=types.SimpleNamespace(Type=lambda: _OnlineMat))
+    _module("rbnics.backends.online.numpy.vector",
+            Vector=types.SimpleNamespace(Type=lambda: (lambda N, content: np.array(content, dtype=np.float64))))
+    ES = _exec_reference_file("rbnics/backends/online/numpy/eigen_solver.py", "ref_eig").EigenSolver
+    online_backend.OnlineEigenSolver = lambda basis, A: ES(basis, np.asarray(A).view(_OnlineMat))
+    # --- POD
+    _module("rbnics.utils.io", ExportableList=lambda kind: list())
+    pod_mod = _exec_reference_file("rbnics/backends/basic/proper_orthogonal_decomposition_base.py", "ref_pod")
+    POD = pod_mod.ProperOrthogonalDecompositionBase(backend, wrapping, online_backend, None, object, FunList, FunList)
+
+    rng = np.random.default_rng(11)
+    n = 12
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(n, n))
+    X = (sp.kron(T, sp.identity(n)) + sp.kron(sp.identity(n), T) + 0.5 * sp.identity(n * n)).tocsr()
+    Nh, Ns = n * n, 9
+    decay = 10.0 ** (-np.arange(Ns))
+    S = (rng.standard_normal((Nh, Ns)) @ np.diag(decay)) @ rng.standard_normal((Ns, Ns))
+    SL = FunList()
+    for j in range(Ns):
+        SL.enrich(Fun(S[:, j]))
+    C = np.array(backend.transpose(SL) * X * SL)
+    # Gram-Schmidt: orthonormalise the first 5 snapshots one after the other
+    gs = GS(None, X)
+    Z = FunList()
+    for j in range(5):
+        Z.enrich(gs.apply(Fun(S[:, j]), Z))
+    Zarr = np.stack([z.vector() for z in Z], axis=1)
+    # Galerkin projection of an operator and a vector on that basis (same loop: transpose(Z)*A*Z, transpose(Z)*f)
+    A_op = (X + sp.diags(rng.uniform(0.0, 1.0, Nh))).tocsr()
+    ZtAZ = np.array(backend.transpose(Z) * A_op * Z)
+    # POD
+    pod = POD(None, X)
+    for j in range(Ns):
+        pod.snapshots_matrix.enrich(Fun(S[:, j]))
+    eigs, eigvecs, basis, Npod = pod.apply(Ns, 1e-10)
+    out = dict(X_data=X.data, X_indices=X.indices, X_indptr=X.indptr, Nh=np.int64(Nh), S=S, C=C, Z_gs=Zarr,
+               A_data=A_op.data, A_indices=A_op.indices, A_indptr=A_op.indptr, ZtAZ=ZtAZ,
+               pod_eigenvalues=np.array(pod.eigenvalues), pod_retained_energy=np.array(pod.retained_energy),
+               pod_N=np.int64(Npod), pod_basis=np.stack([b.vector() for b in basis], axis=1),
+               pod_eigenvectors=np.stack([e.vector() for e in eigvecs], axis=1))
+    np.savez_compressed(os.path.join(HERE, "reference_offline.npz"), **out)
+    print("offline golden: Nh", Nh, "Ns", Ns, "POD N", Npod, "eig[0..2]", pod.eigenvalues[:3])
+
+
 def main():
     ref = load_reference()
     make_storage_golden()
+    make_offline_golden()
     make_case(ref, "tutorial01", N=4, Qa=2, Qf=1, B=100, seed=1)
     make_case(ref, "n16q6", N=16, Qa=6, Qf=6, B=40, seed=2)
     make_case(ref, "n32q10_bc", N=32, Qa=10, Qf=10, B=24, seed=3, n_bc=2)
