@@ -157,7 +157,7 @@ def run_reference_arm(args):
         "gflops_fp64_F_alg": fl["F_alg"] * value * 1e-9,
         "wall_s": wall,
     }
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -371,12 +371,34 @@ def run_b200_arm(args):
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
             line["cpu_vectorized"] = cpu_vec
-        print(json.dumps(line), flush=True)
+        emit_json_line(line)
     pinned_free(hT)
     pinned_free(hB)
     eng.close()
     if dist is not None:
         dist.close()
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner) must not add lines to stdout: route fd 1 to stderr and keep the
+    real stdout for the single JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
@@ -390,6 +412,7 @@ def main():
                     help="sample size per host core of the CPU reference loop (~34 ms per parameter)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -202,6 +202,7 @@ struct EstArgs {
   long long B;
   int nblk, KS, N, ldu, QT, v_off, v_len, LVS, nsplit, n_ctile, stage_ksteps;
   int nstage;  // stages of the G' ring; a stage never crosses a z-block boundary
+  int tri16;   // 1: tiles are made of 16-column ranges (enables the half-width head of folded blocks)
 };
 
 // shared-memory footprint of rb_estimator_kernel (host + device agree through this one function)
@@ -230,14 +231,16 @@ __device__ __forceinline__ void est_load_frag(EstFrag<NTN>& f, const double* gs,
   for (int mt = 0; mt < 4; ++mt) f.a[mt] = vp[mt * 8 * LVS];
 }
 
-template <int NTN>
+// HEAD: only the first 8-column tile of every 16-column range (the second one is structurally zero in the first two
+// k-steps of a folded block: columns m >= 16r+8 against rows n < 16r+8).
+template <int NTN, bool HEAD = false>
 __device__ __forceinline__ void est_mma(double (&T)[4][NTN][2], const EstFrag<NTN>& f) {
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
 #pragma unroll
     for (int h = 0; h < NTN / 2; ++h) {
       dmma884(T[mt][2 * h][0], T[mt][2 * h][1], f.a[mt], f.b[h].x);
-      dmma884(T[mt][2 * h + 1][0], T[mt][2 * h + 1][1], f.a[mt], f.b[h].y);
+      if (!HEAD) dmma884(T[mt][2 * h + 1][0], T[mt][2 * h + 1][1], f.a[mt], f.b[h].y);
     }
   }
 }
@@ -373,6 +376,7 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
     int kend = s_ks_begin[b + 1];
     const int src = s_src[b] + 4 * (ks - s_ks_begin[b]);
     int kin = 0;                   // k-step within the current stage
+    bool tri_head = a.tri16 && (s_cls[b] == s_tile_cls[ct]);  // the next segment starts a folded block
     int nin = min(SK, kend - ks);  // k-steps held by the current stage (a stage never crosses a block boundary)
     double th[4], thn[4];
     {
@@ -396,6 +400,17 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
     while (true) {
       const int nseg = min(kend - ks, nin - kin);
       int i = nseg;
+      if (tri_head && i > 2) {  // first two k-steps of a folded block: half of the column tiles are zero
+        est_mma<NTN, true>(T, f0);
+        gp += EST_KSTEP_DOUBLES;
+        vp += 4;
+        est_load_frag(f0, gp, vp, LVS);
+        est_mma<NTN, true>(T, f0);
+        gp += EST_KSTEP_DOUBLES;
+        vp += 4;
+        est_load_frag(f0, gp, vp, LVS);
+        i -= 2;
+      }
       while (i > 2) {  // steady state, two k-steps per trip (ping-pong fragment buffers)
         est_mma(T, f0);
         est_load_frag(f1, gp + EST_KSTEP_DOUBLES, vp + 4, LVS);
@@ -418,8 +433,10 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
       vp += 4;
       const bool blk_done = (ks == kend);
       const bool tile_done = blk_done && (b + 1 == a.nblk);
+      tri_head = false;
       if (blk_done && !tile_done) {
         ++b;
+        tri_head = a.tri16 && (s_cls[b] == s_tile_cls[ct]);
         ks = blk_first_ks(ct, b);
         kend = s_ks_begin[b + 1];
         vp = vrow + s_src[b] + 4 * (ks - s_ks_begin[b]);
@@ -851,6 +868,14 @@ extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col,
       }
     tile_cost[ct] = (int)(rec_tile.size() - tile_off[ct] / EST_KSTEP_DOUBLES);
   }
+  // multiply-adds per parameter issued on the tensor pipe: every record is 4 rows x 64 columns, minus the half-width
+  // heads (first two k-steps of every folded block visit longer than two k-steps, see est_mma<HEAD>)
+  const bool tri16 = (RW == 16 && !(getenv("RB_EST_TRI") && atoi(getenv("RB_EST_TRI")) == 0));
+  long long issued_macs = (long long)rec_tile.size() * EST_KSTEP_DOUBLES;
+  if (tri16)
+    for (int ct = 0; ct < n_ctile; ++ct)
+      for (int b = tiles[ct].b0; b < nblk; ++b)
+        if (cls[b] == tiles[ct].cls && ks_begin[b + 1] - ks_begin[b] - tiles[ct].skip > 2) issued_macs -= EST_KSTEP_DOUBLES;
   const long long total_rec = (long long)rec_tile.size();
   const long long off = total_rec * EST_KSTEP_DOUBLES;
   // V tile pitch: >= LV + 4 (A fragments of a padded block may read 3 entries past it; one zero slot) and == 4 mod 8
@@ -877,6 +902,8 @@ extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col,
   ctx->LVS = LVS;
   ctx->stage_ksteps = stage_ksteps;
   ctx->est_nstage = nstage;
+  ctx->est_tri16 = tri16 ? 1 : 0;
+  ctx->est_issued_macs = issued_macs;
   ctx->h_blk_ks_begin = ks_begin;
   ctx->h_tile_cost = tile_cost;
   ctx->gp_doubles = off;
@@ -1121,6 +1148,7 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     ea.n_ctile = ctx->n_ctile;
     ea.stage_ksteps = ctx->stage_ksteps;
     ea.nstage = ctx->est_nstage;
+    ea.tri16 = ctx->est_tri16;
     const size_t smem = est_smem_bytes(ctx->est_nstage, ctx->stage_ksteps, ctx->LVS, ctx->nblk, ctx->n_ctile);
     static const bool est16 = getenv("RB_EST_WARPS") && atoi(getenv("RB_EST_WARPS")) == 16;  // A/B switch (default 8)
     if (est16)
@@ -1189,7 +1217,7 @@ extern "C" int rb_result_device_ptrs(rb_ctx* ctx, void** maxloc16, double** delt
 extern "C" int rb_estimator_work(rb_ctx* ctx, int64_t* issued_macs_per_param, int* n_column_tiles) {
   if (!ctx) return RB_ERR_ARG;
   if (!ctx->have_est) RB_FAIL(RB_ERR_STATE, "rb_estimator_work: no estimator set");
-  if (issued_macs_per_param) *issued_macs_per_param = ctx->gp_doubles;  // one packed double = one multiply-add per row
+  if (issued_macs_per_param) *issued_macs_per_param = ctx->est_issued_macs;
   if (n_column_tiles) *n_column_tiles = ctx->n_ctile;
   return RB_OK;
 }
