@@ -410,3 +410,75 @@ def residual_norm_squared_stokes(u, theta, E, N):
         + 2.0 * np.dot(u, o2("a", "bt", mat) @ u)
         + np.dot(u, o2("bt", "bt", mat) @ u)
         + np.dot(u, o2("b", "b", mat) @ u))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Parabolic problems: POD-Greedy sweep
+# ----------------------------------------------------------------------------------------------------------------------
+
+def parabolic_solve(theta_m, theta_a, theta_f, M_q, A_q, f_q, N, dt, K):
+    """Linear implicit Euler from a zero initial condition, K steps.
+
+    rbnics/problems/parabolic/abstract_parabolic_reduced_problem.py:17-36 (residual = M udot + A u - f,
+    jacobian = M * coef + A) driven by rbnics/backends/online/numpy/time_stepping.py:104-112 (lhs = jacobian(1/dt),
+    rhs = -residual(0, -u_prev/dt)) and :226-238 (udot = (u - u_prev)/dt).  The reference refactorises every step.
+    Returns (solution_over_time[K+1][N], solution_dot_over_time[K+1][N])."""
+    M = np.array(product_order1(theta_m, [m[:N, :N] for m in M_q]))
+    A = np.array(product_order1(theta_a, [a[:N, :N] for a in A_q]))
+    f = np.array(product_order1(theta_f, [v[:N] for v in f_q]))
+    zero = np.zeros(N)
+    u_prev = np.zeros(N)
+    sols, dots = [u_prev.copy()], [np.zeros(N)]
+    for _ in range(K):
+        minus_prev_over_dt = u_prev.copy()
+        minus_prev_over_dt /= -dt
+        lhs = M * (1.0 / dt) + A
+        rhs = -(M @ minus_prev_over_dt + A @ zero - f)
+        u = np.linalg.solve(lhs, rhs)
+        sols.append(u)
+        dots.append((u - u_prev) / dt)
+        u_prev = u.copy()
+    return np.array(sols), np.array(dots)
+
+
+def parabolic_residual_norm_squared(u, udot, theta_m, theta_a, theta_f, G_ff, G_af, G_aa, G_mf, G_ma, G_mm, N):
+    """Elliptic residual + the three time-derivative term pairs (m,f), (m,a), (m,m).
+
+    rbnics/problems/parabolic/abstract_parabolic_rb_reduced_problem.py:62-92."""
+    elliptic = residual_norm_squared(u, theta_a, theta_f, G_ff, G_af, G_aa, N)
+    mf = product_order2(theta_m, [[g[:N] for g in row] for row in G_mf], theta_f)
+    ma = product_order2(theta_m, [[g[:N, :N] for g in row] for row in G_ma], theta_a)
+    mm = product_order2(theta_m, [[g[:N, :N] for g in row] for row in G_mm], theta_m)
+    return float(elliptic + 2.0 * np.dot(udot, mf) + 2.0 * np.dot(udot, ma @ u) + np.dot(udot, mm @ udot))
+
+
+def parabolic_estimate_error(eps2_over_time, beta, dt):
+    """Error bound over time (0 at t0 for a homogeneous initial condition, sqrt(|eps2|/beta) afterwards) and its time
+    quadrature sqrt(simpson(bound^2, dx=dt)).
+
+    rbnics/problems/parabolic/abstract_parabolic_rb_reduced_problem.py:29-46,
+    rbnics/reduction_methods/base/time_dependent_rb_reduction.py:280-288,
+    rbnics/backends/common/time_quadrature.py:22-29 (scipy.integrate.simpson)."""
+    from scipy.integrate import simpson
+    bound = [0.0] + [sqrt(abs(e) / beta) for e in eps2_over_time[1:]]
+    return sqrt(simpson([v ** 2 for v in bound], dx=dt)), bound
+
+
+def parabolic_sweep_loop(Theta_m, Theta_a, Theta_f, beta, M_q, A_q, f_q, G, N, dt, K):
+    """The reference's POD-Greedy closure over a training set (serial).  G = dict of the six Gram storages
+    ("ff", "af", "aa", "mf", "ma", "mm").  Returns (delta[B], argmax, eps2[B][K+1], U[B][K+1][N])."""
+    B = Theta_a.shape[0]
+    deltas = np.zeros(B)
+    eps2_all = np.zeros((B, K + 1))
+    U_all = np.zeros((B, K + 1, N))
+    for p in range(B):
+        tm = tuple(float(x) for x in Theta_m[p])
+        ta = tuple(float(x) for x in Theta_a[p])
+        tf = tuple(float(x) for x in Theta_f[p])
+        sols, dots = parabolic_solve(tm, ta, tf, M_q, A_q, f_q, N, dt, K)
+        for k in range(1, K + 1):
+            eps2_all[p, k] = parabolic_residual_norm_squared(sols[k], dots[k], tm, ta, tf, G["ff"], G["af"], G["aa"],
+                                                             G["mf"], G["ma"], G["mm"], N)
+        deltas[p], _ = parabolic_estimate_error(eps2_all[p], float(beta[p]), dt)
+        U_all[p] = sols
+    return deltas, argmax_first(deltas), eps2_all, U_all

@@ -705,10 +705,147 @@ def make_offline_golden():
     print("offline golden: Nh", Nh, "Ns", Ns, "POD N", Npod, "eig[0..2]", pod.eigenvalues[:3])
 
 
+def make_parabolic_golden(ref):
+    """POD-Greedy sweep of a parabolic reduced problem by the reference's own source:
+      rbnics/problems/parabolic/abstract_parabolic_reduced_problem.py   residual_eval / jacobian_eval
+      rbnics/problems/parabolic/abstract_parabolic_rb_reduced_problem.py   get_residual_norm_squared / estimate_error
+      rbnics/backends/common/time_series.py, time_quadrature.py         TimeSeries, TimeQuadrature_Numbers.integrate
+    driven by the linear implicit-Euler loop of rbnics/backends/online/numpy/time_stepping.py:104-112,226-238 (restated
+    here line by line: the class itself is tied to the backend's Function type) and the closure of
+    time_dependent_rb_reduction.py:280-288.  -> tests/golden/reference_parabolic.npz"""
+    _module("rbnics.backends.abstract", TimeSeries=object, TimeQuadrature=object, ParametrizedTensorFactory=type("PTF", (), {}))
+    _module("rbnics.utils.decorators", overload=overload, ThetaType=ThetaType, DictOfThetaType=DictOfThetaType,
+            BackendFor=lambda *a, **k: (lambda cls: cls), backend_for=lambda *a, **k: (lambda f: f),
+            tuple_of=lambda *a: tuple, list_of=lambda *a: list)
+    TimeSeries = _exec_reference_file("rbnics/backends/common/time_series.py", "ref_time_series").TimeSeries
+    _module("rbnics.backends.common")
+    _module("rbnics.backends.common.time_series", TimeSeries=TimeSeries)
+    tq = _exec_reference_file("rbnics/backends/common/time_quadrature.py", "ref_time_quadrature")
+    class Mat(np.ndarray):  # online Matrix: `*` with a vector is the matrix-vector product (online/numpy/matrix.py:31-41)
+        def __mul__(self, other):
+            if isinstance(other, np.ndarray) and other.ndim == 1:
+                return np.asarray(self) @ np.asarray(other)
+            return np.ndarray.__mul__(self, other)
+
+    def ref_sum(product_output):
+        out = ref.sum(product_output)
+        return out.view(Mat) if isinstance(out, np.ndarray) and out.ndim == 2 else out
+
+    ns = {"product": ref.product, "sum": ref_sum, "transpose": transpose, "sqrt": sqrt, "isclose": np.isclose,
+          "abs": abs, "TimeSeries": TimeSeries, "assign": lambda dst, src: dst.__setitem__(slice(None), src)}
+
+    class EllipticBase:  # AbstractParabolicRBReducedProblem_Base.get_residual_norm_squared == the elliptic one
+        get_residual_norm_squared = staticmethod(ref.get_residual_norm_squared)
+
+    ns["AbstractParabolicRBReducedProblem_Base"] = EllipticBase
+    exec(_method_source("rbnics/problems/parabolic/abstract_parabolic_rb_reduced_problem.py", "get_residual_norm_squared"), ns)
+    exec(_method_source("rbnics/problems/parabolic/abstract_parabolic_rb_reduced_problem.py", "estimate_error"), ns)
+    exec(_method_source("rbnics/problems/parabolic/abstract_parabolic_reduced_problem.py", "residual_eval"), ns)
+    exec(_method_source("rbnics/problems/parabolic/abstract_parabolic_reduced_problem.py", "jacobian_eval"), ns)
+
+    rng = np.random.default_rng(21)
+    N, Qm, Qa, Qf, B, K, dt = 12, 2, 3, 2, 20, 10, 0.05
+    spd = lambda: (lambda Bq: Bq @ Bq.T / N + np.eye(N))(rng.standard_normal((N, N)))  # noqa: E731
+    Mq = np.stack([spd() for _ in range(Qm)])
+    Aq = np.stack([spd() for _ in range(Qa)])
+    Fq = rng.standard_normal((Qf, N))
+    Kz = Qa * N + Qm * N + Qf
+    R = rng.standard_normal((Kz + 9, Kz))
+    Gm = R.T @ R / R.shape[0]
+    off = {"a": 0, "m": Qa * N, "f": Qa * N + Qm * N}
+    Q = {"a": Qa, "m": Qm, "f": Qf}
+
+    def block(t1, t2):
+        o1, o2 = t1 != "f", t2 != "f"
+        n1, n2 = Q[t1] * (N if o1 else 1), Q[t2] * (N if o2 else 1)
+        M = Gm[off[t1]:off[t1] + n1, off[t2]:off[t2] + n2]
+        if o1 and o2:
+            return M.reshape(Q[t1], N, Q[t2], N).transpose(0, 2, 1, 3).copy()
+        if o1:
+            return M.reshape(Q[t1], N, Q[t2]).transpose(0, 2, 1).copy()
+        return M.copy()
+
+    E = {k: block(*k) for k in [("f", "f"), ("a", "f"), ("a", "a"), ("m", "f"), ("m", "a"), ("m", "m")]}
+    Theta_m = rng.uniform(0.5, 2.0, (B, Qm))
+    Theta_a = rng.uniform(0.1, 10.0, (B, Qa))
+    Theta_f = rng.uniform(-1.0, 1.0, (B, Qf))
+    beta = Theta_a.min(axis=1)
+
+    class Prob:
+        def __init__(self):
+            self.operator = {"m": Storage([Mq[q] for q in range(Qm)]), "a": Storage([Aq[q] for q in range(Qa)]),
+                             "f": Storage([Fq[q] for q in range(Qf)])}
+            self.error_estimation_operator = {}
+            for (t1, t2), blk in E.items():
+                content = ([[float(blk[i, j]) for j in range(blk.shape[1])] for i in range(blk.shape[0])]
+                           if blk.ndim == 2 else [[blk[i, j] for j in range(blk.shape[1])] for i in range(blk.shape[0])])
+                self.error_estimation_operator[t1, t2] = Storage(content)
+            self.N, self.problem, self.truth_problem = N, self, self
+            self.t0, self.dt, self.T = 0.0, dt, K * dt
+
+        def compute_theta(self, term):
+            return self._th[term]
+
+        def get_stability_factor_lower_bound(self):
+            return self._beta
+
+        def set_time(self, t):
+            self.t = t
+
+        def get_initial_error_estimate_squared(self):
+            return 0.0  # homogeneous initial condition (time_dependent_rb_reduced_problem.py:127-160)
+
+        def get_residual_norm_squared(self):
+            return ns["get_residual_norm_squared"](self)
+
+    prob = Prob()
+    U = np.zeros((B, K + 1, N))
+    eps2 = np.zeros((B, K + 1))
+    bound = np.zeros((B, K + 1))
+    delta = np.zeros(B)
+    for p in range(B):
+        prob._th = {"m": tuple(float(x) for x in Theta_m[p]), "a": tuple(float(x) for x in Theta_a[p]),
+                    "f": tuple(float(x) for x in Theta_f[p])}
+        prob._beta = float(beta[p])
+        # _ScipyImplicitEuler, linear problem (time_stepping.py:104-112, 226-238)
+        solution = np.zeros(N).view(Solution)
+        solution_previous = np.zeros(N)
+        zero = np.zeros(N)
+        sol_t, dot_t = TimeSeries((0.0, K * dt), dt), TimeSeries((0.0, K * dt), dt)
+        sol_t.append(solution.copy().view(Solution))
+        dot_t.append(np.zeros(N).view(Solution))
+        for t in sol_t.expected_times()[1:]:
+            minus_prev_over_dt = solution_previous.copy()
+            minus_prev_over_dt /= -dt
+            lhs = np.array(ns["jacobian_eval"](prob, t, zero, zero, 1.0 / dt))
+            rhs = -np.array(ns["residual_eval"](prob, t, zero, minus_prev_over_dt))
+            solution = np.linalg.solve(lhs, rhs)
+            solution_dot = (solution - solution_previous) / dt
+            sol_t.append(solution.copy().view(Solution))
+            dot_t.append(solution_dot.copy().view(Solution))
+            solution_previous = solution.copy()
+        prob._solution_over_time, prob._solution_dot_over_time = sol_t, dot_t
+        prob._solution = np.zeros(N).view(Solution)
+        prob._solution_dot = np.zeros(N).view(Solution)
+        e_t = ns["get_residual_norm_squared"](prob)
+        b_t = ns["estimate_error"](prob)
+        squared = [v ** 2 for v in b_t]
+        delta[p] = sqrt(tq.TimeQuadrature_Numbers((0.0, K * dt), squared).integrate())
+        U[p] = np.array([np.asarray(s) for s in sol_t])
+        eps2[p] = np.array(list(e_t))
+        bound[p] = np.array(list(b_t))
+    out = dict(M=Mq, A=Aq, F=Fq, Theta_m=Theta_m, Theta_a=Theta_a, Theta_f=Theta_f, beta=beta, dt=np.float64(dt),
+               K=np.int64(K), U=U, eps2=eps2, bound=bound, delta=delta)
+    out.update({"E_%s_%s" % k: v for k, v in E.items()})
+    np.savez_compressed(os.path.join(HERE, "reference_parabolic.npz"), **out)
+    print("parabolic golden: N", N, "K", K, "B", B, "delta[0]", delta[0], "argmax", int(np.argmax(delta)))
+
+
 def main():
     ref = load_reference()
     make_storage_golden()
     make_offline_golden()
+    make_parabolic_golden(ref)
     make_case(ref, "tutorial01", N=4, Qa=2, Qf=1, B=100, seed=1)
     make_case(ref, "n16q6", N=16, Qa=6, Qf=6, B=40, seed=2)
     make_case(ref, "n32q10_bc", N=32, Qa=10, Qf=10, B=24, seed=3, n_bc=2)

@@ -1,0 +1,50 @@
+"""POD-Greedy sweep of parabolic reduced problems against outputs of the reference's own source
+(tests/golden/reference_parabolic.npz; generator: tests/golden/make_golden.py:make_parabolic_golden).
+CPU: the oracle restatement; GPU: rbnics_b200.parabolic through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import rb_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = dict(np.load(os.path.join(HERE, "golden", "reference_parabolic.npz")))
+K, DT = int(G["K"]), float(G["dt"])
+N = G["A"].shape[1]
+
+
+def _lists():
+    def storage(blk):
+        if blk.ndim == 2:
+            return [[float(blk[i, j]) for j in range(blk.shape[1])] for i in range(blk.shape[0])]
+        return [[blk[i, j] for j in range(blk.shape[1])] for i in range(blk.shape[0])]
+    Gd = {"ff": storage(G["E_f_f"]), "af": storage(G["E_a_f"]), "aa": storage(G["E_a_a"]), "mf": storage(G["E_m_f"]),
+          "ma": storage(G["E_m_a"]), "mm": storage(G["E_m_m"])}
+    return ([G["M"][q] for q in range(G["M"].shape[0])], [G["A"][q] for q in range(G["A"].shape[0])],
+            [G["F"][q] for q in range(G["F"].shape[0])], Gd)
+
+
+def test_oracle_parabolic_sweep_matches_reference():
+    M_q, A_q, f_q, Gd = _lists()
+    d, i, eps2, U = O.parabolic_sweep_loop(G["Theta_m"], G["Theta_a"], G["Theta_f"], G["beta"], M_q, A_q, f_q, Gd, N,
+                                           DT, K)
+    assert np.array_equal(U, G["U"])                       # same numpy calls in the same order
+    assert np.array_equal(eps2, G["eps2"])
+    assert np.max(np.abs(d - G["delta"]) / G["delta"]) <= 1e-15
+    assert i == int(np.argmax(G["delta"]))
+
+
+@pytest.mark.gpu
+def test_cuda_parabolic_sweep_matches_reference(engine):
+    from rbnics_b200.parabolic import ParabolicSweep
+    E = {("f", "f"): G["E_f_f"], ("a", "f"): G["E_a_f"], ("a", "a"): G["E_a_a"], ("m", "f"): G["E_m_f"],
+         ("m", "a"): G["E_m_a"], ("m", "m"): G["E_m_m"]}
+    sw = ParabolicSweep(engine, G["M"], G["A"], G["F"], E, dt=DT, K=K)
+    r = sw.sweep(G["Theta_m"], G["Theta_a"], G["Theta_f"], G["beta"], want_delta=True, want_eps2=True, want_u=True)
+    assert np.max(np.abs(r["u"] - G["U"])) <= 1e-10 * np.max(np.abs(G["U"]))
+    scale = np.max(np.abs(G["eps2"]), axis=1, keepdims=True)
+    assert np.max(np.abs(r["eps2"] - G["eps2"]) / scale) <= 1e-10
+    assert np.max(np.abs(r["delta"] - G["delta"]) / G["delta"]) <= 1e-10
+    assert r["argmax"] == int(np.argmax(G["delta"]))
+    assert abs(r["max"] - G["delta"].max()) <= 1e-10 * G["delta"].max()
