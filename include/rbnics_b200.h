@@ -66,6 +66,12 @@ int rb_set_system(rb_ctx* ctx, int N, int Ql, int Qr, const double* A, const dou
 int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col, const int* blk_src_off, const int* blk_len,
                      int v_theta_off, int v_theta_len, const double* G);
 
+/* Same with an explicit length of the solution part of V (rb_set_estimator uses N): the parabolic estimator works on
+ * V = [ u^k (N) | udot^k (N) | Theta[v_theta_off ..) | 1 ], solution_len = 2 N
+ * (rbnics/problems/parabolic/abstract_parabolic_rb_reduced_problem.py:62-92).                                      */
+int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_col, const int* blk_src_off, const int* blk_len,
+                        int v_theta_off, int v_theta_len, const double* G, int solution_len);
+
 /* ---- training set: replaces ParameterSpaceSubset + compute_theta / get_stability_factor_lower_bound --------------
  * rbnics/sampling/parameter_space_subset.py:52-77.  Theta: B x (Ql+Qr) (theta of every lhs then rhs term, already
  * evaluated for every mu of this rank's shard), ThetaBC: B x n_bc or NULL, beta: B.
@@ -85,6 +91,20 @@ int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_val, int64_t*
 int rb_sweep(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta, int n_bc, const double* ThetaBC,
              const double* beta, int64_t index_offset, int64_t index_stride, int estimator_kind,
              double* max_val, int64_t* max_idx, double* delta_out, double* u_out, double* eps2_out);
+/* ---- POD-Greedy sweep of a parabolic problem: replaces training_set.max(solve_and_estimate_error) of
+ * rbnics/reduction_methods/base/time_dependent_rb_reduction.py:262-295 for the whole resident training set.
+ * Per parameter: K implicit-Euler steps from a zero initial condition
+ *     (M(mu)/dt + A(mu)) u^k = M(mu) u^{k-1}/dt + f(mu)       udot^k = (u^k - u^{k-1}) / dt
+ * (rbnics/backends/online/numpy/time_stepping.py:104-112,226-238; abstract_parabolic_reduced_problem.py:17-36),
+ * eps2_k = z_k^T G z_k with the estimator set by rb_set_estimator_ex(solution_len = 2N), bound_k = sqrt(|eps2_k|/beta)
+ * (bound_0 = 0), Delta(mu) = sqrt(sum_k weights[k] * bound_k^2): weights = the time quadrature of
+ * rbnics/backends/common/time_quadrature.py:22-29 (Simpson) as a linear functional, K + 1 entries.
+ * Conventions: rb_set_system was called with the lhs terms [ M_q / dt (Qm of them) | A_q ] and the rhs terms f_q;
+ * Theta columns [theta_m | theta_a | theta_f].  thetas are constant in time.
+ * delta_out: B, eps2_out: B x (K+1), u_out: B x (K+1) x N (any may be NULL).                                      */
+int rb_sweep_parabolic(rb_ctx* ctx, int Qm, int K, double dt, const double* weights, double* max_val,
+                       int64_t* max_idx, double* delta_out, double* eps2_out, double* u_out);
+
 /* Device pointer to the 16-byte {double max_val; int64 max_idx} result of the last sweep (for a NCCL all-gather
  * issued by the host layer without a host round trip), and to the per-parameter estimators. */
 int rb_result_device_ptrs(rb_ctx* ctx, void** maxloc16, double** delta);

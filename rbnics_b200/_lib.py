@@ -33,6 +33,10 @@ SIGNATURES = {
     "rb_device_info": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_int_p]),
     "rb_set_system": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, C.c_int, c_int_p]),
     "rb_set_estimator": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_int_p, C.c_int, C.c_int, c_double_p]),
+    "rb_set_estimator_ex": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_int_p, C.c_int, C.c_int, c_double_p,
+                                      C.c_int]),
+    "rb_sweep_parabolic": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, c_double_p, c_double_p, c_int64_p,
+                                     c_double_p, c_double_p, c_double_p]),
     "rb_set_training_set": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_double_p, C.c_int, c_double_p, c_double_p,
                                       C.c_int64, C.c_int64]),
     "rb_sweep_resident": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_int64_p, c_double_p, c_double_p, c_double_p]),

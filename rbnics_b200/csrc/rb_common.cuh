@@ -43,7 +43,7 @@ struct rb_ctx {
 
   // estimator
   bool have_est = false;
-  int nblk = 0, Kz = 0, Kp = 0, KS = 0, n_ctile = 0, v_off = 0, v_len = 0, LV = 0, LVS = 0, stage_ksteps = 16, est_nstage = 3, est_align = 0, est_tri16 = 0;
+  int nblk = 0, Kz = 0, Kp = 0, KS = 0, n_ctile = 0, v_off = 0, v_len = 0, LV = 0, LVS = 0, stage_ksteps = 16, est_nstage = 3, est_align = 0, est_tri16 = 0, est_vecN = 0;
   std::vector<int> h_blk_scale, h_blk_src, h_blk_len, h_blk_ks_begin, h_tile_cost, h_tile_b0;
   std::vector<long long> h_tile_off;
   double* dGp = nullptr;            // packed lower-triangular G' in fragment order

@@ -49,7 +49,12 @@ __global__ void __launch_bounds__(128) rb_lu_smem_kernel(LuArgs args, int NP) {
   for (int i = tid; i < NP; i += 128) {
     double b = 0.0;
     if (i < N)
-      for (int q = 0; q < args.Qr; ++q) b = fma(th[q], args.F[q * NP + i], b);
+    {
+      if (args.rhs_in)
+        b = args.rhs_in[sys * (long long)N + i];
+      else
+        for (int q = 0; q < args.Qr; ++q) b = fma(th[q], args.F[q * NP + i], b);
+    }
     bs[i] = b;
   }
   __syncthreads();
@@ -176,6 +181,28 @@ int rb_launch_lu_args(rb_ctx* ctx, const LuArgs& a, int NP) {
     return RB_ERR_CUDA;
   }
   return RB_OK;
+}
+
+// same with a per-system right-hand side (time stepping) and an explicit pitch of the solution array
+int rb_launch_lu_rhs(rb_ctx* ctx, int64_t count, const double* Ab, const double* theta, const double* thetaBC,
+                     const double* rhs_in, double* u, int ldu) {
+  LuArgs a;
+  a.Ab = Ab;
+  a.theta = theta;
+  a.thetaBC = thetaBC;
+  a.F = ctx->dF;
+  a.bc_rows = ctx->dBcRows;
+  a.U = u;
+  a.rhs_in = rhs_in;
+  a.count = count;
+  a.N = ctx->N;
+  a.EP = ctx->EP;
+  a.QT = ctx->QT;
+  a.Ql = ctx->Ql;
+  a.Qr = ctx->Qr;
+  a.n_bc = ctx->n_bc;
+  a.ldu = ldu;
+  return rb_launch_lu_args(ctx, a, ctx->NP);
 }
 
 int rb_launch_lu(rb_ctx* ctx, int64_t count, const double* Ab, const double* theta, const double* thetaBC, double* u) {

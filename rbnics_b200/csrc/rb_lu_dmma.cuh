@@ -316,7 +316,12 @@ __global__ void __launch_bounds__(LudCfg<NT, NC>::THREADS, 2) rb_lu_dmma_kernel(
         if (bc_t >= 0)
           rhs = __ldg(args.thetaBC + sys * (long long)args.n_bc + bc_t);
         else
-          for (int q = 0; q < args.Qr; ++q) rhs = fma(__ldg(th + q), __ldg(args.F + q * NPc + row), rhs);
+        {
+          if (args.rhs_in)
+            rhs = args.rhs_in[sys * (long long)N + row];
+          else
+            for (int q = 0; q < args.Qr; ++q) rhs = fma(__ldg(th + q), __ldg(args.F + q * NPc + row), rhs);
+        }
       }
 #pragma unroll
       for (int tc = 0; tc < NC; ++tc) {

@@ -21,6 +21,7 @@ struct LuArgs {
   const double* F;        // [Qr][NP]
   const int* bc_rows;     // [n_bc]
   double* U;              // [count][ldu]
+  const double* rhs_in = nullptr;  // optional [count][N]: per-system right-hand side (replaces sum theta_f F)
   long long count;
   int N, EP, QT, Ql, Qr, n_bc, ldu;
 };
@@ -144,7 +145,10 @@ __global__ void __launch_bounds__(128, (NP > 48 ? 2 : (NP > 32 ? 3 : 4))) rb_lu_
     }
     const double* th = args.theta + sys * (long long)args.QT + args.Ql;
     if (i < N) {
-      for (int q = 0; q < args.Qr; ++q) b = fma(__ldg(th + q), __ldg(args.F + q * NP + i), b);
+      if (args.rhs_in)
+        b = args.rhs_in[sys * (long long)N + i];
+      else
+        for (int q = 0; q < args.Qr; ++q) b = fma(__ldg(th + q), __ldg(args.F + q * NP + i), b);
     }
     // lifting rows (DirichletBC.py:41-56) and identity padding rows N <= i < NP
     bool unit_row = (i >= N && i < NP);

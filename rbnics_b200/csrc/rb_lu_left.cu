@@ -168,7 +168,10 @@ __global__ void __launch_bounds__(32, 8) rb_lu_left_kernel(LuArgs args, double* 
       const int row = lane + 32 * j;
       double v = 0.0;
       if (row < N) {
-        for (int q = 0; q < args.Qr; ++q) v = fma(__ldg(th + q), __ldg(args.F + q * NP + row), v);
+        if (args.rhs_in)
+          v = args.rhs_in[sys * (long long)N + row];
+        else
+          for (int q = 0; q < args.Qr; ++q) v = fma(__ldg(th + q), __ldg(args.F + q * NP + row), v);
         for (int t = 0; t < args.n_bc; ++t)
           if (__ldg(args.bc_rows + t) == row) v = __ldg(args.thetaBC + sys * (long long)args.n_bc + t);
       } else {

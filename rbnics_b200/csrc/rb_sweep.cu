@@ -754,13 +754,21 @@ extern "C" int rb_set_system(rb_ctx* ctx, int N, int Ql, int Qr, const double* A
 extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col, const int* blk_src_off,
                                 const int* blk_len, int v_theta_off, int v_theta_len, const double* G) {
   if (!ctx) return RB_ERR_ARG;
+  return rb_set_estimator_ex(ctx, nblk, blk_scale_col, blk_src_off, blk_len, v_theta_off, v_theta_len, G, ctx->N);
+}
+
+extern "C" int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_col, const int* blk_src_off,
+                                   const int* blk_len, int v_theta_off, int v_theta_len, const double* G,
+                                   int solution_len) {
+  if (!ctx) return RB_ERR_ARG;
   RB_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->have_system) RB_FAIL(RB_ERR_STATE, "rb_set_estimator: call rb_set_system first");
   if (nblk <= 0 || !blk_scale_col || !blk_src_off || !blk_len || !G) RB_FAIL(RB_ERR_ARG, "rb_set_estimator: bad arguments");
   const int QT = ctx->Ql + ctx->Qr;
   if (v_theta_off < 0 || v_theta_len < 0 || v_theta_off + v_theta_len > QT)
     RB_FAIL(RB_ERR_ARG, "rb_set_estimator: v_theta range outside [0, Ql+Qr)");
-  const int LV = ctx->N + v_theta_len + 1;
+  if (solution_len < 0) RB_FAIL(RB_ERR_ARG, "rb_set_estimator: negative solution length");
+  const int LV = solution_len + v_theta_len + 1;
   int Kz = 0, Kp = 0;
   std::vector<int> ks_begin(nblk + 1, 0);
   for (int b = 0; b < nblk; ++b) {
@@ -902,6 +910,7 @@ extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col,
   ctx->LVS = LVS;
   ctx->stage_ksteps = stage_ksteps;
   ctx->est_nstage = nstage;
+  ctx->est_vecN = solution_len;
   ctx->est_tri16 = tri16 ? 1 : 0;
   ctx->est_issued_macs = issued_macs;
   ctx->h_blk_ks_begin = ks_begin;
@@ -1019,6 +1028,121 @@ static int choose_nsplit(long long nrb, int sms, int n_ctile) {
   return best;
 }
 
+// ---- helpers shared by the elliptic and the parabolic sweep -------------------------------------------------------------
+// column splits of the estimator for `rows` parameters: chooses nsplit, uploads the split table (balanced by the number
+// of k-step records of the tiles) and sizes the partial-sum buffer
+static int prepare_estimator_splits(rb_ctx* ctx, long long rows, int* nsplit_out) {
+  cudaStream_t st = ctx->stream;
+  const long long nrb = (rows + EST_BM - 1) / EST_BM;
+  const int nsplit = choose_nsplit(nrb, ctx->sm_count, ctx->n_ctile);
+  if ((long long)nsplit * rows > ctx->part_cap) {
+    if (int rc = dev_realloc(ctx, &ctx->dPart, (size_t)nsplit * rows)) return rc;
+    ctx->part_cap = (long long)nsplit * rows;
+  }
+  if (nsplit + 1 > ctx->split_cap) {
+    if (int rc = dev_realloc(ctx, &ctx->dSplitBegin, (size_t)nsplit + 1)) return rc;
+    ctx->split_cap = nsplit + 1;
+  }
+  std::vector<int> sb(nsplit + 1, ctx->n_ctile);
+  long long total = 0;
+  for (int ct = 0; ct < ctx->n_ctile; ++ct) total += ctx->h_tile_cost[ct];
+  long long accum = 0;
+  int s = 0;
+  sb[0] = 0;
+  for (int ct = 0; ct < ctx->n_ctile && s + 1 < nsplit; ++ct) {
+    accum += ctx->h_tile_cost[ct];
+    if (accum * nsplit >= total * (s + 1)) sb[++s] = ct + 1;
+  }
+  for (int t = s + 1; t <= nsplit; ++t) sb[t] = ctx->n_ctile;
+  RB_CUDA(cudaMemcpyAsync(ctx->dSplitBegin, sb.data(), (nsplit + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaStreamSynchronize(st));  // sb is a stack vector
+  *nsplit_out = nsplit;
+  return RB_OK;
+}
+
+// one estimator launch over `rows` parameters: V = [Uvec (vecN entries, pitch ldu) | theta[v_off : v_off+v_len] | 1]
+static int launch_estimator(rb_ctx* ctx, const double* Uvec, int ldu, int vecN, const double* theta, long long rows,
+                            int nsplit) {
+  EstArgs ea;
+  ea.Gp = ctx->dGp;
+  ea.tile_off = ctx->dTileOff;
+  ea.tile_skip = ctx->dTileKs0;
+  ea.tile_cls = ctx->dTileCls;
+  ea.tile_b0 = ctx->dTileB0;
+  ea.blk_ks_begin = ctx->dBlkKsBegin;
+  ea.blk_scale = ctx->dBlkScale;
+  ea.blk_src = ctx->dBlkSrc;
+  ea.blk_cls = ctx->dBlkCls;
+  ea.col_scale = ctx->dColScale;
+  ea.col_src = ctx->dColSrc;
+  ea.split_begin = ctx->dSplitBegin;
+  ea.U = Uvec;
+  ea.theta = theta;
+  ea.partial = ctx->dPart;
+  ea.B = rows;
+  ea.nblk = ctx->nblk;
+  ea.KS = ctx->KS;
+  ea.N = vecN;
+  ea.ldu = ldu;
+  ea.QT = ctx->QT;
+  ea.v_off = ctx->v_off;
+  ea.v_len = ctx->v_len;
+  ea.LVS = ctx->LVS;
+  ea.nsplit = nsplit;
+  ea.n_ctile = ctx->n_ctile;
+  ea.stage_ksteps = ctx->stage_ksteps;
+  ea.nstage = ctx->est_nstage;
+  ea.tri16 = ctx->est_tri16;
+  const long long nrb = (rows + EST_BM - 1) / EST_BM;
+  const size_t smem = est_smem_bytes(ctx->est_nstage, ctx->stage_ksteps, ctx->LVS, ctx->nblk, ctx->n_ctile);
+  static const bool est16 = getenv("RB_EST_WARPS") && atoi(getenv("RB_EST_WARPS")) == 16;  // A/B switch (default 8)
+  if (est16)
+    rb_estimator_kernel<2><<<(unsigned)(nrb * nsplit), 512, smem, ctx->stream>>>(ea);
+  else
+    rb_estimator_kernel<4><<<(unsigned)(nrb * nsplit), 256, smem, ctx->stream>>>(ea);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+
+// chunk size of the assembly scratch and its (re)allocation
+static int prepare_assembly(rb_ctx* ctx, long long B, long long* chunk_out, size_t* asm_smem_out) {
+  long long chunk = (long long)ctx->sm_count * ASM_BM;
+  if (getenv("RB_LU_CHUNK")) chunk = atoll(getenv("RB_LU_CHUNK"));
+  chunk = std::min<long long>(B, chunk);
+  if (chunk * ctx->EP > ctx->ab_cap) {
+    if (int rc = dev_realloc(ctx, &ctx->dAb, (size_t)chunk * ctx->EP)) return rc;
+    ctx->ab_cap = chunk * ctx->EP;
+  }
+  const int TS = ctx->QlP + ((ctx->QlP % 8 == 4) ? 0 : 4);
+  const size_t asm_smem = ((size_t)ASM_BM * TS + 2 * (size_t)ctx->QlP * (ASM_BE + 4)) * sizeof(double);
+  if (asm_smem > 227 * 1024) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_sweep: too many lhs terms for the assembly tile");
+  RB_CUDA(cudaFuncSetAttribute(rb_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_smem));
+  *chunk_out = chunk;
+  *asm_smem_out = asm_smem;
+  return RB_OK;
+}
+
+// Ab[0..n) = sum_q Theta[c0 + p][q] A_q for the chunk starting at parameter c0
+static int launch_assembly(rb_ctx* ctx, long long c0, long long n, size_t asm_smem) {
+  AsmArgs aa;
+  aa.theta = ctx->dTheta + c0 * ctx->QT;
+  aa.Aq = ctx->dAq;
+  aa.Ab = ctx->dAb;
+  aa.count = n;
+  aa.QT = ctx->QT;
+  aa.Ql = ctx->Ql;
+  aa.QlP = ctx->QlP;
+  aa.EP = ctx->EP;
+  // row blocks x entry-tile splits: 2 resident CTAs per SM, ~2 waves
+  const unsigned nrb_asm = (unsigned)((n + ASM_BM - 1) / ASM_BM);
+  unsigned esplit = (unsigned)std::max<long long>(1, (4LL * ctx->sm_count + nrb_asm - 1) / nrb_asm);
+  esplit = std::min<unsigned>(esplit, (unsigned)(ctx->EP / ASM_BE));
+  dim3 grid(esplit, nrb_asm);
+  rb_assemble_kernel<<<grid, 256, asm_smem, ctx->stream>>>(aa);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+
 extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_val, int64_t* max_idx, double* delta_out,
                                  double* u_out, double* eps2_out) {
   if (!ctx) return RB_ERR_ARG;
@@ -1034,16 +1158,13 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
   cudaStream_t st = ctx->stream;
   int launches = 0;
 
+  if (ctx->est_vecN != N) RB_FAIL(RB_ERR_STATE, "rb_sweep: the estimator was set for a different solution length");
   // ---- work buffers
-  const long long nrb = (B + EST_BM - 1) / EST_BM;
-  const int nsplit = choose_nsplit(nrb, ctx->sm_count, ctx->n_ctile);
+  int nsplit = 1;
+  if (int rc = prepare_estimator_splits(ctx, B, &nsplit)) return rc;
   if ((long long)B * ctx->ldu > ctx->u_cap) {
     if (int rc = dev_realloc(ctx, &ctx->dU, (size_t)B * ctx->ldu)) return rc;
     ctx->u_cap = (long long)B * ctx->ldu;
-  }
-  if ((long long)nsplit * B > ctx->part_cap) {
-    if (int rc = dev_realloc(ctx, &ctx->dPart, (size_t)nsplit * B)) return rc;
-    ctx->part_cap = (long long)nsplit * B;
   }
   if (B > ctx->delta_cap) {
     if (int rc = dev_realloc(ctx, &ctx->dDelta, (size_t)B)) return rc;
@@ -1056,60 +1177,16 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     if (int rc = dev_realloc(ctx, &ctx->dBlkIdx, (size_t)fin_blocks * 2)) return rc;
     ctx->blk_cap = fin_blocks;
   }
-  if (nsplit + 1 > ctx->split_cap) {
-    if (int rc = dev_realloc(ctx, &ctx->dSplitBegin, (size_t)nsplit + 1)) return rc;
-    ctx->split_cap = nsplit + 1;
-  }
-  {
-    // balance the splits by the number of k-step records of their tiles
-    std::vector<int> sb(nsplit + 1, ctx->n_ctile);
-    long long total = 0;
-    for (int ct = 0; ct < ctx->n_ctile; ++ct) total += ctx->h_tile_cost[ct];
-    long long accum = 0;
-    int s = 0;
-    sb[0] = 0;
-    for (int ct = 0; ct < ctx->n_ctile && s + 1 < nsplit; ++ct) {
-      accum += ctx->h_tile_cost[ct];
-      if (accum * nsplit >= total * (s + 1)) sb[++s] = ct + 1;
-    }
-    for (int t = s + 1; t <= nsplit; ++t) sb[t] = ctx->n_ctile;
-    RB_CUDA(cudaMemcpyAsync(ctx->dSplitBegin, sb.data(), (nsplit + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-    RB_CUDA(cudaStreamSynchronize(st));  // sb is a stack vector
-  }
 
   RB_CUDA(cudaEventRecord(ctx->ev[0], st));
-  float ms_asm = 0.f, ms_lu = 0.f;
   if (N > 0) {
     // chunked assembly + LU; scratch = chunk x EP doubles
-    long long chunk = (long long)ctx->sm_count * ASM_BM;
-    if (getenv("RB_LU_CHUNK")) chunk = atoll(getenv("RB_LU_CHUNK"));
-    chunk = std::min<long long>(B, chunk);
-    if (chunk * ctx->EP > ctx->ab_cap) {
-      if (int rc = dev_realloc(ctx, &ctx->dAb, (size_t)chunk * ctx->EP)) return rc;
-      ctx->ab_cap = chunk * ctx->EP;
-    }
-    const int TS = ctx->QlP + ((ctx->QlP % 8 == 4) ? 0 : 4);
-    const size_t asm_smem = ((size_t)ASM_BM * TS + 2 * (size_t)ctx->QlP * (ASM_BE + 4)) * sizeof(double);
-    if (asm_smem > 227 * 1024) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_sweep: too many lhs terms for the assembly tile");
-    RB_CUDA(cudaFuncSetAttribute(rb_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asm_smem));
+    long long chunk = 0;
+    size_t asm_smem = 0;
+    if (int rc = prepare_assembly(ctx, B, &chunk, &asm_smem)) return rc;
     for (long long c0 = 0; c0 < B; c0 += chunk) {
       const long long n = std::min(chunk, B - c0);
-      AsmArgs aa;
-      aa.theta = ctx->dTheta + c0 * ctx->QT;
-      aa.Aq = ctx->dAq;
-      aa.Ab = ctx->dAb;
-      aa.count = n;
-      aa.QT = ctx->QT;
-      aa.Ql = ctx->Ql;
-      aa.QlP = ctx->QlP;
-      aa.EP = ctx->EP;
-      // row blocks x entry-tile splits: 2 resident CTAs per SM, ~2 waves
-      const unsigned nrb_asm = (unsigned)((n + ASM_BM - 1) / ASM_BM);
-      unsigned esplit = (unsigned)std::max<long long>(1, (4LL * ctx->sm_count + nrb_asm - 1) / nrb_asm);
-      esplit = std::min<unsigned>(esplit, (unsigned)(ctx->EP / ASM_BE));
-      dim3 grid(esplit, nrb_asm);
-      rb_assemble_kernel<<<grid, 256, asm_smem, st>>>(aa);
-      RB_CUDA(cudaGetLastError());
+      if (int rc = launch_assembly(ctx, c0, n, asm_smem)) return rc;
       ++launches;
       if (int rc = rb_launch_lu(ctx, n, ctx->dAb, ctx->dTheta + c0 * ctx->QT,
                                 ctx->n_bc ? ctx->dThetaBC + c0 * ctx->n_bc : nullptr, ctx->dU + c0 * ctx->ldu))
@@ -1118,46 +1195,8 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     }
   }
   RB_CUDA(cudaEventRecord(ctx->ev[1], st));
-  {
-    EstArgs ea;
-    ea.Gp = ctx->dGp;
-    ea.tile_off = ctx->dTileOff;
-    ea.tile_skip = ctx->dTileKs0;
-    ea.tile_cls = ctx->dTileCls;
-    ea.tile_b0 = ctx->dTileB0;
-    ea.blk_ks_begin = ctx->dBlkKsBegin;
-    ea.blk_scale = ctx->dBlkScale;
-    ea.blk_src = ctx->dBlkSrc;
-    ea.blk_cls = ctx->dBlkCls;
-    ea.col_scale = ctx->dColScale;
-    ea.col_src = ctx->dColSrc;
-    ea.split_begin = ctx->dSplitBegin;
-    ea.U = ctx->dU;
-    ea.theta = ctx->dTheta;
-    ea.partial = ctx->dPart;
-    ea.B = B;
-    ea.nblk = ctx->nblk;
-    ea.KS = ctx->KS;
-    ea.N = N;
-    ea.ldu = ctx->ldu;
-    ea.QT = ctx->QT;
-    ea.v_off = ctx->v_off;
-    ea.v_len = ctx->v_len;
-    ea.LVS = ctx->LVS;
-    ea.nsplit = nsplit;
-    ea.n_ctile = ctx->n_ctile;
-    ea.stage_ksteps = ctx->stage_ksteps;
-    ea.nstage = ctx->est_nstage;
-    ea.tri16 = ctx->est_tri16;
-    const size_t smem = est_smem_bytes(ctx->est_nstage, ctx->stage_ksteps, ctx->LVS, ctx->nblk, ctx->n_ctile);
-    static const bool est16 = getenv("RB_EST_WARPS") && atoi(getenv("RB_EST_WARPS")) == 16;  // A/B switch (default 8)
-    if (est16)
-      rb_estimator_kernel<2><<<(unsigned)(nrb * nsplit), 512, smem, st>>>(ea);
-    else
-      rb_estimator_kernel<4><<<(unsigned)(nrb * nsplit), 256, smem, st>>>(ea);
-    RB_CUDA(cudaGetLastError());
-    ++launches;
-  }
+  if (int rc = launch_estimator(ctx, ctx->dU, ctx->ldu, N, ctx->dTheta, B, nsplit)) return rc;
+  ++launches;
   RB_CUDA(cudaEventRecord(ctx->ev[2], st));
   {
     long long* blk_nf = ctx->dBlkIdx + fin_blocks;
@@ -1176,8 +1215,6 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
   if (eps2_out) RB_CUDA(cudaMemcpyAsync(eps2_out, ctx->dEps2, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (u_out && N > 0) RB_CUDA(cudaMemcpyAsync(u_out, ctx->dU, (size_t)B * N * sizeof(double), cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaStreamSynchronize(st));
-  (void)ms_asm;
-  (void)ms_lu;
   float t01 = 0, t12 = 0, t23 = 0, t03 = 0;
   cudaEventElapsedTime(&t01, ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&t12, ctx->ev[1], ctx->ev[2]);
@@ -1195,6 +1232,210 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     ctx->err = "rb_sweep: " + std::to_string(res.n_nonfinite) +
                " non-finite error estimators (singular reduced matrix or beta == 0); numpy.linalg.solve would raise "
                "LinAlgError";
+    return RB_ERR_SINGULAR;
+  }
+  return RB_OK;
+}
+
+// =====================================================================================================================
+// Parabolic (POD-Greedy) sweep: K implicit-Euler steps per parameter on top of the same assembly / LU / estimator
+// kernels.  rbnics/reduction_methods/base/time_dependent_rb_reduction.py:262-295.
+// =====================================================================================================================
+// r[p][i] = sum_q theta_f[p][q] F[q][i] + sum_q theta_m[p][q] sum_j (M_q/dt)[i][j] u_prev[p][j]
+// (Aq holds the lhs terms column-major: entry (i, j) of term q at q*EP + j*NP + i; the first Qm terms are M_q/dt)
+__global__ void __launch_bounds__(128) rb_parabolic_rhs_kernel(const double* __restrict__ theta, int QT, int Ql, int Qr,
+                                                               int Qm, const double* __restrict__ Aq, int EP, int NP,
+                                                               const double* __restrict__ F, const double* __restrict__ UV,
+                                                               int ldu, int N, long long n, double* __restrict__ rhs) {
+  extern __shared__ double prs[];  // u_prev of the 4 parameters of this CTA
+  const int lp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * 4 + lp;
+  if (p < n)
+    for (int j = lane; j < N; j += 32) prs[lp * N + j] = UV[p * ldu + j];
+  __syncthreads();
+  if (p >= n) return;
+  const double* th = theta + p * QT;
+  const double* up = prs + lp * N;
+  for (int i = lane; i < N; i += 32) {
+    double acc = 0.0;
+    for (int q = 0; q < Qr; ++q) acc = fma(th[Ql + q], __ldg(F + q * NP + i), acc);
+    for (int q = 0; q < Qm; ++q) {
+      const double* Mq = Aq + (long long)q * EP + i;
+      double s = 0.0;
+      for (int j = 0; j < N; ++j) s = fma(__ldg(Mq + (long long)j * NP), up[j], s);
+      acc = fma(th[q], s, acc);
+    }
+    rhs[p * N + i] = acc;
+  }
+}
+
+// UV[p] = [u_new | (u_new - u_prev)/dt]; optional history u_hist[(c0 + p)][k][:]
+__global__ void rb_parabolic_advance_kernel(const double* __restrict__ unew, double* __restrict__ UV, int ldu, int N,
+                                            long long n, double inv_dt, double* __restrict__ u_hist, long long hist_pitch) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n * N) return;
+  const long long p = t / N;
+  const int i = (int)(t % N);
+  const double un = unew[p * N + i], up = UV[p * ldu + i];
+  UV[p * ldu + i] = un;
+  UV[p * ldu + N + i] = (un - up) * inv_dt;
+  if (u_hist) u_hist[p * hist_pitch + i] = un;
+}
+
+// eps2_k = sum of split partials; acc += w_k * |eps2_k| / beta
+__global__ void rb_parabolic_accumulate_kernel(const double* __restrict__ partial, int nsplit, long long n,
+                                               const double* __restrict__ beta, double w, double* __restrict__ acc,
+                                               double* __restrict__ eps2_hist, long long hist_pitch) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double e = 0.0;
+  for (int s = 0; s < nsplit; ++s) e += partial[(long long)s * n + p];
+  acc[p] = fma(w, fabs(e) / beta[p], acc[p]);
+  if (eps2_hist) eps2_hist[p * hist_pitch] = e;
+}
+
+// Delta = sqrt(acc), block arg-max
+__global__ void __launch_bounds__(256) rb_parabolic_finalize_kernel(const double* __restrict__ acc, long long B,
+                                                                    long long idx_off, long long idx_stride,
+                                                                    double* __restrict__ delta,
+                                                                    double* __restrict__ blk_val,
+                                                                    long long* __restrict__ blk_idx,
+                                                                    long long* __restrict__ blk_nf) {
+  double best = -INFINITY;
+  long long besti = 0x7fffffffffffffffLL, nf = 0;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < B; p += (long long)gridDim.x * blockDim.x) {
+    const double d = sqrt(acc[p]);
+    delta[p] = d;
+    if (!isfinite(d)) ++nf;
+    const long long gi = idx_off + p * idx_stride;
+    if (argmax_better(d, gi, best, besti)) {
+      best = d;
+      besti = gi;
+    }
+  }
+  block_argmax(best, besti, nf);
+  if (threadIdx.x == 0) {
+    blk_val[blockIdx.x] = best;
+    blk_idx[blockIdx.x] = besti;
+    blk_nf[blockIdx.x] = nf;
+  }
+}
+
+int rb_launch_lu_rhs(rb_ctx* ctx, int64_t count, const double* Ab, const double* theta, const double* thetaBC,
+                     const double* rhs_in, double* u, int ldu);
+
+extern "C" int rb_sweep_parabolic(rb_ctx* ctx, int Qm, int K, double dt, const double* weights, double* max_val,
+                                  int64_t* max_idx, double* delta_out, double* eps2_out, double* u_out) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->have_system || !ctx->have_est || !ctx->have_train)
+    RB_FAIL(RB_ERR_STATE, "rb_sweep_parabolic: system, estimator and training set must all be set");
+  const int N = ctx->N;
+  if (N <= 0) RB_FAIL(RB_ERR_ARG, "rb_sweep_parabolic: empty reduced space");
+  if (Qm <= 0 || Qm >= ctx->Ql || K <= 0 || !(dt > 0.0) || !weights) RB_FAIL(RB_ERR_ARG, "rb_sweep_parabolic: bad arguments");
+  if (ctx->QT != ctx->Ql + ctx->Qr) RB_FAIL(RB_ERR_ARG, "rb_sweep_parabolic: training set theta width != Ql + Qr");
+  if (ctx->n_bc_train != ctx->n_bc) RB_FAIL(RB_ERR_ARG, "rb_sweep_parabolic: training set n_bc != system n_bc");
+  if (ctx->est_vecN != 2 * N) RB_FAIL(RB_ERR_STATE, "rb_sweep_parabolic: set the estimator with solution_len = 2 N");
+  const long long B = ctx->B;
+  cudaStream_t st = ctx->stream;
+  long long chunk = 0;
+  size_t asm_smem = 0;
+  if (int rc = prepare_assembly(ctx, B, &chunk, &asm_smem)) return rc;
+  int nsplit = 1;
+  if (int rc = prepare_estimator_splits(ctx, chunk, &nsplit)) return rc;
+  if (B > ctx->delta_cap) {
+    if (int rc = dev_realloc(ctx, &ctx->dDelta, (size_t)B)) return rc;
+    if (int rc = dev_realloc(ctx, &ctx->dEps2, (size_t)B)) return rc;
+    ctx->delta_cap = B;
+  }
+  const int fin_blocks = (int)std::min<long long>((B + 255) / 256, ctx->sm_count * 8);
+  if (fin_blocks > ctx->blk_cap) {
+    if (int rc = dev_realloc(ctx, &ctx->dBlkVal, (size_t)fin_blocks)) return rc;
+    if (int rc = dev_realloc(ctx, &ctx->dBlkIdx, (size_t)fin_blocks * 2)) return rc;
+    ctx->blk_cap = fin_blocks;
+  }
+  // chunk-sized work arrays: [u | udot], rhs, new solution; optional histories (device side, whole training set)
+  double *dUV = nullptr, *dRhs = nullptr, *dUnew = nullptr, *dHistE = nullptr, *dHistU = nullptr;
+  auto free_all = [&]() {
+    for (double* q : {dUV, dRhs, dUnew, dHistE, dHistU})
+      if (q) cudaFree(q);
+  };
+#define RB_PB(call)                                                                                  \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess) {                                                                        \
+      free_all();                                                                                    \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                \
+      return RB_ERR_CUDA;                                                                            \
+    }                                                                                                \
+  } while (0)
+  RB_PB(cudaMalloc(&dUV, (size_t)chunk * 2 * N * sizeof(double)));
+  RB_PB(cudaMalloc(&dRhs, (size_t)chunk * N * sizeof(double)));
+  RB_PB(cudaMalloc(&dUnew, (size_t)chunk * N * sizeof(double)));
+  if (eps2_out) RB_PB(cudaMalloc(&dHistE, (size_t)B * (K + 1) * sizeof(double)));
+  if (u_out) RB_PB(cudaMalloc(&dHistU, (size_t)B * (K + 1) * N * sizeof(double)));
+  if (dHistE) RB_PB(cudaMemsetAsync(dHistE, 0, (size_t)B * (K + 1) * sizeof(double), st));
+  if (dHistU) RB_PB(cudaMemsetAsync(dHistU, 0, (size_t)B * (K + 1) * N * sizeof(double), st));
+  RB_PB(cudaMemsetAsync(ctx->dEps2, 0, (size_t)B * sizeof(double), st));  // accumulator of w_k bound_k^2
+  int launches = 0;
+  RB_PB(cudaEventRecord(ctx->ev[0], st));
+  for (long long c0 = 0; c0 < B; c0 += chunk) {
+    const long long n = std::min(chunk, B - c0);
+    if (int rc = launch_assembly(ctx, c0, n, asm_smem)) {
+      free_all();
+      return rc;
+    }
+    ++launches;
+    RB_PB(cudaMemsetAsync(dUV, 0, (size_t)n * 2 * N * sizeof(double), st));  // zero initial condition
+    const double* th = ctx->dTheta + c0 * ctx->QT;
+    for (int k = 1; k <= K; ++k) {
+      rb_parabolic_rhs_kernel<<<(unsigned)((n + 3) / 4), 128, 4 * N * sizeof(double), st>>>(
+          th, ctx->QT, ctx->Ql, ctx->Qr, Qm, ctx->dAq, ctx->EP, ctx->NP, ctx->dF, dUV, 2 * N, N, n, dRhs);
+      RB_PB(cudaGetLastError());
+      if (int rc = rb_launch_lu_rhs(ctx, n, ctx->dAb, th, ctx->n_bc ? ctx->dThetaBC + c0 * ctx->n_bc : nullptr, dRhs,
+                                    dUnew, N)) {
+        free_all();
+        return rc;
+      }
+      rb_parabolic_advance_kernel<<<(unsigned)((n * N + 255) / 256), 256, 0, st>>>(
+          dUnew, dUV, 2 * N, N, n, 1.0 / dt, dHistU ? dHistU + (c0 * (K + 1) + k) * N : nullptr, (long long)(K + 1) * N);
+      RB_PB(cudaGetLastError());
+      if (int rc = launch_estimator(ctx, dUV, 2 * N, 2 * N, th, n, nsplit)) {
+        free_all();
+        return rc;
+      }
+      rb_parabolic_accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+          ctx->dPart, nsplit, n, ctx->dBeta + c0, weights[k], ctx->dEps2 + c0,
+          dHistE ? dHistE + c0 * (K + 1) + k : nullptr, (long long)(K + 1));
+      RB_PB(cudaGetLastError());
+      launches += 5;
+    }
+  }
+  long long* blk_nf = ctx->dBlkIdx + fin_blocks;
+  rb_parabolic_finalize_kernel<<<fin_blocks, 256, 0, st>>>(ctx->dEps2, B, ctx->idx_off, ctx->idx_stride, ctx->dDelta,
+                                                           ctx->dBlkVal, ctx->dBlkIdx, blk_nf);
+  RB_PB(cudaGetLastError());
+  rb_argmax_final_kernel<<<1, 256, 0, st>>>(ctx->dBlkVal, ctx->dBlkIdx, blk_nf, fin_blocks, (MaxLoc*)ctx->dResult);
+  RB_PB(cudaGetLastError());
+  launches += 2;
+  RB_PB(cudaEventRecord(ctx->ev[3], st));
+  MaxLoc res;
+  RB_PB(cudaMemcpyAsync(&res, ctx->dResult, sizeof(MaxLoc), cudaMemcpyDeviceToHost, st));
+  if (delta_out) RB_PB(cudaMemcpyAsync(delta_out, ctx->dDelta, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (eps2_out) RB_PB(cudaMemcpyAsync(eps2_out, dHistE, (size_t)B * (K + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (u_out) RB_PB(cudaMemcpyAsync(u_out, dHistU, (size_t)B * (K + 1) * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_PB(cudaStreamSynchronize(st));
+#undef RB_PB
+  free_all();
+  float t03 = 0;
+  cudaEventElapsedTime(&t03, ctx->ev[0], ctx->ev[3]);
+  ctx->last_ms[0] = ctx->last_ms[1] = ctx->last_ms[2] = ctx->last_ms[3] = 0.f;
+  ctx->last_ms[4] = t03;
+  ctx->last_launches = launches;
+  if (max_val) *max_val = res.val;
+  if (max_idx) *max_idx = res.idx;
+  if (res.n_nonfinite > 0) {
+    ctx->err = "rb_sweep_parabolic: " + std::to_string(res.n_nonfinite) + " non-finite error estimators";
     return RB_ERR_SINGULAR;
   }
   return RB_OK;

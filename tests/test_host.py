@@ -99,10 +99,14 @@ print("rank", d.rank, "ok")
 def test_world_size_2_gloo_maxloc_and_allreduce(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER.format(root=ROOT))
+    import socket
+    with socket.socket() as sock:   # a free port: a fixed one collides with concurrent runs on the same host
+        sock.bind(("127.0.0.1", 0))
+        port = str(sock.getsockname()[1])
     env = dict(os.environ)
-    env.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29533"})
+    env.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": port})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", str(script)]
+           "127.0.0.1", "--master-port", port, str(script)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout

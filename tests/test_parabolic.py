@@ -35,6 +35,24 @@ def test_oracle_parabolic_sweep_matches_reference():
     assert i == int(np.argmax(G["delta"]))
 
 
+def test_parabolic_quadratic_form_and_simpson_weights_match_reference():
+    """CPU, numpy only: z^T G z of the packed form == the reference's eps2 at every step; the Simpson functional."""
+    from rbnics_b200.parabolic import parabolic_quadratic_form, simpson_weights
+    E = {("f", "f"): G["E_f_f"], ("a", "f"): G["E_a_f"], ("a", "a"): G["E_a_a"], ("m", "f"): G["E_m_f"],
+         ("m", "a"): G["E_m_a"], ("m", "m"): G["E_m_m"]}
+    Qm, Qa, Qf = G["M"].shape[0], G["A"].shape[0], G["F"].shape[0]
+    Gq, (scale, src, length, v_off, v_len) = parabolic_quadratic_form(E, Qa, Qm, Qf, N)
+    w = simpson_weights(K, DT)
+    for p in range(G["U"].shape[0]):
+        Theta = np.concatenate([G["Theta_m"][p], G["Theta_a"][p], G["Theta_f"][p]])
+        for k in range(1, K + 1):
+            u, udot = G["U"][p, k], (G["U"][p, k] - G["U"][p, k - 1]) / DT
+            V = np.concatenate([u, udot, Theta[v_off:v_off + v_len], [1.0]])
+            z = np.concatenate([(Theta[sc] if sc >= 0 else 1.0) * V[so:so + ln] for sc, so, ln in zip(scale, src, length)])
+            assert abs(z @ Gq @ z - G["eps2"][p, k]) <= 1e-11 * np.max(np.abs(G["eps2"][p]))
+        assert abs(np.sqrt(np.dot(w, G["bound"][p] ** 2)) - G["delta"][p]) <= 1e-14 * G["delta"][p]
+
+
 @pytest.mark.gpu
 def test_cuda_parabolic_sweep_matches_reference(engine):
     from rbnics_b200.parabolic import ParabolicSweep
