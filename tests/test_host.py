@@ -92,7 +92,7 @@ assert np.all(part == 3.0)
 assert d.max_float(d.rank) == 1.0
 d.barrier()
 d.close()
-print("rank", d.rank, "ok")
+sys.stdout.write(f"rank {d.rank} ok\n"); sys.stdout.flush()
 """
 
 
