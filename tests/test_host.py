@@ -92,7 +92,7 @@ assert np.all(part == 3.0)
 assert d.max_float(d.rank) == 1.0
 d.barrier()
 d.close()
-sys.stdout.write(f"rank {d.rank} ok\n"); sys.stdout.flush()
+sys.stdout.write("rank %d ok\n" % d.rank); sys.stdout.flush()
 """
 
 
