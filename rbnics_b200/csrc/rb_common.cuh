@@ -52,6 +52,7 @@ struct rb_ctx {
   long long* dTileOff = nullptr;    // [n_ctile]
   int* dTileKs0 = nullptr;          // [n_ctile] k-steps skipped per row block of the tile's class
   int* dTileCls = nullptr;          // [n_ctile]
+  int* dTileCb = nullptr;           // [4 n_ctile] first row block with data per 16-column range of a tile
   int* dBlkCls = nullptr;           // [nblk] slice class of every z block
   int* dTileB0 = nullptr;           // [n_ctile] block containing the tile's first k-step
   int* dBlkKsBegin = nullptr;       // [nblk+1]

@@ -189,6 +189,7 @@ struct EstArgs {
   const int* tile_skip;    // k-steps skipped at the start of every row block of the tile's slice class
   const int* tile_cls;
   const int* tile_b0;      // first row block of the tile
+  const int* tile_cb;      // [4 n_ctile] per 16-column range of the tile: first row block that has data for it
   const int* blk_ks_begin;
   const int* blk_scale;
   const int* blk_src;
@@ -212,7 +213,7 @@ __host__ __device__ inline size_t est_smem_bytes(int nstage, int stage_ksteps, i
   b += (size_t)3 * EST_BM * 8;                                            // cross-warp reduction
   b += (size_t)EST_BM * LVS * 8;                                          // V tile
   b += (size_t)n_ctile * 8;                                               // tile offsets
-  b += (size_t)(3 * n_ctile + 4 * nblk + 1 + EST_NSTAGE) * 4;             // int tables + release counters
+  b += (size_t)(7 * n_ctile + 4 * nblk + 1 + EST_NSTAGE) * 4;             // int tables + release counters
   return b + 16;
 }
 
@@ -233,12 +234,13 @@ __device__ __forceinline__ void est_load_frag(EstFrag<NTN>& f, const double* gs,
 
 // HEAD: only the first 8-column tile of every 16-column range (the second one is structurally zero in the first two
 // k-steps of a folded block: columns m >= 16r+8 against rows n < 16r+8).
-template <int NTN, bool HEAD = false>
+// FIRST_ONLY: only the warp's first 16-column range (the block of its second range lies below this row block).
+template <int NTN, bool HEAD = false, bool FIRST_ONLY = false>
 __device__ __forceinline__ void est_mma(double (&T)[4][NTN][2], const EstFrag<NTN>& f) {
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
 #pragma unroll
-    for (int h = 0; h < NTN / 2; ++h) {
+    for (int h = 0; h < (FIRST_ONLY ? 1 : NTN / 2); ++h) {
       dmma884(T[mt][2 * h][0], T[mt][2 * h][1], f.a[mt], f.b[h].x);
       if (!HEAD) dmma884(T[mt][2 * h + 1][0], T[mt][2 * h + 1][1], f.a[mt], f.b[h].y);
     }
@@ -267,7 +269,8 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
   int* s_scale = s_ks_begin + (a.nblk + 1);                                 // [nblk]
   int* s_src = s_scale + a.nblk;                                            // [nblk]
   int* s_cls = s_src + a.nblk;                                              // [nblk]
-  int* s_cnt = s_cls + a.nblk;                                              // [NSTAGE] release counters
+  int* s_tile_cb = s_cls + a.nblk;                                          // [4 n_ctile] first row block with data per 16-column range
+  int* s_cnt = s_tile_cb + 4 * a.n_ctile;                                   // [NSTAGE] release counters
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int split = blockIdx.x % a.nsplit;
@@ -297,6 +300,7 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
     s_tile_cls[t] = a.tile_cls[t];
     s_tile_b0[t] = a.tile_b0[t];
   }
+  for (int t = tid; t < 4 * a.n_ctile; t += NTHREADS) s_tile_cb[t] = a.tile_cb[t];
   for (int t = tid; t <= a.nblk; t += NTHREADS) {
     s_ks_begin[t] = a.blk_ks_begin[t];
     if (t < a.nblk) {
@@ -377,6 +381,7 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
     const int src = s_src[b] + 4 * (ks - s_ks_begin[b]);
     int kin = 0;                   // k-step within the current stage
     bool tri_head = a.tri16 && (s_cls[b] == s_tile_cls[ct]);  // the next segment starts a folded block
+    int nvalid = (b >= s_tile_cb[4 * ct + 2 * wn]) + (b >= s_tile_cb[4 * ct + 2 * wn + 1]);  // ranges with data
     int nin = min(SK, kend - ks);  // k-steps held by the current stage (a stage never crosses a block boundary)
     double th[4], thn[4];
     {
@@ -400,6 +405,17 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
     while (true) {
       const int nseg = min(kend - ks, nin - kin);
       int i = nseg;
+      if (nvalid < 2) {
+        // one of the first row blocks of a tile group: the column blocks of one or both of this warp's 16-column
+        // ranges lie below it (structural zeros) -> half or none of the DMMAs; fragments are still stepped through
+        for (; i > 1; --i) {
+          if (nvalid == 1) est_mma<NTN, false, true>(T, f0);
+          gp += EST_KSTEP_DOUBLES;
+          vp += 4;
+          est_load_frag(f0, gp, vp, LVS);
+        }
+        if (nvalid == 1) est_mma<NTN, false, true>(T, f0);
+      } else {
       if (tri_head && i > 2) {  // first two k-steps of a folded block: half of the column tiles are zero
         est_mma<NTN, true>(T, f0);
         gp += EST_KSTEP_DOUBLES;
@@ -427,6 +443,7 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
         est_load_frag(f0, gp, vp, LVS);
       }
       est_mma(T, f0);  // last k-step of the segment; its successor is loaded after the boundary bookkeeping
+      }
       ks += nseg;
       kin += nseg;
       gp += EST_KSTEP_DOUBLES;
@@ -436,6 +453,7 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
       tri_head = false;
       if (blk_done && !tile_done) {
         ++b;
+        nvalid = (b >= s_tile_cb[4 * ct + 2 * wn]) + (b >= s_tile_cb[4 * ct + 2 * wn + 1]);
         tri_head = a.tri16 && (s_cls[b] == s_tile_cls[ct]);
         ks = blk_first_ks(ct, b);
         kend = s_ks_begin[b + 1];
@@ -674,7 +692,7 @@ extern "C" void rb_ctx_destroy(rb_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dAq,       ctx->dF,       ctx->dBcRows,  ctx->dGp,      ctx->dTileOff, ctx->dTileKs0,
                   ctx->dTileB0,   ctx->dBlkKsBegin, ctx->dBlkScale, ctx->dBlkSrc, ctx->dColScale, ctx->dColSrc,
-                  ctx->dTileCls,  ctx->dBlkCls,
+                  ctx->dTileCls,  ctx->dBlkCls,  ctx->dTileCb,
                   ctx->dTheta,    ctx->dThetaBC, ctx->dBeta,    ctx->dAb,      ctx->dU,       ctx->dPart,
                   ctx->dDelta,    ctx->dEps2,    ctx->dBlkVal,  ctx->dBlkIdx,  ctx->dResult,  ctx->dSplitBegin,
                   ctx->dLuScratch};
@@ -864,6 +882,17 @@ extern "C" int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_c
   // ---- records (k-steps) of every tile, in stream order
   std::vector<long long> tile_off(n_ctile);
   std::vector<int> tile_b0(n_ctile), tile_skip(n_ctile), tile_cls(n_ctile), tile_cost(n_ctile), rec_tile, rec_ks;
+  // per 16-column range of a tile: the lowest column block in it (row blocks above it are structural zeros there);
+  // -1 = always process (empty ranges cost nothing to skip but keep the fast path for mixed / narrow layouts)
+  std::vector<int> tile_cb(4 * (size_t)n_ctile, -1);
+  static const bool est_skip = !(getenv("RB_EST_SKIP") && atoi(getenv("RB_EST_SKIP")) == 0);
+  for (int ct = 0; ct < n_ctile && est_skip; ++ct)
+    for (int rg = 0; rg < 4; ++rg) {
+      int lo = 0x7fffffff;
+      for (int j = 0; j < 16; ++j)
+        if (col_unpad[(size_t)ct * EST_BN + 16 * rg + j] >= 0) lo = std::min(lo, col_blk[(size_t)ct * EST_BN + 16 * rg + j]);
+      tile_cb[4 * (size_t)ct + rg] = lo;  // an empty range never has data: 0x7fffffff skips it for every row block
+    }
   for (int ct = 0; ct < n_ctile; ++ct) {
     tile_off[ct] = (long long)rec_tile.size() * EST_KSTEP_DOUBLES;
     tile_b0[ct] = tiles[ct].b0;
@@ -923,6 +952,7 @@ extern "C" int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_c
   if (int rc = dev_realloc(ctx, &ctx->dTileKs0, (size_t)n_ctile)) return rc;   // tile_skip
   if (int rc = dev_realloc(ctx, &ctx->dTileCls, (size_t)n_ctile)) return rc;
   if (int rc = dev_realloc(ctx, &ctx->dTileB0, (size_t)n_ctile)) return rc;
+  if (int rc = dev_realloc(ctx, &ctx->dTileCb, (size_t)4 * n_ctile)) return rc;
   if (int rc = dev_realloc(ctx, &ctx->dBlkKsBegin, (size_t)nblk + 1)) return rc;
   if (int rc = dev_realloc(ctx, &ctx->dBlkScale, (size_t)nblk)) return rc;
   if (int rc = dev_realloc(ctx, &ctx->dBlkSrc, (size_t)nblk)) return rc;
@@ -933,6 +963,7 @@ extern "C" int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_c
   RB_CUDA(cudaMemcpy(ctx->dTileKs0, tile_skip.data(), n_ctile * sizeof(int), cudaMemcpyHostToDevice));
   RB_CUDA(cudaMemcpy(ctx->dTileCls, tile_cls.data(), n_ctile * sizeof(int), cudaMemcpyHostToDevice));
   RB_CUDA(cudaMemcpy(ctx->dTileB0, tile_b0.data(), n_ctile * sizeof(int), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(ctx->dTileCb, tile_cb.data(), 4 * n_ctile * sizeof(int), cudaMemcpyHostToDevice));
   RB_CUDA(cudaMemcpy(ctx->dBlkKsBegin, ks_begin.data(), (nblk + 1) * sizeof(int), cudaMemcpyHostToDevice));
   RB_CUDA(cudaMemcpy(ctx->dBlkScale, scale_norm.data(), nblk * sizeof(int), cudaMemcpyHostToDevice));
   RB_CUDA(cudaMemcpy(ctx->dBlkSrc, blk_src_off, nblk * sizeof(int), cudaMemcpyHostToDevice));
@@ -1069,6 +1100,7 @@ static int launch_estimator(rb_ctx* ctx, const double* Uvec, int ldu, int vecN, 
   ea.tile_skip = ctx->dTileKs0;
   ea.tile_cls = ctx->dTileCls;
   ea.tile_b0 = ctx->dTileB0;
+  ea.tile_cb = ctx->dTileCb;
   ea.blk_ks_begin = ctx->dBlkKsBegin;
   ea.blk_scale = ctx->dBlkScale;
   ea.blk_src = ctx->dBlkSrc;
