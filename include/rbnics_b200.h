@@ -105,6 +105,12 @@ int rb_sweep(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta, int n_bc,
 int rb_sweep_parabolic(rb_ctx* ctx, int Qm, int K, double dt, const double* weights, double* max_val,
                        int64_t* max_idx, double* delta_out, double* eps2_out, double* u_out);
 
+/* ---- output functional of the solutions of the last sweep (testing-set sweeps of error_analysis / speedup_analysis,
+ * rbnics/reduction_methods/base/rb_reduction.py:312-390):  out[p] = u_p^T ( sum_q ThetaS[p][q] * S[q] ),
+ * rbnics/problems/elliptic/elliptic_reduced_problem.py:31-32 (_compute_output).  S: Qs x N, ThetaS: B x Qs (host),
+ * out: B (host).  Uses the solutions left on the device by rb_sweep / rb_sweep_resident.                          */
+int rb_compute_outputs(rb_ctx* ctx, int Qs, const double* S, const double* ThetaS, double* out);
+
 /* Device pointer to the 16-byte {double max_val; int64 max_idx} result of the last sweep (for a NCCL all-gather
  * issued by the host layer without a host round trip), and to the per-parameter estimators. */
 int rb_result_device_ptrs(rb_ctx* ctx, void** maxloc16, double** delta);

@@ -1480,6 +1480,51 @@ extern "C" int rb_sweep(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta
   return rb_sweep_resident(ctx, estimator_kind, max_val, max_idx, delta_out, u_out, eps2_out);
 }
 
+// out[p] = sum_q ThetaS[p][q] * (S[q] . u_p): one warp per parameter
+__global__ void __launch_bounds__(256) rb_outputs_kernel(const double* __restrict__ U, int ldu, int N, long long B, int Qs,
+                                                         const double* __restrict__ S, const double* __restrict__ ThetaS,
+                                                         double* __restrict__ out) {
+  const long long p = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= B) return;
+  double acc = 0.0;
+  for (int q = 0; q < Qs; ++q) {
+    double d = 0.0;
+    for (int i = lane; i < N; i += 32) d = fma(__ldg(S + q * N + i), U[p * ldu + i], d);
+    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+    acc = fma(ThetaS[p * Qs + q], d, acc);
+  }
+  if (lane == 0) out[p] = acc;
+}
+
+extern "C" int rb_compute_outputs(rb_ctx* ctx, int Qs, const double* S, const double* ThetaS, double* out) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->have_system || !ctx->have_train || !ctx->dU || ctx->N <= 0)
+    RB_FAIL(RB_ERR_STATE, "rb_compute_outputs: run a sweep first");
+  if (Qs <= 0 || !S || !ThetaS || !out) RB_FAIL(RB_ERR_ARG, "rb_compute_outputs: bad arguments");
+  const long long B = ctx->B;
+  const int N = ctx->N;
+  cudaStream_t st = ctx->stream;
+  double *dS = nullptr, *dT = nullptr, *dO = nullptr;
+  cudaError_t e = cudaMalloc(&dS, (size_t)Qs * N * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dT, (size_t)B * Qs * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dO, (size_t)B * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dS, S, (size_t)Qs * N * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dT, ThetaS, (size_t)B * Qs * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    rb_outputs_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, st>>>(ctx->dU, ctx->ldu, N, B, Qs, dS, dT, dO);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dO, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  for (double* q : {dS, dT, dO})
+    if (q) cudaFree(q);
+  if (e != cudaSuccess) RB_FAIL(RB_ERR_CUDA, std::string("rb_compute_outputs: ") + cudaGetErrorString(e));
+  ctx->last_launches = 1;
+  return RB_OK;
+}
+
 extern "C" int rb_result_device_ptrs(rb_ctx* ctx, void** maxloc16, double** delta) {
   if (!ctx) return RB_ERR_ARG;
   if (maxloc16) *maxloc16 = ctx->dResult;

@@ -155,6 +155,15 @@ class SweepEngine:
         return {"assemble_lu_ms": ms[0], "estimator_ms": ms[2], "finalize_ms": ms[3], "total_ms": ms[4],
                 "launches": n.value}
 
+    def compute_outputs(self, S, ThetaS):
+        """s_N(mu) = u(mu)^T sum_q theta_s_q(mu) s_q for the solutions of the last sweep (elliptic_reduced_problem.py:31-32)."""
+        S = _f64(S)
+        ThetaS = _f64(ThetaS, (self.B, S.shape[0]))
+        assert S.shape[1] == self.N
+        out = np.empty(self.B)
+        self._check(self._lib.rb_compute_outputs(self._h, S.shape[0], L.dptr(S), L.dptr(ThetaS), L.dptr(out)))
+        return out
+
     def estimator_work(self):
         """Multiply-adds per parameter issued by the estimator kernel (padding included) and its tile count."""
         m, n = C.c_int64(), C.c_int()

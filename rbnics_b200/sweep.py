@@ -157,3 +157,21 @@ class TrainingSetSweep:
         if want_delta:
             return v, i, r["delta"]
         return v, i
+
+
+class TestingSetSweep(TrainingSetSweep):
+    """Reduced solutions, error estimators and outputs for a whole testing set: the reduced-order half of
+    ``error_analysis`` / ``speedup_analysis`` (rbnics/reduction_methods/base/rb_reduction.py:312-390,478-580;
+    the truth solves they compare against stay with the reference)."""
+
+    __test__ = False  # not a pytest class
+
+    def evaluate(self, kind=L.RB_EST_SQRT_EPS2_OVER_BETA, S=None, ThetaS=None):
+        """-> dict(u (local B x N), delta, eps2[, output])  for this rank's shard (rows rank::size)."""
+        self._ensure_resident()
+        r = self.engine.sweep_resident(kind=kind, want_delta=True, want_u=True, want_eps2=True)
+        out = {"u": r["u"], "delta": r["delta"], "eps2": r["eps2"]}
+        if S is not None:
+            ThetaS = np.ascontiguousarray(np.asarray(ThetaS, dtype=np.float64)[self.rank::self.size])
+            out["output"] = self.engine.compute_outputs(S, ThetaS)
+        return out

@@ -113,3 +113,23 @@ def test_global_index_mapping_cyclic_shard(engine):
         if r["max"] > best[0] or (r["max"] == best[0] and r["argmax"] < best[1]):
             best = (r["max"], r["argmax"])
     assert best[1] == full[2]
+
+
+def test_testing_set_sweep_with_outputs(engine):
+    """error_analysis' reduced-order half: u, Delta and the output s_N = u^T sum theta_s s_q for a testing set
+    (rb_reduction.py:312-390, elliptic_reduced_problem.py:31-32)."""
+    from rbnics_b200.sweep import TestingSetSweep
+    N, Qa, Qf, Qs, B = 40, 4, 3, 2, 700
+    prob = synthetic.elliptic_reduced_problem(N, Qa, Qf, seed=8, riesz_rank=48)
+    Theta, beta, _ = synthetic.training_set(B, Qa, Qf, seed=3)
+    rng = np.random.default_rng(4)
+    S, ThetaS = rng.standard_normal((Qs, N)), rng.uniform(-1, 1, (B, Qs))
+    engine.set_system(prob["A"], prob["F"])
+    engine.set_elliptic_estimator(prob["Gff"], prob["Gaf"], prob["Gaa"])
+    r = TestingSetSweep(engine, Theta, beta).evaluate(S=S, ThetaS=ThetaS)
+    d_ref, U_ref, _, _ = O.sweep_batched(Theta[:, :Qa], Theta[:, Qa:], beta, prob["A"], prob["F"], prob["Gff"],
+                                         prob["Gaf"], prob["Gaa"])
+    s_ref = np.array([np.dot(U_ref[p], O.product_order1(tuple(ThetaS[p]), [S[q] for q in range(Qs)])) for p in range(B)])
+    assert np.max(np.abs(r["u"] - U_ref)) <= RTOL * np.max(np.abs(U_ref))
+    assert np.max(np.abs(r["delta"] - d_ref) / d_ref) <= RTOL
+    assert np.max(np.abs(r["output"] - s_ref)) <= RTOL * np.max(np.abs(s_ref))
