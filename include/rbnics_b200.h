@@ -166,6 +166,24 @@ int rb_lincomb(rb_ctx* ctx, int64_t Nh, int Ns, int n, const double* S, const do
 int rb_gram_schmidt(rb_ctx* ctx, int64_t Nh, int n, const double* Zb, const int64_t* indptr, const int32_t* indices,
                     const double* data, double* z, double* norm_out);
 
+/* ---- device-resident offline workspace -------------------------------------------------------------------------
+ * The reference rebuilds every reduced operator from the truth vectors at every greedy iteration
+ * (rbnics/reduction_methods/base/rb_reduction.py:106,112).  Here the sparse operators (X, A_q) and the dense column
+ * blocks (basis Z, snapshots S, Riesz representers) stay in HBM in numbered slots (0..31 each kind); only new columns
+ * cross PCIe.  Blocks are dof-major: Nh rows, up to `capacity` columns.                                            */
+int rb_off_csr(rb_ctx* ctx, int slot, int64_t Nh, const int64_t* indptr, const int32_t* indices, const double* data);
+int rb_off_block(rb_ctx* ctx, int slot, int64_t Nh, int capacity);             /* (re)create an empty block            */
+int rb_off_append(rb_ctx* ctx, int slot, int n, const double* cols);           /* cols: Nh x n row-major on the host   */
+int rb_off_size(rb_ctx* ctx, int slot, int64_t* Nh, int* ncols);
+int rb_off_read(rb_ctx* ctx, int slot, int c0, int n, double* out);            /* out: Nh x n row-major                */
+/* C (ns x ns2, host) = S[:, s0:s0+ns]^T X S2[:, t0:t0+ns2] over the dof rows [row_begin, row_end); csrX < 0: identity
+ * (rbnics/backends/basic/transpose.py:304-313, 441-468, 365-400).                                                  */
+int rb_off_gram(rb_ctx* ctx, int blkS, int s0, int ns, int csrX, int blkS2, int t0, int ns2, int64_t row_begin,
+                int64_t row_end, double* C);
+/* z (host, Nh, in/out) orthonormalised against ALL columns of block blkZ like rb_gram_schmidt; append != 0 also
+ * appends the result to the block (RBReduction.update_basis_matrix, rb_reduction.py:130-142).                       */
+int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, double* norm_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,20 @@ constexpr int ASM_BE = 64;   // matrix entries per CTA
 constexpr int LU_MAX_NP_REG = 104;  // largest padded N served by the register-resident LU
 constexpr int LU_MAX_NP = 160;      // largest padded N served at all (shared-memory fallback)
 
+// device-resident offline workspace (rb_off_*)
+constexpr int RB_OFF_SLOTS = 32;
+struct rb_off_csr_t {
+  long long* ip = nullptr;
+  int* ix = nullptr;
+  double* dt = nullptr;
+  long long Nh = 0, nnz = 0;
+};
+struct rb_off_blk_t {
+  double* d = nullptr;  // [Nh][cap] row-major (dof-major)
+  long long Nh = 0;
+  int cap = 0, n = 0;
+};
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Handle
 // ---------------------------------------------------------------------------------------------------------------------
@@ -77,6 +91,9 @@ struct rb_ctx {
   double* dBlkVal = nullptr; long long* dBlkIdx = nullptr; int blk_cap = 0;
   void* dResult = nullptr;           // {double val; int64 idx; int64 n_nonfinite}
   int* dSplitBegin = nullptr; int split_cap = 0;
+
+  rb_off_csr_t off_csr[RB_OFF_SLOTS];
+  rb_off_blk_t off_blk[RB_OFF_SLOTS];
 
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float last_ms[5] = {0, 0, 0, 0, 0};

@@ -166,7 +166,7 @@ struct DevBuf {
 };
 
 // C (host, ns x ns2) = S^T (X S2) over rows [rb, re); all operands already on the device.
-int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, const double* dS2,
+int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, int lds, const double* dS2, int ld2,
                 const long long* dIndptr, const int* dIndices, const double* dData, long long rb, long long re,
                 double* C_host, float* ms_spmm, float* ms_tsmm) {
   cudaStream_t st = ctx->stream;
@@ -195,15 +195,16 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, co
     const long long warps = (re - rb) * nchunk;
     const long long blocks = (warps * 32 + 255) / 256;
     if (blocks > 0) {
-      rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIndptr, dIndices, dData, dS2, ns2, ns2, Ybuf.as<double>(), ns2,
+      rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIndptr, dIndices, dData, dS2, ld2, ns2, Ybuf.as<double>(), ns2,
                                                       rb, re);
       RB_CUDA(cudaGetLastError());
     }
     dY = Ybuf.as<double>();
   }
+  const int ldy = dIndptr ? ns2 : ld2;
   RB_CUDA(cudaEventRecord(ctx->ev[5], st));
   dim3 grid(ti, tj, (unsigned)nsplit);
-  rb_tsmm_kernel<<<grid, TS_THREADS, smem, st>>>(dS, ns, ns, dY, ns2, ns2, rb, re, rps, ws.as<double>(), ldw);
+  rb_tsmm_kernel<<<grid, TS_THREADS, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw);
   RB_CUDA(cudaGetLastError());
   rb_split_reduce_kernel<<<(ns * ns2 + 255) / 256, 256, 0, st>>>(ws.as<double>(), ldw, (int)nsplit, ns, ns2,
                                                                  dC.as<double>());
@@ -253,7 +254,7 @@ extern "C" int rb_gram(rb_ctx* ctx, int64_t Nh, int Ns, int Ns2, const double* S
     RB_CUDA(cudaMemcpyAsync(dIx.p, indices, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, st));
     RB_CUDA(cudaMemcpyAsync(dDt.p, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, st));
   }
-  return gram_device(ctx, Nh, Ns, Ns2, dS.as<double>(), pS2, indptr ? dIp.as<long long>() : nullptr,
+  return gram_device(ctx, Nh, Ns, Ns2, dS.as<double>(), Ns, pS2, Ns2, indptr ? dIp.as<long long>() : nullptr,
                      indptr ? dIx.as<int>() : nullptr, indptr ? dDt.as<double>() : nullptr, row_begin, row_end, C,
                      nullptr, nullptr);
 }
@@ -278,7 +279,7 @@ extern "C" int rb_project(rb_ctx* ctx, int64_t Nh, int N, int Q, const double* Z
   float tot_a = 0, tot_b = 0;
   for (int q = 0; q < Q; ++q) {
     float a = 0, b = 0;
-    if (int rc = gram_device(ctx, Nh, N, N, dZ.as<double>(), dZ.as<double>(), dIp.as<long long>() + (size_t)q * (Nh + 1),
+    if (int rc = gram_device(ctx, Nh, N, N, dZ.as<double>(), N, dZ.as<double>(), N, dIp.as<long long>() + (size_t)q * (Nh + 1),
                              dIx.as<int>() + nnz_off[q], dDt.as<double>() + nnz_off[q], 0, Nh,
                              out + (size_t)q * N * N, &a, &b))
       return rc;
@@ -447,6 +448,49 @@ __global__ void __launch_bounds__(GS_THREADS) rb_normalize_kernel(const double* 
   }
 }
 
+namespace {
+// z (device, Nh) is orthonormalised in place against the n columns of dZ (row-major, pitch ldz) in the X inner
+// product (identity if dIp == nullptr): single-pass MGS, deterministic dots.  *launches is incremented.
+int gs_device(rb_ctx* ctx, long long Nh, int n, const double* dZ, int ldz, const long long* dIp, const int* dIx,
+              const double* dDt, double* dz, double* dNorm, int* launches) {
+  cudaStream_t st = ctx->stream;
+  DevBuf dXZ, dXz, dPart;
+  RB_CUDA(dPart.alloc(GS_BLOCKS * sizeof(double)));
+  const double* dXZp = dZ;
+  int ldxz = ldz;
+  if (dIp && n > 0) {
+    RB_CUDA(dXZ.alloc((size_t)Nh * n * sizeof(double)));
+    const int nchunk = (n + 127) / 128;
+    const long long blocks = (Nh * nchunk * 32 + 255) / 256;
+    rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIp, dIx, dDt, dZ, ldz, n, dXZ.as<double>(), n, 0, Nh);
+    RB_CUDA(cudaGetLastError());
+    dXZp = dXZ.as<double>();
+    ldxz = n;
+    ++*launches;
+  }
+  for (int k = 0; k < n; ++k) {
+    rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dz, 1, dXZp + k, ldxz, Nh, dPart.as<double>());
+    rb_axpy_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dPart.as<double>(), dZ + k, ldz, dz, Nh);
+    *launches += 2;
+  }
+  RB_CUDA(cudaGetLastError());
+  const double* dXzp = dz;
+  if (dIp) {
+    RB_CUDA(dXz.alloc((size_t)Nh * sizeof(double)));
+    const long long blocks = (Nh * 32 + 255) / 256;
+    rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIp, dIx, dDt, dz, 1, 1, dXz.as<double>(), 1, 0, Nh);
+    dXzp = dXz.as<double>();
+    ++*launches;
+  }
+  rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dz, 1, dXzp, 1, Nh, dPart.as<double>());
+  rb_normalize_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dPart.as<double>(), dz, Nh, dNorm);
+  *launches += 2;
+  RB_CUDA(cudaGetLastError());
+  RB_CUDA(cudaStreamSynchronize(st));  // the temporaries are freed on return
+  return RB_OK;
+}
+}  // namespace
+
 extern "C" int rb_gram_schmidt(rb_ctx* ctx, int64_t Nh, int n, const double* Zb, const int64_t* indptr,
                                const int32_t* indices, const double* data, double* z, double* norm_out) {
   if (!ctx) return RB_ERR_ARG;
@@ -454,9 +498,8 @@ extern "C" int rb_gram_schmidt(rb_ctx* ctx, int64_t Nh, int n, const double* Zb,
   if (Nh <= 0 || n < 0 || (n > 0 && !Zb) || !z) RB_FAIL(RB_ERR_ARG, "rb_gram_schmidt: bad arguments");
   if (indptr && (!indices || !data)) RB_FAIL(RB_ERR_ARG, "rb_gram_schmidt: CSR arrays incomplete");
   cudaStream_t st = ctx->stream;
-  DevBuf dZ, dXZ, dz, dXz, dIp, dIx, dDt, dPart, dNorm;
+  DevBuf dZ, dz, dIp, dIx, dDt, dNorm;
   RB_CUDA(dz.alloc((size_t)Nh * sizeof(double)));
-  RB_CUDA(dPart.alloc(GS_BLOCKS * sizeof(double)));
   RB_CUDA(dNorm.alloc(sizeof(double)));
   RB_CUDA(cudaMemcpyAsync(dz.p, z, (size_t)Nh * sizeof(double), cudaMemcpyHostToDevice, st));
   if (n > 0) {
@@ -473,40 +516,163 @@ extern "C" int rb_gram_schmidt(rb_ctx* ctx, int64_t Nh, int n, const double* Zb,
     RB_CUDA(cudaMemcpyAsync(dDt.p, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, st));
   }
   int launches = 0;
-  const double* dXZp = dZ.as<double>();
-  if (indptr && n > 0) {
-    RB_CUDA(dXZ.alloc((size_t)Nh * n * sizeof(double)));
-    const int nchunk = (n + 127) / 128;
-    const long long blocks = (Nh * nchunk * 32 + 255) / 256;
-    rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIp.as<long long>(), dIx.as<int>(), dDt.as<double>(),
-                                                    dZ.as<double>(), n, n, dXZ.as<double>(), n, 0, Nh);
-    RB_CUDA(cudaGetLastError());
-    dXZp = dXZ.as<double>();
-    ++launches;
-  }
-  for (int k = 0; k < n; ++k) {
-    rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dz.as<double>(), 1, dXZp + k, n, Nh, dPart.as<double>());
-    rb_axpy_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dPart.as<double>(), dZ.as<double>() + k, n, dz.as<double>(), Nh);
-    launches += 2;
-  }
-  RB_CUDA(cudaGetLastError());
-  const double* dXzp = dz.as<double>();
-  if (indptr) {
-    RB_CUDA(dXz.alloc((size_t)Nh * sizeof(double)));
-    const long long blocks = (Nh * 32 + 255) / 256;
-    rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIp.as<long long>(), dIx.as<int>(), dDt.as<double>(),
-                                                    dz.as<double>(), 1, 1, dXz.as<double>(), 1, 0, Nh);
-    dXzp = dXz.as<double>();
-    ++launches;
-  }
-  rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dz.as<double>(), 1, dXzp, 1, Nh, dPart.as<double>());
-  rb_normalize_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dPart.as<double>(), dz.as<double>(), Nh, dNorm.as<double>());
-  launches += 2;
-  RB_CUDA(cudaGetLastError());
+  if (int rc = gs_device(ctx, Nh, n, dZ.as<double>(), n, indptr ? dIp.as<long long>() : nullptr,
+                         indptr ? dIx.as<int>() : nullptr, indptr ? dDt.as<double>() : nullptr, dz.as<double>(),
+                         dNorm.as<double>(), &launches))
+    return rc;
   double nrm = 0.0;
   RB_CUDA(cudaMemcpyAsync(z, dz.p, (size_t)Nh * sizeof(double), cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaMemcpyAsync(&nrm, dNorm.p, sizeof(double), cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaStreamSynchronize(st));
+  if (norm_out) *norm_out = nrm;
+  ctx->last_launches = launches;
+  return RB_OK;
+}
+
+// =====================================================================================================================
+// Device-resident offline workspace: sparse operators and dense column blocks stay in HBM across greedy iterations,
+// only the new snapshot / basis function / Riesz representer crosses PCIe.
+// =====================================================================================================================
+static rb_off_csr_t* off_csr(rb_ctx* ctx, int slot) {
+  return (slot >= 0 && slot < RB_OFF_SLOTS && ctx->off_csr[slot].ip) ? &ctx->off_csr[slot] : nullptr;
+}
+static rb_off_blk_t* off_blk(rb_ctx* ctx, int slot) {
+  return (slot >= 0 && slot < RB_OFF_SLOTS && ctx->off_blk[slot].d) ? &ctx->off_blk[slot] : nullptr;
+}
+
+extern "C" int rb_off_csr(rb_ctx* ctx, int slot, int64_t Nh, const int64_t* indptr, const int32_t* indices,
+                          const double* data) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (slot < 0 || slot >= RB_OFF_SLOTS || Nh <= 0 || !indptr || !indices || !data) RB_FAIL(RB_ERR_ARG, "rb_off_csr: bad arguments");
+  rb_off_csr_t& c = ctx->off_csr[slot];
+  for (void* q : {(void*)c.ip, (void*)c.ix, (void*)c.dt})
+    if (q) cudaFree(q);
+  c = rb_off_csr_t();
+  const long long nnz = indptr[Nh];
+  RB_CUDA(cudaMalloc((void**)&c.ip, (size_t)(Nh + 1) * sizeof(long long)));
+  RB_CUDA(cudaMalloc((void**)&c.ix, (size_t)std::max<long long>(nnz, 1) * sizeof(int)));
+  RB_CUDA(cudaMalloc((void**)&c.dt, (size_t)std::max<long long>(nnz, 1) * sizeof(double)));
+  RB_CUDA(cudaMemcpy(c.ip, indptr, (size_t)(Nh + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(c.ix, indices, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice));
+  RB_CUDA(cudaMemcpy(c.dt, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice));
+  c.Nh = Nh;
+  c.nnz = nnz;
+  return RB_OK;
+}
+
+extern "C" int rb_off_block(rb_ctx* ctx, int slot, int64_t Nh, int capacity) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (slot < 0 || slot >= RB_OFF_SLOTS || Nh <= 0 || capacity <= 0) RB_FAIL(RB_ERR_ARG, "rb_off_block: bad arguments");
+  rb_off_blk_t& b = ctx->off_blk[slot];
+  if (b.d) cudaFree(b.d);
+  b = rb_off_blk_t();
+  RB_CUDA(cudaMalloc((void**)&b.d, (size_t)Nh * capacity * sizeof(double)));
+  RB_CUDA(cudaMemset(b.d, 0, (size_t)Nh * capacity * sizeof(double)));
+  b.Nh = Nh;
+  b.cap = capacity;
+  b.n = 0;
+  return RB_OK;
+}
+
+// dst[r * cap + c0 + j] = src[r * n + j]
+__global__ void rb_off_scatter_kernel(const double* __restrict__ src, int n, double* __restrict__ dst, int cap, int c0,
+                                      long long Nh) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= Nh * n) return;
+  dst[(t / n) * cap + c0 + (t % n)] = src[t];
+}
+__global__ void rb_off_gather_kernel(const double* __restrict__ src, int cap, int c0, int n, double* __restrict__ dst,
+                                     long long Nh) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= Nh * n) return;
+  dst[t] = src[(t / n) * cap + c0 + (t % n)];
+}
+
+extern "C" int rb_off_append(rb_ctx* ctx, int slot, int n, const double* cols) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  rb_off_blk_t* b = off_blk(ctx, slot);
+  if (!b || n <= 0 || !cols) RB_FAIL(RB_ERR_ARG, "rb_off_append: bad arguments");
+  if (b->n + n > b->cap) RB_FAIL(RB_ERR_ARG, "rb_off_append: block capacity exceeded");
+  DevBuf tmp;
+  RB_CUDA(tmp.alloc((size_t)b->Nh * n * sizeof(double)));
+  RB_CUDA(cudaMemcpyAsync(tmp.p, cols, (size_t)b->Nh * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  rb_off_scatter_kernel<<<(unsigned)((b->Nh * n + 255) / 256), 256, 0, ctx->stream>>>(tmp.as<double>(), n, b->d, b->cap,
+                                                                                     b->n, b->Nh);
+  RB_CUDA(cudaGetLastError());
+  RB_CUDA(cudaStreamSynchronize(ctx->stream));
+  b->n += n;
+  return RB_OK;
+}
+
+extern "C" int rb_off_size(rb_ctx* ctx, int slot, int64_t* Nh, int* ncols) {
+  if (!ctx) return RB_ERR_ARG;
+  rb_off_blk_t* b = off_blk(ctx, slot);
+  if (!b) RB_FAIL(RB_ERR_ARG, "rb_off_size: empty slot");
+  if (Nh) *Nh = b->Nh;
+  if (ncols) *ncols = b->n;
+  return RB_OK;
+}
+
+extern "C" int rb_off_read(rb_ctx* ctx, int slot, int c0, int n, double* out) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  rb_off_blk_t* b = off_blk(ctx, slot);
+  if (!b || c0 < 0 || n <= 0 || c0 + n > b->n || !out) RB_FAIL(RB_ERR_ARG, "rb_off_read: bad arguments");
+  DevBuf tmp;
+  RB_CUDA(tmp.alloc((size_t)b->Nh * n * sizeof(double)));
+  rb_off_gather_kernel<<<(unsigned)((b->Nh * n + 255) / 256), 256, 0, ctx->stream>>>(b->d, b->cap, c0, n, tmp.as<double>(),
+                                                                                    b->Nh);
+  RB_CUDA(cudaGetLastError());
+  RB_CUDA(cudaMemcpyAsync(out, tmp.p, (size_t)b->Nh * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  RB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RB_OK;
+}
+
+extern "C" int rb_off_gram(rb_ctx* ctx, int blkS, int s0, int ns, int csrX, int blkS2, int t0, int ns2,
+                           int64_t row_begin, int64_t row_end, double* C) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  rb_off_blk_t* S = off_blk(ctx, blkS);
+  rb_off_blk_t* S2 = off_blk(ctx, blkS2);
+  rb_off_csr_t* X = csrX >= 0 ? off_csr(ctx, csrX) : nullptr;
+  if (!S || !S2 || !C || (csrX >= 0 && !X)) RB_FAIL(RB_ERR_ARG, "rb_off_gram: empty slot");
+  if (S->Nh != S2->Nh || (X && X->Nh != S->Nh)) RB_FAIL(RB_ERR_ARG, "rb_off_gram: inconsistent number of dofs");
+  if (s0 < 0 || ns <= 0 || s0 + ns > S->n || t0 < 0 || ns2 <= 0 || t0 + ns2 > S2->n)
+    RB_FAIL(RB_ERR_ARG, "rb_off_gram: column range outside the block");
+  if (row_begin < 0 || row_end > S->Nh || row_begin > row_end) RB_FAIL(RB_ERR_ARG, "rb_off_gram: bad row range");
+  return gram_device(ctx, S->Nh, ns, ns2, S->d + s0, S->cap, S2->d + t0, S2->cap, X ? X->ip : nullptr,
+                     X ? X->ix : nullptr, X ? X->dt : nullptr, row_begin, row_end, C, nullptr, nullptr);
+}
+
+extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, double* norm_out) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  rb_off_blk_t* Z = off_blk(ctx, blkZ);
+  rb_off_csr_t* X = csrX >= 0 ? off_csr(ctx, csrX) : nullptr;
+  if (!Z || !z || (csrX >= 0 && !X)) RB_FAIL(RB_ERR_ARG, "rb_off_gram_schmidt: empty slot");
+  if (append && Z->n + 1 > Z->cap) RB_FAIL(RB_ERR_ARG, "rb_off_gram_schmidt: block capacity exceeded");
+  cudaStream_t st = ctx->stream;
+  DevBuf dz, dNorm;
+  RB_CUDA(dz.alloc((size_t)Z->Nh * sizeof(double)));
+  RB_CUDA(dNorm.alloc(sizeof(double)));
+  RB_CUDA(cudaMemcpyAsync(dz.p, z, (size_t)Z->Nh * sizeof(double), cudaMemcpyHostToDevice, st));
+  int launches = 0;
+  if (int rc = gs_device(ctx, Z->Nh, Z->n, Z->d, Z->cap, X ? X->ip : nullptr, X ? X->ix : nullptr, X ? X->dt : nullptr,
+                         dz.as<double>(), dNorm.as<double>(), &launches))
+    return rc;
+  if (append) {
+    rb_off_scatter_kernel<<<(unsigned)((Z->Nh + 255) / 256), 256, 0, st>>>(dz.as<double>(), 1, Z->d, Z->cap, Z->n, Z->Nh);
+    RB_CUDA(cudaGetLastError());
+    ++launches;
+  }
+  double nrm = 0.0;
+  RB_CUDA(cudaMemcpyAsync(z, dz.p, (size_t)Z->Nh * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaMemcpyAsync(&nrm, dNorm.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  if (append) Z->n += 1;
   if (norm_out) *norm_out = nrm;
   ctx->last_launches = launches;
   return RB_OK;

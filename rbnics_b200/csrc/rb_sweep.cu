@@ -698,6 +698,10 @@ extern "C" void rb_ctx_destroy(rb_ctx* ctx) {
                   ctx->dLuScratch};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (int t = 0; t < RB_OFF_SLOTS; ++t) {
+    for (void* p : {(void*)ctx->off_csr[t].ip, (void*)ctx->off_csr[t].ix, (void*)ctx->off_csr[t].dt, (void*)ctx->off_blk[t].d})
+      if (p) cudaFree(p);
+  }
   for (int i = 0; i < 6; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

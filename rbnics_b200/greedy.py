@@ -30,7 +30,7 @@ class ReducedBasisGreedy:
     product at every iteration (rb_reduction.py:106,112).  ``incremental=False`` is that full recomputation."""
 
     def __init__(self, engine, truth_problem, training_set, Nmax, tol, estimator_kind=L.RB_EST_SQRT_EPS2_OVER_BETA,
-                 dist=None, verbose=False, incremental=True):
+                 dist=None, verbose=False, incremental=True, resident=False):
         self.engine = engine
         self.truth_problem = truth_problem
         self.training_set = [tuple(mu) for mu in training_set]
@@ -40,6 +40,9 @@ class ReducedBasisGreedy:
         self.dist = dist
         self.verbose = verbose
         self.incremental = incremental
+        # resident=True keeps the truth operators, the basis and the Riesz representers in HBM (offline.OfflineWorkspace)
+        # and computes only the new rows / columns there: nothing but new vectors crosses PCIe
+        self.resident = resident
         tp = truth_problem
         self.Qa, self.Qf = len(tp.operators_a), len(tp.operators_f)
         self.Nh = tp.operators_f[0].shape[0]
@@ -57,6 +60,17 @@ class ReducedBasisGreedy:
         self.riesz_a = [np.zeros((self.Nh, 0)) for _ in range(self.Qa)]   # Nh x N each
         self.G = None
         self.GS = offline.GramSchmidt(engine, tp.inner_product)
+        self.ws = None
+        if resident:
+            ws = offline.OfflineWorkspace(engine, dist=dist)
+            ws.set_operator("X", tp.inner_product)
+            for q, A in enumerate(tp.operators_a):
+                ws.set_operator(f"A{q}", A)
+            ws.new_block("Z", self.Nh, Nmax + 1)
+            ws.new_block("F", self.Nh, self.Qf)
+            ws.append("F", np.stack([np.asarray(f, dtype=np.float64) for f in tp.operators_f], axis=1))
+            ws.new_block("R", self.Nh, self.Qa * (Nmax + 1) + self.Qf)   # Riesz representers: r_f first, then (n, q)
+            self.ws = ws
         self.greedy_selected_parameters = []
         self.greedy_selected_indices = []
         self.greedy_error_estimators = []
@@ -68,6 +82,18 @@ class ReducedBasisGreedy:
         if self.N == 0:
             self.operator_a = np.zeros((self.Qa, 0, 0))
             self.operator_f = np.zeros((self.Qf, 0))
+        elif self.resident:
+            ws, N = self.ws, self.N
+            A_new = np.zeros((self.Qa, N, N))
+            A_new[:, :N - 1, :N - 1] = self.operator_a
+            for q in range(self.Qa):
+                A_new[q, :, N - 1] = ws.gram("Z", f"A{q}", "Z", cols2=(N - 1, N))[:, 0]
+                A_new[q, N - 1, :] = ws.gram("Z", f"A{q}", "Z", cols=(N - 1, N))[0, :]
+            self.operator_a = A_new
+            f_new = np.zeros((self.Qf, N))
+            f_new[:, :N - 1] = self.operator_f
+            f_new[:, N - 1] = ws.gram("Z", None, "F", cols=(N - 1, N))[0, :]
+            self.operator_f = f_new
         elif self.incremental and self.operator_a.shape[1] == self.N - 1:
             # only the new row and column: A^N[:, N-1] = Z^T (A_q z), A^N[N-1, :] = z^T (A_q Z); Z is unchanged for the
             # first N-1 functions because the Gram-Schmidt step never modifies earlier basis functions
@@ -93,6 +119,8 @@ class ReducedBasisGreedy:
     # -- reduced_problem.build_error_estimation_operators() ------------------------------------------------------
     def build_error_estimation_operators(self):
         tp = self.truth_problem
+        if self.resident:
+            return self._build_error_estimation_operators_resident()
         if self.riesz_f is None:   # does not depend on N: computed once (rb_reduced_problem.py:156-163)
             self.riesz_f = np.stack([tp.riesz_solve(f) for f in tp.operators_f], axis=1)
         for q in range(self.Qa):   # Riesz representers of -A_q z_n for the new basis functions (:183-195)
@@ -123,6 +151,36 @@ class ReducedBasisGreedy:
             scale, src, length = [-1], [0], [Qf]
         self.engine.set_estimator(scale, src, length, Qa, Qf, self.G)
 
+    def _build_error_estimation_operators_resident(self):
+        """Same Gram blocks from the device-resident Riesz block R = [r_f | (n=0: q=0..Qa-1) | (n=1: ...) | ...]: only
+        the Qa new representers are uploaded, only their rows of the Gram matrix are computed."""
+        tp, ws = self.truth_problem, self.ws
+        N, Qa, Qf = self.N, self.Qa, self.Qf
+        if ws.ncols("R") == 0:
+            ws.append("R", np.stack([tp.riesz_solve(f) for f in tp.operators_f], axis=1))
+            self._Gr = ws.gram("R", "X")                      # (Qf x Qf) in R-order
+        have = (ws.ncols("R") - Qf) // Qa
+        for n in range(have, N):
+            zn = self.basis_functions[:, n]
+            ws.append("R", np.stack([tp.riesz_solve(-(tp.operators_a[q] @ zn)) for q in range(Qa)], axis=1))
+            c0 = Qf + n * Qa
+            rows = ws.gram("R", "X", "R", cols=(c0, c0 + Qa))  # new representers against everything so far
+            G = np.empty((c0 + Qa, c0 + Qa))
+            G[:c0, :c0] = self._Gr
+            G[c0:, :] = rows
+            G[:, c0:] = rows.T
+            self._Gr = G
+        # R-order -> z-order [(q, n) ... | f]
+        perm = [Qf + n * Qa + q for q in range(Qa) for n in range(N)] + list(range(Qf))
+        self.G = self._Gr[np.ix_(perm, perm)]
+        if N > 0:
+            scale = list(range(Qa)) + [-1]
+            src = [0] * Qa + [N]
+            length = [N] * Qa + [Qf]
+        else:
+            scale, src, length = [-1], [0], [Qf]
+        self.engine.set_estimator(scale, src, length, Qa, Qf, self.G)
+
     # -- RBReduction.greedy / _greedy ----------------------------------------------------------------------------
     def _greedy(self):
         return self._sweep.max(kind=self.kind)
@@ -136,7 +194,10 @@ class ReducedBasisGreedy:
         return (error_estimator_max, error_estimator_max / self.greedy_error_estimators[0])
 
     def update_basis_matrix(self, snapshot):
-        new_basis_function = self.GS.apply(snapshot, self.basis_functions)
+        if self.resident:
+            new_basis_function, _ = self.ws.gram_schmidt("Z", "X", snapshot, append=True)
+        else:
+            new_basis_function = self.GS.apply(snapshot, self.basis_functions)
         self.basis_functions = np.concatenate([self.basis_functions, new_basis_function[:, None]], axis=1)
         self.N += 1
 

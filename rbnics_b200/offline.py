@@ -185,3 +185,82 @@ class GramSchmidt:
         self.engine._check(self.engine._lib.rb_gram_schmidt(self.engine._h, Nh, n, L.dptr(Zb) if n else None, *args,
                                                             L.dptr(z), C.byref(norm)))
         return z
+
+
+class OfflineWorkspace:
+    """Device-resident truth-space data of one greedy run (C ABI ``rb_off_*``): named sparse operators and named dense
+    column blocks (basis functions, snapshots, Riesz representers) stay in HBM; every product below runs on them
+    without re-uploading anything but new columns.  The reference rebuilds all reduced operators from host/PETSc
+    vectors at every iteration (rbnics/reduction_methods/base/rb_reduction.py:106,112)."""
+
+    SLOTS = 32
+
+    def __init__(self, engine, dist=None):
+        self.engine = engine
+        self.dist = dist
+        self._csr = {}
+        self._blk = {}
+        self.Nh = None
+
+    def _slot(self, table, name):
+        if name not in table:
+            if len(table) >= self.SLOTS:
+                raise ValueError("OfflineWorkspace: out of slots")
+            table[name] = len(table)
+        return table[name]
+
+    def set_operator(self, name, X):
+        ip, ix, dt = _csr_arrays(X)
+        e = self.engine
+        e._check(e._lib.rb_off_csr(e._h, self._slot(self._csr, name), X.shape[0], ip.ctypes.data_as(L.c_int64_p),
+                                   ix.ctypes.data_as(L.c_int32_p), L.dptr(dt)))
+        self.Nh = X.shape[0]
+
+    def new_block(self, name, Nh, capacity):
+        e = self.engine
+        e._check(e._lib.rb_off_block(e._h, self._slot(self._blk, name), int(Nh), int(capacity)))
+        self.Nh = int(Nh)
+
+    def ncols(self, name):
+        e = self.engine
+        nh, n = C.c_int64(), C.c_int()
+        e._check(e._lib.rb_off_size(e._h, self._blk[name], C.byref(nh), C.byref(n)))
+        return n.value
+
+    def append(self, name, cols):
+        cols = np.asarray(cols, dtype=np.float64)
+        if cols.ndim == 1:
+            cols = cols[:, None]
+        cols = np.ascontiguousarray(cols)
+        e = self.engine
+        e._check(e._lib.rb_off_append(e._h, self._blk[name], cols.shape[1], L.dptr(cols)))
+
+    def read(self, name, c0=0, n=None):
+        n = self.ncols(name) - c0 if n is None else n
+        out = np.empty((self.Nh, n))
+        e = self.engine
+        e._check(e._lib.rb_off_read(e._h, self._blk[name], int(c0), int(n), L.dptr(out)))
+        return out
+
+    def gram(self, S, X=None, S2=None, cols=None, cols2=None):
+        """C = S[:, cols]^T X S2[:, cols2]; S, S2 block names, X operator name or None (identity); cols = (begin, end)."""
+        S2 = S if S2 is None else S2
+        s0, s1 = cols if cols is not None else (0, self.ncols(S))
+        t0, t1 = cols2 if cols2 is not None else (0, self.ncols(S2))
+        Cm = np.empty((s1 - s0, t1 - t0))
+        rb, re = _dist_range(self.Nh, self.dist)
+        e = self.engine
+        e._check(e._lib.rb_off_gram(e._h, self._blk[S], int(s0), int(s1 - s0), self._csr[X] if X is not None else -1,
+                                    self._blk[S2], int(t0), int(t1 - t0), rb, re, L.dptr(Cm)))
+        if self.dist is not None and self.dist.size > 1:
+            self.dist.allreduce_sum_(Cm)
+        return Cm
+
+    def gram_schmidt(self, Z, X, new_function, append=True):
+        """Orthonormalise ``new_function`` against the columns of block Z (X inner product); optionally append it."""
+        z = np.ascontiguousarray(new_function, dtype=np.float64).copy()
+        norm = C.c_double()
+        e = self.engine
+        e._check(e._lib.rb_off_gram_schmidt(e._h, self._blk[Z], self._csr[X] if X is not None else -1, L.dptr(z),
+                                            1 if append else 0, C.byref(norm)))
+        return z, norm.value

@@ -53,3 +53,20 @@ def test_incremental_offline_updates_equal_full_recomputation(engine):
     assert np.max(np.abs(inc.G - full.G)) <= 1e-11 * np.max(np.abs(full.G))
     e1, e2 = np.array(inc.greedy_error_estimators), np.array(full.greedy_error_estimators)
     assert np.max(np.abs(e1 - e2) / e2) <= 1e-6
+
+
+def test_device_resident_offline_workspace_equals_host_path(engine):
+    """rb_off_*: operators, basis and Riesz representers resident in HBM; same reduced operators, estimator operators
+    and greedy sequence as the upload-every-call path."""
+    tp = ThermalBlock(n=14, nblocks=3, nloads=2)
+    train = tp.sample_training_set(200, seed=2)
+    res = ReducedBasisGreedy(engine, tp, train, Nmax=6, tol=1e-6, resident=True).offline()
+    host = ReducedBasisGreedy(engine, tp, train, Nmax=6, tol=1e-6, incremental=False).offline()
+    assert res.greedy_selected_indices == host.greedy_selected_indices
+    assert res.N == host.N and res.N >= 4
+    assert np.max(np.abs(res.basis_functions - host.basis_functions)) <= 1e-12 * np.max(np.abs(host.basis_functions))
+    assert np.max(np.abs(res.operator_a - host.operator_a)) <= 1e-12 * np.max(np.abs(host.operator_a))
+    assert np.max(np.abs(res.operator_f - host.operator_f)) <= 1e-12 * np.max(np.abs(host.operator_f))
+    assert np.max(np.abs(res.G - host.G)) <= 1e-11 * np.max(np.abs(host.G))
+    Z = res.ws.read("Z")
+    assert Z.shape == res.basis_functions.shape and np.array_equal(Z, res.basis_functions)
