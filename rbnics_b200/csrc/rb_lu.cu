@@ -14,7 +14,9 @@ long long rb_lu_left_scratch_doubles(int N);
 // Which kernel serves 32 < N (A/B switch for profiling): "left" (default; one warp per system, left-looking, L records
 // streamed from L2, 8 systems per SM), "dmma" (register-resident, 2 systems per SM), "rowreg" (row per thread).
 // Two right-looking variants that kept the trailing matrix in global memory (thread-per-row and warp-per-system with
-// DMMA updates) were measured at the same 0.27 us/system as "dmma" (read-modify-write latency through L2) and removed.
+// DMMA updates) were measured at the same 0.27 us/system as "dmma" (read-modify-write latency through L2) and removed;
+// so was a two-warps-per-system variant of "left" (rows / tile rows split between the warps, one block barrier per pivot
+// step): 7 % slower than one warp per system, the barriers cost more than the shorter chain saves.
 int rb_lu_variant() {
   static const int v = [] {
     const char* e = getenv("RB_LU_KERNEL");
