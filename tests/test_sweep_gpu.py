@@ -133,3 +133,16 @@ def test_testing_set_sweep_with_outputs(engine):
     assert np.max(np.abs(r["u"] - U_ref)) <= RTOL * np.max(np.abs(U_ref))
     assert np.max(np.abs(r["delta"] - d_ref) / d_ref) <= RTOL
     assert np.max(np.abs(r["output"] - s_ref)) <= RTOL * np.max(np.abs(s_ref))
+
+
+@pytest.mark.parametrize("N,Qa,Qf,B", [(1, 1, 1, 1), (2, 1, 1, 3), (3, 2, 1, 129), (5, 1, 2, 127), (31, 3, 1, 257),
+                                        (32, 2, 2, 1), (33, 2, 1, 1), (128, 2, 1, 130)])
+def test_sweep_edge_shapes(engine, N, Qa, Qf, B):
+    """Smallest / ragged shapes: N = 1..3, a single parameter, batch sizes around the 128-row tile, the kernel
+    switch-over points N = 32 / 33 and the largest register-panel size N = 128."""
+    prob = synthetic.elliptic_reduced_problem(N, Qa, Qf, seed=N + B, riesz_rank=16)
+    Theta, beta, _ = synthetic.training_set(B, Qa, Qf, seed=N)
+    res = _run(engine, prob, Theta, beta)
+    ref = O.sweep_batched(Theta[:, :Qa], Theta[:, Qa:], beta, prob["A"], prob["F"], prob["Gff"], prob["Gaf"],
+                          prob["Gaa"], return_eps2=True)
+    _check(res, ref, N)
