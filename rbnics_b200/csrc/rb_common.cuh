@@ -130,6 +130,13 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
       : "d"(a), "d"(b));
 }
 
+// D = A*B (zero C operand): starts an accumulation without a separate clearing pass over the accumulator registers
+__device__ __forceinline__ void dmma884_init(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};"
+      : "=d"(c0), "=d"(c1)
+      : "d"(a), "d"(b), "d"(0.0));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -235,14 +235,24 @@ __device__ __forceinline__ void est_load_frag(EstFrag<NTN>& f, const double* gs,
 // HEAD: only the first 8-column tile of every 16-column range (the second one is structurally zero in the first two
 // k-steps of a folded block: columns m >= 16r+8 against rows n < 16r+8).
 // FIRST_ONLY: only the warp's first 16-column range (the block of its second range lies below this row block).
-template <int NTN, bool HEAD = false, bool FIRST_ONLY = false>
+// INIT: 1 = every accumulator this call touches starts from zero (D = A*B), 2 = only the odd 8-column tiles do
+// (the even ones were started by the HEAD steps), 0 = accumulate.
+template <int NTN, bool HEAD = false, bool FIRST_ONLY = false, int INIT = 0>
 __device__ __forceinline__ void est_mma(double (&T)[4][NTN][2], const EstFrag<NTN>& f) {
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
 #pragma unroll
     for (int h = 0; h < (FIRST_ONLY ? 1 : NTN / 2); ++h) {
-      dmma884(T[mt][2 * h][0], T[mt][2 * h][1], f.a[mt], f.b[h].x);
-      if (!HEAD) dmma884(T[mt][2 * h + 1][0], T[mt][2 * h + 1][1], f.a[mt], f.b[h].y);
+      if (INIT == 1)
+        dmma884_init(T[mt][2 * h][0], T[mt][2 * h][1], f.a[mt], f.b[h].x);
+      else
+        dmma884(T[mt][2 * h][0], T[mt][2 * h][1], f.a[mt], f.b[h].x);
+      if (!HEAD) {
+        if (INIT != 0)
+          dmma884_init(T[mt][2 * h + 1][0], T[mt][2 * h + 1][1], f.a[mt], f.b[h].y);
+        else
+          dmma884(T[mt][2 * h + 1][0], T[mt][2 * h + 1][1], f.a[mt], f.b[h].y);
+      }
     }
   }
 }
@@ -360,28 +370,46 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
   const int r0 = wm * 32 + g;  // + mt*8
   const double* vrow = Vs + r0 * LVS + q4;
   const double* gsw = Gs + wn * (32 * NTN) + lane * 2;
-  const double* th_base = a.theta;
-  long long prow[4];
+  const double* thp[4];  // theta rows of this thread's four parameters
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) prow[mt] = min(p0 + r0 + mt * 8, a.B - 1) * a.QT;
+  for (int mt = 0; mt < 4; ++mt) thp[mt] = a.theta + min(p0 + r0 + mt * 8, a.B - 1) * a.QT;
   double rowacc[4] = {0.0, 0.0, 0.0, 0.0};
   int stage = 0;
   uint32_t phase = 0;
 
+  double T[4][NTN][2];  // accumulator of the current block
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NTN; ++nt) T[mt][nt][0] = T[mt][nt][1] = 0.0;
+
   for (int ct = ct_begin; ct < ct_end; ++ct) {
-    double Y[4][NTN][2], T[4][NTN][2];
+    double Y[4][NTN][2];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < NTN; ++nt) Y[mt][nt][0] = Y[mt][nt][1] = T[mt][nt][0] = T[mt][nt][1] = 0.0;
+      for (int nt = 0; nt < NTN; ++nt) Y[mt][nt][0] = Y[mt][nt][1] = 0.0;
 
+    const int tcls = s_tile_cls[ct], tskip = s_tile_skip[ct];
+    const int cb0 = s_tile_cb[4 * ct + 2 * wn], cb1 = s_tile_cb[4 * ct + 2 * wn + 1];
+    auto first_ks = [&](int bb) { return s_ks_begin[bb] + ((s_cls[bb] == tcls) ? tskip : 0); };
     int b = s_tile_b0[ct];
-    int ks = blk_first_ks(ct, b);
+    int ks = first_ks(b);
     int kend = s_ks_begin[b + 1];
     const int src = s_src[b] + 4 * (ks - s_ks_begin[b]);
     int kin = 0;                   // k-step within the current stage
-    bool tri_head = a.tri16 && (s_cls[b] == s_tile_cls[ct]);  // the next segment starts a folded block
-    int nvalid = (b >= s_tile_cb[4 * ct + 2 * wn]) + (b >= s_tile_cb[4 * ct + 2 * wn + 1]);  // ranges with data
+    bool tri_head = a.tri16 && (s_cls[b] == tcls);  // the next segment starts a folded block
+    int nvalid = (b >= cb0) + (b >= cb1);           // ranges with data
+    // fresh: T holds the (already folded) sums of the previous block; the first k-step of the block overwrites it
+    // with D = A*B instead of a clearing pass.  Partially empty ranges (nvalid < 2) clear T explicitly instead.
+    int fresh = 1;
+    if (nvalid < 2) {
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTN; ++nt) T[mt][nt][0] = T[mt][nt][1] = 0.0;
+      fresh = 0;
+    }
     int nin = min(SK, kend - ks);  // k-steps held by the current stage (a stage never crosses a block boundary)
     double th[4], thn[4];
     {
@@ -389,8 +417,8 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
       const int scn = (b + 1 < a.nblk) ? s_scale[b + 1] : -1;
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
-        th[mt] = (sc < 0) ? 1.0 : __ldg(th_base + prow[mt] + sc);
-        thn[mt] = (scn < 0) ? 1.0 : __ldg(th_base + prow[mt] + scn);
+        th[mt] = (sc < 0) ? 1.0 : __ldg(thp[mt] + sc);
+        thn[mt] = (scn < 0) ? 1.0 : __ldg(thp[mt] + scn);
       }
     }
     mbar_wait(full_bar + stage, phase);
@@ -416,8 +444,9 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
         }
         if (nvalid == 1) est_mma<NTN, false, true>(T, f0);
       } else {
-      if (tri_head && i > 2) {  // first two k-steps of a folded block: half of the column tiles are zero
-        est_mma<NTN, true>(T, f0);
+      int init_last = fresh;    // how the last k-step of the segment starts T if no earlier k-step did
+      if (tri_head && i > 2) {  // first two k-steps of a folded block (fresh): half of the column tiles are zero
+        est_mma<NTN, true, false, 1>(T, f0);
         gp += EST_KSTEP_DOUBLES;
         vp += 4;
         est_load_frag(f0, gp, vp, LVS);
@@ -426,6 +455,22 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
         vp += 4;
         est_load_frag(f0, gp, vp, LVS);
         i -= 2;
+        init_last = 2;
+        if (i > 1) {
+          est_mma<NTN, false, false, 2>(T, f0);
+          gp += EST_KSTEP_DOUBLES;
+          vp += 4;
+          est_load_frag(f0, gp, vp, LVS);
+          --i;
+          init_last = 0;
+        }
+      } else if (fresh && i > 1) {
+        est_mma<NTN, false, false, 1>(T, f0);
+        gp += EST_KSTEP_DOUBLES;
+        vp += 4;
+        est_load_frag(f0, gp, vp, LVS);
+        --i;
+        init_last = 0;
       }
       while (i > 2) {  // steady state, two k-steps per trip (ping-pong fragment buffers)
         est_mma(T, f0);
@@ -442,7 +487,14 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
         vp += 4;
         est_load_frag(f0, gp, vp, LVS);
       }
-      est_mma(T, f0);  // last k-step of the segment; its successor is loaded after the boundary bookkeeping
+      // last k-step of the segment; its successor is loaded after the boundary bookkeeping
+      if (init_last == 0)
+        est_mma(T, f0);
+      else if (init_last == 1)
+        est_mma<NTN, false, false, 1>(T, f0);
+      else
+        est_mma<NTN, false, false, 2>(T, f0);
+      fresh = 0;
       }
       ks += nseg;
       kin += nseg;
@@ -453,9 +505,9 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
       tri_head = false;
       if (blk_done && !tile_done) {
         ++b;
-        nvalid = (b >= s_tile_cb[4 * ct + 2 * wn]) + (b >= s_tile_cb[4 * ct + 2 * wn + 1]);
-        tri_head = a.tri16 && (s_cls[b] == s_tile_cls[ct]);
-        ks = blk_first_ks(ct, b);
+        nvalid = (b >= cb0) + (b >= cb1);
+        tri_head = a.tri16 && (s_cls[b] == tcls);
+        ks = first_ks(b);
         kend = s_ks_begin[b + 1];
         vp = vrow + s_src[b] + 4 * (ks - s_ks_begin[b]);
       }
@@ -486,15 +538,21 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
           for (int nt = 0; nt < NTN; ++nt) {
             Y[mt][nt][0] = fma(th[mt], T[mt][nt][0], Y[mt][nt][0]);
             Y[mt][nt][1] = fma(th[mt], T[mt][nt][1], Y[mt][nt][1]);
-            T[mt][nt][0] = 0.0;
-            T[mt][nt][1] = 0.0;
           }
           th[mt] = thn[mt];
         }
         if (!tile_done) {
           const int scn = (b + 1 < a.nblk) ? s_scale[b + 1] : -1;
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt) thn[mt] = (scn < 0) ? 1.0 : __ldg(th_base + prow[mt] + scn);
+          for (int mt = 0; mt < 4; ++mt) thn[mt] = (scn < 0) ? 1.0 : __ldg(thp[mt] + scn);
+          fresh = 1;
+          if (nvalid < 2) {  // (nvalid already describes the next block)
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+              for (int nt = 0; nt < NTN; ++nt) T[mt][nt][0] = T[mt][nt][1] = 0.0;
+            fresh = 0;
+          }
         }
       }
       if (tile_done) break;
@@ -511,7 +569,7 @@ __global__ void __launch_bounds__(32 * 4 * (8 / NTN), 1) rb_estimator_kernel(Est
         const int csr = __ldg(a.col_src + c);
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
-          const double thc = (csc < 0) ? 1.0 : __ldg(th_base + prow[mt] + csc);
+          const double thc = (csc < 0) ? 1.0 : __ldg(thp[mt] + csc);
           const double zc = thc * Vs[(r0 + mt * 8) * LVS + csr];
           rowacc[mt] = fma(Y[mt][nt][e], zc, rowacc[mt]);
         }
