@@ -31,11 +31,13 @@ struct rb_off_csr_t {
   int* ix = nullptr;
   double* dt = nullptr;
   long long Nh = 0, nnz = 0;
+  int sym = 0;  // 1 if the matrix equals its transpose entry by entry (checked on the device at upload)
 };
 struct rb_off_blk_t {
-  double* d = nullptr;  // [Nh][cap] row-major (dof-major)
+  double* d = nullptr;  // [Nh][ld] row-major (dof-major)
   long long Nh = 0;
   int cap = 0, n = 0;
+  int ld = 0;             // row pitch: cap rounded up to an even count (16-byte aligned rows for the bulk copies)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------

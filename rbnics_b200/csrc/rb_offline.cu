@@ -139,19 +139,194 @@ __global__ void __launch_bounds__(TS_THREADS) rb_tsmm_kernel(const double* __res
   }
 }
 
-__global__ void rb_split_reduce_kernel(const double* __restrict__ ws, int ldw, int nsplit, int ns, int ns2,
-                                       double* __restrict__ C) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ns * ns2) return;
-  const int i = t / ns2, j = t % ns2;
+// ---------------------------------------------------------------------------------------------------------------------
+// Second generation of the same product for 16-byte aligned operands (even pitches): TM x TM tile per CTA
+// ((TM/32)^2 warps of 32 x 32), rows of S and Y brought in by 1-D bulk copies (TMA engine) into a 3-stage ring of
+// 32-row chunks with padded rows (pitch == 4 mod 16: conflict-free fragment loads); the warp that is last to release
+// a stage refills it, so there is no producer warp.  Warps whose 32 x 32 tile lies outside ns x ns2 retire at once.
+// Per DMMA k-step a 128 x 128 tile moves 8 KB from L2 for 256 DMMAs (a 64 x 64 tile: 4 KB for 64).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int T2_KC = 32, T2_NST = 3;
+
+template <int TM>
+__global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
+    rb_tsmm2_kernel(const double* __restrict__ S, int lds, int ns, const double* __restrict__ Y, int ldy, int ns2,
+                    long long row_begin, long long row_end, long long rows_per_split, double* __restrict__ ws, int ldw,
+                    int sym) {
+  constexpr int WM = TM / 32, P = TM + 4;
+  if (sym && blockIdx.y < blockIdx.x) return;  // C == C^T: tiles below the diagonal are mirrored by the reduction
+  extern __shared__ __align__(128) unsigned char t2_smem[];
+  double* As = reinterpret_cast<double*>(t2_smem);               // [NST][KC][P]
+  double* Bs = As + T2_NST * T2_KC * P;                          // [NST][KC][P]
+  uint64_t* full = reinterpret_cast<uint64_t*>(Bs + T2_NST * T2_KC * P);
+  int* cnt = reinterpret_cast<int*>(full + T2_NST);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp / WM, wn = (warp + wm) % WM;  // rotated so that a single active row or column of warps still
+                                                    // spreads over the four SM sub-partitions
+  // rows of the tile grid are TM wide (the last one narrower); its columns deal the ceil(ns2/32) warp columns out
+  // evenly (4,3,3,3 rather than 4,4,4,1), which keeps am*an a multiple of 4 in most tiles -- a CTA takes as long as
+  // its busiest SM sub-partition.  The symmetric variant needs the same cut in both directions.
+  const int i0 = blockIdx.x * TM;
+  const int am = min(WM, (ns - i0 + 31) / 32);
+  int j0, an;
+  if (sym) {
+    j0 = blockIdx.y * TM;
+    an = min(WM, (ns2 - j0 + 31) / 32);
+  } else {
+    const int Wb = (ns2 + 31) / 32, Tb = gridDim.y, bb = Wb / Tb, rbm = Wb % Tb, tb = blockIdx.y;
+    an = bb + (tb < rbm);
+    j0 = 32 * (tb * bb + min(tb, rbm));
+  }
+  const int split = blockIdx.z;
+  const long long rs = row_begin + split * rows_per_split;
+  const long long re = min(row_end, rs + rows_per_split);
+  const int nchunks = (int)((re - rs + T2_KC - 1) / T2_KC);
+  const int nactive = am * an;
+  const int wa = min(am * 32, ((ns + 1) & ~1) - i0), wb = min(an * 32, ((ns2 + 1) & ~1) - j0);  // columns copied per row
+  if (tid == 0) {
+    for (int s = 0; s < T2_NST; ++s) {
+      mbar_init(full + s, 1);
+      cnt[s] = 0;
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (wm >= am || wn >= an) return;
+
+  auto issue = [&](int st, int c) {  // executed by one whole warp: lane l brings row l of the chunk
+    const long long r0 = rs + (long long)c * T2_KC;
+    const int nrows = (int)min((long long)T2_KC, re - r0);
+    double* as = As + (st * T2_KC + lane) * P;
+    double* bs = Bs + (st * T2_KC + lane) * P;
+    if (lane >= nrows) {  // rows past the end of the split count as zeros
+      for (int c2 = 0; c2 < TM; ++c2) as[c2] = bs[c2] = 0.0;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_expect_tx(full + st, (uint32_t)nrows * (uint32_t)(wa + wb) * 8u);
+    __syncwarp();
+    if (lane < nrows) {
+      bulk_g2s(as, S + (r0 + lane) * lds + i0, (uint32_t)wa * 8u, full + st);
+      bulk_g2s(bs, Y + (r0 + lane) * ldy + j0, (uint32_t)wb * 8u, full + st);
+    }
+  };
+  if (warp == 0) {
+    for (int s = 0; s < T2_NST && s < nchunks; ++s) issue(s, s);
+  }
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  const int g = lane >> 2, q4 = lane & 3;
+  const int aoff = q4 * P + wm * 32 + g, boff = q4 * P + wn * 32 + g;
+  int st = 0;
+  uint32_t phase = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    mbar_wait(full + st, phase);
+    const double* as = As + st * T2_KC * P + aoff;
+    const double* bs = Bs + st * T2_KC * P + boff;
+#pragma unroll
+    for (int ks = 0; ks < T2_KC / 4; ++ks) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) af[mt] = as[4 * ks * P + mt * 8];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) bf[nt] = bs[4 * ks * P + nt * 8];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    }
+    __syncwarp();
+    int old = 0;
+    if (lane == 0) old = atomicAdd(&cnt[st], 1);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old == nactive - 1) {  // last warp out refills the slot
+      if (lane == 0) cnt[st] = 0;
+      if (c + T2_NST < nchunks) issue(st, c + T2_NST);
+    }
+    if (++st == T2_NST) {
+      st = 0;
+      phase ^= 1u;
+    }
+  }
+  double* w = ws + (long long)split * ldw * ldw;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const int i = i0 + wm * 32 + mt * 8 + g;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int j = j0 + wn * 32 + nt * 8 + q4 * 2;
+      *reinterpret_cast<double2*>(w + (long long)i * ldw + j) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+    }
+  }
+}
+
+// C[i][j] = sum over splits, in a fixed order that depends on nsplit only (deterministic): four quarter sums of
+// consecutive splits, then their sum.  256 threads = 64 entries x 4 quarters.
+__global__ void __launch_bounds__(256) rb_split_reduce_kernel(const double* __restrict__ ws, int ldw, int nsplit,
+                                                              int ns, int ns2, double* __restrict__ C,
+                                                              int sym_tm) {
+  __shared__ double part[4][64];
+  const int e = blockIdx.x * 64 + (threadIdx.x & 63), quarter = threadIdx.x >> 6;
+  const int per = (nsplit + 3) / 4;
+  const int k0 = quarter * per, k1 = min(nsplit, k0 + per);
   double s = 0.0;
-  for (int k = 0; k < nsplit; ++k) s += ws[(long long)k * ldw * ldw + (long long)i * ldw + j];
-  C[t] = s;
+  if (e < ns * ns2) {
+    int i = e / ns2, j = e % ns2;
+    if (sym_tm && j / sym_tm < i / sym_tm) {  // tile below the diagonal: take the mirrored entry
+      const int t = i;
+      i = j;
+      j = t;
+    }
+    const double* w = ws + (long long)i * ldw + j;
+    const long long stride = (long long)ldw * ldw;
+    int k = k0;
+    for (; k + 8 <= k1; k += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(w + (k + u) * stride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; k < k1; ++k) s += __ldg(w + k * stride);
+  }
+  part[quarter][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (quarter == 0 && e < ns * ns2) C[e] = ((part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x]) + part[3][threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Host
 // ---------------------------------------------------------------------------------------------------------------------
+__global__ void rb_csr_symmetric_kernel(const long long* __restrict__ ip, const int* __restrict__ ix,
+                                        const double* __restrict__ dt, long long Nh, int* __restrict__ flag) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= Nh) return;
+  for (long long k = ip[r]; k < ip[r + 1]; ++k) {
+    const int c = ix[k];
+    if (c == r) continue;
+    bool found = false;
+    if (c >= 0 && c < Nh) {
+      for (long long k2 = ip[c]; k2 < ip[c + 1]; ++k2)
+        if (ix[k2] == r) {
+          found = dt[k2] == dt[k];
+          break;
+        }
+    }
+    if (!found) {
+      *flag = 0;
+      return;
+    }
+  }
+}
+
+namespace {
+struct DevBuf;
+}
+__global__ void rb_off_scatter_kernel(const double* __restrict__ src, int n, double* __restrict__ dst, int cap, int c0,
+                                      long long Nh);
 namespace {
 struct DevBuf {
   void* p = nullptr;
@@ -165,49 +340,119 @@ struct DevBuf {
   }
 };
 
+// Host matrix (Nh x n, row-major, dense) -> device with an even row pitch *ld (16-byte aligned rows).
+int upload_cols(rb_ctx* ctx, const double* host, long long Nh, int n, DevBuf& out, int* ld) {
+  cudaStream_t st = ctx->stream;
+  *ld = (n + 1) & ~1;
+  RB_CUDA(out.alloc((size_t)Nh * *ld * sizeof(double)));
+  if (*ld == n) {
+    RB_CUDA(cudaMemcpyAsync(out.p, host, (size_t)Nh * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    return RB_OK;
+  }
+  DevBuf tmp;
+  RB_CUDA(tmp.alloc((size_t)Nh * n * sizeof(double)));
+  RB_CUDA(cudaMemsetAsync(out.p, 0, (size_t)Nh * *ld * sizeof(double), st));
+  RB_CUDA(cudaMemcpyAsync(tmp.p, host, (size_t)Nh * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  rb_off_scatter_kernel<<<(unsigned)((Nh * n + 255) / 256), 256, 0, st>>>(tmp.as<double>(), n, out.as<double>(), *ld, 0, Nh);
+  RB_CUDA(cudaGetLastError());
+  RB_CUDA(cudaStreamSynchronize(st));  // tmp is freed on return
+  return RB_OK;
+}
+
+// *out = 1 iff the CSR matrix equals its transpose entry by entry (one thread per row, rows are short).
+int csr_is_symmetric(rb_ctx* ctx, long long Nh, const long long* dIp, const int* dIx, const double* dDt, int* out) {
+  DevBuf flag;
+  RB_CUDA(flag.alloc(sizeof(int)));
+  const int one = 1;
+  RB_CUDA(cudaMemcpyAsync(flag.p, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  rb_csr_symmetric_kernel<<<(unsigned)((Nh + 255) / 256), 256, 0, ctx->stream>>>(dIp, dIx, dDt, Nh, flag.as<int>());
+  RB_CUDA(cudaGetLastError());
+  RB_CUDA(cudaMemcpyAsync(out, flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  RB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RB_OK;
+}
+
 // C (host, ns x ns2) = S^T (X S2) over rows [rb, re); all operands already on the device.
 int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, int lds, const double* dS2, int ld2,
                 const long long* dIndptr, const int* dIndices, const double* dData, long long rb, long long re,
-                double* C_host, float* ms_spmm, float* ms_tsmm) {
+                double* C_host, float* ms_spmm, float* ms_tsmm, int x_sym = -1) {
   cudaStream_t st = ctx->stream;
   DevBuf Ybuf, ws, dC;
   const double* dY = dS2;
   // every allocation happens BEFORE the timed region (cudaMalloc synchronises and costs milliseconds)
-  const int ti = (ns + TS_TM - 1) / TS_TM, tj = (ns2 + TS_TN - 1) / TS_TN;
-  const int ldw = std::max(ti * TS_TM, tj * TS_TN);
+  const int ldy = dIndptr ? ((ns2 + 1) & ~1) : ld2;
+  if (dIndptr) {
+    RB_CUDA(Ybuf.alloc((size_t)Nh * ldy * sizeof(double)));
+    dY = Ybuf.as<double>();
+  }
+  // bulk-copy kernel needs 16-byte aligned rows; anything else (odd pitch, odd column offset) takes the cp.async one
+  static const int force_v1 = getenv("RB_TSMM_V1") ? atoi(getenv("RB_TSMM_V1")) : 0;
+  const bool v2 = !force_v1 && (((uintptr_t)dS | (uintptr_t)dY) & 15) == 0 && (lds % 2 == 0) && (ldy % 2 == 0);
+  const int TM = !v2 ? TS_TM : ((ns <= 64 && ns2 <= 64) ? 64 : 128);
+  const int ti = (ns + TM - 1) / TM, tj = (ns2 + TM - 1) / TM;
+  // S^T X S with X == X^T over ALL dof rows is symmetric: only the tiles on and above the diagonal are computed (the
+  // partial product of a row partition is not symmetric, and neither is S^T A S for a general operator A)
+  static const int no_sym = getenv("RB_GRAM_NOSYM") ? atoi(getenv("RB_GRAM_NOSYM")) : 0;
+  bool sym = v2 && !no_sym && ti > 1 && dS == dS2 && lds == ld2 && ns == ns2 && (!dIndptr || (rb == 0 && re == Nh));
+  if (sym && dIndptr) {
+    if (x_sym < 0) {
+      if (int rc = csr_is_symmetric(ctx, Nh, dIndptr, dIndices, dData, &x_sym)) return rc;
+    }
+    sym = x_sym == 1;
+  }
+  const int ntiles = sym ? ti * (ti + 1) / 2 : ti * tj;
+  const int ldw = v2 ? 32 * std::max((ns + 31) / 32, (ns2 + 31) / 32) : std::max(ti, tj) * TM;
   const long long rows = std::max<long long>(re - rb, 0);
-  // enough splits for ~3 waves of 148 SMs x 3 resident CTAs, at least TS_KC*8 rows each
-  long long nsplit = std::max<long long>(1, (long long)ctx->sm_count * 9 / (ti * tj));
-  nsplit = std::min(nsplit, std::max<long long>(1, rows / (TS_KC * 8)));
+  const int KC = v2 ? T2_KC : TS_KC;
+  long long nsplit;
+  if (v2) {
+    // one wave of equal CTAs for a single tile; several tiles have unequal numbers of active warps, so ~6 waves
+    // let the block scheduler balance them
+    const long long slots = (long long)ctx->sm_count * (TM == 64 ? 2 : 1);
+    nsplit = std::max<long long>(1, slots * (ntiles > 1 ? 6 : 1) / ntiles);
+  } else {
+    // enough splits for ~3 waves of 148 SMs x 3 resident CTAs
+    nsplit = std::max<long long>(1, (long long)ctx->sm_count * 9 / (ti * tj));
+  }
+  nsplit = std::min(nsplit, std::max<long long>(1, rows / (KC * 8)));
   nsplit = std::min<long long>(nsplit, 65535);
   long long rps = (rows + nsplit - 1) / nsplit;
-  rps = (rps + TS_KC - 1) / TS_KC * TS_KC;
-  if (rps == 0) rps = TS_KC;
+  rps = (rps + KC - 1) / KC * KC;
+  if (rps == 0) rps = KC;
   nsplit = std::max<long long>(1, (rows + rps - 1) / rps);
-  if (dIndptr) RB_CUDA(Ybuf.alloc((size_t)Nh * ns2 * sizeof(double)));
   RB_CUDA(ws.alloc((size_t)nsplit * ldw * ldw * sizeof(double)));
   RB_CUDA(dC.alloc((size_t)ns * ns2 * sizeof(double)));
-  const size_t smem = (size_t)2 * TS_STAGES * TS_KC * TS_PITCH * sizeof(double);
-  RB_CUDA(cudaFuncSetAttribute(rb_tsmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = v2 ? (size_t)2 * T2_NST * T2_KC * (TM + 4) * sizeof(double) + T2_NST * 16
+                         : (size_t)2 * TS_STAGES * TS_KC * TS_PITCH * sizeof(double);
+  if (!v2)
+    RB_CUDA(cudaFuncSetAttribute(rb_tsmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (TM == 64)
+    RB_CUDA(cudaFuncSetAttribute(rb_tsmm2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else
+    RB_CUDA(cudaFuncSetAttribute(rb_tsmm2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RB_CUDA(cudaEventRecord(ctx->ev[4], st));
   if (dIndptr) {
     const int nchunk = (ns2 + 127) / 128;
     const long long warps = (re - rb) * nchunk;
     const long long blocks = (warps * 32 + 255) / 256;
     if (blocks > 0) {
-      rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIndptr, dIndices, dData, dS2, ld2, ns2, Ybuf.as<double>(), ns2,
+      rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIndptr, dIndices, dData, dS2, ld2, ns2, Ybuf.as<double>(), ldy,
                                                       rb, re);
       RB_CUDA(cudaGetLastError());
     }
-    dY = Ybuf.as<double>();
   }
-  const int ldy = dIndptr ? ns2 : ld2;
   RB_CUDA(cudaEventRecord(ctx->ev[5], st));
   dim3 grid(ti, tj, (unsigned)nsplit);
-  rb_tsmm_kernel<<<grid, TS_THREADS, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw);
+  if (!v2)
+    rb_tsmm_kernel<<<grid, TS_THREADS, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw);
+  else if (TM == 64)
+    rb_tsmm2_kernel<64><<<grid, 128, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw, 0);
+  else
+    rb_tsmm2_kernel<128><<<grid, 512, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw,
+                                                  sym ? 1 : 0);
   RB_CUDA(cudaGetLastError());
-  rb_split_reduce_kernel<<<(ns * ns2 + 255) / 256, 256, 0, st>>>(ws.as<double>(), ldw, (int)nsplit, ns, ns2,
-                                                                 dC.as<double>());
+  rb_split_reduce_kernel<<<(ns * ns2 + 63) / 64, 256, 0, st>>>(ws.as<double>(), ldw, (int)nsplit, ns, ns2,
+                                                               dC.as<double>(), sym ? TM : 0);
   RB_CUDA(cudaGetLastError());
   RB_CUDA(cudaEventRecord(ctx->ev[0], st));
   RB_CUDA(cudaMemcpyAsync(C_host, dC.p, (size_t)ns * ns2 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -237,12 +482,12 @@ extern "C" int rb_gram(rb_ctx* ctx, int64_t Nh, int Ns, int Ns2, const double* S
   if (Ns2 <= 0) RB_FAIL(RB_ERR_ARG, "rb_gram: Ns2 must be positive");
   cudaStream_t st = ctx->stream;
   DevBuf dS, dS2, dIp, dIx, dDt;
-  RB_CUDA(dS.alloc((size_t)Nh * Ns * sizeof(double)));
-  RB_CUDA(cudaMemcpyAsync(dS.p, S, (size_t)Nh * Ns * sizeof(double), cudaMemcpyHostToDevice, st));
+  int lds = Ns, ld2 = Ns;
+  if (int rc = upload_cols(ctx, S, Nh, Ns, dS, &lds)) return rc;
   const double* pS2 = dS.as<double>();
+  ld2 = lds;
   if (S2) {
-    RB_CUDA(dS2.alloc((size_t)Nh * Ns2 * sizeof(double)));
-    RB_CUDA(cudaMemcpyAsync(dS2.p, S2, (size_t)Nh * Ns2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (int rc = upload_cols(ctx, S2, Nh, Ns2, dS2, &ld2)) return rc;
     pS2 = dS2.as<double>();
   }
   if (indptr) {
@@ -254,7 +499,7 @@ extern "C" int rb_gram(rb_ctx* ctx, int64_t Nh, int Ns, int Ns2, const double* S
     RB_CUDA(cudaMemcpyAsync(dIx.p, indices, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, st));
     RB_CUDA(cudaMemcpyAsync(dDt.p, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, st));
   }
-  return gram_device(ctx, Nh, Ns, Ns2, dS.as<double>(), Ns, pS2, Ns2, indptr ? dIp.as<long long>() : nullptr,
+  return gram_device(ctx, Nh, Ns, Ns2, dS.as<double>(), lds, pS2, ld2, indptr ? dIp.as<long long>() : nullptr,
                      indptr ? dIx.as<int>() : nullptr, indptr ? dDt.as<double>() : nullptr, row_begin, row_end, C,
                      nullptr, nullptr);
 }
@@ -267,8 +512,8 @@ extern "C" int rb_project(rb_ctx* ctx, int64_t Nh, int N, int Q, const double* Z
     RB_FAIL(RB_ERR_ARG, "rb_project: bad arguments");
   cudaStream_t st = ctx->stream;
   DevBuf dZ, dIp, dIx, dDt;
-  RB_CUDA(dZ.alloc((size_t)Nh * N * sizeof(double)));
-  RB_CUDA(cudaMemcpyAsync(dZ.p, Z, (size_t)Nh * N * sizeof(double), cudaMemcpyHostToDevice, st));
+  int ldz = N;
+  if (int rc = upload_cols(ctx, Z, Nh, N, dZ, &ldz)) return rc;
   const long long nnz_total = nnz_off[Q];
   RB_CUDA(dIp.alloc((size_t)Q * (Nh + 1) * sizeof(long long)));
   RB_CUDA(dIx.alloc((size_t)nnz_total * sizeof(int)));
@@ -279,7 +524,7 @@ extern "C" int rb_project(rb_ctx* ctx, int64_t Nh, int N, int Q, const double* Z
   float tot_a = 0, tot_b = 0;
   for (int q = 0; q < Q; ++q) {
     float a = 0, b = 0;
-    if (int rc = gram_device(ctx, Nh, N, N, dZ.as<double>(), N, dZ.as<double>(), N, dIp.as<long long>() + (size_t)q * (Nh + 1),
+    if (int rc = gram_device(ctx, Nh, N, N, dZ.as<double>(), ldz, dZ.as<double>(), ldz, dIp.as<long long>() + (size_t)q * (Nh + 1),
                              dIx.as<int>() + nnz_off[q], dDt.as<double>() + nnz_off[q], 0, Nh,
                              out + (size_t)q * N * N, &a, &b))
       return rc;
@@ -558,6 +803,10 @@ extern "C" int rb_off_csr(rb_ctx* ctx, int slot, int64_t Nh, const int64_t* indp
   RB_CUDA(cudaMemcpy(c.dt, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice));
   c.Nh = Nh;
   c.nnz = nnz;
+  {
+    // (DevBuf lives in the anonymous namespace above)
+    if (int rc = csr_is_symmetric(ctx, Nh, c.ip, c.ix, c.dt, &c.sym)) return rc;
+  }
   return RB_OK;
 }
 
@@ -568,10 +817,12 @@ extern "C" int rb_off_block(rb_ctx* ctx, int slot, int64_t Nh, int capacity) {
   rb_off_blk_t& b = ctx->off_blk[slot];
   if (b.d) cudaFree(b.d);
   b = rb_off_blk_t();
-  RB_CUDA(cudaMalloc((void**)&b.d, (size_t)Nh * capacity * sizeof(double)));
-  RB_CUDA(cudaMemset(b.d, 0, (size_t)Nh * capacity * sizeof(double)));
+  const int ld = (capacity + 1) & ~1;
+  RB_CUDA(cudaMalloc((void**)&b.d, (size_t)Nh * ld * sizeof(double)));
+  RB_CUDA(cudaMemset(b.d, 0, (size_t)Nh * ld * sizeof(double)));
   b.Nh = Nh;
   b.cap = capacity;
+  b.ld = ld;
   b.n = 0;
   return RB_OK;
 }
@@ -599,7 +850,7 @@ extern "C" int rb_off_append(rb_ctx* ctx, int slot, int n, const double* cols) {
   DevBuf tmp;
   RB_CUDA(tmp.alloc((size_t)b->Nh * n * sizeof(double)));
   RB_CUDA(cudaMemcpyAsync(tmp.p, cols, (size_t)b->Nh * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  rb_off_scatter_kernel<<<(unsigned)((b->Nh * n + 255) / 256), 256, 0, ctx->stream>>>(tmp.as<double>(), n, b->d, b->cap,
+  rb_off_scatter_kernel<<<(unsigned)((b->Nh * n + 255) / 256), 256, 0, ctx->stream>>>(tmp.as<double>(), n, b->d, b->ld,
                                                                                      b->n, b->Nh);
   RB_CUDA(cudaGetLastError());
   RB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -623,7 +874,7 @@ extern "C" int rb_off_read(rb_ctx* ctx, int slot, int c0, int n, double* out) {
   if (!b || c0 < 0 || n <= 0 || c0 + n > b->n || !out) RB_FAIL(RB_ERR_ARG, "rb_off_read: bad arguments");
   DevBuf tmp;
   RB_CUDA(tmp.alloc((size_t)b->Nh * n * sizeof(double)));
-  rb_off_gather_kernel<<<(unsigned)((b->Nh * n + 255) / 256), 256, 0, ctx->stream>>>(b->d, b->cap, c0, n, tmp.as<double>(),
+  rb_off_gather_kernel<<<(unsigned)((b->Nh * n + 255) / 256), 256, 0, ctx->stream>>>(b->d, b->ld, c0, n, tmp.as<double>(),
                                                                                     b->Nh);
   RB_CUDA(cudaGetLastError());
   RB_CUDA(cudaMemcpyAsync(out, tmp.p, (size_t)b->Nh * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -643,8 +894,8 @@ extern "C" int rb_off_gram(rb_ctx* ctx, int blkS, int s0, int ns, int csrX, int 
   if (s0 < 0 || ns <= 0 || s0 + ns > S->n || t0 < 0 || ns2 <= 0 || t0 + ns2 > S2->n)
     RB_FAIL(RB_ERR_ARG, "rb_off_gram: column range outside the block");
   if (row_begin < 0 || row_end > S->Nh || row_begin > row_end) RB_FAIL(RB_ERR_ARG, "rb_off_gram: bad row range");
-  return gram_device(ctx, S->Nh, ns, ns2, S->d + s0, S->cap, S2->d + t0, S2->cap, X ? X->ip : nullptr,
-                     X ? X->ix : nullptr, X ? X->dt : nullptr, row_begin, row_end, C, nullptr, nullptr);
+  return gram_device(ctx, S->Nh, ns, ns2, S->d + s0, S->ld, S2->d + t0, S2->ld, X ? X->ip : nullptr,
+                     X ? X->ix : nullptr, X ? X->dt : nullptr, row_begin, row_end, C, nullptr, nullptr, X ? X->sym : -1);
 }
 
 extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, double* norm_out) {
@@ -660,11 +911,11 @@ extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, i
   RB_CUDA(dNorm.alloc(sizeof(double)));
   RB_CUDA(cudaMemcpyAsync(dz.p, z, (size_t)Z->Nh * sizeof(double), cudaMemcpyHostToDevice, st));
   int launches = 0;
-  if (int rc = gs_device(ctx, Z->Nh, Z->n, Z->d, Z->cap, X ? X->ip : nullptr, X ? X->ix : nullptr, X ? X->dt : nullptr,
+  if (int rc = gs_device(ctx, Z->Nh, Z->n, Z->d, Z->ld, X ? X->ip : nullptr, X ? X->ix : nullptr, X ? X->dt : nullptr,
                          dz.as<double>(), dNorm.as<double>(), &launches))
     return rc;
   if (append) {
-    rb_off_scatter_kernel<<<(unsigned)((Z->Nh + 255) / 256), 256, 0, st>>>(dz.as<double>(), 1, Z->d, Z->cap, Z->n, Z->Nh);
+    rb_off_scatter_kernel<<<(unsigned)((Z->Nh + 255) / 256), 256, 0, st>>>(dz.as<double>(), 1, Z->d, Z->ld, Z->n, Z->Nh);
     RB_CUDA(cudaGetLastError());
     ++launches;
   }

@@ -29,6 +29,55 @@ def test_gram_matches_loop_oracle(engine, n, Ns):
     assert np.max(np.abs(C - ref)) <= 1e-10 * np.max(np.abs(ref))
 
 
+@pytest.mark.parametrize("Ns", [129, 200, 257, 400])
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_gram_multi_tile(engine, Ns, symmetric):
+    """Several 128-column tiles: a symmetric X lets the kernel mirror the tiles below the diagonal; a general operator
+    (S^T A S of a Galerkin projection) and the identity inner product take the full tile grid."""
+    rng = np.random.default_rng(Ns)
+    n = 24
+    X = _lap2d(n)
+    if not symmetric:
+        X = (X + sp.diags([0.3], [1], shape=X.shape)).tocsr()
+    S = rng.standard_normal((n * n, Ns))
+    C = offline.gram(engine, S, X)
+    ref = O.gram_blas(S, X)
+    assert np.max(np.abs(C - ref)) <= 1e-10 * np.max(np.abs(ref))
+    if symmetric:
+        assert np.max(np.abs(C - C.T)) <= 1e-12 * np.max(np.abs(ref))
+    C0 = offline.gram(engine, S, None)
+    ref0 = S.T @ S
+    assert np.max(np.abs(C0 - ref0)) <= 1e-10 * np.max(np.abs(ref0))
+
+
+def test_gram_rectangular_multi_tile(engine):
+    rng = np.random.default_rng(8)
+    n = 20
+    X = _lap2d(n)
+    S = rng.standard_normal((n * n, 150))
+    S2 = rng.standard_normal((n * n, 301))
+    C = offline.gram(engine, S, X, S2)
+    ref = S.T @ (X @ S2)
+    assert np.max(np.abs(C - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
+def test_workspace_gram_odd_column_offsets(engine):
+    """Column ranges that start at odd columns of a resident block are not 16-byte aligned: the cp.async kernel takes
+    them; results equal the aligned path."""
+    rng = np.random.default_rng(9)
+    n = 18
+    X = _lap2d(n)
+    S = np.ascontiguousarray(rng.standard_normal((n * n, 37)))
+    ws = offline.OfflineWorkspace(engine)
+    ws.set_operator("X", X)
+    ws.new_block("S", n * n, 37)
+    ws.append("S", S)
+    for (s0, ns, t0, ns2) in [(0, 37, 0, 37), (1, 20, 3, 11), (2, 35, 1, 36), (5, 1, 0, 37)]:
+        C = ws.gram("S", "X", cols=(s0, s0 + ns), cols2=(t0, t0 + ns2))
+        ref = S[:, s0:s0 + ns].T @ (X @ S[:, t0:t0 + ns2])
+        assert np.max(np.abs(C - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
 def test_gram_identity_inner_product_and_rectangular(engine):
     rng = np.random.default_rng(5)
     S = rng.standard_normal((1000, 13))
