@@ -263,6 +263,243 @@ __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused Gram for ns, ns2 <= 64: C += S^T (X S2) over a range of dof rows WITHOUT writing Y = X S2 to HBM
+// (algorithmic bytes 12 nnz + 8 Nh Ns).  One warp-specialised CTA of 28 warps per SM; registers move
+// from the gather warps (64) to the DMMA warps (120) with setmaxnreg -- the sum has to fit the CTA's launch
+// allocation of 28 x 72, an inc beyond what the decs released blocks for ever:
+//   24 gather warps, 6 teams of 4: team t owns the 16-row chunks c == t (mod 6).  Its first warp starts the bulk
+//                    copies of the chunk's S rows (A operand); every warp builds 4 rows of the 16 x ns2 block of Y in
+//                    shared memory with one pair of columns per lane.  The CSR entries of its four rows sit one per
+//                    lane (prefetched one chunk ahead, the row pointers two chunks ahead); a ballot splits them into
+//                    entries whose column lies inside the chunk -- those read the S rows the bulk copy is bringing
+//                    in anyway (when S2 is S) -- and the others, whose rows come from L2 four loads at a time.
+//                    Two FP64 FMAs per entry and lane: the FP64 pipe is shared with the DMMA warps.
+//    4 DMMA warps  : 32 x 32 tile each of C += A^T B per stage, release the stage.
+// Eight stages: six in production, one being consumed, one slack.  Measured at Nh = 10^6, Ns = 61, 5 nnz/row:
+// 0.49 ms (SpMM 0.49 ms + tall-skinny product 0.36 ms unfused); 0.34 ms with the gather switched off, i.e. the
+// per-chunk barrier hand-over of the DMMA warps, not the gather, is what is left above the 0.22 ms DMMA time.
+// 16-row chunks are dealt round-robin to the CTAs: at any moment the grid works on one moving window of
+// gridDim.x * 16 consecutive dof rows, so the matrix columns outside a chunk (neighbouring mesh rows) are rows that
+// some other CTA has just brought through L2 -- with one contiguous row range per CTA they came from HBM (measured:
+// 1.59 GB DRAM reads against 0.55 GB algorithmic; 0.56 GB with the round-robin deal).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int FG_KC = 16, FG_NST = 8, FG_NWD = 4, FG_NKG = FG_NWD / 4, FG_TEAMS = 6, FG_TW = FG_KC / 4,
+              FG_NWG = FG_TW * FG_TEAMS, FG_P = 68;  // FG_TW warps per team, 4 rows each
+constexpr int FG_THREADS = 32 * (FG_NWD + FG_NWG);
+
+__global__ void __launch_bounds__(FG_THREADS, 1)
+    rb_gram_fused_kernel(const double* __restrict__ S, int lds, int ns, const double* __restrict__ S2, int ld2, int ns2,
+                         int reuse, const long long* __restrict__ ip, const int* __restrict__ ix,
+                         const double* __restrict__ dt, long long row_begin, long long row_end,
+                         double* __restrict__ ws, int ldw) {
+  extern __shared__ __align__(128) unsigned char fg_smem[];
+  double* As = reinterpret_cast<double*>(fg_smem);               // [NST][KC][P]
+  double* Bs = As + FG_NST * FG_KC * FG_P;                       // [NST][KC][P]
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(Bs + FG_NST * FG_KC * FG_P);
+  uint64_t* fullB = fullA + FG_NST;
+  uint64_t* empty = fullB + FG_NST;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long CS = (long long)gridDim.x * FG_KC;               // row stride between consecutive chunks of a CTA
+  const long long rs = row_begin + (long long)blockIdx.x * FG_KC;  // first row of chunk 0 of this CTA
+  const long long re = row_end;
+  const long long tot_chunks = (row_end - row_begin + FG_KC - 1) / FG_KC;
+  const int nchunks = tot_chunks > blockIdx.x ? (int)((tot_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int wa = (ns + 1) & ~1, wb = (ns2 + 1) & ~1;
+  if (tid == 0) {
+    for (int s = 0; s < FG_NST; ++s) {
+      mbar_init(fullA + s, 1);
+      mbar_init(fullB + s, FG_TW);
+      mbar_init(empty + s, FG_NWD);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp < FG_NWD) {
+    // ---------------------------------------------------------------- DMMA warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;\n");
+    const int kgrp = warp >> 2, tw = warp & 3;
+    const int wm = tw & 1, wn = tw >> 1;
+    double acc[4][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    const int g = lane >> 2, q4 = lane & 3;
+    const int aoff = q4 * FG_P + wm * 32 + g, boff = q4 * FG_P + wn * 32 + g;
+    int st = 0;
+    uint32_t phase = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(fullA + st, phase);
+      mbar_wait(fullB + st, phase);
+      const double* as = As + st * FG_KC * FG_P + aoff;
+      const double* bs = Bs + st * FG_KC * FG_P + boff;
+#pragma unroll
+      for (int kk = 0; kk < FG_KC / 4 / FG_NKG; ++kk) {
+        const int ks = FG_NKG * kk + kgrp;
+        double af[4], bf[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) af[mt] = as[4 * ks * FG_P + mt * 8];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) bf[nt] = bs[4 * ks * FG_P + nt * 8];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + st);
+      if (++st == FG_NST) {
+        st = 0;
+        phase ^= 1u;
+      }
+    }
+    double* w = ws + ((long long)blockIdx.x * FG_NKG + kgrp) * ldw * ldw;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const int i = wm * 32 + mt * 8 + g;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int j = wn * 32 + nt * 8 + q4 * 2;
+        *reinterpret_cast<double2*>(w + (long long)i * ldw + j) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ gather warps
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
+  const int team = (warp - FG_NWD) / FG_TW, u = (warp - FG_NWD) % FG_TW;  // this warp builds rows 4u .. 4u+3 of a chunk
+  const int cp = min(2 * lane, wb - 2);                            // this lane's pair of columns (clamped)
+  // rows of the warp in chunk c: [r0 + 4u, r0 + 4u + 4) cut at row_end; lane l <= 4 holds indptr of row 4u + l
+  auto first_row = [&](int c) { return rs + (long long)c * CS + 4 * u; };
+  auto load_ptr = [&](int c) -> long long {
+    if (c >= nchunks) return 0;
+    const long long r = min(first_row(c) + min(lane, 4), re);
+    return __ldg(ip + r);
+  };
+  auto load_entries = [&](long long p, int& col, double& val) {  // lane l: entry l of the warp's four rows
+    const long long base = __shfl_sync(0xffffffffu, p, 0), end = __shfl_sync(0xffffffffu, p, 4);
+    col = 0;
+    val = 0.0;
+    if (base + lane < end) {
+      col = __ldg(ix + base + lane);
+      val = __ldg(dt + base + lane);
+    }
+  };
+  int c = team;
+  long long p_cur = load_ptr(c), p_nxt = load_ptr(c + FG_TEAMS);
+  int col_cur = 0, col_nxt = 0;
+  double val_cur = 0.0, val_nxt = 0.0;
+  load_entries(p_cur, col_cur, val_cur);
+  for (; c < nchunks; c += FG_TEAMS) {
+    const long long p_nn = load_ptr(c + 2 * FG_TEAMS);
+    load_entries(p_nxt, col_nxt, val_nxt);
+    const int st = c % FG_NST, n = c / FG_NST;
+    if (n > 0) mbar_wait(empty + st, (uint32_t)(n - 1) & 1u);
+    const long long r0 = rs + (long long)c * CS;
+    const int nrows = (int)min((long long)FG_KC, re - r0);
+    if (u == 0) {
+      double* as = As + (st * FG_KC + lane) * FG_P;
+      if (lane < FG_KC && lane >= nrows) {  // rows past the end count as zeros
+        for (int c2 = 0; c2 < 64; ++c2) as[c2] = 0.0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(fullA + st, (uint32_t)nrows * (uint32_t)wa * 8u);
+      __syncwarp();
+      if (lane < nrows) bulk_g2s(as, S + (r0 + lane) * lds, (uint32_t)wa * 8u, fullA + st);
+    }
+    const long long base = __shfl_sync(0xffffffffu, p_cur, 0);
+    const int r0i = (int)r0;  // CSR column indices are 32-bit, so dof rows are too
+    const double* a_stage = As + st * FG_KC * FG_P + cp;
+    double2 acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = make_double2(0.0, 0.0);
+    int kb1, kb2, kb3, cnt;  // entry offsets (relative to base) at which rows 1, 2, 3 of the warp start; total count
+    kb1 = (int)(__shfl_sync(0xffffffffu, p_cur, 1) - base);
+    kb2 = (int)(__shfl_sync(0xffffffffu, p_cur, 2) - base);
+    kb3 = (int)(__shfl_sync(0xffffffffu, p_cur, 3) - base);
+    cnt = (int)(__shfl_sync(0xffffffffu, p_cur, 4) - base);
+    const bool mine = lane < cnt;                                             // this lane holds an entry
+    const bool in_chunk = reuse && (unsigned)(col_cur - r0i) < (unsigned)nrows;
+    auto add = [&](int e, double v, const double2& x) {  // entry e belongs to row (e>=kb1)+(e>=kb2)+(e>=kb3)
+      // e is warp-uniform: plain branches, two FMAs per entry (the FP64 pipe is shared with the DMMA warps)
+      if (e < kb2) {
+        if (e < kb1) {
+          acc[0].x = fma(v, x.x, acc[0].x);
+          acc[0].y = fma(v, x.y, acc[0].y);
+        } else {
+          acc[1].x = fma(v, x.x, acc[1].x);
+          acc[1].y = fma(v, x.y, acc[1].y);
+        }
+      } else {
+        if (e < kb3) {
+          acc[2].x = fma(v, x.x, acc[2].x);
+          acc[2].y = fma(v, x.y, acc[2].y);
+        } else {
+          acc[3].x = fma(v, x.x, acc[3].x);
+          acc[3].y = fma(v, x.y, acc[3].y);
+        }
+      }
+    };
+    // entries whose column lies outside the chunk (or all of them if S2 is not S): rows of S2 from L2 / HBM.  The
+    // entries sit one per lane; a ballot marks the far ones and the warp walks the set bits four at a time, so the
+    // loads of four entries (of any of the four rows) are in flight together.
+    unsigned farmask = __ballot_sync(0xffffffffu, mine && !in_chunk);
+    while (farmask) {
+      double2 x[4];
+      double v[4];
+      int eb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        x[j] = make_double2(0.0, 0.0);
+        v[j] = 0.0;
+        eb[j] = 0;
+        if (farmask) {
+          eb[j] = __ffs(farmask) - 1;
+          farmask &= farmask - 1;
+          const int col = __shfl_sync(0xffffffffu, col_cur, eb[j]);
+          v[j] = __shfl_sync(0xffffffffu, val_cur, eb[j]);
+          x[j] = __ldg(reinterpret_cast<const double2*>(S2 + (long long)col * ld2 + cp));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) add(eb[j], v[j], x[j]);
+    }
+    for (int e = 32; e < cnt; ++e) {  // (rows with so many entries that four of them exceed one entry per lane)
+      const int col = __ldg(ix + base + e);
+      if (!(reuse && (unsigned)(col - r0i) < (unsigned)nrows))
+        add(e, __ldg(dt + base + e), __ldg(reinterpret_cast<const double2*>(S2 + (long long)col * ld2 + cp)));
+    }
+    if (reuse) {
+      // entries inside the chunk: the S rows are (being) staged in shared memory as the A operand of this stage
+      mbar_wait(fullA + st, (uint32_t)n & 1u);
+      unsigned nearmask = __ballot_sync(0xffffffffu, mine && in_chunk);
+      while (nearmask) {
+        const int e = __ffs(nearmask) - 1;
+        nearmask &= nearmask - 1;
+        const int d = __shfl_sync(0xffffffffu, col_cur, e) - r0i;
+        const double v = __shfl_sync(0xffffffffu, val_cur, e);
+        add(e, v, *reinterpret_cast<const double2*>(a_stage + d * FG_P));
+      }
+      for (int e = 32; e < cnt; ++e) {
+        const int d = __ldg(ix + base + e) - r0i;
+        if ((unsigned)d < (unsigned)nrows) add(e, __ldg(dt + base + e), *reinterpret_cast<const double2*>(a_stage + d * FG_P));
+      }
+    }
+    double* dst = Bs + (st * FG_KC + 4 * u) * FG_P + 2 * lane;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<double2*>(dst + q * FG_P) = acc[q];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(fullB + st);
+    p_cur = p_nxt;
+    p_nxt = p_nn;
+    col_cur = col_nxt;
+    val_cur = val_nxt;
+  }
+}
+
 // C[i][j] = sum over splits, in a fixed order that depends on nsplit only (deterministic): four quarter sums of
 // consecutive splits, then their sum.  256 threads = 64 entries x 4 quarters.
 __global__ void __launch_bounds__(256) rb_split_reduce_kernel(const double* __restrict__ ws, int ldw, int nsplit,
@@ -372,6 +609,44 @@ int csr_is_symmetric(rb_ctx* ctx, long long Nh, const long long* dIp, const int*
   return RB_OK;
 }
 
+// Fused path of gram_device for ns, ns2 <= 64 with an operator: one kernel + the split reduction.
+int gram_fused_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, int lds, const double* dS2, int ld2,
+                      const long long* dIndptr, const int* dIndices, const double* dData, long long rb, long long re,
+                      double* C_host, float* ms_spmm, float* ms_tsmm) {
+  cudaStream_t st = ctx->stream;
+  DevBuf ws, dC;
+  const int ldw = 64;
+  const long long rows = std::max<long long>(re - rb, 0);
+  long long nsplit = (long long)ctx->sm_count;  // one wave, one CTA per SM
+  nsplit = std::max<long long>(1, std::min(nsplit, (rows + FG_KC - 1) / FG_KC));
+  RB_CUDA(ws.alloc((size_t)FG_NKG * nsplit * ldw * ldw * sizeof(double)));  // one partial per k-step group
+  RB_CUDA(dC.alloc((size_t)ns * ns2 * sizeof(double)));
+  const size_t smem = (size_t)2 * FG_NST * FG_KC * FG_P * sizeof(double) + 3 * FG_NST * sizeof(uint64_t);
+  RB_CUDA(cudaFuncSetAttribute(rb_gram_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // a partially filled tile leaves accumulator rows / columns >= ns, ns2 undefined; they are never read back
+  RB_CUDA(cudaEventRecord(ctx->ev[4], st));
+  const int reuse = (dS == dS2 && lds == ld2) ? 1 : 0;
+  rb_gram_fused_kernel<<<(unsigned)nsplit, FG_THREADS, smem, st>>>(dS, lds, ns, dS2, ld2, ns2, reuse, dIndptr,
+                                                                              dIndices, dData, rb, re,
+                                                                              ws.as<double>(), ldw);
+  RB_CUDA(cudaGetLastError());
+  rb_split_reduce_kernel<<<(ns * ns2 + 63) / 64, 256, 0, st>>>(ws.as<double>(), ldw, (int)(FG_NKG * nsplit), ns, ns2,
+                                                               dC.as<double>(), 0);
+  RB_CUDA(cudaGetLastError());
+  RB_CUDA(cudaEventRecord(ctx->ev[0], st));
+  RB_CUDA(cudaMemcpyAsync(C_host, dC.p, (size_t)ns * ns2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  float a = 0;
+  cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[0]);
+  if (ms_spmm) *ms_spmm = 0.f;
+  if (ms_tsmm) *ms_tsmm = a;
+  ctx->last_ms[0] = 0.f;
+  ctx->last_ms[1] = a;
+  ctx->last_ms[4] = a;
+  ctx->last_launches = 2;
+  return RB_OK;
+}
+
 // C (host, ns x ns2) = S^T (X S2) over rows [rb, re); all operands already on the device.
 int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, int lds, const double* dS2, int ld2,
                 const long long* dIndptr, const int* dIndices, const double* dData, long long rb, long long re,
@@ -381,6 +656,10 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
   const double* dY = dS2;
   // every allocation happens BEFORE the timed region (cudaMalloc synchronises and costs milliseconds)
   const int ldy = dIndptr ? ((ns2 + 1) & ~1) : ld2;
+  static const int no_fuse = getenv("RB_GRAM_NOFUSE") ? atoi(getenv("RB_GRAM_NOFUSE")) : 0;
+  const bool fused = dIndptr && !no_fuse && ns <= 64 && ns2 <= 64 && (((uintptr_t)dS | (uintptr_t)dS2) & 15) == 0 &&
+                     (lds % 2 == 0) && (ld2 % 2 == 0);
+  if (fused) return gram_fused_device(ctx, Nh, ns, ns2, dS, lds, dS2, ld2, dIndptr, dIndices, dData, rb, re, C_host, ms_spmm, ms_tsmm);
   if (dIndptr) {
     RB_CUDA(Ybuf.alloc((size_t)Nh * ldy * sizeof(double)));
     dY = Ybuf.as<double>();
