@@ -90,9 +90,16 @@ def main():
                 best = (ms, e2e)
         ms, e2e = best
         shape = {"Nh": Nh, "Ns": Ns, "nnz": nnz}
-        emit("rb_spmm_kernel (Y = X S)", shape, ms[0], 12 * nnz + 16 * Nh * Ns, 2 * nnz * Ns, e2e)
-        emit("rb_tsmm_kernel + reduce (C = S^T Y)", shape, ms[1], 16 * Nh * Ns, 2 * Nh * Ns * Ns, e2e,
-             "Y is re-read from HBM (not fused with the SpMM yet)")
+        if ms[0] == 0.0:
+            # ns <= 64: one kernel gathers Y = X S chunk by chunk into shared memory and multiplies by S^T
+            emit("rb_gram_fused_kernel + reduce (C = S^T X S, Y never written)", shape, ms[1], 12 * nnz + 8 * Nh * Ns,
+                 2 * nnz * Ns + 2 * Nh * Ns * Ns, e2e, "algorithmic bytes of SURVEY.md 8d (one pass over S)")
+        else:
+            emit("rb_spmm_kernel (Y = X S)", shape, ms[0], 12 * nnz + 16 * Nh * Ns, 2 * nnz * Ns, e2e)
+            # X == X^T over all dof rows: only tiles on / above the diagonal are computed -> symmetric flop count
+            emit("rb_tsmm2_kernel + reduce (C = S^T Y, symmetric tiles mirrored)", shape, ms[1], 16 * Nh * Ns,
+                 Nh * Ns * (Ns + 1), e2e, "flops counted as Nh*Ns*(Ns+1) (SURVEY.md 8d, symmetry exploited); "
+                 "Y is re-read from HBM")
         del S
     ops = [X, (X + sp.identity(Nh)).tocsr(), (2.0 * X).tocsr()][:args.q]
     for N in args.n:
@@ -102,8 +109,11 @@ def main():
         e2e = (time.perf_counter() - t0) * 1e3
         ms, _ = timings(eng)
         shape = {"Nh": Nh, "N": N, "Q": len(ops), "nnz": nnz}
-        emit("rb_project (Q x (SpMM + Z^T Y))", shape, ms[4], len(ops) * (12 * nnz + 16 * Nh * N) + 8 * Nh * N,
-             len(ops) * (2 * nnz * N + 2 * Nh * N * N), e2e)
+        fused = N <= 64
+        emit("rb_project (Q x fused gather+DMMA)" if fused else "rb_project (Q x (SpMM + Z^T Y))", shape, ms[4],
+             len(ops) * (12 * nnz + (8 if fused else 24) * Nh * N),
+             len(ops) * (2 * nnz * N + 2 * Nh * N * N), e2e,
+             "Z is re-read once per operator" + ("" if fused else "; Y written and re-read"))
         V = np.ascontiguousarray(rng.standard_normal((N, min(N, 20))))
         t0 = time.perf_counter()
         offline.lincomb(eng, Z, V)

@@ -21,4 +21,13 @@ timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_
     -o $OUT/${TAG}_lu_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_lu.log 2>&1
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_assemble_kernel -s 160 -c 1 \
     -o $OUT/${TAG}_asm_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_asm.log 2>&1
+# offline basis linear algebra: kernel times + launch list + full captures of the two Gram kernels
+timeout -s KILL 600 python bench_offline.py > $OUT/${TAG}_offline_kernels.jsonl 2> $OUT/${TAG}_offline.err || tail -5 $OUT/${TAG}_offline.err
+cut -c1-260 $OUT/${TAG}_offline_kernels.jsonl
+timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/${TAG}_offline_launches.csv \
+    python bench_offline.py --reps 1 > $OUT/${TAG}_ncu_offline.log 2>&1
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:rb_gram_fused_kernel -c 1 \
+    -o $OUT/${TAG}_gram_fused_full -f python tools/gram_probe.py 61 > $OUT/${TAG}_ncu_fused.log 2>&1
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:rb_tsmm2_kernel -c 1 \
+    -o $OUT/${TAG}_tsmm2_full -f python tools/gram_probe.py 400 > $OUT/${TAG}_ncu_tsmm2.log 2>&1
 ls -la $OUT | tail -12
