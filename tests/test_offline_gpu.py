@@ -78,6 +78,48 @@ def test_workspace_gram_odd_column_offsets(engine):
         assert np.max(np.abs(C - ref)) <= 1e-10 * np.max(np.abs(ref))
 
 
+@pytest.mark.parametrize("Nh,Ns,density", [(1000, 17, 0.012), (2053, 64, 0.02), (4099, 33, 0.004), (50, 5, 0.5)])
+def test_fused_gram_dense_rows_and_tails(engine, Nh, Ns, density):
+    """Fused kernel (<= 64 columns): rows with far more entries than one per lane (the register-resident window of 32
+    entries per four rows overflows into the slow path), dof counts that are not multiples of the 16-row chunk,
+    unsymmetric operators, columns both inside and outside a chunk."""
+    rng = np.random.default_rng(Nh + Ns)
+    A = sp.random(Nh, Nh, density=density, format="csr", random_state=Nh, data_rvs=rng.standard_normal)
+    A = (A + sp.diags(rng.standard_normal(Nh)) + sp.diags(rng.standard_normal(Nh - 1), 1)).tocsr()
+    A.sort_indices()
+    S = rng.standard_normal((Nh, Ns))
+    C = offline.gram(engine, S, A)
+    ref = S.T @ (A @ S)
+    assert np.max(np.abs(C - ref)) <= 1e-10 * np.max(np.abs(ref))
+    # different right operand (no reuse of the staged S rows), rectangular
+    S2 = rng.standard_normal((Nh, max(1, Ns // 2)))
+    C2 = offline.gram(engine, S, A, S2)
+    ref2 = S.T @ (A @ S2)
+    assert np.max(np.abs(C2 - ref2)) <= 1e-10 * np.max(np.abs(ref2))
+
+
+def test_fused_gram_row_partition_and_empty_rows(engine):
+    """Row partitions of the fused path (any split point, also inside a chunk) add up; empty rows are fine."""
+    import ctypes as C
+    from rbnics_b200 import _lib as L
+    rng = np.random.default_rng(12)
+    Nh, Ns = 777, 40
+    A = sp.random(Nh, Nh, density=0.01, format="lil", random_state=3)
+    A[100:140, :] = 0.0  # a band of empty rows
+    A = A.tocsr()
+    A.eliminate_zeros()
+    S = np.ascontiguousarray(rng.standard_normal((Nh, Ns)))
+    ip, ix, dt = offline._csr_arrays(A)
+    total = np.zeros((Ns, Ns))
+    for (rb, re) in [(0, 1), (1, 250), (250, 250), (250, 601), (601, Nh)]:
+        part = np.empty((Ns, Ns))
+        engine._check(engine._lib.rb_gram(engine._h, Nh, Ns, Ns, L.dptr(S), None, ip.ctypes.data_as(L.c_int64_p),
+                                          ix.ctypes.data_as(L.c_int32_p), L.dptr(dt), rb, re, L.dptr(part)))
+        total += part
+    ref = S.T @ (A @ S)
+    assert np.max(np.abs(total - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
 def test_gram_identity_inner_product_and_rectangular(engine):
     rng = np.random.default_rng(5)
     S = rng.standard_normal((1000, 13))
