@@ -182,6 +182,19 @@ def test_lincomb(engine):
     assert np.max(np.abs(Z - ref)) <= 1e-10 * np.max(np.abs(ref))
 
 
+@pytest.mark.parametrize("Nh,Ns,n", [(1, 1, 1), (127, 3, 2), (129, 32, 32), (1000, 33, 31), (4097, 100, 20),
+                                     (513, 61, 65), (2000, 130, 7)])
+def test_lincomb_shapes(engine, Nh, Ns, n):
+    """Row-block tails, partial last column chunks of S, odd n (scalar stores), both tile widths."""
+    rng = np.random.default_rng(Nh + Ns + n)
+    S = rng.standard_normal((Nh, Ns))
+    V = rng.standard_normal((Ns, n))
+    Z = offline.lincomb(engine, S, V)
+    ref = S @ V
+    assert Z.shape == ref.shape
+    assert np.max(np.abs(Z - ref)) <= 1e-10 * max(np.max(np.abs(ref)), 1e-300)
+
+
 def test_gram_schmidt_step(engine):
     tp = ThermalBlock(n=12, nblocks=2)
     X = tp.inner_product
