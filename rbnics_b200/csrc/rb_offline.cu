@@ -3,11 +3,18 @@
 // Galerkin projections Z^T A_q Z / Z^T f_q (transpose.py:441-468, 365-400; parametrized_reduced_differential_
 // problem.py:727-790) and the Riesz Gram blocks R_q^T X R_q' (rb_reduced_problem.py:238-258).
 //
-// The reference does Ns sparse mat-vecs and Ns^2 PETSc VecDot calls (each an MPI all-reduce).  Here:
-//   K_spmm : Y = X S2        CSR x dense (dof-major, so every non-zero reads one contiguous row of S2)   -- HBM bound
-//   K_tsmm : C += S^T Y      tall-skinny FP64 GEMM on DMMA.8x8x4, split over dof rows, cp.async double buffering
-//   K_red  : fixed-order sum of the split partials (deterministic)
+// The reference does Ns sparse mat-vecs and Ns^2 PETSc VecDot calls (each an MPI all-reduce).  Here (DESIGN.md 4.3):
+//   K_fused : C += S^T (X S2) for <= 64 columns, Y = X S2 only ever exists as 16-row blocks in shared memory
+//             (warp-specialised gather + DMMA CTA)                                                -- one pass over S
+//   K_spmm  : Y = X S2        CSR x dense (dof-major, so every non-zero reads one contiguous row of S2)   -- HBM / L2
+//   K_tsmm2 : C += S^T Y      tall-skinny FP64 GEMM on DMMA.8x8x4, 128x128 / 64x64 tiles fed by 1-D bulk copies,
+//             split over dof rows, symmetric tiles mirrored when X == X^T         (K_tsmm: cp.async fallback for
+//             operands whose rows are not 16-byte aligned)
+//   K_red   : fixed-order sum of the split partials (deterministic)
 // Rows [row_begin, row_end) select this rank's dof partition; the host layer all-reduces the Ns x Ns2 partials.
+// Note on bulk copies: cp.async.bulk takes its operands from uniform registers, so a copy per LANE is issued one
+// lane at a time (~40 clk each) -- fine for 16-64 row copies per stage next to thousands of DMMA cycles, but a
+// Z = S V kernel built on 160 small row copies per stage measured 2x SLOWER than the cp.async one below (kept).
 #include <algorithm>
 
 #include "rb_common.cuh"
