@@ -147,7 +147,11 @@ void rb_host_free(void* p);
  * C = S^T X S2: rbnics/backends/basic/transpose.py:304-313 (POD correlation), :441-468 (Z^T A_q Z), :365-400 (Z^T f).
  * S: Nh x Ns, S2: Nh x Ns2 row-major (dof-major: row = dof, column = snapshot), X: CSR (Nh x Nh) or indptr == NULL
  * for the identity.  C: Ns x Ns2 row-major.  If S2 == NULL, S2 = S.  Rows [row_begin, row_end) of X/S are this
- * rank's dof partition (the partial result is all-reduced by the host layer); pass 0, Nh for a single GPU.       */
+ * rank's dof partition (the partial result is all-reduced by the host layer); pass 0, Nh for a single GPU.
+ * For S2 == S with more than 128 columns and X == X^T (checked on the device) only the 128-column tiles on and above
+ * the diagonal are computed and mirrored: a rank's partial then holds the transposed upper tiles of ITS partial
+ * below the diagonal tiles -- the sum over the ranks is the exact (symmetric) product, a single partial is not the
+ * rank's true contribution there.                                                                                 */
 int rb_gram(rb_ctx* ctx, int64_t Nh, int Ns, int Ns2, const double* S, const double* S2, const int64_t* indptr,
             const int32_t* indices, const double* data, int64_t row_begin, int64_t row_end, double* C);
 /* Batched projection of Q operators sharing one basis: out[q] = Z^T A_q Z (Q x N x N); CSR arrays concatenated,

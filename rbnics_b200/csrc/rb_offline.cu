@@ -676,10 +676,13 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
   const bool v2 = !force_v1 && (((uintptr_t)dS | (uintptr_t)dY) & 15) == 0 && (lds % 2 == 0) && (ldy % 2 == 0);
   const int TM = !v2 ? TS_TM : ((ns <= 64 && ns2 <= 64) ? 64 : 128);
   const int ti = (ns + TM - 1) / TM, tj = (ns2 + TM - 1) / TM;
-  // S^T X S with X == X^T over ALL dof rows is symmetric: only the tiles on and above the diagonal are computed (the
-  // partial product of a row partition is not symmetric, and neither is S^T A S for a general operator A)
+  // S^T X S with X == X^T is symmetric: only the tiles on and above the diagonal are computed and the reduction mirrors
+  // them (S^T A S for a general operator A takes the full grid).  The partial of a dof-row partition is not symmetric
+  // by itself, but mirroring is linear: the SUM over the ranks of the mirrored partials is the mirrored sum, which is
+  // what the host layer all-reduces -- so with a symmetric X a rank's block below the diagonal tiles holds the
+  // transposed upper tiles of ITS partial, and only the sum over ranks is meaningful there.
   static const int no_sym = getenv("RB_GRAM_NOSYM") ? atoi(getenv("RB_GRAM_NOSYM")) : 0;
-  bool sym = v2 && !no_sym && ti > 1 && dS == dS2 && lds == ld2 && ns == ns2 && (!dIndptr || (rb == 0 && re == Nh));
+  bool sym = v2 && !no_sym && ti > 1 && dS == dS2 && lds == ld2 && ns == ns2;
   if (sym && dIndptr) {
     if (x_sym < 0) {
       if (int rc = csr_is_symmetric(ctx, Nh, dIndptr, dIndices, dData, &x_sym)) return rc;

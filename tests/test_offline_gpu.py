@@ -160,6 +160,26 @@ def test_gram_row_partition_sums_to_full(engine):
     assert np.max(np.abs(total - ref)) <= 1e-10 * np.max(np.abs(ref))
 
 
+def test_gram_row_partition_multi_tile_symmetric(engine):
+    """Several tiles + symmetric X + row partition: each rank mirrors the upper tiles of ITS partial; the sum over the
+    ranks is the full (symmetric) Gram matrix."""
+    from rbnics_b200 import _lib as L
+    rng = np.random.default_rng(21)
+    n, Ns = 26, 200
+    X = _lap2d(n)
+    S = np.ascontiguousarray(rng.standard_normal((n * n, Ns)))
+    ip, ix, dt = offline._csr_arrays(X)
+    total = np.zeros((Ns, Ns))
+    for rank in range(3):
+        rb, re = offline.row_range(n * n, rank, 3)
+        part = np.empty((Ns, Ns))
+        engine._check(engine._lib.rb_gram(engine._h, n * n, Ns, Ns, L.dptr(S), None, ip.ctypes.data_as(L.c_int64_p),
+                                          ix.ctypes.data_as(L.c_int32_p), L.dptr(dt), rb, re, L.dptr(part)))
+        total += part
+    ref = O.gram_blas(S, X)
+    assert np.max(np.abs(total - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
 def test_projection_of_operators_and_vectors(engine):
     tp = ThermalBlock(n=14, nblocks=3, nloads=2)
     rng = np.random.default_rng(1)
