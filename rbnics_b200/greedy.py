@@ -137,7 +137,8 @@ class ReducedBasisGreedy:
             new_idx = [q * N + (N - 1) for q in range(Qa)]
             G = np.empty((Qa * N + Qf, Qa * N + Qf))
             G[np.ix_(old_idx, old_idx)] = self.G
-            rows = offline.gram(self.engine, np.ascontiguousarray(S[:, new_idx]), tp.inner_product, S, dist=self.dist)
+            # (X r_new is the narrow product: the operator is applied to the Qa new columns, not to all of S)
+            rows = offline.gram(self.engine, S, tp.inner_product, np.ascontiguousarray(S[:, new_idx]), dist=self.dist).T
             G[new_idx, :] = rows
             G[:, new_idx] = rows.T
             self.G = G
@@ -164,7 +165,9 @@ class ReducedBasisGreedy:
             zn = self.basis_functions[:, n]
             ws.append("R", np.stack([tp.riesz_solve(-(tp.operators_a[q] @ zn)) for q in range(Qa)], axis=1))
             c0 = Qf + n * Qa
-            rows = ws.gram("R", "X", "R", cols=(c0, c0 + Qa))  # new representers against everything so far
+            # new representers against everything so far; X is symmetric, so X is applied to the Qa new columns only
+            # (R_all^T (X R_new))^T instead of R_new^T (X R_all)
+            rows = ws.gram("R", "X", "R", cols2=(c0, c0 + Qa)).T
             G = np.empty((c0 + Qa, c0 + Qa))
             G[:c0, :c0] = self._Gr
             G[c0:, :] = rows
