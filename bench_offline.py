@@ -129,6 +129,43 @@ def main():
         print(json.dumps({"kernel": "rb_gram_schmidt (MGS step, N dots + axpys)", "shape": {"Nh": Nh, "N": N},
                           "e2e_ms_with_copies": e2e}), flush=True)
         del Z
+    # incremental reduced-operator update of one greedy iteration on resident operands: the new
+    # column Z^T A_q z and the new row z^T A_q Z of Q operators -- 2Q fused Gram launches against 2Q sparse mat-vecs
+    # written side by side + ONE pass over Z
+    Q, N = 10, 20
+    ws = offline.OfflineWorkspace(eng)
+    ws.new_block("Z", Nh, N)
+    ws.append("Z", np.ascontiguousarray(rng.standard_normal((Nh, N))))
+    ws.new_block("YA", Nh, 2 * Q)
+    for q in range(Q):
+        A = (X + 0.1 * (q + 1) * sp.identity(Nh)).tocsr()
+        ws.set_operator(f"A{q}", A)
+        ws.set_operator(f"A{q}T", A.T.tocsr())
+
+    def old_way():
+        return [(ws.gram("Z", f"A{q}", "Z", cols2=(N - 1, N)), ws.gram("Z", f"A{q}", "Z", cols=(N - 1, N)))
+                for q in range(Q)]
+
+    def new_way():
+        for q in range(Q):
+            ws.spmm(f"A{q}", "Z", (N - 1, N), "YA", q)
+            ws.spmm(f"A{q}T", "Z", (N - 1, N), "YA", Q + q)
+        return ws.gram("Z", None, "YA")
+
+    res = {}
+    for name, fn in (("2Q fused Gram launches", old_way), ("2Q mat-vecs + one Gram", new_way)):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            out = fn()
+        res[name] = (time.perf_counter() - t0) / 3 * 1e3
+    ref = old_way()
+    new = new_way()
+    err = max(max(np.max(np.abs(new[:, q] - ref[q][0][:, 0])), np.max(np.abs(new[:, Q + q] - ref[q][1][0, :])))
+              for q in range(Q)) / max(np.max(np.abs(r[0])) for r in ref)
+    print(json.dumps({"kernel": "incremental reduced-operator update (new row + column of Q operators)",
+                      "shape": {"Nh": Nh, "N": N, "Q": Q, "nnz": nnz}, "wall_ms": res, "max_rel_diff": err,
+                      "algorithmic_bytes": 2 * Q * 12 * nnz + 8 * Nh * (N + 2 * Q)}), flush=True)
     eng.close()
 
 

@@ -173,7 +173,7 @@ int rb_gram_schmidt(rb_ctx* ctx, int64_t Nh, int n, const double* Zb, const int6
 /* ---- device-resident offline workspace -------------------------------------------------------------------------
  * The reference rebuilds every reduced operator from the truth vectors at every greedy iteration
  * (rbnics/reduction_methods/base/rb_reduction.py:106,112).  Here the sparse operators (X, A_q) and the dense column
- * blocks (basis Z, snapshots S, Riesz representers) stay in HBM in numbered slots (0..31 each kind); only new columns
+ * blocks (basis Z, snapshots S, Riesz representers) stay in HBM in numbered slots (0..127 each kind); only new columns
  * cross PCIe.  Blocks are dof-major: Nh rows, up to `capacity` columns.                                            */
 int rb_off_csr(rb_ctx* ctx, int slot, int64_t Nh, const int64_t* indptr, const int32_t* indices, const double* data);
 int rb_off_block(rb_ctx* ctx, int slot, int64_t Nh, int capacity);             /* (re)create an empty block            */
@@ -184,6 +184,11 @@ int rb_off_read(rb_ctx* ctx, int slot, int c0, int n, double* out);            /
  * (rbnics/backends/basic/transpose.py:304-313, 441-468, 365-400).                                                  */
 int rb_off_gram(rb_ctx* ctx, int blkS, int s0, int ns, int csrX, int blkS2, int t0, int ns2, int64_t row_begin,
                 int64_t row_end, double* C);
+/* Y[:, y0:y0+n] = A * S[:, s0:s0+n] on resident operands (block blkY grows to y0+n columns if shorter): the operator
+ * applied to a few new columns, e.g. A_q z_new for all q side by side, so that ONE rb_off_gram(Z, identity, Y) gives
+ * the new column of every reduced operator Z^T A_q z_new (parametrized_reduced_differential_problem.py:727-790 computes
+ * them one inner product at a time).                                                                              */
+int rb_off_spmm(rb_ctx* ctx, int csrA, int blkS, int s0, int n, int blkY, int y0);
 /* z (host, Nh, in/out) orthonormalised against ALL columns of block blkZ like rb_gram_schmidt; append != 0 also
  * appends the result to the block (RBReduction.update_basis_matrix, rb_reduction.py:130-142).                       */
 int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, double* norm_out);

@@ -66,6 +66,7 @@ SIGNATURES = {
     "rb_off_append": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p]),
     "rb_off_size": (C.c_int, [C.c_void_p, C.c_int, c_int64_p, c_int_p]),
     "rb_off_read": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
+    "rb_off_spmm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "rb_off_gram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                               C.c_int64, c_double_p]),
     "rb_off_gram_schmidt": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p]),

@@ -25,7 +25,7 @@ constexpr int LU_MAX_NP_REG = 104;  // largest padded N served by the register-r
 constexpr int LU_MAX_NP = 160;      // largest padded N served at all (shared-memory fallback)
 
 // device-resident offline workspace (rb_off_*)
-constexpr int RB_OFF_SLOTS = 32;
+constexpr int RB_OFF_SLOTS = 128;
 struct rb_off_csr_t {
   long long* ip = nullptr;
   int* ix = nullptr;

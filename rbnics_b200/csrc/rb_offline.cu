@@ -1187,6 +1187,58 @@ extern "C" int rb_off_gram(rb_ctx* ctx, int blkS, int s0, int ns, int csrX, int 
                      X ? X->ix : nullptr, X ? X->dt : nullptr, row_begin, row_end, C, nullptr, nullptr, X ? X->sym : -1);
 }
 
+// Y[r, c] = sum_k data[k] * S[indices[k], c] for a FEW columns (n <= 8): one thread per (dof row, column) -- the
+// one-warp-per-row kernel above would idle 31 lanes of 32.
+__global__ void __launch_bounds__(256) rb_spmm_narrow_kernel(const long long* __restrict__ indptr,
+                                                             const int* __restrict__ indices,
+                                                             const double* __restrict__ data,
+                                                             const double* __restrict__ S, int lds, int n,
+                                                             double* __restrict__ Y, int ldy, long long Nh) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long r = t / n;
+  const int c = (int)(t % n);
+  if (r >= Nh) return;
+  double acc = 0.0;
+  for (long long k = __ldg(indptr + r); k < __ldg(indptr + r + 1); ++k)
+    acc = fma(__ldg(data + k), __ldg(S + (long long)__ldg(indices + k) * lds + c), acc);
+  Y[r * ldy + c] = acc;
+}
+
+extern "C" int rb_off_spmm(rb_ctx* ctx, int csrA, int blkS, int s0, int n, int blkY, int y0) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  rb_off_csr_t* A = off_csr(ctx, csrA);
+  rb_off_blk_t* S = off_blk(ctx, blkS);
+  rb_off_blk_t* Y = off_blk(ctx, blkY);
+  if (!A || !S || !Y) RB_FAIL(RB_ERR_ARG, "rb_off_spmm: empty slot");
+  if (A->Nh != S->Nh || A->Nh != Y->Nh) RB_FAIL(RB_ERR_ARG, "rb_off_spmm: inconsistent number of dofs");
+  if (s0 < 0 || n <= 0 || s0 + n > S->n || y0 < 0 || y0 + n > Y->cap)  // (columns never written are zero)
+    RB_FAIL(RB_ERR_ARG, "rb_off_spmm: column range outside the block");
+  if (S == Y && !(y0 >= s0 + n || y0 + n <= s0)) RB_FAIL(RB_ERR_ARG, "rb_off_spmm: source and target columns overlap");
+  cudaStream_t st = ctx->stream;
+  RB_CUDA(cudaEventRecord(ctx->ev[4], st));
+  if (n <= 8) {
+    const long long threads = A->Nh * n;
+    rb_spmm_narrow_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A->ip, A->ix, A->dt, S->d + s0, S->ld, n,
+                                                                            Y->d + y0, Y->ld, A->Nh);
+  } else {
+    const int nchunk = (n + 127) / 128;
+    const long long blocks = (A->Nh * nchunk * 32 + 255) / 256;
+    rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(A->ip, A->ix, A->dt, S->d + s0, S->ld, n, Y->d + y0, Y->ld, 0, A->Nh);
+  }
+  RB_CUDA(cudaGetLastError());
+  RB_CUDA(cudaEventRecord(ctx->ev[5], st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  float a = 0;
+  cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]);
+  ctx->last_ms[0] = a;
+  ctx->last_ms[1] = 0.f;
+  ctx->last_ms[4] = a;
+  ctx->last_launches = 1;
+  if (Y->n < y0 + n) Y->n = y0 + n;
+  return RB_OK;
+}
+
 extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, double* norm_out) {
   if (!ctx) return RB_ERR_ARG;
   RB_CUDA(cudaSetDevice(ctx->device));

@@ -64,9 +64,16 @@ class ReducedBasisGreedy:
         if resident:
             ws = offline.OfflineWorkspace(engine, dist=dist)
             ws.set_operator("X", tp.inner_product)
+            self._a_symmetric = []
             for q, A in enumerate(tp.operators_a):
                 ws.set_operator(f"A{q}", A)
+                A = A.tocsr()
+                sym = (A != A.T).nnz == 0
+                self._a_symmetric.append(sym)
+                if not sym:   # z^T A_q Z_j = (A_q^T z) . Z_j: the transposed operator gives the new ROW as a mat-vec too
+                    ws.set_operator(f"A{q}T", A.T.tocsr())
             ws.new_block("Z", self.Nh, Nmax + 1)
+            ws.new_block("YA", self.Nh, 2 * self.Qa)   # [A_q z_new | A_q^T z_new] for all q, side by side
             ws.new_block("F", self.Nh, self.Qf)
             ws.append("F", np.stack([np.asarray(f, dtype=np.float64) for f in tp.operators_f], axis=1))
             ws.new_block("R", self.Nh, self.Qa * (Nmax + 1) + self.Qf)   # Riesz representers: r_f first, then (n, q)
@@ -86,9 +93,25 @@ class ReducedBasisGreedy:
             ws, N = self.ws, self.N
             A_new = np.zeros((self.Qa, N, N))
             A_new[:, :N - 1, :N - 1] = self.operator_a
-            for q in range(self.Qa):
-                A_new[q, :, N - 1] = ws.gram("Z", f"A{q}", "Z", cols2=(N - 1, N))[:, 0]
-                A_new[q, N - 1, :] = ws.gram("Z", f"A{q}", "Z", cols=(N - 1, N))[0, :]
+            # new column Z^T (A_q z_N) and new row (A_q^T z_N)^T Z of every operator: 2 Qa sparse mat-vecs written side
+            # by side, then ONE pass over Z for all of them (the reference: 2 Qa N inner products, each a pass)
+            Qa = self.Qa
+            for q in range(Qa):
+                ws.spmm(f"A{q}", "Z", (N - 1, N), "YA", q)
+                if not self._a_symmetric[q]:
+                    ws.spmm(f"A{q}T", "Z", (N - 1, N), "YA", Qa + q)
+            if all(self._a_symmetric):
+                C = ws.gram("Z", None, "YA", cols2=(0, Qa))            # N x Qa
+                Crow = C
+            else:
+                for q in range(Qa):
+                    if self._a_symmetric[q]:
+                        ws.spmm(f"A{q}", "Z", (N - 1, N), "YA", Qa + q)
+                C2 = ws.gram("Z", None, "YA", cols2=(0, 2 * Qa))       # N x 2 Qa
+                C, Crow = C2[:, :Qa], C2[:, Qa:]
+            for q in range(Qa):
+                A_new[q, :, N - 1] = C[:, q]
+                A_new[q, N - 1, :] = Crow[:, q]
             self.operator_a = A_new
             f_new = np.zeros((self.Qf, N))
             f_new[:, :N - 1] = self.operator_f

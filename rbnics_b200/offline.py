@@ -193,7 +193,7 @@ class OfflineWorkspace:
     without re-uploading anything but new columns.  The reference rebuilds all reduced operators from host/PETSc
     vectors at every iteration (rbnics/reduction_methods/base/rb_reduction.py:106,112)."""
 
-    SLOTS = 32
+    SLOTS = 128
 
     def __init__(self, engine, dist=None):
         self.engine = engine
@@ -241,6 +241,12 @@ class OfflineWorkspace:
         e = self.engine
         e._check(e._lib.rb_off_read(e._h, self._blk[name], int(c0), int(n), L.dptr(out)))
         return out
+
+    def spmm(self, A, S, cols, Y, col0):
+        """Y[:, col0:col0+n] = A * S[:, cols[0]:cols[1]] on resident operands (operator and block names)."""
+        e = self.engine
+        e._check(e._lib.rb_off_spmm(e._h, self._csr[A], self._blk[S], int(cols[0]), int(cols[1] - cols[0]),
+                                    self._blk[Y], int(col0)))
 
     def gram(self, S, X=None, S2=None, cols=None, cols2=None):
         """C = S[:, cols]^T X S2[:, cols2]; S, S2 block names, X operator name or None (identity); cols = (begin, end)."""

@@ -70,3 +70,21 @@ def test_device_resident_offline_workspace_equals_host_path(engine):
     assert np.max(np.abs(res.G - host.G)) <= 1e-11 * np.max(np.abs(host.G))
     Z = res.ws.read("Z")
     assert Z.shape == res.basis_functions.shape and np.array_equal(Z, res.basis_functions)
+
+
+def test_device_resident_workspace_with_unsymmetric_operator(engine):
+    """An advection-like (unsymmetric) A_q: the new ROW of the reduced operator comes from the transposed operator
+    (z^T A_q Z_j = (A_q^T z) . Z_j), the new column from A_q itself; same result as the full recomputation."""
+    import scipy.sparse as sp
+    tp = ThermalBlock(n=12, nblocks=3, nloads=1)
+    Nh = tp.Nh
+    adv = sp.diags([0.05, -0.05], [1, -1], shape=(Nh, Nh))
+    tp.operators_a[1] = (tp.operators_a[1] + adv @ sp.diags(np.linspace(0.5, 1.5, Nh))).tocsr()
+    assert (tp.operators_a[1] != tp.operators_a[1].T).nnz > 0
+    train = tp.sample_training_set(120, seed=4)
+    res = ReducedBasisGreedy(engine, tp, train, Nmax=5, tol=1e-7, resident=True).offline()
+    host = ReducedBasisGreedy(engine, tp, train, Nmax=5, tol=1e-7, incremental=False).offline()
+    assert res._a_symmetric == [True, False, True]
+    assert res.greedy_selected_indices == host.greedy_selected_indices
+    assert np.max(np.abs(res.operator_a - host.operator_a)) <= 1e-12 * np.max(np.abs(host.operator_a))
+    assert np.max(np.abs(res.G - host.G)) <= 1e-11 * np.max(np.abs(host.G))

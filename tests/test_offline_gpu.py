@@ -120,6 +120,38 @@ def test_fused_gram_row_partition_and_empty_rows(engine):
     assert np.max(np.abs(total - ref)) <= 1e-10 * np.max(np.abs(ref))
 
 
+def test_workspace_spmm_then_single_gram(engine):
+    """rb_off_spmm: operators applied to one new column each, written side by side; one identity Gram then yields
+    Z^T A_q z for all q (and with the transposed operators z^T A_q Z)."""
+    rng = np.random.default_rng(31)
+    Nh, N, Q = 900, 12, 5
+    ops = [(sp.random(Nh, Nh, density=0.01, format="csr", random_state=q) + sp.identity(Nh)).tocsr() for q in range(Q)]
+    Z = np.ascontiguousarray(rng.standard_normal((Nh, N)))
+    ws = offline.OfflineWorkspace(engine)
+    ws.new_block("Z", Nh, N)
+    ws.append("Z", Z)
+    ws.new_block("Y", Nh, 2 * Q)
+    for q, A in enumerate(ops):
+        ws.set_operator(f"A{q}", A)
+        ws.set_operator(f"A{q}T", A.T.tocsr())
+    for q in range(Q):   # out of order on purpose: columns never written stay zero
+        ws.spmm(f"A{q}T", "Z", (N - 1, N), "Y", Q + q)
+        ws.spmm(f"A{q}", "Z", (N - 1, N), "Y", q)
+    C = ws.gram("Z", None, "Y")
+    assert C.shape == (N, 2 * Q)
+    for q, A in enumerate(ops):
+        col = Z.T @ (A @ Z[:, -1])
+        row = (Z[:, -1] @ A) @ Z
+        assert np.max(np.abs(C[:, q] - col)) <= 1e-10 * np.max(np.abs(col))
+        assert np.max(np.abs(C[:, Q + q] - row)) <= 1e-10 * np.max(np.abs(row))
+    # wide product through the warp-per-row kernel (n > 8)
+    ws.new_block("W", Nh, N)
+    ws.spmm("A0", "Z", (0, N), "W", 0)
+    assert np.max(np.abs(ws.read("W") - ops[0] @ Z)) <= 1e-10 * np.max(np.abs(ops[0] @ Z))
+    with pytest.raises(ValueError):
+        ws.spmm("A0", "Z", (0, N), "Y", 0)   # 12 columns do not fit a block of capacity 10
+
+
 def test_gram_identity_inner_product_and_rectangular(engine):
     rng = np.random.default_rng(5)
     S = rng.standard_normal((1000, 13))
