@@ -96,6 +96,8 @@ struct rb_ctx {
 
   rb_off_csr_t off_csr[RB_OFF_SLOTS];
   rb_off_blk_t off_blk[RB_OFF_SLOTS];
+  void* off_scratch[3] = {nullptr, nullptr, nullptr};  // grow-only scratch of the Gram path: Y = X S2, split partials, C
+  size_t off_scratch_cap[3] = {0, 0, 0};
 
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float last_ms[5] = {0, 0, 0, 0, 0};

@@ -584,6 +584,32 @@ struct DevBuf {
   }
 };
 
+// Scratch of the Gram path kept in the context between calls (cudaMalloc / cudaFree cost more than the kernels of a
+// small product); grow-only, freed with the context.  Same interface as DevBuf.
+struct PoolBuf {
+  rb_ctx* ctx;
+  int slot;
+  void* p = nullptr;
+  PoolBuf(rb_ctx* c, int s) : ctx(c), slot(s) {}
+  cudaError_t alloc(size_t bytes) {
+    bytes = std::max<size_t>(bytes, 16);
+    if (ctx->off_scratch_cap[slot] < bytes) {
+      if (ctx->off_scratch[slot]) cudaFree(ctx->off_scratch[slot]);
+      ctx->off_scratch[slot] = nullptr;
+      ctx->off_scratch_cap[slot] = 0;
+      cudaError_t e = cudaMalloc(&ctx->off_scratch[slot], bytes);
+      if (e != cudaSuccess) return e;
+      ctx->off_scratch_cap[slot] = bytes;
+    }
+    p = ctx->off_scratch[slot];
+    return cudaSuccess;
+  }
+  template <typename T>
+  T* as() {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
 // Host matrix (Nh x n, row-major, dense) -> device with an even row pitch *ld (16-byte aligned rows).
 int upload_cols(rb_ctx* ctx, const double* host, long long Nh, int n, DevBuf& out, int* ld) {
   cudaStream_t st = ctx->stream;
@@ -621,7 +647,7 @@ int gram_fused_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* 
                       const long long* dIndptr, const int* dIndices, const double* dData, long long rb, long long re,
                       double* C_host, float* ms_spmm, float* ms_tsmm) {
   cudaStream_t st = ctx->stream;
-  DevBuf ws, dC;
+  PoolBuf ws(ctx, 1), dC(ctx, 2);
   const int ldw = 64;
   const long long rows = std::max<long long>(re - rb, 0);
   long long nsplit = (long long)ctx->sm_count;  // one wave, one CTA per SM
@@ -659,7 +685,7 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
                 const long long* dIndptr, const int* dIndices, const double* dData, long long rb, long long re,
                 double* C_host, float* ms_spmm, float* ms_tsmm, int x_sym = -1) {
   cudaStream_t st = ctx->stream;
-  DevBuf Ybuf, ws, dC;
+  PoolBuf Ybuf(ctx, 0), ws(ctx, 1), dC(ctx, 2);
   const double* dY = dS2;
   // every allocation happens BEFORE the timed region (cudaMalloc synchronises and costs milliseconds)
   const int ldy = dIndptr ? ((ns2 + 1) & ~1) : ld2;

@@ -760,6 +760,8 @@ extern "C" void rb_ctx_destroy(rb_ctx* ctx) {
     for (void* p : {(void*)ctx->off_csr[t].ip, (void*)ctx->off_csr[t].ix, (void*)ctx->off_csr[t].dt, (void*)ctx->off_blk[t].d})
       if (p) cudaFree(p);
   }
+  for (void* p : ctx->off_scratch)
+    if (p) cudaFree(p);
   for (int i = 0; i < 6; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
