@@ -110,6 +110,13 @@ int rb_sweep_parabolic(rb_ctx* ctx, int Qm, int K, double dt, const double* weig
  * rbnics/problems/elliptic/elliptic_reduced_problem.py:31-32 (_compute_output).  S: Qs x N, ThetaS: B x Qs (host),
  * out: B (host).  Uses the solutions left on the device by rb_sweep / rb_sweep_resident.                          */
 int rb_compute_outputs(rb_ctx* ctx, int Qs, const double* S, const double* ThetaS, double* out);
+/* Reduced supremizers of B parameters at once (StokesReducedProblem._solve_supremizer,
+ * rbnics/problems/stokes/stokes_reduced_problem.py:80-103): s_p = X_s^{-1} (sum_q Theta[p][q] Bt_q) u_p.  The caller
+ * passes W[q] = X_s^{-1} Bt_q (Q x Ns x Nu, row-major; X_s does not depend on the parameter, so one host LU serves
+ * all of them), Theta (B x Q), the reduced solutions U (B x Nu, or NULL for the solutions left in HBM by the last
+ * sweep, which must have B parameters and N == Nu) and receives S (B x Ns).  Homogeneous lifting only.            */
+int rb_supremizers(rb_ctx* ctx, int Ns, int Nu, int Q, const double* W, int64_t B, const double* Theta,
+                   const double* U, double* S);
 
 /* Device pointer to the 16-byte {double max_val; int64 max_idx} result of the last sweep (for a NCCL all-gather
  * issued by the host layer without a host round trip), and to the per-parameter estimators. */

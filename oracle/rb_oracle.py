@@ -386,6 +386,21 @@ def reduced_solve_stokes(theta, op, N, theta_bc=None):
     return np.linalg.solve(lhs, rhs)
 
 
+def supremizer_solve(inner_product_s, operator_bt_restricted, theta_bt, solution, N_us, theta_bc_s=None):
+    """Reduced supremizer of one parameter: X_s[:N_us, :N_us] s = (sum_q theta_q Bt_q[:N_us, :N_usp]) u, then the
+    lifting rows (homogeneous for the supremizer component) and dgesv.
+
+    rbnics/problems/stokes/stokes_reduced_problem.py:80-103 (_solve_supremizer): lhs is the single inner-product
+    matrix of the component "s", the right-hand side the assembled "bt_restricted" operator times the reduced
+    solution [u; s; p] of the same parameter."""
+    N_usp = solution.shape[0]
+    lhs = np.array(inner_product_s[:N_us, :N_us], dtype=np.float64)
+    bt = product_order1(theta_bt, [B[:N_us, :N_usp] for B in operator_bt_restricted])
+    rhs = np.array(bt @ solution, dtype=np.float64)
+    apply_dirichlet_rows(lhs, rhs, theta_bc_s)
+    return np.linalg.solve(lhs, rhs)
+
+
 STOKES_ERROR_ESTIMATION_TERMS = [("f", "f"), ("g", "g"), ("a", "f"), ("bt", "f"), ("b", "g"),
                                  ("a", "a"), ("a", "bt"), ("bt", "bt"), ("b", "b")]
 

@@ -1589,6 +1589,90 @@ extern "C" int rb_compute_outputs(rb_ctx* ctx, int Qs, const double* S, const do
   return RB_OK;
 }
 
+// Reduced supremizers of a batch of parameters (rbnics/problems/stokes/stokes_reduced_problem.py:80-103): the left-hand
+// side X_s is the same for every parameter, so with W_q = X_s^{-1} Bt_q (host, once) the per-parameter solve becomes
+//   s_p = sum_q theta_pq W_q u_p,   Wt[q][j][i] = W_q[i][j].
+// One CTA of 128 threads per 8 parameters: theta and u of the 8 in shared memory, thread i owns entry i of the 8
+// supremizers and walks Wt (contiguous in i, L2 resident) once for all 8.
+constexpr int SUP_PB = 8;
+__global__ void __launch_bounds__(128) rb_supremizer_kernel(const double* __restrict__ Wt, int Ns, int Nu, int Q,
+                                                            const double* __restrict__ Theta,
+                                                            const double* __restrict__ U, int ldu, long long B,
+                                                            double* __restrict__ S) {
+  extern __shared__ double sup_smem[];
+  double* th = sup_smem;               // [PB][Q]
+  double* us = sup_smem + SUP_PB * Q;  // [PB][Nu]
+  const long long p0 = (long long)blockIdx.x * SUP_PB;
+  for (int t = threadIdx.x; t < SUP_PB * Q; t += blockDim.x) {
+    const long long p = min(p0 + t / Q, B - 1);
+    th[t] = Theta[p * Q + t % Q];
+  }
+  for (int t = threadIdx.x; t < SUP_PB * Nu; t += blockDim.x) {
+    const long long p = min(p0 + t / Nu, B - 1);
+    us[t] = U[p * ldu + t % Nu];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Ns; i += blockDim.x) {
+    double acc[SUP_PB];
+#pragma unroll
+    for (int p = 0; p < SUP_PB; ++p) acc[p] = 0.0;
+    for (int q = 0; q < Q; ++q) {
+      for (int j = 0; j < Nu; ++j) {
+        const double w = __ldg(Wt + ((long long)q * Nu + j) * Ns + i);
+#pragma unroll
+        for (int p = 0; p < SUP_PB; ++p) acc[p] = fma(w, th[p * Q + q] * us[p * Nu + j], acc[p]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < SUP_PB; ++p)
+      if (p0 + p < B) S[(p0 + p) * Ns + i] = acc[p];
+  }
+}
+
+extern "C" int rb_supremizers(rb_ctx* ctx, int Ns, int Nu, int Q, const double* W, int64_t B, const double* Theta,
+                              const double* U, double* S) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  if (Ns <= 0 || Nu <= 0 || Q <= 0 || B <= 0 || !W || !Theta || !S) RB_FAIL(RB_ERR_ARG, "rb_supremizers: bad arguments");
+  if (!U && (!ctx->dU || ctx->B != B || ctx->N != Nu))
+    RB_FAIL(RB_ERR_STATE, "rb_supremizers: no resident solutions of a sweep with B parameters and N == Nu");
+  if ((size_t)SUP_PB * (Q + Nu) * sizeof(double) > 200 * 1024) RB_FAIL(RB_ERR_ARG, "rb_supremizers: Q + Nu too large");
+  cudaStream_t st = ctx->stream;
+  std::vector<double> Wt((size_t)Q * Nu * Ns);
+  for (int q = 0; q < Q; ++q)
+    for (int i = 0; i < Ns; ++i)
+      for (int j = 0; j < Nu; ++j) Wt[((size_t)q * Nu + j) * Ns + i] = W[((size_t)q * Ns + i) * Nu + j];
+  double *dW = nullptr, *dT = nullptr, *dUu = nullptr, *dS = nullptr;
+  cudaError_t e = cudaMalloc(&dW, Wt.size() * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dT, (size_t)B * Q * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dS, (size_t)B * Ns * sizeof(double));
+  if (e == cudaSuccess && U) e = cudaMalloc(&dUu, (size_t)B * Nu * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dW, Wt.data(), Wt.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dT, Theta, (size_t)B * Q * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && U) e = cudaMemcpyAsync(dUu, U, (size_t)B * Nu * sizeof(double), cudaMemcpyHostToDevice, st);
+  const size_t smem = (size_t)SUP_PB * (Q + Nu) * sizeof(double);
+  if (e == cudaSuccess && smem > 48 * 1024)
+    e = cudaFuncSetAttribute(rb_supremizer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    cudaEventRecord(ctx->ev[4], st);
+    rb_supremizer_kernel<<<(unsigned)((B + SUP_PB - 1) / SUP_PB), 128, smem, st>>>(
+        dW, Ns, Nu, Q, dT, U ? dUu : ctx->dU, U ? Nu : ctx->ldu, B, dS);
+    e = cudaGetLastError();
+    cudaEventRecord(ctx->ev[5], st);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S, dS, (size_t)B * Ns * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  for (double* q : {dW, dT, dUu, dS})
+    if (q) cudaFree(q);
+  if (e != cudaSuccess) RB_FAIL(RB_ERR_CUDA, std::string("rb_supremizers: ") + cudaGetErrorString(e));
+  float a = 0;
+  cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]);
+  ctx->last_ms[0] = a;
+  ctx->last_ms[4] = a;
+  ctx->last_launches = 1;
+  return RB_OK;
+}
+
 extern "C" int rb_result_device_ptrs(rb_ctx* ctx, void** maxloc16, double** delta) {
   if (!ctx) return RB_ERR_ARG;
   if (maxloc16) *maxloc16 = ctx->dResult;

@@ -164,6 +164,29 @@ class SweepEngine:
         self._check(self._lib.rb_compute_outputs(self._h, S.shape[0], L.dptr(S), L.dptr(ThetaS), L.dptr(out)))
         return out
 
+    def solve_supremizers(self, inner_product_s, operator_bt_restricted, Theta_bt, U=None, N_us=None):
+        """Reduced supremizers of a whole batch, ``StokesReducedProblem._solve_supremizer`` for every mu at once
+        (rbnics/problems/stokes/stokes_reduced_problem.py:80-103): ``X_s s = (sum_q theta_q Bt_q) u``.
+
+        inner_product_s: the single matrix of ``inner_product["s"]``; operator_bt_restricted: (Q, N_us, N_usp);
+        Theta_bt: (B, Q); U: (B, N_usp) reduced solutions, or None for those left in HBM by the last sweep.
+        X_s does not depend on mu: it is factorised once on the host (``W_q = X_s^-1 Bt_q``)."""
+        Bt = _f64(operator_bt_restricted)
+        Q, n_us, n_usp = Bt.shape
+        N_us = n_us if N_us is None else int(N_us)
+        Xs = _f64(inner_product_s)[:N_us, :N_us]
+        W = np.ascontiguousarray(np.stack([np.linalg.solve(Xs, Bt[q, :N_us, :]) for q in range(Q)]))
+        Theta_bt = _f64(Theta_bt)
+        B = Theta_bt.shape[0]
+        assert Theta_bt.shape == (B, Q)
+        Uc = None
+        if U is not None:
+            Uc = _f64(U, (B, n_usp))
+        S = np.empty((B, N_us))
+        self._check(self._lib.rb_supremizers(self._h, N_us, n_usp, Q, L.dptr(W), B, L.dptr(Theta_bt), L.dptr(Uc),
+                                             L.dptr(S)))
+        return S
+
     def estimator_work(self):
         """Multiply-adds per parameter issued by the estimator kernel (padding included) and its tile count."""
         m, n = C.c_int64(), C.c_int()

@@ -841,8 +841,79 @@ def make_parabolic_golden(ref):
     print("parabolic golden: N", N, "K", K, "B", B, "delta[0]", delta[0], "argmax", int(np.argmax(delta)))
 
 
+def make_supremizer_golden(ref):
+    """Reduced supremizer solves by the reference's own source: StokesReducedProblem._solve_supremizer
+    (rbnics/problems/stokes/stokes_reduced_problem.py:80-103) with the numpy LinearSolver.solve
+    (rbnics/backends/online/numpy/linear_solver.py:29-31) -> tests/golden/reference_supremizer.npz"""
+    class Mat(np.ndarray):  # online Matrix: `*` with a vector is the matrix-vector product (online/numpy/matrix.py:31-41)
+        def __mul__(self, other):
+            if isinstance(other, np.ndarray) and other.ndim == 1:
+                return np.asarray(self) @ np.asarray(other)
+            return np.ndarray.__mul__(self, other)
+
+    def ref_sum(product_output):
+        out = ref.sum(product_output)
+        return out.view(Mat) if isinstance(out, np.ndarray) and out.ndim == 2 else out
+
+    class Fun(np.ndarray):  # OnlineFunction: .N and .vector()
+        @property
+        def N(self):
+            return self.shape[0]
+
+        def vector(self):
+            return self
+
+    class OnlineLinearSolver:  # rbnics/backends/online/numpy/linear_solver.py:25-33 (+ basic/linear_solver.py bcs)
+        def __init__(self, lhs, solution, rhs, bcs=None):
+            self.lhs, self.solution, self.rhs = np.array(lhs), solution, np.array(rhs)
+            assert bcs is None
+
+        def set_parameters(self, parameters):
+            assert len(parameters) == 0
+
+        def solve(self):
+            self.solution.vector()[:] = np.linalg.solve(self.lhs, self.rhs)
+
+    ns = {"product": ref.product, "sum": ref_sum, "OnlineLinearSolver": OnlineLinearSolver}
+    exec(_method_source("rbnics/problems/stokes/stokes_reduced_problem.py", "_solve_supremizer"), ns)
+    solve_supremizer = ns["_solve_supremizer"]
+
+    rng = np.random.default_rng(33)
+    n_u, n_s, n_p, Q, B = 9, 7, 6, 4, 30
+    N_us, N_usp = n_u + n_s, n_u + n_s + n_p
+    Rm = rng.standard_normal((N_us + 5, N_us))
+    Xs = Rm.T @ Rm / Rm.shape[0] + np.eye(N_us)
+    Bt = ref_rand(rng, Q, N_us, N_usp)
+    Theta = rng.uniform(-2.0, 2.0, (B, Q))
+    U = ref_rand(rng, B, N_usp)
+    S = np.empty((B, N_us))
+
+    class Problem:
+        def __init__(self):
+            self.inner_product = {"s": Storage([Xs])}
+            self.operator = {"bt_restricted": Storage([Bt[q] for q in range(Q)])}
+            self.dirichlet_bc = {"u": False, "s": False}
+            self.dirichlet_bc_are_homogeneous = {"u": True, "s": True}
+            self._linear_solver_parameters = {}
+
+        def compute_theta(self, term):
+            assert term == "bt_restricted"
+            return self._theta
+
+    prob = Problem()
+    for p in range(B):
+        prob._theta = tuple(Theta[p])
+        prob._supremizer = np.zeros(N_us).view(Fun)
+        solve_supremizer(prob, U[p].copy().view(Fun))
+        S[p] = np.asarray(prob._supremizer)
+    np.savez_compressed(os.path.join(HERE, "reference_supremizer.npz"), Xs=Xs, Bt=Bt, Theta=Theta, U=U, S=S,
+                        N_us=np.int64(N_us))
+    print("supremizer golden: N_us", N_us, "N_usp", N_usp, "Q", Q, "B", B, "s[0][:3]", S[0][:3])
+
+
 def main():
     ref = load_reference()
+    make_supremizer_golden(ref)
     make_storage_golden()
     make_offline_golden()
     make_parabolic_golden(ref)

@@ -279,3 +279,55 @@ def test_cuda_stokes_sweep_matches_reference_golden(engine, case):
     assert np.max(np.abs(r["eps2"] - g["eps2"]) / np.abs(g["eps2"])) <= RTOL
     assert np.max(np.abs(r["delta"] - g["delta"]) / g["delta"]) <= RTOL
     assert r["argmax"] == int(np.argmax(g["delta"]))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Reduced supremizer solve: golden vectors from the reference's own _solve_supremizer source
+# (tests/golden/make_golden.py:make_supremizer_golden)
+# ----------------------------------------------------------------------------------------------------------------------
+def _load_supremizer():
+    return dict(np.load(os.path.join(HERE, "golden", "reference_supremizer.npz")))
+
+
+def test_oracle_supremizer_is_bit_identical_to_reference():
+    g = _load_supremizer()
+    N_us = int(g["N_us"])
+    Bt = [g["Bt"][q] for q in range(g["Bt"].shape[0])]
+    for p in range(g["U"].shape[0]):
+        s = O.supremizer_solve(g["Xs"], Bt, tuple(g["Theta"][p]), g["U"][p], N_us)
+        assert np.array_equal(s, g["S"][p])
+
+
+@pytest.mark.gpu
+def test_cuda_supremizers_match_reference_golden(engine):
+    g = _load_supremizer()
+    S = engine.solve_supremizers(g["Xs"], g["Bt"], g["Theta"], g["U"])
+    err = np.max(np.abs(S - g["S"]), axis=1) / np.max(np.abs(g["S"]), axis=1)
+    assert err.max() <= RTOL
+
+
+@pytest.mark.gpu
+def test_cuda_supremizers_from_resident_sweep_solutions(engine):
+    """U = None: the supremizers are computed from the solutions the Stokes sweep left in HBM; ragged batch, more
+    supremizer entries than the 128 threads of a CTA."""
+    g, op, E, theta = _load_stokes("n12_bc")
+    N = op["a"].shape[1]
+    Q = {t: op[t].shape[0] for t in op}
+    nbc = int(g["n_bc"])
+    A = np.concatenate([op["a"], op["b"], op["bt"]])
+    F = np.concatenate([op["f"], op["g"]])
+    Theta = np.concatenate([theta[t] for t in ("a", "b", "bt", "f", "g")], axis=1)
+    engine.set_system(A, F, bc_rows=list(range(nbc)) if nbc else None)
+    engine.set_stokes_estimator(E, Q)
+    engine.set_training_set(Theta, g["beta"], g.get("Theta_bc"))
+    r = engine.sweep_resident(want_u=True)
+    rng = np.random.default_rng(5)
+    N_us, Qbt = 150, 3
+    Rm = rng.standard_normal((N_us + 3, N_us))
+    Xs = Rm.T @ Rm / N_us + np.eye(N_us)
+    Bt = rng.standard_normal((Qbt, N_us, N))
+    Th = rng.uniform(-1.0, 1.0, (Theta.shape[0], Qbt))
+    S = engine.solve_supremizers(Xs, Bt, Th)
+    for p in range(Theta.shape[0]):
+        ref = O.supremizer_solve(Xs, [Bt[q] for q in range(Qbt)], tuple(Th[p]), r["u"][p], N_us)
+        assert np.max(np.abs(S[p] - ref)) <= RTOL * np.max(np.abs(ref))
