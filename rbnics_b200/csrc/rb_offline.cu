@@ -658,7 +658,8 @@ int gram_fused_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* 
   RB_CUDA(cudaFuncSetAttribute(rb_gram_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // a partially filled tile leaves accumulator rows / columns >= ns, ns2 undefined; they are never read back
   RB_CUDA(cudaEventRecord(ctx->ev[4], st));
-  const int reuse = (dS == dS2 && lds == ld2) ? 1 : 0;
+  // in-chunk rows of S2 are read from the staged A operand only if that holds all the columns S2 needs
+  const int reuse = (dS == dS2 && lds == ld2 && ((ns2 + 1) & ~1) <= ((ns + 1) & ~1)) ? 1 : 0;
   rb_gram_fused_kernel<<<(unsigned)nsplit, FG_THREADS, smem, st>>>(dS, lds, ns, dS2, ld2, ns2, reuse, dIndptr,
                                                                               dIndices, dData, rb, re,
                                                                               ws.as<double>(), ldw);

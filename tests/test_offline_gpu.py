@@ -72,7 +72,9 @@ def test_workspace_gram_odd_column_offsets(engine):
     ws.set_operator("X", X)
     ws.new_block("S", n * n, 37)
     ws.append("S", S)
-    for (s0, ns, t0, ns2) in [(0, 37, 0, 37), (1, 20, 3, 11), (2, 35, 1, 36), (5, 1, 0, 37)]:
+    # (same first column with different widths: the right operand may need columns the staged left one lacks)
+    for (s0, ns, t0, ns2) in [(0, 37, 0, 37), (1, 20, 3, 11), (2, 35, 1, 36), (5, 1, 0, 37), (0, 5, 0, 30), (0, 30, 0, 5),
+                              (4, 2, 4, 33), (4, 1, 4, 1)]:
         C = ws.gram("S", "X", cols=(s0, s0 + ns), cols2=(t0, t0 + ns2))
         ref = S[:, s0:s0 + ns].T @ (X @ S[:, t0:t0 + ns2])
         assert np.max(np.abs(C - ref)) <= 1e-10 * np.max(np.abs(ref))
