@@ -855,75 +855,106 @@ extern "C" int rb_project(rb_ctx* ctx, int64_t Nh, int N, int Q, const double* Z
 }
 
 // =====================================================================================================================
-// Z = S V  (tall GEMM, M = Nh): 128 rows x 64 columns per CTA, K chunks of 32, cp.async double buffering, DMMA
+// Z = S V  (tall GEMM, M = Nh; rbnics/backends/dolfin/wrapping/functions_list_mul.py:10-36).  S is read once and Z
+// written once, but n is small (Nmax modes), so the DMMA work on a padded tile is what decides: the first version
+// (128 x 64 tile) issued 2 Nh ns 64 flops for n = 20 and sat at 22 % of HBM.  Now: 128 rows x 32 columns per CTA (4
+// warps of 32 x 32, grid.y walks wider n), only the NTC = ceil(columns / 8) 8-column tiles that exist are multiplied
+// (compile-time count), K chunks of 16 through a 4-stage ring of 16-byte cp.async copies (operands are uploaded with
+// even pitches), two CTAs per SM.  A ring of per-row bulk copies measured slower: cp.async.bulk is issued one lane
+// at a time.
 // =====================================================================================================================
-constexpr int LC_BM = 128, LC_BN = 64, LC_KC = 32, LC_THREADS = 256;
+constexpr int LC_BM = 128, LC_BN = 32, LC_KC = 16, LC_THREADS = 128, LC_NST = 4;
 constexpr int LC_APITCH = LC_KC + 4;  // == 4 (mod 8)
 constexpr int LC_BPITCH = LC_BN + 4;  // == 4 (mod 16)
 
-__global__ void __launch_bounds__(LC_THREADS) rb_lincomb_kernel(const double* __restrict__ S, int ns,
-                                                                const double* __restrict__ V, int n,
-                                                                double* __restrict__ Z, long long Nh) {
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t d = smem_u32(dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+template <int NTC>
+__global__ void __launch_bounds__(LC_THREADS, 2) rb_lincomb_kernel(const double* __restrict__ S, int lds, int ns,
+                                                                   const double* __restrict__ V, int ldv, int n,
+                                                                   double* __restrict__ Z, long long Nh, int col0) {
   extern __shared__ __align__(16) double lc_smem[];
   double(*As)[LC_BM * LC_APITCH] = reinterpret_cast<double(*)[LC_BM * LC_APITCH]>(lc_smem);
-  double(*Bs)[LC_KC * LC_BPITCH] = reinterpret_cast<double(*)[LC_KC * LC_BPITCH]>(lc_smem + 2 * LC_BM * LC_APITCH);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp & 3, wn = warp >> 2, g = lane >> 2, q4 = lane & 3;
+  double(*Bs)[LC_KC * LC_BPITCH] = reinterpret_cast<double(*)[LC_KC * LC_BPITCH]>(lc_smem + LC_NST * LC_BM * LC_APITCH);
+  const int tid = threadIdx.x, lane = tid & 31, wm = tid >> 5;
+  const int g = lane >> 2, q4 = lane & 3;
   const long long r0 = (long long)blockIdx.x * LC_BM;
-  const int n0 = blockIdx.y * LC_BN;
+  const int n0 = col0 + blockIdx.y * LC_BN;
   const int nchunks = (ns + LC_KC - 1) / LC_KC;
+  // pairs of doubles; lds and ldv are even, a pair that straddles ns / n brings one padding element that meets a zero
+  // (rows of V past ns are zero-filled) or lands in a column that is never stored
   auto load_stage = [&](int stage, int chunk) {
     const int k0 = chunk * LC_KC;
-    for (int t = tid; t < LC_BM * LC_KC; t += LC_THREADS) {
-      const int rr = t / LC_KC, kk = t % LC_KC;
+    for (int t = tid; t < LC_BM * LC_KC / 2; t += LC_THREADS) {
+      const int rr = t / (LC_KC / 2), kk = 2 * (t % (LC_KC / 2));
       const bool v = (r0 + rr < Nh) && (k0 + kk < ns);
-      cp_async8(&As[stage][rr * LC_APITCH + kk], v ? (S + (r0 + rr) * ns + k0 + kk) : S, v);
+      cp_async16(&As[stage][rr * LC_APITCH + kk], v ? (S + (r0 + rr) * lds + k0 + kk) : S, v);
     }
-    for (int t = tid; t < LC_KC * LC_BN; t += LC_THREADS) {
-      const int kk = t / LC_BN, cc = t % LC_BN;
+    for (int t = tid; t < LC_KC * LC_BN / 2; t += LC_THREADS) {
+      const int kk = t / (LC_BN / 2), cc = 2 * (t % (LC_BN / 2));
       const bool v = (k0 + kk < ns) && (n0 + cc < n);
-      cp_async8(&Bs[stage][kk * LC_BPITCH + cc], v ? (V + (long long)(k0 + kk) * n + n0 + cc) : V, v);
+      cp_async16(&Bs[stage][kk * LC_BPITCH + cc], v ? (V + (long long)(k0 + kk) * ldv + n0 + cc) : V, v);
     }
   };
-  double acc[4][4][2];
+  double acc[4][NTC][2];
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-  load_stage(0, 0);
-  cp_async_commit();
-  for (int c = 0; c < nchunks; ++c) {
-    if (c + 1 < nchunks) load_stage((c + 1) & 1, c + 1);
+    for (int nt = 0; nt < NTC; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  for (int s = 0; s < LC_NST - 1; ++s) {
+    if (s < nchunks) load_stage(s, s);
     cp_async_commit();
-    cp_async_wait<1>();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<LC_NST - 2>();
     __syncthreads();
-    const double* as = As[c & 1];
-    const double* bs = Bs[c & 1];
+    {
+      const int nxt = c + LC_NST - 1;
+      if (nxt < nchunks) load_stage(nxt % LC_NST, nxt);
+      cp_async_commit();
+    }
+    const double* as = As[c % LC_NST];
+    const double* bs = Bs[c % LC_NST];
 #pragma unroll
     for (int ks = 0; ks < LC_KC / 4; ++ks) {
-      double af[4], bf[4];
+      double af[4], bf[NTC];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) af[mt] = as[(wm * 32 + mt * 8 + g) * LC_APITCH + 4 * ks + q4];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) bf[nt] = bs[(4 * ks + q4) * LC_BPITCH + wn * 32 + nt * 8 + g];
+      for (int nt = 0; nt < NTC; ++nt) bf[nt] = bs[(4 * ks + q4) * LC_BPITCH + nt * 8 + g];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        for (int nt = 0; nt < NTC; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
     const long long r = r0 + wm * 32 + mt * 8 + g;
     if (r >= Nh) continue;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int c = n0 + wn * 32 + nt * 8 + q4 * 2;
+    for (int nt = 0; nt < NTC; ++nt) {
+      const int c = n0 + nt * 8 + q4 * 2;
       if (c < n) Z[r * n + c] = acc[mt][nt][0];
       if (c + 1 < n) Z[r * n + c + 1] = acc[mt][nt][1];
     }
   }
+}
+
+// ny column tiles of 32 starting at column col0 of V / Z
+template <int NTC>
+static cudaError_t lincomb_launch(cudaStream_t st, size_t smem, const double* dS, int lds, int ns, const double* dV,
+                                  int ldv, int n, double* dZ, long long Nh, int ny, int col0) {
+  cudaError_t e = cudaFuncSetAttribute(rb_lincomb_kernel<NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)((Nh + LC_BM - 1) / LC_BM), ny);
+  rb_lincomb_kernel<NTC><<<grid, LC_THREADS, smem, st>>>(dS, lds, ns, dV, ldv, n, dZ, Nh, col0);
+  return cudaGetLastError();
 }
 
 extern "C" int rb_lincomb(rb_ctx* ctx, int64_t Nh, int Ns, int n, const double* S, const double* V, double* Z) {
@@ -932,17 +963,24 @@ extern "C" int rb_lincomb(rb_ctx* ctx, int64_t Nh, int Ns, int n, const double* 
   if (Nh <= 0 || Ns <= 0 || n <= 0 || !S || !V || !Z) RB_FAIL(RB_ERR_ARG, "rb_lincomb: bad arguments");
   cudaStream_t st = ctx->stream;
   DevBuf dS, dV, dZ;
-  RB_CUDA(dS.alloc((size_t)Nh * Ns * sizeof(double)));
-  RB_CUDA(dV.alloc((size_t)Ns * n * sizeof(double)));
+  int lds = Ns, ldv = n;
+  if (int rc = upload_cols(ctx, S, Nh, Ns, dS, &lds)) return rc;
+  if (int rc = upload_cols(ctx, V, Ns, n, dV, &ldv)) return rc;
   RB_CUDA(dZ.alloc((size_t)Nh * n * sizeof(double)));
-  RB_CUDA(cudaMemcpyAsync(dS.p, S, (size_t)Nh * Ns * sizeof(double), cudaMemcpyHostToDevice, st));
-  RB_CUDA(cudaMemcpyAsync(dV.p, V, (size_t)Ns * n * sizeof(double), cudaMemcpyHostToDevice, st));
-  dim3 grid((unsigned)((Nh + LC_BM - 1) / LC_BM), (n + LC_BN - 1) / LC_BN);
+  const size_t smem = (size_t)LC_NST * (LC_BM * LC_APITCH + LC_KC * LC_BPITCH) * sizeof(double);
   RB_CUDA(cudaEventRecord(ctx->ev[4], st));
-  const size_t lc_smem_bytes = (size_t)(2 * LC_BM * LC_APITCH + 2 * LC_KC * LC_BPITCH) * sizeof(double);
-  RB_CUDA(cudaFuncSetAttribute(rb_lincomb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc_smem_bytes));
-  rb_lincomb_kernel<<<grid, LC_THREADS, lc_smem_bytes, st>>>(dS.as<double>(), Ns, dV.as<double>(), n, dZ.as<double>(), Nh);
-  RB_CUDA(cudaGetLastError());
+  // full 32-column tiles in one launch, the narrower last tile with the 8-column tile count it needs
+  const int nfull = n / LC_BN, rem = n % LC_BN;
+  const double *pS = dS.as<double>(), *pV = dV.as<double>();
+  double* pZ = dZ.as<double>();
+  if (nfull > 0) RB_CUDA(lincomb_launch<4>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, Nh, nfull, 0));
+  if (rem > 0) {
+    const int c0 = nfull * LC_BN, ntc = (rem + 7) / 8;
+    RB_CUDA(ntc == 1   ? lincomb_launch<1>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, Nh, 1, c0)
+            : ntc == 2 ? lincomb_launch<2>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, Nh, 1, c0)
+            : ntc == 3 ? lincomb_launch<3>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, Nh, 1, c0)
+                       : lincomb_launch<4>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, Nh, 1, c0));
+  }
   RB_CUDA(cudaEventRecord(ctx->ev[5], st));
   RB_CUDA(cudaMemcpyAsync(Z, dZ.p, (size_t)Nh * n * sizeof(double), cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaStreamSynchronize(st));
@@ -950,7 +988,7 @@ extern "C" int rb_lincomb(rb_ctx* ctx, int64_t Nh, int Ns, int n, const double* 
   cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]);
   ctx->last_ms[0] = a;
   ctx->last_ms[4] = a;
-  ctx->last_launches = 1;
+  ctx->last_launches = (nfull > 0) + (rem > 0);
   return RB_OK;
 }
 
