@@ -271,6 +271,152 @@ __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Single-tile variant of rb_tsmm2_kernel (ns, ns2 <= TM) with the 8-column sub-tiles dealt evenly to the warps: a
+// product with 100 columns has 13 x 13 sub-tiles, which 4 x 4 warps of fixed 32 x 32 tiles cover with 16 x 16 (61 %
+// useful DMMAs, and the busiest SM sub-partition decides).  Here warp row r owns M8/WM (+1) consecutive sub-tile rows,
+// warp column likewise; the k loop of every (rows, columns) count is its own fully unrolled instantiation, chosen
+// once per warp, so there are no predicates inside the DMMA stream.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int MT, int NT>
+__device__ __forceinline__ void t2_chunk(double (&acc)[4][4][2], const double* __restrict__ as,
+                                         const double* __restrict__ bs, int PA, int PB) {
+#pragma unroll
+  for (int ks = 0; ks < T2_KC / 4; ++ks) {
+    double af[MT], bf[NT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) af[mt] = as[4 * ks * PA + mt * 8];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) bf[nt] = bs[4 * ks * PB + nt * 8];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+  }
+}
+
+template <int MT>
+__device__ __forceinline__ void t2_chunk_nt(int nt_w, double (&acc)[4][4][2], const double* as, const double* bs, int PA,
+                                            int PB) {
+  switch (nt_w) {
+    case 1: t2_chunk<MT, 1>(acc, as, bs, PA, PB); break;
+    case 2: t2_chunk<MT, 2>(acc, as, bs, PA, PB); break;
+    case 3: t2_chunk<MT, 3>(acc, as, bs, PA, PB); break;
+    default: t2_chunk<MT, 4>(acc, as, bs, PA, PB); break;
+  }
+}
+
+template <int TM>
+__global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
+    rb_tsmm2_bal_kernel(const double* __restrict__ S, int lds, int ns, const double* __restrict__ Y, int ldy, int ns2,
+                        long long row_begin, long long row_end, long long rows_per_split, double* __restrict__ ws,
+                        int ldw, int contig) {
+  constexpr int WM = TM / 32, P = TM + 4;
+  // contig: both operands start at column 0 of rows no longer than a stage row, so the 32 rows of a chunk are ONE piece
+  // of memory per operand -- one bulk copy each instead of 64 per-lane copies (~40 clk apiece on the refilling warp,
+  // more than its DMMA time per chunk once the sub-tiles are balanced); the stage then keeps the global pitch.
+  const int PA = contig ? lds : P, PB = contig ? ldy : P;
+  extern __shared__ __align__(128) unsigned char t2_smem[];
+  double* As = reinterpret_cast<double*>(t2_smem);               // [NST][KC][P]
+  double* Bs = As + T2_NST * T2_KC * P;                          // [NST][KC][P]
+  uint64_t* full = reinterpret_cast<uint64_t*>(Bs + T2_NST * T2_KC * P);
+  int* cnt = reinterpret_cast<int*>(full + T2_NST);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp / WM, wn = (warp + wm) % WM;
+  const int split = blockIdx.x;
+  const long long rs = row_begin + split * rows_per_split;
+  const long long re = min(row_end, rs + rows_per_split);
+  const int nchunks = (int)((re - rs + T2_KC - 1) / T2_KC);
+  const int M8 = (ns + 7) / 8, N8 = (ns2 + 7) / 8;  // 8-column sub-tiles (<= 4 WM each way)
+  const int mt_w = M8 / WM + (wm < M8 % WM), m8 = wm * (M8 / WM) + min(wm, M8 % WM);
+  const int nt_w = N8 / WM + (wn < N8 % WM), n8 = wn * (N8 / WM) + min(wn, N8 % WM);
+  const int nactive = min(WM, M8) * min(WM, N8);
+  const int wa = (ns + 1) & ~1, wb = (ns2 + 1) & ~1;  // columns copied per row
+  if (tid == 0) {
+    for (int s = 0; s < T2_NST; ++s) {
+      mbar_init(full + s, 1);
+      cnt[s] = 0;
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (mt_w == 0 || nt_w == 0) return;
+
+  auto issue = [&](int st, int c) {  // executed by one whole warp: lane l brings row l of the chunk
+    const long long r0 = rs + (long long)c * T2_KC;
+    const int nrows = (int)min((long long)T2_KC, re - r0);
+    double* as = As + st * T2_KC * P + lane * PA;
+    double* bs = Bs + st * T2_KC * P + lane * PB;
+    if (lane >= nrows) {  // rows past the end of the split count as zeros
+      for (int c2 = 0; c2 < PA; ++c2) as[c2] = 0.0;
+      for (int c2 = 0; c2 < PB; ++c2) bs[c2] = 0.0;
+    }
+    __syncwarp();
+    if (contig) {
+      if (lane == 0) {
+        const uint32_t ba = (uint32_t)nrows * (uint32_t)lds * 8u, bb = (uint32_t)nrows * (uint32_t)ldy * 8u;
+        mbar_arrive_expect_tx(full + st, ba + bb);
+        bulk_g2s(As + st * T2_KC * P, S + r0 * lds, ba, full + st);
+        bulk_g2s(Bs + st * T2_KC * P, Y + r0 * ldy, bb, full + st);
+      }
+      return;
+    }
+    if (lane == 0) mbar_arrive_expect_tx(full + st, (uint32_t)nrows * (uint32_t)(wa + wb) * 8u);
+    __syncwarp();
+    if (lane < nrows) {
+      bulk_g2s(as, S + (r0 + lane) * lds, (uint32_t)wa * 8u, full + st);
+      bulk_g2s(bs, Y + (r0 + lane) * ldy, (uint32_t)wb * 8u, full + st);
+    }
+  };
+  if (warp == 0) {  // (warp 0 owns sub-tile row 0 and column 0: always active)
+    for (int s = 0; s < T2_NST && s < nchunks; ++s) issue(s, s);
+  }
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  const int g = lane >> 2, q4 = lane & 3;
+  const int aoff = q4 * PA + m8 * 8 + g, boff = q4 * PB + n8 * 8 + g;
+  int st = 0;
+  uint32_t phase = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    mbar_wait(full + st, phase);
+    const double* as = As + st * T2_KC * P + aoff;
+    const double* bs = Bs + st * T2_KC * P + boff;
+    switch (mt_w) {
+      case 1: t2_chunk_nt<1>(nt_w, acc, as, bs, PA, PB); break;
+      case 2: t2_chunk_nt<2>(nt_w, acc, as, bs, PA, PB); break;
+      case 3: t2_chunk_nt<3>(nt_w, acc, as, bs, PA, PB); break;
+      default: t2_chunk_nt<4>(nt_w, acc, as, bs, PA, PB); break;
+    }
+    __syncwarp();
+    int old = 0;
+    if (lane == 0) old = atomicAdd(&cnt[st], 1);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old == nactive - 1) {  // last warp out refills the slot
+      if (lane == 0) cnt[st] = 0;
+      if (c + T2_NST < nchunks) issue(st, c + T2_NST);
+    }
+    if (++st == T2_NST) {
+      st = 0;
+      phase ^= 1u;
+    }
+  }
+  double* w = ws + (long long)split * ldw * ldw;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const int i = (m8 + mt) * 8 + g;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int j = (n8 + nt) * 8 + q4 * 2;
+      if (mt < mt_w && nt < nt_w)
+        *reinterpret_cast<double2*>(w + (long long)i * ldw + j) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Fused Gram for ns, ns2 <= 64: C += S^T (X S2) over a range of dof rows WITHOUT writing Y = X S2 to HBM
 // (algorithmic bytes 12 nnz + 8 Nh Ns).  One warp-specialised CTA of 28 warps per SM; registers move
 // from the gather warps (64) to the DMMA warps (120) with setmaxnreg -- the sum has to fit the CTA's launch
@@ -610,10 +756,15 @@ struct PoolBuf {
   }
 };
 
+// Row pitch of a dense dof-major operand with n columns: even (16-byte aligned rows for the bulk copies); 65..128
+// columns go through the single-tile product with one bulk copy per chunk and the global pitch kept in shared memory,
+// where a pitch == 4 (mod 16) keeps the fragment loads conflict-free.
+inline int dense_pitch(int n) { return (n > 64 && n <= 128) ? (n + 11) / 16 * 16 + 4 : ((n + 1) & ~1); }
+
 // Host matrix (Nh x n, row-major, dense) -> device with an even row pitch *ld (16-byte aligned rows).
 int upload_cols(rb_ctx* ctx, const double* host, long long Nh, int n, DevBuf& out, int* ld) {
   cudaStream_t st = ctx->stream;
-  *ld = (n + 1) & ~1;
+  *ld = dense_pitch(n);
   RB_CUDA(out.alloc((size_t)Nh * *ld * sizeof(double)));
   if (*ld == n) {
     RB_CUDA(cudaMemcpyAsync(out.p, host, (size_t)Nh * n * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -684,12 +835,12 @@ int gram_fused_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* 
 // C (host, ns x ns2) = S^T (X S2) over rows [rb, re); all operands already on the device.
 int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, int lds, const double* dS2, int ld2,
                 const long long* dIndptr, const int* dIndices, const double* dData, long long rb, long long re,
-                double* C_host, float* ms_spmm, float* ms_tsmm, int x_sym = -1) {
+                double* C_host, float* ms_spmm, float* ms_tsmm, int x_sym = -1, bool at_col0 = true) {
   cudaStream_t st = ctx->stream;
   PoolBuf Ybuf(ctx, 0), ws(ctx, 1), dC(ctx, 2);
   const double* dY = dS2;
   // every allocation happens BEFORE the timed region (cudaMalloc synchronises and costs milliseconds)
-  const int ldy = dIndptr ? ((ns2 + 1) & ~1) : ld2;
+  const int ldy = dIndptr ? dense_pitch(ns2) : ld2;
   static const int no_fuse = getenv("RB_GRAM_NOFUSE") ? atoi(getenv("RB_GRAM_NOFUSE")) : 0;
   const bool fused = dIndptr && !no_fuse && ns <= 64 && ns2 <= 64 && (((uintptr_t)dS | (uintptr_t)dS2) & 15) == 0 &&
                      (lds % 2 == 0) && (ld2 % 2 == 0);
@@ -717,6 +868,8 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
     sym = x_sym == 1;
   }
   const int ntiles = sym ? ti * (ti + 1) / 2 : ti * tj;
+  static const int no_bal = getenv("RB_TSMM_NOBAL") ? atoi(getenv("RB_TSMM_NOBAL")) : 0;
+  const bool bal = v2 && ti == 1 && tj == 1 && !no_bal;  // one tile: sub-tiles dealt evenly to the warps
   const int ldw = v2 ? 32 * std::max((ns + 31) / 32, (ns2 + 31) / 32) : std::max(ti, tj) * TM;
   const long long rows = std::max<long long>(re - rb, 0);
   const int KC = v2 ? T2_KC : TS_KC;
@@ -742,6 +895,10 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
                          : (size_t)2 * TS_STAGES * TS_KC * TS_PITCH * sizeof(double);
   if (!v2)
     RB_CUDA(cudaFuncSetAttribute(rb_tsmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (bal && TM == 64)
+    RB_CUDA(cudaFuncSetAttribute(rb_tsmm2_bal_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (bal)
+    RB_CUDA(cudaFuncSetAttribute(rb_tsmm2_bal_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (TM == 64)
     RB_CUDA(cudaFuncSetAttribute(rb_tsmm2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else
@@ -761,6 +918,14 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
   dim3 grid(ti, tj, (unsigned)nsplit);
   if (!v2)
     rb_tsmm_kernel<<<grid, TS_THREADS, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw);
+  else if (bal && TM == 64)
+    rb_tsmm2_bal_kernel<64><<<dim3((unsigned)nsplit), 128, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps,
+                                                                      ws.as<double>(), ldw,
+                                                                      (at_col0 && lds <= TM + 4 && ldy <= TM + 4) ? 1 : 0);
+  else if (bal)
+    rb_tsmm2_bal_kernel<128><<<dim3((unsigned)nsplit), 512, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps,
+                                                                       ws.as<double>(), ldw,
+                                                                       (at_col0 && lds <= TM + 4 && ldy <= TM + 4) ? 1 : 0);
   else if (TM == 64)
     rb_tsmm2_kernel<64><<<grid, 128, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw, 0);
   else
@@ -1249,7 +1414,8 @@ extern "C" int rb_off_gram(rb_ctx* ctx, int blkS, int s0, int ns, int csrX, int 
     RB_FAIL(RB_ERR_ARG, "rb_off_gram: column range outside the block");
   if (row_begin < 0 || row_end > S->Nh || row_begin > row_end) RB_FAIL(RB_ERR_ARG, "rb_off_gram: bad row range");
   return gram_device(ctx, S->Nh, ns, ns2, S->d + s0, S->ld, S2->d + t0, S2->ld, X ? X->ip : nullptr,
-                     X ? X->ix : nullptr, X ? X->dt : nullptr, row_begin, row_end, C, nullptr, nullptr, X ? X->sym : -1);
+                     X ? X->ix : nullptr, X ? X->dt : nullptr, row_begin, row_end, C, nullptr, nullptr, X ? X->sym : -1,
+                     s0 == 0 && t0 == 0);
 }
 
 // Y[r, c] = sum_k data[k] * S[indices[k], c] for a FEW columns (n <= 8): one thread per (dof row, column) -- the

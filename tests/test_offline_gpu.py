@@ -19,7 +19,8 @@ def _lap2d(n):
     return (sp.kron(T, I) + sp.kron(I, T) + 0.5 * sp.identity(n * n)).tocsr()
 
 
-@pytest.mark.parametrize("n,Ns", [(9, 1), (20, 7), (31, 61), (40, 64), (33, 130), (50, 200)])
+@pytest.mark.parametrize("n,Ns", [(9, 1), (20, 7), (31, 61), (40, 64), (17, 65), (22, 97), (20, 100), (25, 128),
+                                  (33, 130), (50, 200)])
 def test_gram_matches_loop_oracle(engine, n, Ns):
     rng = np.random.default_rng(n + Ns)
     X = _lap2d(n)
@@ -48,6 +49,21 @@ def test_gram_multi_tile(engine, Ns, symmetric):
     C0 = offline.gram(engine, S, None)
     ref0 = S.T @ S
     assert np.max(np.abs(C0 - ref0)) <= 1e-10 * np.max(np.abs(ref0))
+
+
+@pytest.mark.parametrize("Ns,Ns2", [(70, 3), (3, 70), (100, 100), (65, 128), (128, 9), (104, 105)])
+def test_gram_single_wide_tile_shapes(engine, Ns, Ns2):
+    """65..128 columns on either side: one 128-wide tile whose 8-column sub-tiles are dealt evenly to the 16 warps
+    (also when one side has fewer sub-tiles than warp rows)."""
+    rng = np.random.default_rng(Ns * 131 + Ns2)
+    n = 19
+    X = _lap2d(n)
+    S = rng.standard_normal((n * n, Ns))
+    S2 = rng.standard_normal((n * n, Ns2))
+    for Xop in (X, None):
+        C = offline.gram(engine, S, Xop, S2)
+        ref = S.T @ ((X @ S2) if Xop is not None else S2)
+        assert np.max(np.abs(C - ref)) <= 1e-10 * np.max(np.abs(ref))
 
 
 def test_gram_rectangular_multi_tile(engine):
