@@ -54,6 +54,25 @@ __global__ void __launch_bounds__(256) rb_spmm_kernel(const long long* __restric
   }
 }
 
+// Y[r, c] = sum_k data[k] * S[indices[k], c] for a FEW columns (n <= 32): one thread per (dof row, column), rows
+// [row_begin, row_end) -- the one-warp-per-row kernel above idles most of its lanes and pays its latency chain per row.
+__global__ void __launch_bounds__(256) rb_spmm_narrow_kernel(const long long* __restrict__ indptr,
+                                                             const int* __restrict__ indices,
+                                                             const double* __restrict__ data,
+                                                             const double* __restrict__ S, int lds, int n,
+                                                             double* __restrict__ Y, int ldy, long long row_begin,
+                                                             long long row_end) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long r = row_begin + t / n;
+  const int c = (int)(t % n);
+  if (r >= row_end) return;
+  double acc = 0.0;
+  const long long k1 = __ldg(indptr + r + 1);
+  for (long long k = __ldg(indptr + r); k < k1; ++k)
+    acc = fma(__ldg(data + k), __ldg(S + (long long)__ldg(indices + k) * lds + c), acc);
+  Y[r * ldy + c] = acc;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Partial C tile (64 x 64) over a contiguous range of dof rows: ws[split][i][j] = sum_r S[r][i] * Y[r][j]
 // ---------------------------------------------------------------------------------------------------------------------
@@ -842,8 +861,10 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
   // every allocation happens BEFORE the timed region (cudaMalloc synchronises and costs milliseconds)
   const int ldy = dIndptr ? dense_pitch(ns2) : ld2;
   static const int no_fuse = getenv("RB_GRAM_NOFUSE") ? atoi(getenv("RB_GRAM_NOFUSE")) : 0;
-  const bool fused = dIndptr && !no_fuse && ns <= 64 && ns2 <= 64 && (((uintptr_t)dS | (uintptr_t)dS2) & 15) == 0 &&
-                     (lds % 2 == 0) && (ld2 % 2 == 0);
+  // (up to 32 columns of S2 the thread-per-entry SpMM + the single-tile product are faster than the fused kernel, whose
+  //  time is set by its per-chunk hand-over, not by the width: 0.28 ms against 0.48 ms at 20 columns, N_h = 10^6)
+  const bool fused = dIndptr && !no_fuse && ns <= 64 && ns2 > 32 && ns2 <= 64 &&
+                     (((uintptr_t)dS | (uintptr_t)dS2) & 15) == 0 && (lds % 2 == 0) && (ld2 % 2 == 0);
   if (fused) return gram_fused_device(ctx, Nh, ns, ns2, dS, lds, dS2, ld2, dIndptr, dIndices, dData, rb, re, C_host, ms_spmm, ms_tsmm);
   if (dIndptr) {
     RB_CUDA(Ybuf.alloc((size_t)Nh * ldy * sizeof(double)));
@@ -908,7 +929,12 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
     const int nchunk = (ns2 + 127) / 128;
     const long long warps = (re - rb) * nchunk;
     const long long blocks = (warps * 32 + 255) / 256;
-    if (blocks > 0) {
+    if (blocks > 0 && ns2 <= 32) {
+      const long long threads = (re - rb) * ns2;
+      rb_spmm_narrow_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dIndptr, dIndices, dData, dS2, ld2, ns2,
+                                                                              Ybuf.as<double>(), ldy, rb, re);
+      RB_CUDA(cudaGetLastError());
+    } else if (blocks > 0) {
       rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIndptr, dIndices, dData, dS2, ld2, ns2, Ybuf.as<double>(), ldy,
                                                       rb, re);
       RB_CUDA(cudaGetLastError());
@@ -1418,23 +1444,6 @@ extern "C" int rb_off_gram(rb_ctx* ctx, int blkS, int s0, int ns, int csrX, int 
                      s0 == 0 && t0 == 0);
 }
 
-// Y[r, c] = sum_k data[k] * S[indices[k], c] for a FEW columns (n <= 8): one thread per (dof row, column) -- the
-// one-warp-per-row kernel above would idle 31 lanes of 32.
-__global__ void __launch_bounds__(256) rb_spmm_narrow_kernel(const long long* __restrict__ indptr,
-                                                             const int* __restrict__ indices,
-                                                             const double* __restrict__ data,
-                                                             const double* __restrict__ S, int lds, int n,
-                                                             double* __restrict__ Y, int ldy, long long Nh) {
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long r = t / n;
-  const int c = (int)(t % n);
-  if (r >= Nh) return;
-  double acc = 0.0;
-  for (long long k = __ldg(indptr + r); k < __ldg(indptr + r + 1); ++k)
-    acc = fma(__ldg(data + k), __ldg(S + (long long)__ldg(indices + k) * lds + c), acc);
-  Y[r * ldy + c] = acc;
-}
-
 extern "C" int rb_off_spmm(rb_ctx* ctx, int csrA, int blkS, int s0, int n, int blkY, int y0) {
   if (!ctx) return RB_ERR_ARG;
   RB_CUDA(cudaSetDevice(ctx->device));
@@ -1448,10 +1457,10 @@ extern "C" int rb_off_spmm(rb_ctx* ctx, int csrA, int blkS, int s0, int n, int b
   if (S == Y && !(y0 >= s0 + n || y0 + n <= s0)) RB_FAIL(RB_ERR_ARG, "rb_off_spmm: source and target columns overlap");
   cudaStream_t st = ctx->stream;
   RB_CUDA(cudaEventRecord(ctx->ev[4], st));
-  if (n <= 8) {
+  if (n <= 32) {
     const long long threads = A->Nh * n;
     rb_spmm_narrow_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A->ip, A->ix, A->dt, S->d + s0, S->ld, n,
-                                                                            Y->d + y0, Y->ld, A->Nh);
+                                                                            Y->d + y0, Y->ld, 0, A->Nh);
   } else {
     const int nchunk = (n + 127) / 128;
     const long long blocks = (A->Nh * nchunk * 32 + 255) / 256;
