@@ -96,8 +96,9 @@ struct rb_ctx {
 
   rb_off_csr_t off_csr[RB_OFF_SLOTS];
   rb_off_blk_t off_blk[RB_OFF_SLOTS];
-  void* off_scratch[3] = {nullptr, nullptr, nullptr};  // grow-only scratch of the Gram path: Y = X S2, split partials, C
-  size_t off_scratch_cap[3] = {0, 0, 0};
+  // grow-only scratch of the Gram path: Y = X S2, split partials, C, realigned copies of S and S2
+  void* off_scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t off_scratch_cap[5] = {0, 0, 0, 0, 0};
 
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float last_ms[5] = {0, 0, 0, 0, 0};

@@ -851,12 +851,57 @@ int gram_fused_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* 
   return RB_OK;
 }
 
+// dst[r * ldd + c] = src[r * lds + c], c < n: an operand whose rows are not 16-byte aligned (odd column offset inside a
+// resident block) is copied once into aligned scratch instead of taking the slow 8-byte cp.async product.
+__global__ void rb_copy_cols_kernel(const double* __restrict__ src, int lds, int n, double* __restrict__ dst, int ldd,
+                                    long long r0, long long r1) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long r = r0 + t / n;
+  if (r >= r1) return;
+  dst[r * ldd + t % n] = src[r * lds + t % n];
+}
+
 // C (host, ns x ns2) = S^T (X S2) over rows [rb, re); all operands already on the device.
 int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, int lds, const double* dS2, int ld2,
                 const long long* dIndptr, const int* dIndices, const double* dData, long long rb, long long re,
                 double* C_host, float* ms_spmm, float* ms_tsmm, int x_sym = -1, bool at_col0 = true) {
   cudaStream_t st = ctx->stream;
-  PoolBuf Ybuf(ctx, 0), ws(ctx, 1), dC(ctx, 2);
+  PoolBuf Ybuf(ctx, 0), ws(ctx, 1), dC(ctx, 2), alS(ctx, 3), alS2(ctx, 4);
+  bool s_at0 = at_col0, y_at0 = at_col0 || dIndptr != nullptr;  // operand starts at column 0 of its rows (Y always does)
+  static const int force_v1 = getenv("RB_TSMM_V1") ? atoi(getenv("RB_TSMM_V1")) : 0;
+  if (!force_v1) {
+    // realign: S always feeds the product; S2 does only without an operator (with one, the SpMM reads it at any
+    // alignment and writes an aligned Y)
+    const bool same = dS == dS2 && lds == ld2 && ns == ns2;
+    auto misaligned = [](const double* p, int ld) { return ((uintptr_t)p & 15) != 0 || (ld & 1) != 0; };
+    if (misaligned(dS, lds)) {
+      const int l = dense_pitch(ns);
+      RB_CUDA(alS.alloc((size_t)Nh * l * sizeof(double)));
+      const long long rows = std::max<long long>(re - rb, 0);
+      if (rows > 0)
+        rb_copy_cols_kernel<<<(unsigned)((rows * ns + 255) / 256), 256, 0, st>>>(dS, lds, ns, alS.as<double>(), l, rb, re);
+      RB_CUDA(cudaGetLastError());
+      dS = alS.as<double>();
+      lds = l;
+      s_at0 = true;
+      if (same && !dIndptr) {
+        dS2 = dS;
+        ld2 = l;
+        y_at0 = true;
+      }
+    }
+    if (!dIndptr && misaligned(dS2, ld2)) {
+      const int l = dense_pitch(ns2);
+      RB_CUDA(alS2.alloc((size_t)Nh * l * sizeof(double)));
+      const long long rows = std::max<long long>(re - rb, 0);
+      if (rows > 0)
+        rb_copy_cols_kernel<<<(unsigned)((rows * ns2 + 255) / 256), 256, 0, st>>>(dS2, ld2, ns2, alS2.as<double>(), l, rb, re);
+      RB_CUDA(cudaGetLastError());
+      dS2 = alS2.as<double>();
+      ld2 = l;
+      y_at0 = true;
+    }
+  }
   const double* dY = dS2;
   // every allocation happens BEFORE the timed region (cudaMalloc synchronises and costs milliseconds)
   const int ldy = dIndptr ? dense_pitch(ns2) : ld2;
@@ -870,8 +915,8 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
     RB_CUDA(Ybuf.alloc((size_t)Nh * ldy * sizeof(double)));
     dY = Ybuf.as<double>();
   }
-  // bulk-copy kernel needs 16-byte aligned rows; anything else (odd pitch, odd column offset) takes the cp.async one
-  static const int force_v1 = getenv("RB_TSMM_V1") ? atoi(getenv("RB_TSMM_V1")) : 0;
+  // bulk-copy kernels need 16-byte aligned rows (guaranteed by the realignment above; RB_TSMM_V1=1 selects the
+  // first-generation cp.async product for A/B runs)
   const bool v2 = !force_v1 && (((uintptr_t)dS | (uintptr_t)dY) & 15) == 0 && (lds % 2 == 0) && (ldy % 2 == 0);
   const int TM = !v2 ? TS_TM : ((ns <= 64 && ns2 <= 64) ? 64 : 128);
   const int ti = (ns + TM - 1) / TM, tj = (ns2 + TM - 1) / TM;
@@ -947,11 +992,11 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
   else if (bal && TM == 64)
     rb_tsmm2_bal_kernel<64><<<dim3((unsigned)nsplit), 128, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps,
                                                                       ws.as<double>(), ldw,
-                                                                      (at_col0 && lds <= TM + 4 && ldy <= TM + 4) ? 1 : 0);
+                                                                      (s_at0 && y_at0 && lds <= TM + 4 && ldy <= TM + 4) ? 1 : 0);
   else if (bal)
     rb_tsmm2_bal_kernel<128><<<dim3((unsigned)nsplit), 512, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps,
                                                                        ws.as<double>(), ldw,
-                                                                       (at_col0 && lds <= TM + 4 && ldy <= TM + 4) ? 1 : 0);
+                                                                       (s_at0 && y_at0 && lds <= TM + 4 && ldy <= TM + 4) ? 1 : 0);
   else if (TM == 64)
     rb_tsmm2_kernel<64><<<grid, 128, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw, 0);
   else

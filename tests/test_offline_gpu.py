@@ -78,8 +78,8 @@ def test_gram_rectangular_multi_tile(engine):
 
 
 def test_workspace_gram_odd_column_offsets(engine):
-    """Column ranges that start at odd columns of a resident block are not 16-byte aligned: the cp.async kernel takes
-    them; results equal the aligned path."""
+    """Column ranges that start at odd columns of a resident block are not 16-byte aligned: they are copied once into
+    aligned scratch (rb_copy_cols_kernel) before the bulk-copy kernels run; results equal the aligned path."""
     rng = np.random.default_rng(9)
     n = 18
     X = _lap2d(n)
