@@ -38,6 +38,13 @@ struct rb_off_blk_t {
   long long Nh = 0;
   int cap = 0, n = 0;
   int ld = 0;             // row pitch: cap rounded up to an even count (16-byte aligned rows for the bulk copies)
+  // Gram-Schmidt mirrors (allocated by the first rb_off_gram_schmidt on the block): the columns once more, each one
+  // contiguous, and X times each column -- the sequential dots / axpys of MGS then read 8 Nh bytes per basis function
+  // instead of a 32-byte sector per entry of a dof-major column, and X Z is not recomputed on every call
+  double* zt = nullptr;   // [cap][Nh]
+  double* xzt = nullptr;  // [cap][Nh]
+  int gs_n = 0;           // columns mirrored so far
+  int gs_csr = -2;        // operator slot the xzt mirror was built with
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -97,8 +104,9 @@ struct rb_ctx {
   rb_off_csr_t off_csr[RB_OFF_SLOTS];
   rb_off_blk_t off_blk[RB_OFF_SLOTS];
   // grow-only scratch of the Gram path: Y = X S2, split partials, C, realigned copies of S and S2
-  void* off_scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t off_scratch_cap[5] = {0, 0, 0, 0, 0};
+  // (5..8: Gram-Schmidt work vectors)
+  void* off_scratch[9] = {};
+  size_t off_scratch_cap[9] = {};
 
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float last_ms[5] = {0, 0, 0, 0, 0};

@@ -1405,7 +1405,8 @@ extern "C" int rb_off_block(rb_ctx* ctx, int slot, int64_t Nh, int capacity) {
   RB_CUDA(cudaSetDevice(ctx->device));
   if (slot < 0 || slot >= RB_OFF_SLOTS || Nh <= 0 || capacity <= 0) RB_FAIL(RB_ERR_ARG, "rb_off_block: bad arguments");
   rb_off_blk_t& b = ctx->off_blk[slot];
-  if (b.d) cudaFree(b.d);
+  for (void* q : {(void*)b.d, (void*)b.zt, (void*)b.xzt})
+    if (q) cudaFree(q);
   b = rb_off_blk_t();
   const int ld = (capacity + 1) & ~1;
   RB_CUDA(cudaMalloc((void**)&b.d, (size_t)Nh * ld * sizeof(double)));
@@ -1532,16 +1533,53 @@ extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, i
   if (!Z || !z || (csrX >= 0 && !X)) RB_FAIL(RB_ERR_ARG, "rb_off_gram_schmidt: empty slot");
   if (append && Z->n + 1 > Z->cap) RB_FAIL(RB_ERR_ARG, "rb_off_gram_schmidt: block capacity exceeded");
   cudaStream_t st = ctx->stream;
-  DevBuf dz, dNorm;
-  RB_CUDA(dz.alloc((size_t)Z->Nh * sizeof(double)));
+  const long long Nh = Z->Nh;
+  const unsigned nb1 = (unsigned)((Nh + 255) / 256);
+  PoolBuf dz(ctx, 5), dNorm(ctx, 6), dXz(ctx, 7), dPart(ctx, 8);
+  RB_CUDA(dz.alloc((size_t)Nh * sizeof(double)));
   RB_CUDA(dNorm.alloc(sizeof(double)));
-  RB_CUDA(cudaMemcpyAsync(dz.p, z, (size_t)Z->Nh * sizeof(double), cudaMemcpyHostToDevice, st));
+  RB_CUDA(dPart.alloc(GS_BLOCKS * sizeof(double)));
+  if (X) RB_CUDA(dXz.alloc((size_t)Nh * sizeof(double)));
+  RB_CUDA(cudaMemcpyAsync(dz.p, z, (size_t)Nh * sizeof(double), cudaMemcpyHostToDevice, st));
   int launches = 0;
-  if (int rc = gs_device(ctx, Z->Nh, Z->n, Z->d, Z->ld, X ? X->ip : nullptr, X ? X->ix : nullptr, X ? X->dt : nullptr,
-                         dz.as<double>(), dNorm.as<double>(), &launches))
-    return rc;
+  // column mirrors (see rb_off_blk_t): bring them up to date with the block (columns appended by rb_off_append, a
+  // different operator than last time)
+  if (!Z->zt) RB_CUDA(cudaMalloc((void**)&Z->zt, (size_t)Z->cap * Nh * sizeof(double)));
+  if (X && !Z->xzt) RB_CUDA(cudaMalloc((void**)&Z->xzt, (size_t)Z->cap * Nh * sizeof(double)));
+  if (Z->gs_csr != csrX) Z->gs_n = 0;
+  auto mirror_column = [&](int k) -> int {  // zt[k] = column k of the block, xzt[k] = X zt[k]
+    rb_off_gather_kernel<<<nb1, 256, 0, st>>>(Z->d, Z->ld, k, 1, Z->zt + (size_t)k * Nh, Nh);
+    if (X)
+      rb_spmm_narrow_kernel<<<nb1, 256, 0, st>>>(X->ip, X->ix, X->dt, Z->zt + (size_t)k * Nh, 1, 1,
+                                                 Z->xzt + (size_t)k * Nh, 1, 0, Nh);
+    RB_CUDA(cudaGetLastError());
+    launches += X ? 2 : 1;
+    return RB_OK;
+  };
+  for (int k = Z->gs_n; k < Z->n; ++k)
+    if (int rc = mirror_column(k)) return rc;
+  Z->gs_n = Z->n;
+  Z->gs_csr = csrX;
+  // single-pass MGS in the reference's order (rbnics/backends/basic/gram_schmidt.py:22-36), deterministic dots
+  const double* xz = X ? Z->xzt : Z->zt;
+  for (int k = 0; k < Z->n; ++k) {
+    rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dz.as<double>(), 1, xz + (size_t)k * Nh, 1, Nh, dPart.as<double>());
+    rb_axpy_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dPart.as<double>(), Z->zt + (size_t)k * Nh, 1, dz.as<double>(), Nh);
+    launches += 2;
+  }
+  RB_CUDA(cudaGetLastError());
+  const double* dXzp = dz.as<double>();
+  if (X) {
+    rb_spmm_narrow_kernel<<<nb1, 256, 0, st>>>(X->ip, X->ix, X->dt, dz.as<double>(), 1, 1, dXz.as<double>(), 1, 0, Nh);
+    dXzp = dXz.as<double>();
+    ++launches;
+  }
+  rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dz.as<double>(), 1, dXzp, 1, Nh, dPart.as<double>());
+  rb_normalize_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dPart.as<double>(), dz.as<double>(), Nh, dNorm.as<double>());
+  launches += 2;
+  RB_CUDA(cudaGetLastError());
   if (append) {
-    rb_off_scatter_kernel<<<(unsigned)((Z->Nh + 255) / 256), 256, 0, st>>>(dz.as<double>(), 1, Z->d, Z->ld, Z->n, Z->Nh);
+    rb_off_scatter_kernel<<<nb1, 256, 0, st>>>(dz.as<double>(), 1, Z->d, Z->ld, Z->n, Nh);
     RB_CUDA(cudaGetLastError());
     ++launches;
   }
@@ -1549,7 +1587,7 @@ extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, i
   RB_CUDA(cudaMemcpyAsync(z, dz.p, (size_t)Z->Nh * sizeof(double), cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaMemcpyAsync(&nrm, dNorm.p, sizeof(double), cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaStreamSynchronize(st));
-  if (append) Z->n += 1;
+  if (append) Z->n += 1;  // (its mirror is made by the next call, from the block itself)
   if (norm_out) *norm_out = nrm;
   ctx->last_launches = launches;
   return RB_OK;

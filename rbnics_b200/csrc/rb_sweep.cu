@@ -757,7 +757,8 @@ extern "C" void rb_ctx_destroy(rb_ctx* ctx) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int t = 0; t < RB_OFF_SLOTS; ++t) {
-    for (void* p : {(void*)ctx->off_csr[t].ip, (void*)ctx->off_csr[t].ix, (void*)ctx->off_csr[t].dt, (void*)ctx->off_blk[t].d})
+    for (void* p : {(void*)ctx->off_csr[t].ip, (void*)ctx->off_csr[t].ix, (void*)ctx->off_csr[t].dt, (void*)ctx->off_blk[t].d,
+                    (void*)ctx->off_blk[t].zt, (void*)ctx->off_blk[t].xzt})
       if (p) cudaFree(p);
   }
   for (void* p : ctx->off_scratch)
