@@ -1271,6 +1271,32 @@ __global__ void __launch_bounds__(GS_THREADS) rb_axpy_kernel(const double* __res
     z[i] = fma(-d, b[i * incb], z[i]);
 }
 
+// One MGS step on contiguous vectors: z -= d_k b_k with d_k = sum(partial_in), and in the same pass the partial dots of
+// the NEXT step <z, xz_next> (same per-thread order as rb_dot_partial_kernel, so the results are bitwise those of the
+// separate kernels); xz_next == nullptr for the last basis function.
+__global__ void __launch_bounds__(GS_THREADS) rb_gs_step_kernel(const double* __restrict__ partial_in,
+                                                                const double* __restrict__ b, double* __restrict__ z,
+                                                                const double* __restrict__ xz_next, long long n,
+                                                                double* __restrict__ partial_out) {
+  __shared__ double sh[GS_THREADS / 32];
+  const double d = gs_sum_partials(partial_in);
+  double s = 0.0;
+  for (long long i = blockIdx.x * (long long)GS_THREADS + threadIdx.x; i < n; i += (long long)GS_BLOCKS * GS_THREADS) {
+    const double zi = fma(-d, b[i], z[i]);
+    z[i] = zi;
+    if (xz_next) s = fma(zi, xz_next[i], s);
+  }
+  if (!xz_next) return;
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < GS_THREADS / 32; ++w) t += sh[w];
+    partial_out[blockIdx.x] = t;
+  }
+}
+
 // z /= sqrt(sum(partial)) unless that is zero; writes the norm
 __global__ void __launch_bounds__(GS_THREADS) rb_normalize_kernel(const double* __restrict__ partial,
                                                                   double* __restrict__ z, long long n,
@@ -1538,7 +1564,7 @@ extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, i
   PoolBuf dz(ctx, 5), dNorm(ctx, 6), dXz(ctx, 7), dPart(ctx, 8);
   RB_CUDA(dz.alloc((size_t)Nh * sizeof(double)));
   RB_CUDA(dNorm.alloc(sizeof(double)));
-  RB_CUDA(dPart.alloc(GS_BLOCKS * sizeof(double)));
+  RB_CUDA(dPart.alloc(2 * GS_BLOCKS * sizeof(double)));
   if (X) RB_CUDA(dXz.alloc((size_t)Nh * sizeof(double)));
   RB_CUDA(cudaMemcpyAsync(dz.p, z, (size_t)Nh * sizeof(double), cudaMemcpyHostToDevice, st));
   int launches = 0;
@@ -1562,10 +1588,17 @@ extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, i
   Z->gs_csr = csrX;
   // single-pass MGS in the reference's order (rbnics/backends/basic/gram_schmidt.py:22-36), deterministic dots
   const double* xz = X ? Z->xzt : Z->zt;
+  // dot of step 0, then one kernel per step: axpy of step k fused with the dots of step k+1 (N+1 launches, not 2N)
+  double* part[2] = {dPart.as<double>(), dPart.as<double>() + GS_BLOCKS};
+  if (Z->n > 0) {
+    rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dz.as<double>(), 1, xz, 1, Nh, part[0]);
+    ++launches;
+  }
   for (int k = 0; k < Z->n; ++k) {
-    rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dz.as<double>(), 1, xz + (size_t)k * Nh, 1, Nh, dPart.as<double>());
-    rb_axpy_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dPart.as<double>(), Z->zt + (size_t)k * Nh, 1, dz.as<double>(), Nh);
-    launches += 2;
+    rb_gs_step_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(part[k & 1], Z->zt + (size_t)k * Nh, dz.as<double>(),
+                                                       k + 1 < Z->n ? xz + (size_t)(k + 1) * Nh : nullptr, Nh,
+                                                       part[(k + 1) & 1]);
+    ++launches;
   }
   RB_CUDA(cudaGetLastError());
   const double* dXzp = dz.as<double>();
