@@ -109,7 +109,7 @@ def main():
         e2e = (time.perf_counter() - t0) * 1e3
         ms, _ = timings(eng)
         shape = {"Nh": Nh, "N": N, "Q": len(ops), "nnz": nnz}
-        fused = 32 < N <= 64
+        fused = 48 < N <= 64
         emit("rb_project (Q x fused gather+DMMA)" if fused else "rb_project (Q x (SpMM + Z^T Y))", shape, ms[4],
              len(ops) * (12 * nnz + (8 if fused else 24) * Nh * N),
              len(ops) * (2 * nnz * N + 2 * Nh * N * N), e2e,

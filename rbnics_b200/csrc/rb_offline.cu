@@ -73,6 +73,28 @@ __global__ void __launch_bounds__(256) rb_spmm_narrow_kernel(const long long* __
   Y[r * ldy + c] = acc;
 }
 
+// Same with one thread per (dof row, PAIR of columns) for 33..128 columns of 16-byte aligned operands (even pitches).
+__global__ void __launch_bounds__(256) rb_spmm_pair_kernel(const long long* __restrict__ indptr,
+                                                           const int* __restrict__ indices,
+                                                           const double* __restrict__ data,
+                                                           const double* __restrict__ S, int lds, int npair,
+                                                           double* __restrict__ Y, int ldy, long long row_begin,
+                                                           long long row_end) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long r = row_begin + t / npair;
+  const int c = 2 * (int)(t % npair);
+  if (r >= row_end) return;
+  double2 acc = make_double2(0.0, 0.0);
+  const long long k1 = __ldg(indptr + r + 1);
+  for (long long k = __ldg(indptr + r); k < k1; ++k) {
+    const double v = __ldg(data + k);
+    const double2 x = __ldg(reinterpret_cast<const double2*>(S + (long long)__ldg(indices + k) * lds + c));
+    acc.x = fma(v, x.x, acc.x);
+    acc.y = fma(v, x.y, acc.y);
+  }
+  *reinterpret_cast<double2*>(Y + r * ldy + c) = acc;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Partial C tile (64 x 64) over a contiguous range of dof rows: ws[split][i][j] = sum_r S[r][i] * Y[r][j]
 // ---------------------------------------------------------------------------------------------------------------------
@@ -906,9 +928,10 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
   // every allocation happens BEFORE the timed region (cudaMalloc synchronises and costs milliseconds)
   const int ldy = dIndptr ? dense_pitch(ns2) : ld2;
   static const int no_fuse = getenv("RB_GRAM_NOFUSE") ? atoi(getenv("RB_GRAM_NOFUSE")) : 0;
-  // (up to 32 columns of S2 the thread-per-entry SpMM + the single-tile product are faster than the fused kernel, whose
-  //  time is set by its per-chunk hand-over, not by the width: 0.28 ms against 0.48 ms at 20 columns, N_h = 10^6)
-  const bool fused = dIndptr && !no_fuse && ns <= 64 && ns2 > 32 && ns2 <= 64 &&
+  // (up to 48 columns of S2 the thread-per-entry / per-pair SpMM + the single-tile product are faster than the fused
+  //  kernel, whose time is set by its per-chunk hand-over, not by the width: 0.28 ms against 0.48 ms at 20 columns,
+  //  0.38 against 0.49 ms at 40, 0.60 against 0.50 ms at 61; N_h = 10^6)
+  const bool fused = dIndptr && !no_fuse && ns <= 64 && ns2 > 48 && ns2 <= 64 &&
                      (((uintptr_t)dS | (uintptr_t)dS2) & 15) == 0 && (lds % 2 == 0) && (ld2 % 2 == 0);
   if (fused) return gram_fused_device(ctx, Nh, ns, ns2, dS, lds, dS2, ld2, dIndptr, dIndices, dData, rb, re, C_host, ms_spmm, ms_tsmm);
   if (dIndptr) {
@@ -974,10 +997,18 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
     const int nchunk = (ns2 + 127) / 128;
     const long long warps = (re - rb) * nchunk;
     const long long blocks = (warps * 32 + 255) / 256;
+    static const int pair_max = getenv("RB_SPMM_PAIR_MAX") ? atoi(getenv("RB_SPMM_PAIR_MAX")) : 96;
     if (blocks > 0 && ns2 <= 32) {
       const long long threads = (re - rb) * ns2;
       rb_spmm_narrow_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dIndptr, dIndices, dData, dS2, ld2, ns2,
                                                                               Ybuf.as<double>(), ldy, rb, re);
+      RB_CUDA(cudaGetLastError());
+    } else if (blocks > 0 && ns2 <= pair_max && ((uintptr_t)dS2 & 15) == 0 && (ld2 % 2 == 0)) {
+      // (a pair that straddles ns2 reads / writes the padding column of the even pitch)
+      const int npair = (ns2 + 1) / 2;
+      const long long threads = (re - rb) * npair;
+      rb_spmm_pair_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dIndptr, dIndices, dData, dS2, ld2, npair,
+                                                                            Ybuf.as<double>(), ldy, rb, re);
       RB_CUDA(cudaGetLastError());
     } else if (blocks > 0) {
       rb_spmm_kernel<<<(unsigned)blocks, 256, 0, st>>>(dIndptr, dIndices, dData, dS2, ld2, ns2, Ybuf.as<double>(), ldy,
