@@ -998,12 +998,15 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
     const long long warps = (re - rb) * nchunk;
     const long long blocks = (warps * 32 + 255) / 256;
     static const int pair_max = getenv("RB_SPMM_PAIR_MAX") ? atoi(getenv("RB_SPMM_PAIR_MAX")) : 96;
-    if (blocks > 0 && ns2 <= 32) {
+    const bool s2_aligned = ((uintptr_t)dS2 & 15) == 0 && (ld2 % 2 == 0);
+    // measured at N_h = 10^6, 5 nnz/row: per entry 0.095 ms at 8 columns (per pair: 0.158), per pair 0.131 ms at 20
+    // (per entry: 0.184) and 0.181 ms at 32 (0.293)
+    if (blocks > 0 && ns2 <= 32 && (ns2 <= 12 || !s2_aligned)) {
       const long long threads = (re - rb) * ns2;
       rb_spmm_narrow_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dIndptr, dIndices, dData, dS2, ld2, ns2,
                                                                               Ybuf.as<double>(), ldy, rb, re);
       RB_CUDA(cudaGetLastError());
-    } else if (blocks > 0 && ns2 <= pair_max && ((uintptr_t)dS2 & 15) == 0 && (ld2 % 2 == 0)) {
+    } else if (blocks > 0 && ns2 <= pair_max && s2_aligned) {
       // (a pair that straddles ns2 reads / writes the padding column of the even pitch)
       const int npair = (ns2 + 1) / 2;
       const long long threads = (re - rb) * npair;
