@@ -4,24 +4,33 @@
 #include "rb_lu_kernel.cuh"
 
 int rb_lu_launch_unit0(int NP, const LuArgs& args, cudaStream_t stream);
+int rb_lu_mw_launch(const LuArgs& args, double* scratch, cudaStream_t stream);
+long long rb_lu_mw_scratch_doubles(int N, long long count);
+#ifdef RB_AB_VARIANTS
 int rb_lu_launch_unit1(int NP, const LuArgs& args, cudaStream_t stream);
 int rb_lu_launch_unit2(int NP, const LuArgs& args, cudaStream_t stream);
 int rb_lu_launch_unit3(int NP, const LuArgs& args, cudaStream_t stream);
 int rb_lu_dmma_dispatch(int N, const LuArgs& args, cudaStream_t stream);
 int rb_lu_left_launch(const LuArgs& args, double* scratch, cudaStream_t stream);
 long long rb_lu_left_scratch_doubles(int N);
+#endif
 
-// Which kernel serves 32 < N (A/B switch for profiling): "left" (default; one warp per system, left-looking, L records
-// streamed from L2, 8 systems per SM), "dmma" (register-resident, 2 systems per SM), "rowreg" (row per thread).
+// Which kernel serves 32 < N <= 128: "mw" (default; up to four warps per system, left-looking, persistent CTAs whose
+// L records stay in L2, rb_lu_mw.cu).  Builds with -DRB_AB_VARIANTS (make AB=1) also carry the round-1 kernels for
+// A/B profiling, selected by RB_LU_KERNEL: "left" (one warp per system, left-looking, 8 systems per SM),
+// "dmma" (register-resident, 2 systems per SM), "rowreg" (row per thread).
 // Two right-looking variants that kept the trailing matrix in global memory (thread-per-row and warp-per-system with
 // DMMA updates) were measured at the same 0.27 us/system as "dmma" (read-modify-write latency through L2) and removed;
 // so was a two-warps-per-system variant of "left" (rows / tile rows split between the warps, one block barrier per pivot
 // step): 7 % slower than one warp per system, the barriers cost more than the shorter chain saves.
 int rb_lu_variant() {
   static const int v = [] {
+#ifdef RB_AB_VARIANTS
     const char* e = getenv("RB_LU_KERNEL");
     if (e && e[0] == 'd') return 1;
     if (e && e[0] == 'r') return 2;
+    if (e && e[0] == 'l') return 3;
+#endif
     return 0;
   }();
   return v;
@@ -142,9 +151,7 @@ __global__ void __launch_bounds__(128) rb_lu_smem_kernel(LuArgs args, int NP) {
 int rb_launch_lu_args(rb_ctx* ctx, const LuArgs& a, int NP) {
   int rc;
   const int variant = rb_lu_variant();
-  const bool force_rowreg = variant == 2;  // A/B switches for profiling the older kernels
-  if (NP > 32 && a.N <= 128 && variant == 0) {
-    const long long need = a.count * rb_lu_left_scratch_doubles(a.N);
+  auto ensure_scratch = [&](long long need) -> int {
     if (need > ctx->lu_scratch_cap) {
       if (ctx->dLuScratch) cudaFree(ctx->dLuScratch);
       ctx->dLuScratch = nullptr;
@@ -156,17 +163,29 @@ int rb_launch_lu_args(rb_ctx* ctx, const LuArgs& a, int NP) {
       }
       ctx->lu_scratch_cap = need;
     }
+    return RB_OK;
+  };
+  if (NP > 32 && a.N <= 128 && variant == 0) {
+    if (int rs = ensure_scratch(rb_lu_mw_scratch_doubles(a.N, a.count))) return rs;
+    rc = rb_lu_mw_launch(a, ctx->dLuScratch, ctx->stream);
+  }
+#ifdef RB_AB_VARIANTS
+  else if (NP > 32 && a.N <= 128 && variant == 3) {
+    if (int rs = ensure_scratch(a.count * rb_lu_left_scratch_doubles(a.N))) return rs;
     rc = rb_lu_left_launch(a, ctx->dLuScratch, ctx->stream);
-  } else if (NP > 32 && NP <= LU_MAX_NP_REG && !force_rowreg)
+  } else if (NP > 32 && NP <= LU_MAX_NP_REG && variant == 1)
     rc = rb_lu_dmma_dispatch(a.N, a, ctx->stream);
-  else if (NP <= 52)
+  else if (NP > 32 && NP <= 52)
     rc = rb_lu_launch_unit0(NP, a, ctx->stream);
-  else if (NP <= 80)
+  else if (NP > 32 && NP <= 80)
     rc = rb_lu_launch_unit1(NP, a, ctx->stream);
-  else if (NP <= 96)
+  else if (NP > 32 && NP <= 96)
     rc = rb_lu_launch_unit2(NP, a, ctx->stream);
-  else if (NP <= LU_MAX_NP_REG)
+  else if (NP > 32 && NP <= LU_MAX_NP_REG)
     rc = rb_lu_launch_unit3(NP, a, ctx->stream);
+#endif
+  else if (NP <= 32)
+    rc = rb_lu_launch_unit0(NP, a, ctx->stream);
   else {
     const size_t bytes = ((size_t)NP * (NP + 1) + 2 * (size_t)NP) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(rb_lu_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

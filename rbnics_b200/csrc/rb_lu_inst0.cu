@@ -11,11 +11,13 @@ int rb_lu_launch_unit0(int NP, const LuArgs& args, cudaStream_t stream) {
     case 24: return rb_lu_launch_np<24>(args, stream);
     case 28: return rb_lu_launch_np<28>(args, stream);
     case 32: return rb_lu_launch_np<32>(args, stream);
+#ifdef RB_AB_VARIANTS
     case 36: return rb_lu_launch_np<36>(args, stream);
     case 40: return rb_lu_launch_np<40>(args, stream);
     case 44: return rb_lu_launch_np<44>(args, stream);
     case 48: return rb_lu_launch_np<48>(args, stream);
     case 52: return rb_lu_launch_np<52>(args, stream);
+#endif
     default: return -1000;
   }
 }

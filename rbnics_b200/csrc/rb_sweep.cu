@@ -1076,7 +1076,9 @@ extern "C" int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_c
   if (dTab) cudaFree(dTab);
   if (e != cudaSuccess) RB_FAIL(RB_ERR_CUDA, std::string("rb_set_estimator: ") + cudaGetErrorString(e));
   RB_CUDA(cudaFuncSetAttribute(rb_estimator_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#ifdef RB_AB_VARIANTS
   RB_CUDA(cudaFuncSetAttribute(rb_estimator_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
   ctx->have_est = true;
   return RB_OK;
 }
@@ -1192,10 +1194,12 @@ static int launch_estimator(rb_ctx* ctx, const double* Uvec, int ldu, int vecN, 
   ea.tri16 = ctx->est_tri16;
   const long long nrb = (rows + EST_BM - 1) / EST_BM;
   const size_t smem = est_smem_bytes(ctx->est_nstage, ctx->stage_ksteps, ctx->LVS, ctx->nblk, ctx->n_ctile);
+#ifdef RB_AB_VARIANTS
   static const bool est16 = getenv("RB_EST_WARPS") && atoi(getenv("RB_EST_WARPS")) == 16;  // A/B switch (default 8)
   if (est16)
     rb_estimator_kernel<2><<<(unsigned)(nrb * nsplit), 512, smem, ctx->stream>>>(ea);
   else
+#endif
     rb_estimator_kernel<4><<<(unsigned)(nrb * nsplit), 256, smem, ctx->stream>>>(ea);
   RB_CUDA(cudaGetLastError());
   return RB_OK;
@@ -1204,8 +1208,11 @@ static int launch_estimator(rb_ctx* ctx, const double* Uvec, int ldu, int vecN, 
 // chunk size of the assembly scratch and its (re)allocation
 static int prepare_assembly(rb_ctx* ctx, long long B, long long* chunk_out, size_t* asm_smem_out) {
   long long chunk = (long long)ctx->sm_count * ASM_BM;
-  if (getenv("RB_LU_CHUNK")) chunk = atoll(getenv("RB_LU_CHUNK"));
-  chunk = std::min<long long>(B, chunk);
+  if (const char* e = getenv("RB_LU_CHUNK")) {  // tuning knob; anything that is not a positive count is ignored
+    const long long v = atoll(e);
+    if (v > 0) chunk = v;
+  }
+  chunk = std::max<long long>(1, std::min<long long>(B, chunk));
   if (chunk * ctx->EP > ctx->ab_cap) {
     if (int rc = dev_realloc(ctx, &ctx->dAb, (size_t)chunk * ctx->EP)) return rc;
     ctx->ab_cap = chunk * ctx->EP;
