@@ -1,23 +1,23 @@
 #!/usr/bin/env python
 """Per-source-line instruction / stall-sample breakdown of one kernel in an .ncu-rep (compiled with -lineinfo):
-   python tools/ncu_lines.py report.ncu-rep file.cu [top]"""
+   python tools/ncu_lines.py report.ncu-rep [systems_per_launch] [min_pct]"""
 import collections, csv, subprocess, sys
-rep, fname = sys.argv[1], sys.argv[2]
-top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+rep = sys.argv[1]
+nsys = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+minp = float(sys.argv[3]) if len(sys.argv) > 3 else 0.5
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-by = collections.OrderedDict(); tot = ts = 0; cur = None; hdr = None; infile = False
+by = collections.OrderedDict(); tot = ts = 0; hdr = None; fn = None
 for r in rows:
     if len(r) >= 2 and r[0] == "File Path":
-        infile = r[1].endswith(fname); hdr = None; continue
+        fn = r[1].split("/")[-1]; hdr = None; continue
     if "Line No" in r:
         hdr = r; iL = r.index("Line No"); iE = r.index("Instructions Executed"); iS = r.index("# Samples"); iSrc = r.index("Source"); continue
-    if hdr is None or len(r) < len(hdr): continue
-    if r[iL] != "":
-        cur = (int(r[iL]), r[iSrc].strip()[:74]) if infile else ("other", "")
+    if hdr is None or len(r) < len(hdr) or r[iL] == "": continue   # CUDA-level rows only (SASS rows repeat them)
     try: n = int(r[iE]); smp = int(r[iS])
     except ValueError: continue
-    d = by.setdefault(cur, [0, 0]); d[0] += n; d[1] += smp; tot += n; ts += smp
-print("total warp instructions", tot, "samples", ts)
-for k, (n, smp) in sorted(by.items(), key=lambda kv: -kv[1][1])[:top]:
-    print(f"smp {100*smp/ts:5.1f}%  inst {100*n/tot:5.1f}%  L{k[0]}: {k[1]}")
+    by[(fn, int(r[iL]), r[iSrc].strip()[:86])] = (n, smp); tot += n; ts += smp
+print(f"warp instructions {tot} ({tot / nsys:.0f} per unit), samples {ts}")
+for k, (n, smp) in sorted(by.items(), key=lambda kv: (kv[0][0], kv[0][1])):
+    if n > tot * minp / 100 or smp > ts * minp / 100:
+        print(f"{k[0][:16]:16s} L{k[1]:4d} inst {n / nsys:8.0f} {100 * n / tot:5.1f}%  smp {100 * smp / ts:5.1f}%  {k[2]}")
