@@ -14,6 +14,7 @@ not use these one-at-a-time calls: it uses the batched sweep (``rbnics_b200.swee
 """
 from __future__ import annotations
 
+import builtins
 import ctypes as C
 from numbers import Number
 
@@ -21,6 +22,7 @@ import numpy as np
 
 from . import _lib as L
 
+builtins_sum = builtins.sum  # this module defines its own sum(), as the reference's backend does
 _engine = None
 
 
@@ -157,6 +159,66 @@ Function.Type = lambda: _FunctionType
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# Component dictionaries of block problems (Stokes: components u, s, p)
+# rbnics/utils/io/online_size_dict.py, component_name_to_basis_component_index_dict.py: ordered dicts whose repr() is
+# what the reference writes into component_name_to_basis_component_{index,length}.txt and content_item_shape.txt
+# ----------------------------------------------------------------------------------------------------------------------
+class OnlineSizeDict(dict):
+    """component name -> number of basis functions (insertion-ordered, like the reference's OrderedDict)."""
+
+    def __repr__(self):
+        return "OnlineSizeDict(" + dict.__repr__(self) + ")"
+
+
+class ComponentNameToBasisComponentIndexDict(dict):
+    """component name -> position of the component's block."""
+
+    def __repr__(self):
+        return "ComponentNameToBasisComponentIndexDict(" + dict.__repr__(self) + ")"
+
+
+_DICT_CTORS = {"OnlineSizeDict": OnlineSizeDict,
+               "ComponentNameToBasisComponentIndexDict": ComponentNameToBasisComponentIndexDict}
+
+
+def _parse_reference_text(text):
+    """Safe replacement of the reference's eval() of its text files (rbnics/utils/io/text_io.py:26-44): literals plus
+    the two dict constructors above; anything else raises ValueError."""
+    import ast
+
+    def convert(node):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in _DICT_CTORS \
+                and len(node.args) <= 1 and not node.keywords:
+            return _DICT_CTORS[node.func.id](convert(node.args[0]) if node.args else {})
+        if isinstance(node, ast.Tuple):
+            return tuple(convert(e) for e in node.elts)
+        if isinstance(node, ast.List):
+            return [convert(e) for e in node.elts]
+        if isinstance(node, ast.Dict):
+            return {convert(k): convert(v) for k, v in zip(node.keys, node.values)}
+        return ast.literal_eval(node)
+
+    return convert(ast.parse(text.strip(), mode="eval").body)
+
+
+def _block_indices(stop, start, length_dict, index_dict):
+    """Index set of storage[start:stop] along one axis when start / stop are component dicts
+    (rbnics/backends/online/basic/wrapping/slice_to_array.py:27-45): the blocks are laid out in the order of
+    index_dict with the lengths of length_dict; component c contributes offset_c + [start_c, stop_c)."""
+    names = sorted(index_dict, key=lambda c: index_dict[c])
+    lengths = [int(length_dict[c]) for c in names]
+    offsets = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(int)
+    idx = []
+    for c, off, ln in zip(names, offsets, lengths):
+        lo = int(start[c]) if start is not None else 0
+        hi = int(stop[c])
+        if not (0 <= lo <= hi <= ln):
+            raise ValueError("slice %r:%r outside component %r of length %d" % (lo, hi, c, ln))
+        idx.extend(range(int(off) + lo, int(off) + hi))
+    return np.array(idx, dtype=np.intp)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # AffineExpansionStorage
 # ----------------------------------------------------------------------------------------------------------------------
 class AffineExpansionStorage:
@@ -177,6 +239,26 @@ class AffineExpansionStorage:
             self._content = np.empty((int(arg1), int(arg2)), dtype=object)
         self._slices = {}
         self._stacked = None
+        # per axis of the items: component name -> block position / block length (None: single block)
+        self._component_name_to_basis_component_index = None
+        self._component_name_to_basis_component_length = None
+
+    def set_components(self, length_dicts, index_dicts=None):
+        """Declare the block structure of the items: one OnlineSizeDict per item axis (matrix: rows, columns), as the
+        reference's Matrix(M, N) / Vector(N) do when M, N are dicts (online/basic/matrix.py:32-65)."""
+        if isinstance(length_dicts, dict):
+            length_dicts = (length_dicts,)
+        length_dicts = tuple(OnlineSizeDict(d) for d in length_dicts)
+        if index_dicts is None:
+            index_dicts = tuple(ComponentNameToBasisComponentIndexDict((c, i) for i, c in enumerate(d))
+                                for d in length_dicts)
+        elif isinstance(index_dicts, dict):
+            index_dicts = (index_dicts,)
+        self._component_name_to_basis_component_length = length_dicts
+        self._component_name_to_basis_component_index = tuple(ComponentNameToBasisComponentIndexDict(d)
+                                                              for d in index_dicts)
+        self._slices = {}
+        return self
 
     def order(self):
         return self._content.ndim
@@ -203,11 +285,29 @@ class AffineExpansionStorage:
             return self._content[key]
         ck = repr(key)
         if ck not in self._slices:
+            keys = key if isinstance(key, tuple) else (key,)
+            assert all(isinstance(k, slice) and k.step is None for k in keys)
+            with_dicts = any(isinstance(k.stop, dict) for k in keys)
             out = AffineExpansionStorage.__new__(AffineExpansionStorage)
             out._content = np.empty(self._content.shape, dtype=object)
+            out._component_name_to_basis_component_index = self._component_name_to_basis_component_index
+            out._component_name_to_basis_component_length = self._component_name_to_basis_component_length
+            if with_dicts:
+                # block slicing (slice_to_array.py:27-45): storage[:N] / storage[:N, :N] with N = {"u": .., "s": .., "p": ..}
+                lens, inds = self._component_name_to_basis_component_length, self._component_name_to_basis_component_index
+                if lens is None or len(lens) != len(keys):
+                    raise ValueError("component-dict slicing needs set_components() with one dict per item axis")
+                index_sets = [_block_indices(k.stop, k.start if isinstance(k.start, dict) else None, lens[a], inds[a])
+                              for a, k in enumerate(keys)]
+                take = np.ix_(*index_sets)
+                out._component_name_to_basis_component_length = tuple(
+                    OnlineSizeDict((c, int(k.stop[c]) - (int(k.start[c]) if isinstance(k.start, dict) else 0))
+                                   for c in sorted(inds[a], key=lambda c: inds[a][c])) for a, k in enumerate(keys))
+            else:
+                take = key
             for idx in np.ndindex(self._content.shape):
                 it = self._content[idx]
-                out._content[idx] = it if isinstance(it, float) else np.ascontiguousarray(it[key])
+                out._content[idx] = it if isinstance(it, float) else np.ascontiguousarray(it[take])
             out._slices = {}
             out._stacked = None
             self._slices[ck] = out
@@ -238,17 +338,27 @@ class AffineExpansionStorage:
             for k, idx in enumerate(np.ndindex(self._content.shape)):
                 text("content_item_" + str(k), self._content[idx])
         else:
+            lens = self._component_name_to_basis_component_length
             if first.ndim == 2:
                 text("content_item_type", "matrix")
-                text("content_item_shape", (int(first.shape[0]), int(first.shape[1])))
+                text("content_item_shape", tuple(lens) if lens is not None
+                     else (int(first.shape[0]), int(first.shape[1])))
             else:
                 text("content_item_type", "vector")
-                text("content_item_shape", int(first.shape[0]))
+                text("content_item_shape", lens[0] if lens is not None else int(first.shape[0]))
             for k, idx in enumerate(np.ndindex(self._content.shape)):
                 np.save(os.path.join(full, "content_item_" + str(k) + ".npy"), np.asarray(self._content[idx]),
-                        allow_pickle=True)
-        text("component_name_to_basis_component_index", getattr(self, "_component_name_to_basis_component_index", None))
-        text("component_name_to_basis_component_length", getattr(self, "_component_name_to_basis_component_length", None))
+                        allow_pickle=False)
+
+        def dicts(value, is_vector):
+            # the reference stores one dict per item axis for matrices and a bare dict for vectors
+            if value is None:
+                return (None, None) if (not is_vector and first is not None and not isinstance(first, float)) else None
+            return value[0] if is_vector else tuple(value)
+
+        is_vector = isinstance(first, np.ndarray) and first.ndim == 1
+        text("component_name_to_basis_component_index", dicts(self._component_name_to_basis_component_index, is_vector))
+        text("component_name_to_basis_component_length", dicts(self._component_name_to_basis_component_length, is_vector))
 
     def load(self, directory, filename, globals=None):
         """Fill an (empty) storage of the right order/shape from the reference's directory layout.  Returns False if
@@ -261,10 +371,9 @@ class AffineExpansionStorage:
             return True
 
         def text(name):
-            env = dict(globals or {})
-            env.update({"__builtins__": None})
+            # the reference eval()s these files; only literals and its two dict classes can legitimately appear
             with open(os.path.join(full, name + ".txt")) as f:
-                return eval(f.read(), env, {})
+                return _parse_reference_text(f.read())
 
         kind = text("content_item_type")
         assert kind in ("matrix", "vector", "function", "scalar", "empty"), kind
@@ -275,12 +384,19 @@ class AffineExpansionStorage:
             elif kind == "empty":
                 self._content[idx] = None
             else:
-                arr = np.load(os.path.join(full, "content_item_" + str(k) + ".npy"), allow_pickle=True)
+                arr = np.load(os.path.join(full, "content_item_" + str(k) + ".npy"), allow_pickle=False)
                 expect = tuple(shape) if kind == "matrix" else (shape,)
-                assert arr.shape == tuple(int(x) for x in expect), (arr.shape, expect)
+                expect = tuple(builtins_sum(x.values()) if isinstance(x, dict) else int(x) for x in expect)
+                assert arr.shape == expect, (arr.shape, expect)
                 self._content[idx] = np.ascontiguousarray(arr, dtype=np.float64)
-        self._component_name_to_basis_component_index = text("component_name_to_basis_component_index")
-        self._component_name_to_basis_component_length = text("component_name_to_basis_component_length")
+
+        def as_tuple(value):
+            if value is None or (isinstance(value, tuple) and all(v is None for v in value)):
+                return None
+            return (value,) if isinstance(value, dict) else tuple(value)
+
+        self._component_name_to_basis_component_index = as_tuple(text("component_name_to_basis_component_index"))
+        self._component_name_to_basis_component_length = as_tuple(text("component_name_to_basis_component_length"))
         self._slices = {}
         self._stacked = None
         return True
@@ -388,4 +504,5 @@ class LinearSolver:
             self.monitor(self.solution)
 
 
-__all__ = ["AffineExpansionStorage", "Function", "LinearSolver", "Matrix", "product", "sum", "transpose", "Vector"]
+__all__ = ["AffineExpansionStorage", "ComponentNameToBasisComponentIndexDict", "Function", "LinearSolver", "Matrix",
+           "OnlineSizeDict", "product", "sum", "transpose", "Vector"]

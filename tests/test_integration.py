@@ -1,0 +1,86 @@
+"""The drop-in boundary, executed: `integration/rbnics/backends/online/b200` is imported by the
+reference's OWN `set_online_backend` (rbnics/backends/online/__init__.py:19-53) under the reference's OWN dispatcher
+(rbnics/utils/decorators/dispatch.py) -- the real RBniCS package from baseline/_ref or /root/reference with the
+third-party stand-ins of oracle/shims.  Every backend needs its own interpreter (the choice is made at import), hence
+the subprocesses (tests/refrun/run_reference.py).
+
+CPU: name resolution (29 + 15 names), distinct container types, registrations in the generic dispatchers without
+ambiguity.  GPU: the reference's EllipticCoercive[Compliant]RBReducedProblem.solve() / estimate_error() running on the
+B200 backend reproduce the numpy backend's results (fixtures of tests/golden/make_reference_golden.py)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import reference_driver as R
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+RUN = os.path.join(HERE, "refrun", "run_reference.py")
+needs_reference = pytest.mark.skipif(R.reference_root() is None,
+                                     reason="the reference is neither under baseline/_ref nor under /root/reference")
+
+
+def _run(*args):
+    out = subprocess.run([sys.executable, RUN] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+@needs_reference
+def test_set_online_backend_b200_resolves_every_name():
+    d = _run("names", "b200")
+    strip = lambda n: n[len("Online"):] if n.startswith("Online") else n[len("online_"):]  # noqa: E731
+    assert sorted(strip(n) for n in d["online_all"]) == d["numpy_all"] and len(d["numpy_all"]) == 29
+    assert d["wrapping_all"] == d["numpy_wrapping_all"] and len(d["wrapping_all"]) == 15
+    assert d["wrapping_module"] == "rbnics.backends.online.b200.wrapping"
+    hot = {"OnlineAffineExpansionStorage": "affine_expansion_storage", "OnlineFunction": "function",
+           "OnlineLinearSolver": "linear_solver", "OnlineMatrix": "matrix", "online_product": "product",
+           "online_sum": "sum", "online_transpose": "transpose", "OnlineVector": "vector"}
+    for name, mod in hot.items():
+        assert d["modules"][name] == "rbnics.backends.online.b200." + mod
+    for name, mod in d["modules"].items():
+        if name not in hot:
+            assert mod.startswith("rbnics.backends.online.numpy."), (name, mod)
+    assert d["distinct_types"] and d["subclass_of_numpy_types"]
+    for name in ("product", "sum", "LinearSolver", "transpose"):
+        mods = d["dispatch"][name]
+        assert any(m.startswith("rbnics.backends.online.b200.") for m in mods)
+        assert any(m.startswith("rbnics.backends.online.numpy.") for m in mods)   # both registered, no ambiguity
+    for name in ("Matrix", "Vector"):
+        assert d["dispatch"][name] == ["rbnics.backends.online.b200." + name.lower()]   # replaces= took effect
+
+
+@needs_reference
+def test_numpy_backend_is_untouched_without_the_plugin():
+    d = _run("names", "numpy")
+    assert all(m.startswith("rbnics.backends.online.numpy.") for m in d["modules"].values())
+
+
+@needs_reference
+def test_real_reference_sweep_reproduces_the_committed_fixture(tmp_path):
+    """The fixtures are reproducible: the real package run again gives the committed numbers bit for bit."""
+    g = np.load(os.path.join(HERE, "golden", "reference_real_sweep_n8_q3.npz"))
+    out = tmp_path / "again.npz"
+    _run("sweep", "numpy", 8, 3, 2, 40, 0, 0, out)
+    h = np.load(out)
+    for k in ("u", "delta", "Theta"):
+        assert np.array_equal(g[k], h[k]), k
+    assert (float(g["max"]), int(g["argmax"])) == (float(h["max"]), int(h["argmax"]))
+
+
+@pytest.mark.gpu
+@needs_reference
+@pytest.mark.parametrize("case,args", [("n8_q3", (8, 3, 2, 40, 0, 0)), ("n20_q4", (20, 4, 3, 60, 3, 0)),
+                                       ("n16_q5_compliant", (16, 5, 5, 40, 7, 1))])
+def test_reference_reduced_problem_on_the_b200_backend(tmp_path, case, args):
+    g = np.load(os.path.join(HERE, "golden", "reference_real_sweep_%s.npz" % case))
+    out = tmp_path / "b200.npz"
+    d = _run("sweep", "b200", *args, out)
+    assert d["backend"] == "rbnics.backends.online.b200.matrix"
+    h = np.load(out)
+    assert int(h["argmax"]) == int(g["argmax"])
+    assert np.max(np.abs(h["delta"] - g["delta"]) / np.abs(g["delta"])) <= 1e-10
+    assert np.max(np.abs(h["u"] - g["u"])) <= 1e-10 * np.max(np.abs(g["u"]))

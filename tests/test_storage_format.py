@@ -1,47 +1,62 @@
-"""On-disk format of the reduced operators: a directory written by the reference's own io
-classes (tests/golden/storage_ref, produced by executing rbnics/utils/io/{text_io,numpy_io}.py in
-tests/golden/make_golden.py) loads into rbnics_b200.online.AffineExpansionStorage, and what ours saves is
+"""On-disk format of the reduced operators: directories written by the REAL reference's
+OnlineAffineExpansionStorage.save() load into rbnics_b200.online.AffineExpansionStorage, and what ours saves is
 file-for-file what the reference wrote (text files byte-identical, .npy files equal arrays)."""
 import filecmp
 import os
 
 import numpy as np
+import pytest
 
 from rbnics_b200.online import AffineExpansionStorage
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF = os.path.join(HERE, "golden", "storage_ref")
-G = np.load(os.path.join(HERE, "golden", "reference_sweep_tutorial01.npz"))
 
 
-def test_load_reference_written_storage():
-    Qa, N = G["A"].shape[0], G["A"].shape[1]
-    a = AffineExpansionStorage(Qa)
-    assert a.load(REF, "operator_a") is True
-    assert np.array_equal(a.stacked(), G["A"])
-    assert a.load(REF, "operator_a") is False                      # the reference does not load twice either
-    f = AffineExpansionStorage(G["F"].shape[0])
-    f.load(REF, "operator_f")
-    assert np.array_equal(f.stacked(), G["F"])
-    ff = AffineExpansionStorage(*G["Gff"].shape)
-    ff.load(REF, "error_estimation_ff")
-    assert np.array_equal(ff.stacked(), G["Gff"])
-    assert np.array_equal(a[:2, :2].stacked(), G["A"][:, :2, :2])  # slicing after load
+# ----------------------------------------------------------------------------------------------------------------------
+# Directories written by the REAL reference: OnlineAffineExpansionStorage.save() of the numpy backend executed by
+# tests/golden/make_reference_golden.py (rbnics/backends/online/basic/affine_expansion_storage.py:56-153), including a
+# multi-component (u, s, p) storage and the reference's own component-dict slices of it (slice_to_array.py:27-45).
+# ----------------------------------------------------------------------------------------------------------------------
+REAL = os.path.join(HERE, "golden", "storage_real")
+REAL_STORAGES = {"operator_a": (3,), "operator_f": (2,), "error_estimation_ff": (2, 2), "stokes_block": (2, 1),
+                 "int_sized_matrices": (2,), "int_sized_vectors": (2,)}
 
 
-def test_save_matches_reference_files(tmp_path):
-    a = AffineExpansionStorage(tuple(G["A"][q] for q in range(G["A"].shape[0])))
-    f = AffineExpansionStorage(tuple(G["F"][q] for q in range(G["F"].shape[0])))
-    ff = AffineExpansionStorage(*G["Gff"].shape)
-    for i in range(G["Gff"].shape[0]):
-        for j in range(G["Gff"].shape[1]):
-            ff[i, j] = float(G["Gff"][i, j])
-    for name, st in (("operator_a", a), ("operator_f", f), ("error_estimation_ff", ff)):
-        st.save(tmp_path, name)
-        ours, ref = os.path.join(tmp_path, name), os.path.join(REF, name)
-        assert sorted(os.listdir(ours)) == sorted(os.listdir(ref))
-        for fn in os.listdir(ref):
-            if fn.endswith(".txt"):
-                assert filecmp.cmp(os.path.join(ours, fn), os.path.join(ref, fn), shallow=False), fn
-            else:
-                assert np.array_equal(np.load(os.path.join(ours, fn)), np.load(os.path.join(ref, fn))), fn
+@pytest.mark.parametrize("name", sorted(REAL_STORAGES))
+def test_round_trip_of_reference_written_directories(tmp_path, name):
+    st = AffineExpansionStorage(*REAL_STORAGES[name])
+    assert st.load(REAL, name) is True
+    st.save(tmp_path, name)
+    ours, ref = os.path.join(tmp_path, name), os.path.join(REAL, name)
+    assert sorted(os.listdir(ours)) == sorted(os.listdir(ref))
+    for fn in os.listdir(ref):
+        if fn.endswith(".txt"):
+            assert filecmp.cmp(os.path.join(ours, fn), os.path.join(ref, fn), shallow=False), fn
+        else:
+            assert np.array_equal(np.load(os.path.join(ours, fn)), np.load(os.path.join(ref, fn))), fn
+
+
+def test_component_dict_slicing_equals_the_reference():
+    from rbnics_b200.online import OnlineSizeDict
+    st = AffineExpansionStorage(2, 1)
+    st.load(REAL, "stokes_block")
+    assert st._component_name_to_basis_component_length[0] == {"u": 3, "s": 3, "p": 2}
+    N = OnlineSizeDict()
+    N["u"], N["s"], N["p"] = 2, 1, 2
+    sl = st[:N, :N]
+    for i in range(2):
+        assert np.array_equal(sl[i, 0], np.load(os.path.join(REAL, "stokes_block_sliced_%d.npy" % i)))
+    assert sl._component_name_to_basis_component_length == (N, N)
+    assert st[:N, :N] is sl                                          # cached like the reference's precomputed slices
+    with pytest.raises(ValueError):
+        st[:OnlineSizeDict(u=4, s=1, p=1), :N]                       # more basis functions than the component holds
+
+
+def test_text_files_are_parsed_without_eval(tmp_path):
+    """a reduced-model directory must not be able to run code."""
+    d = tmp_path / "evil"
+    d.mkdir()
+    (d / "content_item_type.txt").write_text("__import__('os').system('true')")
+    (d / "content_item_shape.txt").write_text("None")
+    with pytest.raises(ValueError):
+        AffineExpansionStorage(1).load(tmp_path, "evil")
