@@ -31,6 +31,33 @@ METRIC = "greedy_sweep_params_per_sec"
 UNIT = "params/s"
 
 
+def workload_config(world, ntrain):
+    """The SAME dict in both arms (the driver compares them key by key)."""
+    return {"workload": "synthetic affine elliptic reduced system N=100 Qa=50 Qf=10, training set 10^6 parameters "
+                        "(BASELINE.json configs[2])",
+            "N": N_RB, "Qa": Q_A, "Qf": Q_F, "ntrain": ntrain, "parallelism": f"dp{world} (training-set shards)",
+            "l2": "no flush needed: per-step inputs (Theta 480 MB, assembled-matrix scratch 1.5 GB, packed G' 101 MB) "
+                  "exceed the 126 MB L2",
+            "timing": "device arm: perf_counter around K blocking sweeps bracketed by barrier+stream sync, max over "
+                      "ranks, kernel times from CUDA events on the engine's stream; reference arm: perf_counter around "
+                      "each sampled sweep, max over the worker processes"}
+
+
+TRAIN_CHUNK = 100_000
+
+
+def global_training_rows(n):
+    """The first n <= TRAIN_CHUNK rows (Theta, beta) of the GLOBAL training set every arm works on (the b200 arm
+    generates it chunk by chunk from default_rng(1); this is chunk 0)."""
+    assert n <= TRAIN_CHUNK
+    g = np.random.default_rng(1)
+    m = min(TRAIN_CHUNK, NTRAIN)
+    ta = g.uniform(0.1, 10.0, size=(m, Q_A))
+    tf = g.uniform(-1.0, 1.0, size=(m, Q_F))
+    Theta = np.concatenate([ta[:n], tf[:n]], axis=1)
+    return Theta, Theta[:, :Q_A].min(axis=1)
+
+
 def flops_per_param(N, Qa, Qf):
     """Algorithmic FP64 flops of one parameter (DESIGN.md 'Algorithmic work')."""
     asm = 2 * Qa * N * N + 2 * Qf * N
@@ -45,6 +72,26 @@ def flops_per_param(N, Qa, Qf):
     return {"assembly": asm, "lu": lu, "estimator_reference": est_ref, "estimator_sym": est_sym,
             "estimator_folded": est_fold, "F_alg": asm + lu + est_ref, "F_sym": asm + lu + est_sym,
             "F_fold": asm + lu + est_fold}
+
+
+def estimator_traffic():
+    """dram__bytes_read + dram__bytes_write of one rb_estimator_kernel launch at the bench configuration, from the
+    newest `ncu --set full` summary under profiles/ (tools/ncu_summary.py full ...); (None, reason) if there is none."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_estimator_full.json")),
+                   key=lambda f: [int(x) if x.isdigit() else x for x in re.split(r"(\d+)", os.path.basename(f))])
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for f in reversed(files):
+        try:
+            cap = json.load(open(f))["captures"][0]
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(cap[k]["value"]) * unit[cap[k]["unit"]]
+            return tot, "profiles/" + os.path.basename(f)
+        except Exception:
+            continue
+    return None, "no ncu --set full summary of rb_estimator_kernel under profiles/"
 
 
 def fp64_peak_tflops():
@@ -78,7 +125,7 @@ def _cpu_worker(args):
     from oracle import rb_oracle as O
     from rbnics_b200 import synthetic
     prob = synthetic.elliptic_reduced_problem(N_RB, Q_A, Q_F, seed=seed_prob)
-    Theta, beta, _ = synthetic.training_set(n_sample, Q_A, Q_F, seed=seed_train)
+    Theta, beta = global_training_rows(n_sample)
     A_q = [prob["A"][q] for q in range(Q_A)]
     f_q = [prob["F"][q] for q in range(Q_F)]
     G_ff = [[prob["Gff"][i, j] for j in range(Q_F)] for i in range(Q_F)]
@@ -102,11 +149,73 @@ def cpu_reference_loop(n_per_core, cores):
     return n_sample / tmax, n_sample, tmax
 
 
+# ---- the REAL reference (RBniCS from baseline/_ref or /root/reference, oracle/reference_driver.py), one process per core
+_REF_STATE = {}
+
+
+def _ref_worker_init():
+    """Runs once in every worker: import the unmodified reference (numpy online backend) and build its
+    EllipticCoerciveRBReducedProblem around the bench operators."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    import tempfile as _tf
+    os.chdir(_tf.mkdtemp(prefix="rbnics_ref_"))
+    from oracle import reference_driver as R
+    R.setup_reference_import("numpy")
+    import rbnics  # noqa: F401
+    from rbnics_b200 import synthetic
+    R.disable_reduced_solution_cache()
+    prob = synthetic.elliptic_reduced_problem(N_RB, Q_A, Q_F, seed=0)
+    _REF_STATE["R"] = R
+    _REF_STATE["rp"] = R.elliptic_reduced_problem(prob["A"], prob["F"], prob["Gff"], prob["Gaf"], prob["Gaa"])
+
+
+def _ref_worker_sweep(args):
+    """One rank of the reference's own data-parallel strategy: cyclic shard (parameter_space_subset.py:57), the
+    closure of RBReduction._greedy per parameter, local arg-max."""
+    rank, size, n_sample = args
+    R, rp = _REF_STATE["R"], _REF_STATE["rp"]
+    Theta, _ = global_training_rows(n_sample)
+    idx = list(range(rank, n_sample, size))
+    ts = R.training_set(Theta[idx])
+    t0 = time.perf_counter()
+    v, i = R.greedy_sweep(rp, ts)
+    return time.perf_counter() - t0, len(idx), float(v), idx[int(i)]
+
+
+class ReferencePool:
+    """Worker processes that keep the imported reference alive across steps."""
+
+    def __init__(self, cores):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context("spawn").Pool(cores, initializer=_ref_worker_init)
+
+    def sweep(self, n_per_core):
+        n_sample = n_per_core * self.cores
+        out = self.pool.map(_ref_worker_sweep, [(r, self.cores, n_sample) for r in range(self.cores)])
+        tmax = max(o[0] for o in out)
+        best = max(out, key=lambda o: (o[2], -o[3]))
+        return n_sample / tmax, n_sample, tmax, best[2], best[3]
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def reference_available():
+    from oracle import reference_driver as R
+    return R.reference_root() is not None
+
+
 def cpu_vectorized(n_sample, prob):
     """R3 of BASELINE.md: chunked einsum / batched numpy.linalg.solve with all BLAS threads."""
     from oracle import rb_oracle as O
-    from rbnics_b200 import synthetic
-    Theta, beta, _ = synthetic.training_set(n_sample, Q_A, Q_F, seed=1)
+    Theta, beta = global_training_rows(n_sample)
     t0 = time.perf_counter()
     O.sweep_batched(Theta[:, :Q_A], Theta[:, Q_A:], beta, prob["A"], prob["F"], prob["Gff"], prob["Gaf"], prob["Gaa"],
                     chunk=2048)
@@ -122,37 +231,58 @@ def host_cores():
 
 
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path on the host cores: the REAL RBniCS classes (kind
+    "reference") when the package is present, else the loop-faithful oracle port (kind "port").  Every step is a
+    bounded sample of the workload; `ms_per_step` is the measured time of a sampled step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_cores()
-    per_core = max(20, int(args.cpu_params_per_core))
-    vals = []
-    for _ in range(max(1, args.warmup)):  # warm-up: page in numpy/BLAS in the workers' image
-        cpu_reference_loop(4, cores)
-        break
+    per_core = max(10, int(args.cpu_params_per_core))
+    real = reference_available() and not args.reference_port
+    vals, step_s = [], []
     t_all = time.perf_counter()
-    for _ in range(args.steps):
-        v, n_sample, tmax = cpu_reference_loop(per_core, cores)
-        vals.append(v)
+    if real:
+        pool = ReferencePool(cores)
+        for _ in range(max(1, min(args.warmup, 2))):
+            pool.sweep(4)  # imports + first-call dispatch caches
+        for _ in range(args.steps):
+            v, n_sample, tmax, vmax, imax = pool.sweep(per_core)
+            vals.append(v)
+            step_s.append(tmax)
+        pool.close()
+        kind = "reference"
+        what = ("the unmodified RBniCS package (baseline/_ref): EllipticCoerciveRBReducedProblem.set_mu / solve / "
+                "estimate_error on the numpy online backend, driven by ParameterSpaceSubset.max with the closure of "
+                "RBReduction._greedy; third-party imports absent from the image served by oracle/shims; reduced-"
+                "solution cache disabled")
+    else:
+        cpu_reference_loop(4, cores)
+        for _ in range(args.steps):
+            v, n_sample, tmax = cpu_reference_loop(per_core, cores)
+            vals.append(v)
+            step_s.append(tmax)
+        kind = "port"
+        what = "loop-faithful numpy port of the per-parameter path (oracle/rb_oracle.py sweep_loop)"
     wall = time.perf_counter() - t_all
     value = statistics.median(vals)
     from rbnics_b200 import synthetic
     prob = synthetic.elliptic_reduced_problem(N_RB, Q_A, Q_F, seed=0)
-    vec, vec_dt = cpu_vectorized(4096 * 4, prob)
+    vec, vec_dt = cpu_vectorized(4096 * 2, prob)
     fl = flops_per_param(N_RB, Q_A, Q_F)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * NTRAIN / value,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(step_s),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic affine elliptic reduced system N=100 Qa=50 Qf=10, training set 10^6 "
-                               "(BASELINE.json configs[2])", "N": N_RB, "Qa": Q_A, "Qf": Q_F, "ntrain": NTRAIN},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_sample} parameters per step ({per_core} per core, cyclic shards, one process "
-                                   f"per core emulating the reference's mpirun), extrapolated linearly to 10^6; "
-                                   f"loop-faithful numpy port of the per-parameter path (oracle/rb_oracle.py sweep_loop)"},
+        "config": workload_config(args.gpus, NTRAIN),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{n_sample} parameters per step ({per_core} per core; the first rows of the same "
+                                   f"global training set as the b200 arm, cyclic shards, one process per core = the "
+                                   f"reference's mpirun strategy); value = sampled parameters / max worker time; {what}"},
+        "sampled_params_per_step": n_sample,
+        "extrapolated_ms_per_full_sweep": 1e3 * NTRAIN / value,
         "cpu_vectorized": {"value": vec, "unit": UNIT, "cores": cores,
-                           "sample": f"{4096 * 4} parameters, chunked einsum + batched numpy.linalg.solve"},
+                           "sample": f"{4096 * 2} parameters, chunked einsum + batched numpy.linalg.solve"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gflops_fp64_F_alg": fl["F_alg"] * value * 1e-9,
         "wall_s": wall,
@@ -228,11 +358,21 @@ def run_b200_arm(args):
     cpu_vec = None
     cores = host_cores()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, n_sample, tmax = cpu_reference_loop(max(20, int(args.cpu_params_per_core)), cores)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{n_sample} parameters ({n_sample // cores} per core, cyclic shards over {cores} "
-                                  f"processes emulating the reference's mpirun; {tmax:.1f} s), extrapolated linearly; "
-                                  "loop-faithful numpy port of the per-parameter path (oracle/rb_oracle.py sweep_loop)"}
+        per_core = max(10, int(args.cpu_params_per_core))
+        if reference_available() and not args.reference_port:
+            pool = ReferencePool(cores)
+            pool.sweep(4)
+            v, n_sample, tmax, _, _ = pool.sweep(per_core)
+            pool.close()
+            kind, what = "reference", ("the unmodified RBniCS package (baseline/_ref, numpy online backend): "
+                                       "EllipticCoerciveRBReducedProblem.solve / estimate_error under "
+                                       "ParameterSpaceSubset.max, one process per core")
+        else:
+            v, n_sample, tmax = cpu_reference_loop(per_core, cores)
+            kind, what = "port", "loop-faithful numpy port of the per-parameter path (oracle/rb_oracle.py sweep_loop)"
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"{n_sample} parameters ({n_sample // cores} per core, the first rows of the same "
+                                  f"training set, cyclic shards over {cores} processes; {tmax:.1f} s); {what}"}
 
     from rbnics_b200 import synthetic
     from rbnics_b200.engine import SweepEngine, pinned_empty, pinned_free
@@ -253,7 +393,7 @@ def run_b200_arm(args):
     n_local = len(range(rank, ntrain, world))
     Theta_p, hT = pinned_empty((n_local, Q_A + Q_F))
     beta_p, hB = pinned_empty((n_local,))
-    chunk = 100_000
+    chunk = TRAIN_CHUNK
     rng_done = 0
     # generate the global set in chunks and keep rows rank::world (bitwise identical across ranks)
     g = np.random.default_rng(1)
@@ -325,6 +465,35 @@ def run_b200_arm(args):
     h2d = (n_local * (Q_A + Q_F) + n_local) * 8 * world
     d2h = 24 * world
 
+    # ---- parity with the measurement: oracle on a seeded subsample of the SAME Theta, top-2 gap
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import rb_oracle as O
+        full = eng.sweep_resident(want_delta=True)
+        dl = full["delta"]
+        top2 = np.sort(dl[np.argpartition(dl, -2)[-2:]])
+        sub = np.sort(np.random.default_rng(12345).choice(n_local, size=min(2000, n_local), replace=False))
+        sub[0] = (int(full["argmax"]) - rank) // world  # the arg-max itself is always among the checked rows
+        sub = np.unique(sub)
+        Ts, bs = np.ascontiguousarray(Theta_p[sub]), np.ascontiguousarray(beta_p[sub])
+        gpu = eng.sweep(Ts, bs, want_delta=True, want_u=True)
+        d_ref, U_ref, _, _ = O.sweep_batched(Ts[:, :Q_A], Ts[:, Q_A:], bs, prob["A"], prob["F"], prob["Gff"],
+                                             prob["Gaf"], prob["Gaa"], chunk=500)
+        k = int(np.where(sub == (int(full["argmax"]) - rank) // world)[0][0])
+        parity = {
+            "checked_params": int(sub.size),
+            "u_rel_max": float(np.max(np.max(np.abs(gpu["u"] - U_ref), axis=1) / np.max(np.abs(U_ref), axis=1))),
+            "delta_rel_max": float(np.max(np.abs(gpu["delta"] - d_ref) / np.abs(d_ref))),
+            "delta_rel_resident_vs_subsample": float(np.max(np.abs(gpu["delta"] - dl[sub]) / np.abs(dl[sub]))),
+            "argmax_delta_rel": float(abs(full["max"] - d_ref[k]) / abs(d_ref[k])),
+            "top2_gap_rel": float((top2[1] - top2[0]) / top2[1]),
+            "tolerance": 1e-10,
+            "oracle": "oracle/rb_oracle.py sweep_batched (numpy einsum + LAPACK dgesv) on rows of the timed training set",
+        }
+        parity["ok"] = bool(max(parity["u_rel_max"], parity["delta_rel_max"], parity["argmax_delta_rel"]) <= 1e-10
+                            and parity["top2_gap_rel"] > 1e-10)
+        eng.set_training_set(Theta_p, beta_p, index_offset=rank, index_stride=world)
+
     if rank == 0:
         fl = flops_per_param(N_RB, Q_A, Q_F)
         peak, peak_src = fp64_peak_tflops()
@@ -332,28 +501,18 @@ def run_b200_arm(args):
         achieved = fl["estimator_folded"] * n_local / (est_launch_ms * 1e-3) * 1e-12
         work = eng.estimator_work()
         issued = 2 * work["issued_macs_per_param"] * n_local / (est_launch_ms * 1e-3) * 1e-12
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "estimator_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        traffic, traffic_src = estimator_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic affine elliptic reduced system N=100 Qa=50 Qf=10, training set "
-                                   f"{ntrain} parameters sharded cyclically over {world} GPU(s) (BASELINE.json configs[2])",
-                       "N": N_RB, "Qa": Q_A, "Qf": Q_F, "ntrain": ntrain, "parallelism": f"dp{world} (training-set shards)",
-                       "l2": "no flush needed: per-step inputs (Theta 480 MB, assembled-matrix scratch 1.5 GB, "
-                             "packed G' 101 MB) exceed the 126 MB L2",
-                       "timing": "perf_counter around K blocking sweeps bracketed by barrier+stream sync, max over ranks; "
-                                 "kernel times from CUDA events on the engine's stream"},
+            "config": workload_config(world, ntrain),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "rb_estimator_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src, "launch_ms": est_launch_ms,
                          "algorithmic_flops_per_param": fl["estimator_folded"], "params_per_launch": n_local,
                          "note": "algorithmic = minimal multiply-adds of the executed (doubly folded) quadratic form; "
@@ -368,6 +527,8 @@ def run_b200_arm(args):
                       "kernel_ms_mean": {"assemble_lu": statistics.mean(tot_ms) - est_launch_ms, "estimator": est_launch_ms},
                       "argmax": int(res[1]), "max": float(res[0]), "argmax_e2e": int(res_e2e[1])},
         }
+        if parity is not None:
+            line["parity"] = parity
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
             line["cpu_vectorized"] = cpu_vec
@@ -408,9 +569,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ntrain", type=int, default=NTRAIN)
-    ap.add_argument("--cpu-params-per-core", type=int, default=400,
-                    help="sample size per host core of the CPU reference loop (~34 ms per parameter)")
+    ap.add_argument("--cpu-params-per-core", type=int, default=40,
+                    help="sample size per host core and step of the CPU reference (the real reference takes ~0.14 s per parameter and core at N=100, Q_a=50)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check that runs with the measurement")
+    ap.add_argument("--reference-port", action="store_true",
+                    help="time the oracle port instead of the real reference package even if the latter is present")
     args = ap.parse_args()
     _quiet_stdout()
     if args.impl == "reference":

@@ -94,6 +94,28 @@ class DistributedMaxLoc:
         idxs = out[1::2].clone().view(t.int64).tolist()
         return maxloc_serial_rule(vals, idxs)
 
+    def maxloc_device(self, engine):
+        """The same collective fed straight from the engine's device-resident result {value f64, global index i64,
+        number of non-finite estimators i64} (rb_result_device_ptrs): NCCL all-gathers 24 bytes per rank out of HBM, no
+        host staging of the send buffer.  Returns (value, index, total non-finite count)."""
+        if self.backend != "nccl":
+            raise RuntimeError("maxloc_device needs the NCCL backend")
+        t = self.torch
+        ptr, _ = engine.result_device_ptrs()
+
+        class _Holder:  # zero-copy view of library-owned device memory (CUDA array interface v3)
+            __cuda_array_interface__ = {"shape": (3,), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+        mine = t.as_tensor(_Holder(), device=self.device)
+        out = t.empty(3 * self.size, dtype=t.float64, device=self.device)
+        self.dist.all_gather_into_tensor(out, mine)
+        out = out.cpu()
+        vals = out[0::3].tolist()
+        idxs = out[1::3].clone().view(t.int64).tolist()
+        bad = int(out[2::3].clone().view(t.int64).sum().item())
+        v, i = maxloc_serial_rule(vals, idxs)
+        return v, i, bad
+
     def max_float(self, x):
         t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.device)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
@@ -150,10 +172,22 @@ class TrainingSetSweep:
     def max(self, kind=L.RB_EST_SQRT_EPS2_OVER_BETA, want_delta=False):
         """(max estimator, global arg-max index[, local deltas]) -- the return value of ParameterSpaceSubset.max."""
         self._ensure_resident()
-        r = self.engine.sweep_resident(kind=kind, want_delta=want_delta)
-        v, i = r["max"], r["argmax"]
-        if self.dist is not None:
-            v, i = self.dist.maxloc(v, i)
+        if self.dist is None:
+            r = self.engine.sweep_resident(kind=kind, want_delta=want_delta)
+            v, i = r["max"], r["argmax"]
+        else:
+            # a rank whose shard holds a singular reduced matrix must not raise before the collective (the other ranks
+            # would wait in the all-gather for ever): gather first -- NaN wins the arg-max anyway -- then raise everywhere
+            r = self.engine.sweep_resident(kind=kind, want_delta=want_delta, raise_on_singular=False)
+            if self.dist.backend == "nccl":
+                v, i, bad = self.dist.maxloc_device(self.engine)
+            else:
+                v, i = self.dist.maxloc(r["max"], r["argmax"])
+                bad = int(self.dist.sum_float(float(math.isnan(r["max"]) or math.isinf(r["max"]))))
+            if bad:
+                raise L.SingularReducedMatrixError(
+                    "rb_sweep: non-finite error estimators on at least one rank (singular reduced matrix or beta == 0); "
+                    "numpy.linalg.solve would raise LinAlgError")
         if want_delta:
             return v, i, r["delta"]
         return v, i

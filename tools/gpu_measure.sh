@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round measurement sequence on the GPU box: tests, smoke, bench (both arms), ncu launch list of the bench command,
 # one ncu --set full capture per hot kernel.  Outputs go to gpurun_out/ (tag = $1).
-TAG=${1:-r01}
+TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
@@ -17,7 +17,7 @@ timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 -
 # full captures of the hot kernels at the bench launch configuration (first launch after the warm-up sweeps)
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_estimator_kernel -s 3 -c 1 \
     -o $OUT/${TAG}_estimator_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_est.log 2>&1
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_lu_left_kernel -s 160 -c 1 \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_lu_mw_kernel -s 160 -c 1 \
     -o $OUT/${TAG}_lu_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_lu.log 2>&1
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_assemble_kernel -s 160 -c 1 \
     -o $OUT/${TAG}_asm_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_asm.log 2>&1

@@ -28,12 +28,10 @@ KEYS = [
     "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "sm__sass_inst_executed_op_shared_ld.sum",
     "smsp__inst_executed_pipe_uniform.sum",
     # FP64 tensor pipe (DMMA) -- the counters north_star asks to be reported against peak
-    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
-    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_active",
-    "smsp__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_elapsed",
-    "smsp__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
-    "sm__inst_executed_pipe_tensor_subpipe_dmma.sum", "smsp__inst_executed_pipe_tensor_subpipe_dmma.sum",
-    "sm__inst_executed_pipe_tensor.sum",
+    "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "SM_C.TriageCompute.smsp__pipe_tensor_subpipe_dmma_cycles_active.avg",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.sum", "sm__inst_executed_pipe_tensor_subpipe_dmma.avg",
 ]
 STALL = re.compile(r"smsp__average_warps_issue_stalled_(\w+)_per_issue_active\.ratio")
 
