@@ -7,6 +7,9 @@ from numbers import Number
 from rbnics.backends.online.basic import AffineExpansionStorage as BasicAffineExpansionStorage
 from rbnics.backends.online.numpy.affine_expansion_storage import AffineExpansionStorage as NumpyAffineExpansionStorage
 from rbnics.backends.online.numpy.copy import function_copy, tensor_copy
+from rbnics.backends.online.numpy.function import Function as NumpyFunction
+from rbnics.backends.online.numpy.matrix import Matrix as NumpyMatrix
+from rbnics.backends.online.numpy.vector import Vector as NumpyVector
 from rbnics.backends.online.numpy.wrapping import function_load, function_save, tensor_load, tensor_save
 from rbnics.backends.online.b200.function import Function
 from rbnics.backends.online.b200.matrix import Matrix
@@ -19,14 +22,35 @@ wrapping = ModuleWrapper(function_load, function_save, tensor_load, tensor_save,
 AffineExpansionStorage_Base = BasicAffineExpansionStorage(backend, wrapping)
 
 
+def _as_b200(item):
+    """Tensors produced by numpy-backend code that is not on the hot path (e.g. transpose(Z) * A * Z of the offline
+    stage builds its result with the numpy backend's own Matrix) enter the B200 backend here: same content, same sizes
+    and component dictionaries, B200 type."""
+    if isinstance(item, (Matrix.Type(), Vector.Type(), Function.Type())):
+        return item
+    if isinstance(item, NumpyMatrix.Type()):
+        out = Matrix.Type()(item.M, item.N, item.content)
+    elif isinstance(item, NumpyVector.Type()):
+        out = Vector.Type()(item.N, item.content)
+    elif isinstance(item, NumpyFunction.Type()):
+        return Function.Type()(_as_b200(item.vector()))
+    else:
+        return item
+    out._component_name_to_basis_component_index = item._component_name_to_basis_component_index
+    out._component_name_to_basis_component_length = item._component_name_to_basis_component_length
+    return out
+
+
 class AffineExpansionStorage(AffineExpansionStorage_Base):
     def __init__(self, arg1, arg2=None):
+        if isinstance(arg1, tuple):
+            arg1 = tuple(_as_b200(a) for a in arg1)
         AffineExpansionStorage_Base.__init__(self, arg1, arg2)
         self._b200_stacked = None
 
     def __setitem__(self, key, item):
         self._b200_stacked = None
-        return AffineExpansionStorage_Base.__setitem__(self, key, item)
+        return AffineExpansionStorage_Base.__setitem__(self, key, _as_b200(item))
 
     def b200_stacked(self):
         """(Q, ...) / (Q1, Q2, ...) contiguous FP64 tensor of the items (None if an item is not a tensor / scalar)."""

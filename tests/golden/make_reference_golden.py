@@ -5,6 +5,10 @@ its own classes produce
 
   tests/golden/reference_real_sweep_<case>.npz   EllipticCoercive[Compliant]RBReducedProblem.solve()/estimate_error()
                                                  over a ParameterSpaceSubset, closure of RBReduction._greedy, max()
+  tests/golden/reference_real_greedy_<case>.npz  the COMPLETE offline stage, ReducedBasis(problem).offline(), on a dense
+                                                 FEniCS-free truth problem (oracle/reference_truth.py): training set,
+                                                 greedy-selected indices, error estimators, final reduced operators,
+                                                 error-estimation operators and basis
   tests/golden/storage_real/                     AffineExpansionStorage.save() of the numpy online backend
                                                  (rbnics/backends/online/basic/affine_expansion_storage.py:56-153),
                                                  single- and multi-component (u, s, p) items, plus the reference's own
@@ -33,6 +37,9 @@ def main():
     for name, case in CASES.items():
         out = os.path.join(HERE, "reference_real_sweep_%s.npz" % name)
         subprocess.run([sys.executable, RUN, "sweep", "numpy"] + [str(x) for x in case] + [out], check=True)
+    for case in ("tutorial01", "stress3", "config2"):
+        out = os.path.join(HERE, "reference_real_greedy_%s.npz" % case)
+        subprocess.run([sys.executable, RUN, "greedy", "numpy", case, "0", out], check=True)
     sdir = os.path.join(HERE, "storage_real")
     shutil.rmtree(sdir, ignore_errors=True)
     os.makedirs(sdir)

@@ -5,6 +5,10 @@ backend of RBniCS is chosen at import time, so every backend gets its own interp
     python tests/refrun/run_reference.py names   <backend>           -> JSON: exported names, type modules, dispatch tables
     python tests/refrun/run_reference.py sweep   <backend> <N> <Qa> <Qf> <B> <seed> <compliant> <out.npz>
     python tests/refrun/run_reference.py storage <backend> <directory>   -> writes storages with the reference's own save()
+    python tests/refrun/run_reference.py greedy  <backend> <case> <plugin 0|1> <out.npz>
+                 the reference's complete offline stage, ReducedBasis(problem).offline(), on a dense FEniCS-free truth
+                 problem (oracle/reference_truth.py); plugin = 1 decorates the problem with @B200Sweep(), so that the
+                 reference's own greedy loop calls the batched sweep on the GPU
 """
 import json
 import os
@@ -16,8 +20,24 @@ sys.path.insert(0, ROOT)
 from oracle import reference_driver as R  # noqa: E402
 
 
+# real-reference greedy runs: thermal block of tests/truth_problems.py (n x n grid, vertical strips)
+GREEDY_CASES = {
+    # tutorials/01_thermal_block as it is: Q_a = 2, Q_f = 1, ntrain = 100, Nmax = 4, tol = 1e-5, compliant estimator
+    "tutorial01": dict(n=12, nblocks=2, nloads=1, compliant=True, a_range=(0.1, 10.0), ntrain=100, Nmax=4, tol=1e-5, seed=0),
+    # BASELINE.json configs[0] as written: Q_a = 3, ntrain = 100, N_max = 20
+    # (tol stops the loop above the round-off floor of the estimator, ~1e-8 relative, below which the reference itself
+    # re-selects parameters that are already in the basis)
+    "stress3": dict(n=14, nblocks=3, nloads=1, compliant=True, a_range=(0.1, 10.0), ntrain=100, Nmax=20, tol=2e-7, seed=1),
+    # shapes of tutorials/02_elastic_block: Q_a = 9, Q_f = 3, 11 parameters (8 stiffness in [1, 100] + 3 loads), non-compliant
+    "config2": dict(n=18, nblocks=9, nloads=3, compliant=False, a_range=(1.0, 100.0), ntrain=200, Nmax=20, tol=1e-12, seed=2),
+}
+
+
 def main():
     mode, backend = sys.argv[1], sys.argv[2]
+    for k in range(3, len(sys.argv)):  # output paths are given relative to the caller's directory
+        if sys.argv[k].endswith(".npz") or (mode == "storage" and k == 3):
+            sys.argv[k] = os.path.abspath(sys.argv[k])
     work = tempfile.mkdtemp(prefix="rbnics_ref_")
     os.chdir(work)
     R.setup_reference_import(backend, rbnicsrc_dir=work)
@@ -122,6 +142,49 @@ def main():
         np.save(os.path.join(directory, "stokes_block_sliced_0.npy"), np.asarray(sl[0, 0].content))
         np.save(os.path.join(directory, "stokes_block_sliced_1.npy"), np.asarray(sl[1, 0].content))
         print(json.dumps({"ok": True}))
+        return
+    if mode == "greedy":
+        case, plugin, outfile = sys.argv[3], int(sys.argv[4]), sys.argv[5]
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from truth_problems import ThermalBlock
+        from oracle import reference_truth as T
+        cfg = GREEDY_CASES[case]
+        T.install_numpy_truth_backend_helpers()
+        T.ram_cache_only()
+        decorator = None
+        if plugin:
+            integ = os.path.join(ROOT, "integration")
+            if integ not in sys.path:
+                sys.path.append(integ)
+            from rbnics_b200_plugin.sweep import B200Sweep
+            decorator = B200Sweep()
+        tb = ThermalBlock(n=cfg["n"], nblocks=cfg["nblocks"], nloads=cfg["nloads"])
+        problem = T.make_thermal_block_problem(tb, compliant=cfg["compliant"], decorator=decorator)
+        mu_range = [cfg["a_range"]] * (cfg["nblocks"] - 1) + [(-1.0, 1.0)] * cfg["nloads"]
+        import contextlib
+        import io
+        log = io.StringIO()
+        with contextlib.redirect_stdout(log):
+            rm, rp = T.run_offline(problem, mu_range, cfg["ntrain"], cfg["Nmax"], cfg["tol"], cfg["seed"])
+        ts = [tuple(float(x) for x in mu) for mu in rm.training_set]
+        selected = [tuple(float(x) for x in mu) for mu in rm.greedy_selected_parameters]
+        indices = [ts.index(mu) for mu in selected]
+        N = rp.N
+        Qa, Qf = rp.Q["a"], rp.Q["f"]
+        A = np.array([np.asarray(rp.operator["a"][q].content)[:N, :N] for q in range(Qa)])
+        F = np.array([np.asarray(rp.operator["f"][q].content)[:N] for q in range(Qf)])
+        e = rp.error_estimation_operator
+        Gff = np.array([[e["f", "f"][i, j] for j in range(Qf)] for i in range(Qf)], dtype=np.float64)
+        Gaf = np.array([[np.asarray(e["a", "f"][i, j].content)[:N] for j in range(Qf)] for i in range(Qa)])
+        Gaa = np.array([[np.asarray(e["a", "a"][i, j].content)[:N, :N] for j in range(Qa)] for i in range(Qa)])
+        Z = np.array([np.asarray(rp.basis_functions[i].vector().content) for i in range(N)]).T
+        np.savez(outfile, case=case, training_set=np.array(ts), selected_indices=np.array(indices),
+                 error_estimators=np.array([float(x) for x in rm.greedy_error_estimators]), N=N, A=A, F=F, Gff=Gff,
+                 Gaf=Gaf, Gaa=Gaa, Z=Z, plugin=plugin, backend=online.OnlineMatrix.__module__,
+                 reduction_method=type(rm).__mro__[1].__qualname__ if plugin else type(rm).__qualname__)
+        print(json.dumps({"N": int(N), "selected_indices": indices,
+                          "error_estimators": [float(x) for x in rm.greedy_error_estimators],
+                          "uses_plugin": bool(plugin) and hasattr(rm, "_b200_greedy_sweep")}))
         return
     raise SystemExit("unknown mode " + mode)
 

@@ -88,3 +88,71 @@ def test_device_resident_workspace_with_unsymmetric_operator(engine):
     assert res.greedy_selected_indices == host.greedy_selected_indices
     assert np.max(np.abs(res.operator_a - host.operator_a)) <= 1e-12 * np.max(np.abs(host.operator_a))
     assert np.max(np.abs(res.G - host.G)) <= 1e-11 * np.max(np.abs(host.G))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Against the REAL reference: tests/golden/reference_real_greedy_<case>.npz hold the training set, the greedy-selected
+# indices, the error estimators and the final reduced / error-estimation operators of RBniCS' own
+# ReducedBasis(problem).offline() on the same dense thermal-block truth problem (tests/golden/make_reference_golden.py,
+# oracle/reference_truth.py).  north_star: "an identical sequence of greedy-selected parameter indices".
+# ----------------------------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+from oracle import rb_oracle as O  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REAL_CASES = {   # the configurations of tests/refrun/run_reference.py:GREEDY_CASES
+    "tutorial01": dict(n=12, nblocks=2, nloads=1, compliant=True, a_range=(0.1, 10.0), Nmax=4, tol=1e-5),
+    "stress3": dict(n=14, nblocks=3, nloads=1, compliant=True, a_range=(0.1, 10.0), Nmax=20, tol=2e-7),
+    "config2": dict(n=18, nblocks=9, nloads=3, compliant=False, a_range=(1.0, 100.0), Nmax=20, tol=1e-12),
+}
+
+
+def _eps2_terms(g, n, mu_theta_a, mu_theta_f):
+    """The three terms of eps2 at level n from the nested golden operators (elliptic_rb_reduced_problem.py:55-64)."""
+    A, F = g["A"][:, :n, :n], g["F"][:, :n]
+    u = np.linalg.solve(np.einsum("q,qij->ij", mu_theta_a, A), mu_theta_f @ F) if n else np.zeros(0)
+    ff = float(mu_theta_f @ g["Gff"] @ mu_theta_f)
+    af = 2.0 * float(np.einsum("n,i,ijn,j->", u, mu_theta_a, g["Gaf"][:, :, :n], mu_theta_f)) if n else 0.0
+    aa = float(np.einsum("n,i,ijnm,j,m->", u, mu_theta_a, g["Gaa"][:, :, :n, :n], mu_theta_a, u)) if n else 0.0
+    return ff, af, aa
+
+
+@pytest.mark.parametrize("case", sorted(REAL_CASES))
+@pytest.mark.parametrize("resident", [False, True])
+def test_greedy_sequence_identical_to_the_real_reference(engine, case, resident):
+    cfg = REAL_CASES[case]
+    g = np.load(os.path.join(GOLD, f"reference_real_greedy_{case}.npz"))
+    mu_range = [cfg["a_range"]] * (cfg["nblocks"] - 1) + [(-1.0, 1.0)] * cfg["nloads"]
+    tp = ThermalBlock(n=cfg["n"], nblocks=cfg["nblocks"], nloads=cfg["nloads"], mu_range=mu_range)
+    train = [tuple(mu) for mu in g["training_set"]]
+    kind = L.RB_EST_SQRT_OF_EPS2_OVER_BETA if cfg["compliant"] else L.RB_EST_SQRT_EPS2_OVER_BETA
+    run = ReducedBasisGreedy(engine, tp, train, Nmax=cfg["Nmax"], tol=cfg["tol"], estimator_kind=kind,
+                             resident=resident).offline()
+    ref_idx = g["selected_indices"].tolist()
+    assert run.greedy_selected_indices == ref_idx, (run.greedy_selected_indices, ref_idx)
+    assert run.N == int(g["N"])
+    # estimators: the error of eps2 is bounded relative to the size of the CANCELLING terms (SURVEY.md 7, hard parts):
+    # |eps2 - eps2_ref| <= 1e-10 * (|ff| + |2 af| + |aa|); and the arg-max must be well separated from the runner-up
+    mus = np.asarray(train)
+    Theta_a, Theta_f = tp.compute_theta("a", mus), tp.compute_theta("f", mus)
+    beta = tp.get_stability_factor_lower_bound(mus)
+    worst, min_gap = 0.0, np.inf
+    for it, (i, d_ref, d_run) in enumerate(zip(ref_idx, g["error_estimators"], run.greedy_error_estimators)):
+        ff, af, aa = _eps2_terms(g, it, Theta_a[i], Theta_f[i])
+        scale = abs(ff) + abs(af) + abs(aa)
+        to_eps2 = (lambda d: d * d * beta[i]) if cfg["compliant"] else (lambda d: (d * beta[i]) ** 2)
+        worst = max(worst, abs(to_eps2(d_run) - to_eps2(d_ref)) / scale)
+        # top-2 gap of the reference's own sweep at this level (oracle on the golden operators)
+        n = it
+        d_all, _, _, _ = O.sweep_batched(Theta_a, Theta_f, beta, g["A"][:, :n, :n], g["F"][:, :n], g["Gff"],
+                                         g["Gaf"][:, :, :n], g["Gaa"][:, :, :n, :n],
+                                         kind="sqrt_of_eps2_over_beta" if cfg["compliant"] else "sqrt_eps2_over_beta")
+        top = np.sort(d_all)[-2:]
+        min_gap = min(min_gap, (top[1] - top[0]) / top[1])
+    assert worst <= 1e-10, worst
+    assert min_gap > 1e-8, min_gap           # the selected indices are not decided by round-off
+    # final reduced operators and basis agree with the reference's (same Gram-Schmidt order, same projections)
+    assert np.max(np.abs(run.operator_a - g["A"])) <= 1e-10 * np.max(np.abs(g["A"]))
+    assert np.max(np.abs(run.operator_f - g["F"])) <= 1e-10 * np.max(np.abs(g["F"]))
+    assert np.max(np.abs(run.basis_functions - g["Z"])) <= 1e-9 * np.max(np.abs(g["Z"]))

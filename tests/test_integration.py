@@ -84,3 +84,31 @@ def test_reference_reduced_problem_on_the_b200_backend(tmp_path, case, args):
     assert int(h["argmax"]) == int(g["argmax"])
     assert np.max(np.abs(h["delta"] - g["delta"]) / np.abs(g["delta"])) <= 1e-10
     assert np.max(np.abs(h["u"] - g["u"])) <= 1e-10 * np.max(np.abs(g["u"]))
+
+
+@needs_reference
+def test_real_reference_greedy_reproduces_the_committed_fixture(tmp_path):
+    """ReducedBasis(problem).offline() of the unmodified reference, run again, gives the committed greedy sequence."""
+    g = np.load(os.path.join(HERE, "golden", "reference_real_greedy_tutorial01.npz"))
+    d = _run("greedy", "numpy", "tutorial01", 0, tmp_path / "again.npz")
+    assert d["selected_indices"] == g["selected_indices"].tolist()
+    assert d["error_estimators"] == g["error_estimators"].tolist()
+    assert d["uses_plugin"] is False
+
+
+@pytest.mark.gpu
+@needs_reference
+@pytest.mark.parametrize("case,backend", [("tutorial01", "numpy"), ("tutorial01", "b200"), ("stress3", "numpy"),
+                                          ("config2", "numpy")])
+def test_reference_offline_loop_with_the_b200_greedy_override(tmp_path, case, backend):
+    """@B200Sweep() on the problem: RBniCS' own offline loop (truth solves, Gram-Schmidt, projections, Riesz products
+    -- all the reference's code) with every `training_set.max(closure)` replaced by one batched sweep on the GPU selects
+    the SAME parameters as the unmodified reference."""
+    g = np.load(os.path.join(HERE, "golden", "reference_real_greedy_%s.npz" % case))
+    d = _run("greedy", backend, case, 1, tmp_path / "plugin.npz")
+    assert d["uses_plugin"] is True
+    assert d["selected_indices"] == g["selected_indices"].tolist()
+    est, ref = np.array(d["error_estimators"]), g["error_estimators"]
+    assert np.max(np.abs(est - ref) / ref) <= 1e-6     # estimators cancel by up to 1e-7 of their terms here
+    h = np.load(tmp_path / "plugin.npz")
+    assert np.max(np.abs(h["A"] - g["A"])) <= 1e-10 * np.max(np.abs(g["A"]))
