@@ -109,6 +109,7 @@ def test_reference_offline_loop_with_the_b200_greedy_override(tmp_path, case, ba
     assert d["uses_plugin"] is True
     assert d["selected_indices"] == g["selected_indices"].tolist()
     est, ref = np.array(d["error_estimators"]), g["error_estimators"]
-    assert np.max(np.abs(est - ref) / ref) <= 1e-6     # estimators cancel by up to 1e-7 of their terms here
+    # eps2 cancels down to ~1e-15 of its terms at the last iterations: absolute floor relative to the first estimator
+    assert np.all(np.abs(est - ref) <= 1e-6 * ref + 1e-9 * ref[0])
     h = np.load(tmp_path / "plugin.npz")
     assert np.max(np.abs(h["A"] - g["A"])) <= 1e-10 * np.max(np.abs(g["A"]))
