@@ -200,6 +200,22 @@ int rb_off_spmm(rb_ctx* ctx, int csrA, int blkS, int s0, int n, int blkY, int y0
  * appends the result to the block (RBReduction.update_basis_matrix, rb_reduction.py:130-142).                       */
 int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, double* norm_out);
 
+/* ---- multi-GPU offline path: dof rows partitioned over the ranks ---------------------------------
+ * The reference runs these products under PETSc's row partition: every VecDot is an MPI all-reduce
+ * (rbnics/backends/dolfin/wrapping/vector_mul.py:8-9; N^2 of them per Gram matrix, one per old basis function in
+ * Gram-Schmidt, rbnics/backends/basic/gram_schmidt.py:29-33).  Here every rank computes its partial over
+ * [row_begin, row_end) and the library calls back ONCE per Gram matrix / ONCE per Gram-Schmidt projection to sum a
+ * DEVICE buffer over the ranks in place (the host side does it with NCCL on that very pointer: no staging copy).
+ * fn == NULL (default): single rank.  fn returns 0 on success; it is called with the context's stream idle.        */
+typedef int (*rb_allreduce_fn)(void* user, double* device_buffer, int64_t count);
+int rb_set_allreduce(rb_ctx* ctx, rb_allreduce_fn fn, void* user);
+/* rb_off_gram_schmidt on the rank's dof rows: the projections z -= (z^T X b_k) b_k keep the reference's order (one
+ * all-reduce each, of the per-CTA partial sums, so every rank subtracts the bit-identical coefficient); the rows of z
+ * owned by other ranks are then gathered (sum of zero-padded pieces) for the norm sqrt(z^T X z).  z (host, full length)
+ * is returned complete on every rank.                                                                             */
+int rb_off_gram_schmidt_rows(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, int64_t row_begin,
+                             int64_t row_end, double* norm_out);
+
 #ifdef __cplusplus
 }
 #endif

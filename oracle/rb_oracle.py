@@ -497,3 +497,28 @@ def parabolic_sweep_loop(Theta_m, Theta_a, Theta_f, beta, M_q, A_q, f_q, G, N, d
         deltas[p], _ = parabolic_estimate_error(eps2_all[p], float(beta[p]), dt)
         U_all[p] = sols
     return deltas, argmax_first(deltas), eps2_all, U_all
+
+
+def gram_schmidt_row_partitioned(new, Z, X, row_begin, row_end, allreduce_sum, gather_rows):
+    """What rb_off_gram_schmidt_rows does on one rank, in numpy (TEST INFRASTRUCTURE: the gloo test of the multi-rank
+    orchestration runs this on CPU ranks).  Same order as gram_schmidt above (rbnics/backends/basic/gram_schmidt.py:22-36):
+    for every old basis function one partial dot over the rank's dof rows + one all-reduce, then the projected rows are
+    gathered and the norm is one more partial dot + all-reduce.  `allreduce_sum(x)` sums a float over the ranks,
+    `gather_rows(v)` sums zero-padded vectors over the ranks."""
+    z = np.array(new, dtype=np.float64)
+    rows = slice(row_begin, row_end)
+    Xr = X.tocsr()[rows] if X is not None else None
+    for k in range(Z.shape[1]):
+        b = Z[:, k]
+        xb = Xr @ b if Xr is not None else b[rows]
+        d = allreduce_sum(float(z[rows] @ xb))
+        z[rows] = z[rows] - d * b[rows]
+    piece = np.zeros_like(z)
+    piece[rows] = z[rows]
+    z = gather_rows(piece)
+    xz = Xr @ z if Xr is not None else z[rows]
+    nrm2 = allreduce_sum(float(z[rows] @ xz))
+    nrm = sqrt(nrm2)
+    if nrm != 0.0:
+        z = z / nrm
+    return z, nrm

@@ -72,7 +72,13 @@ SIGNATURES = {
     "rb_off_gram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                               C.c_int64, c_double_p]),
     "rb_off_gram_schmidt": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p]),
+    "rb_set_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rb_off_gram_schmidt_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int64, C.c_int64,
+                                           c_double_p]),
 }
+
+# int (*rb_allreduce_fn)(void* user, double* device_buffer, int64_t count)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
 
 _lib = None
 

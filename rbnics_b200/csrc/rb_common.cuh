@@ -32,6 +32,7 @@ struct rb_off_csr_t {
   double* dt = nullptr;
   long long Nh = 0, nnz = 0;
   int sym = 0;  // 1 if the matrix equals its transpose entry by entry (checked on the device at upload)
+  long long generation = 0;  // bumped by every rb_off_csr into this slot (invalidates the Gram-Schmidt mirrors)
 };
 struct rb_off_blk_t {
   double* d = nullptr;  // [Nh][ld] row-major (dof-major)
@@ -45,6 +46,8 @@ struct rb_off_blk_t {
   double* xzt = nullptr;  // [cap][Nh]
   int gs_n = 0;           // columns mirrored so far
   int gs_csr = -2;        // operator slot the xzt mirror was built with
+  long long gs_csr_generation = -1;  // ... and the generation of that slot
+  long long gs_row_begin = -1, gs_row_end = -1;  // dof rows the xzt mirror holds (a rank's partition)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -107,6 +110,12 @@ struct rb_ctx {
   // (5..8: Gram-Schmidt work vectors)
   void* off_scratch[9] = {};
   size_t off_scratch_cap[9] = {};
+
+  // multi-GPU offline path: in-place SUM all-reduce of a device buffer over the ranks (set by rb_set_allreduce; the
+  // host side implements it with NCCL on the very pointer it is handed); nullptr = single rank
+  rb_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+  long long off_generation = 0;
 
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float last_ms[5] = {0, 0, 0, 0, 0};

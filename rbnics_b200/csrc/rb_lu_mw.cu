@@ -481,18 +481,16 @@ static int mw_sm_count() {
   return n;
 }
 
-static int mw_warps() {
 #ifdef RB_AB_VARIANTS
+static int mw_warps() {
   static const int nw = [] {
     const char* e = getenv("RB_MW_NW");
     const int v = e ? atoi(e) : 2;
     return (v == 1 || v == 4) ? v : 2;
   }();
   return nw;
-#else
-  return 2;
-#endif
 }
+#endif
 
 template <int NT, int NW>
 static int mw_slots(long long count) {

@@ -860,6 +860,11 @@ int gram_fused_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* 
                                                                dC.as<double>(), 0);
   RB_CUDA(cudaGetLastError());
   RB_CUDA(cudaEventRecord(ctx->ev[0], st));
+  if (ctx->allreduce) {  // sum of the ranks' partials, in place in HBM
+    RB_CUDA(cudaStreamSynchronize(st));
+    if (ctx->allreduce(ctx->allreduce_user, dC.as<double>(), (int64_t)ns * ns2))
+      RB_FAIL(RB_ERR_CUDA, "rb_gram: the all-reduce callback failed");
+  }
   RB_CUDA(cudaMemcpyAsync(C_host, dC.p, (size_t)ns * ns2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaStreamSynchronize(st));
   float a = 0;
@@ -1041,6 +1046,11 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
                                                                dC.as<double>(), sym ? TM : 0);
   RB_CUDA(cudaGetLastError());
   RB_CUDA(cudaEventRecord(ctx->ev[0], st));
+  if (ctx->allreduce) {  // sum of the ranks' partials, in place in HBM
+    RB_CUDA(cudaStreamSynchronize(st));
+    if (ctx->allreduce(ctx->allreduce_user, dC.as<double>(), (int64_t)ns * ns2))
+      RB_FAIL(RB_ERR_CUDA, "rb_gram: the all-reduce callback failed");
+  }
   RB_CUDA(cudaMemcpyAsync(C_host, dC.p, (size_t)ns * ns2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaStreamSynchronize(st));
   float a = 0, b = 0;
@@ -1444,6 +1454,7 @@ extern "C" int rb_off_csr(rb_ctx* ctx, int slot, int64_t Nh, const int64_t* indp
   for (void* q : {(void*)c.ip, (void*)c.ix, (void*)c.dt})
     if (q) cudaFree(q);
   c = rb_off_csr_t();
+  c.generation = ++ctx->off_generation;  // mirrors of X z_k built with the previous matrix of this slot are stale
   const long long nnz = indptr[Nh];
   RB_CUDA(cudaMalloc((void**)&c.ip, (size_t)(Nh + 1) * sizeof(long long)));
   RB_CUDA(cudaMalloc((void**)&c.ix, (size_t)std::max<long long>(nnz, 1) * sizeof(int)));
@@ -1582,10 +1593,25 @@ extern "C" int rb_off_spmm(rb_ctx* ctx, int csrA, int blkS, int s0, int n, int b
   ctx->last_ms[4] = a;
   ctx->last_launches = 1;
   if (Y->n < y0 + n) Y->n = y0 + n;
+  if (y0 < Y->gs_n) Y->gs_n = y0;  // mirrored columns were overwritten: re-mirror them in the next Gram-Schmidt call
   return RB_OK;
 }
 
-extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, double* norm_out) {
+// z[i] = 0 outside [rb, re): the rank's piece of a vector that is then summed over the ranks (= gathered)
+__global__ void rb_zero_outside_kernel(double* __restrict__ z, long long n, long long rb, long long re) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (i < rb || i >= re) z[i] = 0.0;
+}
+
+extern "C" int rb_set_allreduce(rb_ctx* ctx, rb_allreduce_fn fn, void* user) {
+  if (!ctx) return RB_ERR_ARG;
+  ctx->allreduce = fn;
+  ctx->allreduce_user = user;
+  return RB_OK;
+}
+
+extern "C" int rb_off_gram_schmidt_rows(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, int64_t row_begin,
+                                        int64_t row_end, double* norm_out) {
   if (!ctx) return RB_ERR_ARG;
   RB_CUDA(cudaSetDevice(ctx->device));
   rb_off_blk_t* Z = off_blk(ctx, blkZ);
@@ -1594,6 +1620,11 @@ extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, i
   if (append && Z->n + 1 > Z->cap) RB_FAIL(RB_ERR_ARG, "rb_off_gram_schmidt: block capacity exceeded");
   cudaStream_t st = ctx->stream;
   const long long Nh = Z->Nh;
+  if (row_begin < 0 || row_end > Nh || row_begin > row_end) RB_FAIL(RB_ERR_ARG, "rb_off_gram_schmidt: bad row range");
+  const bool partitioned = !(row_begin == 0 && row_end == Nh);
+  if (partitioned && !ctx->allreduce)
+    RB_FAIL(RB_ERR_STATE, "rb_off_gram_schmidt_rows: a partial row range needs rb_set_allreduce");
+  const long long rb = row_begin, nrows = row_end - row_begin;
   const unsigned nb1 = (unsigned)((Nh + 255) / 256);
   PoolBuf dz(ctx, 5), dNorm(ctx, 6), dXz(ctx, 7), dPart(ctx, 8);
   RB_CUDA(dz.alloc((size_t)Nh * sizeof(double)));
@@ -1602,16 +1633,25 @@ extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, i
   if (X) RB_CUDA(dXz.alloc((size_t)Nh * sizeof(double)));
   RB_CUDA(cudaMemcpyAsync(dz.p, z, (size_t)Nh * sizeof(double), cudaMemcpyHostToDevice, st));
   int launches = 0;
-  // column mirrors (see rb_off_blk_t): bring them up to date with the block (columns appended by rb_off_append, a
-  // different operator than last time)
+  auto reduce = [&](double* buf, long long count) -> int {  // sum over the ranks (no-op on one rank)
+    if (!ctx->allreduce) return RB_OK;
+    RB_CUDA(cudaStreamSynchronize(st));
+    if (ctx->allreduce(ctx->allreduce_user, buf, (int64_t)count))
+      RB_FAIL(RB_ERR_CUDA, "rb_off_gram_schmidt: the all-reduce callback failed");
+    return RB_OK;
+  };
+  // column mirrors (see rb_off_blk_t): bring them up to date with the block -- columns appended by rb_off_append or
+  // overwritten by rb_off_spmm, a different operator slot, a NEW matrix in the same slot (generation), another row range
   if (!Z->zt) RB_CUDA(cudaMalloc((void**)&Z->zt, (size_t)Z->cap * Nh * sizeof(double)));
   if (X && !Z->xzt) RB_CUDA(cudaMalloc((void**)&Z->xzt, (size_t)Z->cap * Nh * sizeof(double)));
-  if (Z->gs_csr != csrX) Z->gs_n = 0;
-  auto mirror_column = [&](int k) -> int {  // zt[k] = column k of the block, xzt[k] = X zt[k]
+  if (Z->gs_csr != csrX || (X && Z->gs_csr_generation != X->generation) || Z->gs_row_begin != row_begin ||
+      Z->gs_row_end != row_end)
+    Z->gs_n = 0;
+  auto mirror_column = [&](int k) -> int {  // zt[k] = column k of the block, xzt[k] = (X zt[k]) on the rank's rows
     rb_off_gather_kernel<<<nb1, 256, 0, st>>>(Z->d, Z->ld, k, 1, Z->zt + (size_t)k * Nh, Nh);
-    if (X)
-      rb_spmm_narrow_kernel<<<nb1, 256, 0, st>>>(X->ip, X->ix, X->dt, Z->zt + (size_t)k * Nh, 1, 1,
-                                                 Z->xzt + (size_t)k * Nh, 1, 0, Nh);
+    if (X && nrows > 0)
+      rb_spmm_narrow_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(
+          X->ip, X->ix, X->dt, Z->zt + (size_t)k * Nh, 1, 1, Z->xzt + (size_t)k * Nh, 1, row_begin, row_end);
     RB_CUDA(cudaGetLastError());
     launches += X ? 2 : 1;
     return RB_OK;
@@ -1620,30 +1660,48 @@ extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, i
     if (int rc = mirror_column(k)) return rc;
   Z->gs_n = Z->n;
   Z->gs_csr = csrX;
+  Z->gs_csr_generation = X ? X->generation : -1;
+  Z->gs_row_begin = row_begin;
+  Z->gs_row_end = row_end;
   // single-pass MGS in the reference's order (rbnics/backends/basic/gram_schmidt.py:22-36), deterministic dots
   const double* xz = X ? Z->xzt : Z->zt;
-  // dot of step 0, then one kernel per step: axpy of step k fused with the dots of step k+1 (N+1 launches, not 2N)
+  // dot of step 0, then one kernel per step: axpy of step k fused with the dots of step k+1 (N+1 launches, not 2N).
+  // Partitioned: the kernels run on the rank's rows only and the per-CTA partials are summed over the ranks before the
+  // next kernel reads them, so every rank subtracts the same d_k.
   double* part[2] = {dPart.as<double>(), dPart.as<double>() + GS_BLOCKS};
+  double* zr = dz.as<double>() + rb;
   if (Z->n > 0) {
-    rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dz.as<double>(), 1, xz, 1, Nh, part[0]);
+    rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(zr, 1, xz + rb, 1, nrows, part[0]);
     ++launches;
+    if (int rc = reduce(part[0], GS_BLOCKS)) return rc;
   }
   for (int k = 0; k < Z->n; ++k) {
-    rb_gs_step_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(part[k & 1], Z->zt + (size_t)k * Nh, dz.as<double>(),
-                                                       k + 1 < Z->n ? xz + (size_t)(k + 1) * Nh : nullptr, Nh,
+    rb_gs_step_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(part[k & 1], Z->zt + (size_t)k * Nh + rb, zr,
+                                                       k + 1 < Z->n ? xz + (size_t)(k + 1) * Nh + rb : nullptr, nrows,
                                                        part[(k + 1) & 1]);
     ++launches;
+    if (k + 1 < Z->n)
+      if (int rc = reduce(part[(k + 1) & 1], GS_BLOCKS)) return rc;
   }
   RB_CUDA(cudaGetLastError());
+  if (partitioned) {  // gather the rows the other ranks projected: sum of the zero-padded pieces
+    rb_zero_outside_kernel<<<nb1, 256, 0, st>>>(dz.as<double>(), Nh, row_begin, row_end);
+    ++launches;
+    if (int rc = reduce(dz.as<double>(), Nh)) return rc;
+  }
   const double* dXzp = dz.as<double>();
   if (X) {
-    rb_spmm_narrow_kernel<<<nb1, 256, 0, st>>>(X->ip, X->ix, X->dt, dz.as<double>(), 1, 1, dXz.as<double>(), 1, 0, Nh);
+    if (nrows > 0)
+      rb_spmm_narrow_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(X->ip, X->ix, X->dt, dz.as<double>(), 1, 1,
+                                                                            dXz.as<double>(), 1, row_begin, row_end);
     dXzp = dXz.as<double>();
     ++launches;
   }
-  rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dz.as<double>(), 1, dXzp, 1, Nh, dPart.as<double>());
+  rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(zr, 1, dXzp + rb, 1, nrows, dPart.as<double>());
+  ++launches;
+  if (int rc = reduce(dPart.as<double>(), GS_BLOCKS)) return rc;
   rb_normalize_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(dPart.as<double>(), dz.as<double>(), Nh, dNorm.as<double>());
-  launches += 2;
+  ++launches;
   RB_CUDA(cudaGetLastError());
   if (append) {
     rb_off_scatter_kernel<<<nb1, 256, 0, st>>>(dz.as<double>(), 1, Z->d, Z->ld, Z->n, Nh);
@@ -1658,4 +1716,11 @@ extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, i
   if (norm_out) *norm_out = nrm;
   ctx->last_launches = launches;
   return RB_OK;
+}
+
+extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, double* norm_out) {
+  if (!ctx) return RB_ERR_ARG;
+  rb_off_blk_t* Z = off_blk(ctx, blkZ);
+  if (!Z) RB_FAIL(RB_ERR_ARG, "rb_off_gram_schmidt: empty slot");
+  return rb_off_gram_schmidt_rows(ctx, blkZ, csrX, z, append, 0, Z->Nh, norm_out);
 }

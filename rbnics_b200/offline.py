@@ -43,6 +43,24 @@ def _dist_range(Nh, dist):
     return row_range(Nh, dist.rank, dist.size)
 
 
+def install_device_allreduce(engine, dist):
+    """Multi-GPU offline path: hand the library an all-reduce that works on its device buffers (rb_set_allreduce), so
+    the partial Gram / projection / Gram-Schmidt results are summed over the ranks in HBM (NCCL) before they are copied
+    to the host once.  Returns True if installed (NCCL, more than one rank); with gloo (CPU tests) the host-side
+    all-reduce of the returned arrays is used instead."""
+    if dist is None or dist.size == 1 or dist.backend != "nccl":
+        if getattr(engine, "_allreduce_on", False):   # a single-rank call on an engine that also serves partitioned ones
+            engine._check(engine._lib.rb_set_allreduce(engine._h, None, None))
+            engine._allreduce_on = False
+        return False
+    if getattr(engine, "_allreduce_cb", None) is None:
+        engine._allreduce_cb = dist.device_allreduce_callback()   # keep the ctypes thunk alive
+    if not getattr(engine, "_allreduce_on", False):
+        engine._check(engine._lib.rb_set_allreduce(engine._h, C.cast(engine._allreduce_cb, C.c_void_p), None))
+        engine._allreduce_on = True
+    return True
+
+
 def gram(engine, S, X=None, S2=None, dist=None):
     """C[i, j] = s_i . (X s2_j)  (Ns x Ns2)."""
     S = np.ascontiguousarray(S, dtype=np.float64)
@@ -61,8 +79,9 @@ def gram(engine, S, X=None, S2=None, dist=None):
         args = (ip.ctypes.data_as(L.c_int64_p), ix.ctypes.data_as(L.c_int32_p), L.dptr(dt))
     else:
         args = (None, None, None)
+    on_device = install_device_allreduce(engine, dist)
     engine._check(engine._lib.rb_gram(engine._h, Nh, Ns, Ns2, L.dptr(S), L.dptr(S2c), *args, rb, re, L.dptr(Cm)))
-    if dist is not None and dist.size > 1:
+    if dist is not None and dist.size > 1 and not on_device:
         dist.allreduce_sum_(Cm)
     return Cm
 
@@ -201,6 +220,7 @@ class OfflineWorkspace:
         self._csr = {}
         self._blk = {}
         self.Nh = None
+        self._device_allreduce = install_device_allreduce(engine, dist)
 
     def _slot(self, table, name):
         if name not in table:
@@ -256,17 +276,27 @@ class OfflineWorkspace:
         Cm = np.empty((s1 - s0, t1 - t0))
         rb, re = _dist_range(self.Nh, self.dist)
         e = self.engine
+        self._device_allreduce = install_device_allreduce(e, self.dist)
         e._check(e._lib.rb_off_gram(e._h, self._blk[S], int(s0), int(s1 - s0), self._csr[X] if X is not None else -1,
                                     self._blk[S2], int(t0), int(t1 - t0), rb, re, L.dptr(Cm)))
-        if self.dist is not None and self.dist.size > 1:
+        if self.dist is not None and self.dist.size > 1 and not self._device_allreduce:
             self.dist.allreduce_sum_(Cm)
         return Cm
 
     def gram_schmidt(self, Z, X, new_function, append=True):
-        """Orthonormalise ``new_function`` against the columns of block Z (X inner product); optionally append it."""
+        """Orthonormalise ``new_function`` against the columns of block Z (X inner product); optionally append it.
+        With more than one rank the dof rows are partitioned like the Gram products: every projection coefficient is
+        one all-reduce (rbnics/backends/basic/gram_schmidt.py:29-33 under PETSc's row partition: one VecDot each), the
+        order of the reference's modified Gram-Schmidt is kept."""
         z = np.ascontiguousarray(new_function, dtype=np.float64).copy()
         norm = C.c_double()
         e = self.engine
-        e._check(e._lib.rb_off_gram_schmidt(e._h, self._blk[Z], self._csr[X] if X is not None else -1, L.dptr(z),
-                                            1 if append else 0, C.byref(norm)))
+        self._device_allreduce = install_device_allreduce(e, self.dist)
+        if self._device_allreduce:
+            rb, re = _dist_range(self.Nh, self.dist)
+            e._check(e._lib.rb_off_gram_schmidt_rows(e._h, self._blk[Z], self._csr[X] if X is not None else -1,
+                                                     L.dptr(z), 1 if append else 0, rb, re, C.byref(norm)))
+        else:
+            e._check(e._lib.rb_off_gram_schmidt(e._h, self._blk[Z], self._csr[X] if X is not None else -1, L.dptr(z),
+                                                1 if append else 0, C.byref(norm)))
         return z, norm.value

@@ -137,6 +137,29 @@ class DistributedMaxLoc:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return array
 
+    def device_allreduce_callback(self):
+        """`rb_allreduce_fn` for rb_set_allreduce: in-place SUM all-reduce (NCCL) of a device buffer the library hands
+        over by pointer -- zero-copy through the CUDA array interface, no host staging."""
+        if self.backend != "nccl":
+            raise RuntimeError("the device all-reduce callback needs the NCCL backend")
+        t, dist, device = self.torch, self.dist, self.device
+
+        def allreduce(user, ptr, count):
+            try:
+                class _Holder:
+                    __cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False),
+                                                "version": 3}
+                buf = t.as_tensor(_Holder(), device=device)
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                t.cuda.synchronize(device)
+                return 0
+            except Exception:  # an exception must not unwind through the C frames
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        return L.ALLREDUCE_FN(allreduce)
+
     def close(self):
         if self._own and self.dist.is_initialized():
             self.dist.destroy_process_group()

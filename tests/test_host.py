@@ -90,13 +90,35 @@ part = np.full((3, 3), float(d.rank + 1))
 d.allreduce_sum_(part)
 assert np.all(part == 3.0)
 assert d.max_float(d.rank) == 1.0
+# row-partitioned Gram matrix and Gram-Schmidt (SURVEY.md 8e): every rank works on its PETSc-style ownership range,
+# one all-reduce per Gram matrix / per projection coefficient; equal to the single-rank result
+import scipy.sparse as sp
+from oracle import rb_oracle as O
+from rbnics_b200 import offline
+rng = np.random.default_rng(0)
+Nh = 301
+X = (sp.diags([-1.0, 2.5, -1.0], [-1, 0, 1], shape=(Nh, Nh)) + sp.diags([0.2, 0.2], [-9, 9], shape=(Nh, Nh))).tocsr()
+S = rng.standard_normal((Nh, 6))
+rb, re = offline.row_range(Nh, d.rank, d.size)
+assert (rb, re) == ((0, 151) if d.rank == 0 else (151, 301))
+part = S[rb:re].T @ (X[rb:re] @ S)                    # the rank's partial S_g^T (X S)_g
+d.allreduce_sum_(part)
+assert np.max(np.abs(part - O.gram_blas(S, X))) <= 1e-12 * np.max(np.abs(part))
+Z = np.zeros((Nh, 0))
+for k in range(5):
+    v = rng.standard_normal(Nh)
+    gather = lambda piece: d.allreduce_sum_(piece.copy())
+    z, nrm = O.gram_schmidt_row_partitioned(v, Z, X, rb, re, d.sum_float, gather)
+    z1 = O.gram_schmidt(v, Z, X)
+    assert np.max(np.abs(z - z1)) <= 1e-12 * np.max(np.abs(z1)), (k, np.max(np.abs(z - z1)))
+    Z = np.concatenate([Z, z1[:, None]], axis=1)
 d.barrier()
 d.close()
 sys.stdout.write("rank %d ok\n" % d.rank); sys.stdout.flush()
 """
 
 
-def test_world_size_2_gloo_maxloc_and_allreduce(tmp_path):
+def test_world_size_2_gloo_maxloc_allreduce_and_row_partitioned_offline(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER.format(root=ROOT))
     import socket

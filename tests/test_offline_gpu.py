@@ -302,3 +302,40 @@ def test_pod_eigenvalues_and_modes(engine):
             assert np.max(np.abs(s * Z[:, n] - Z_ref[:, n])) <= 1e-6 * np.max(np.abs(Z_ref[:, n]))
     G = O.gram_blas(Z, X)
     assert np.max(np.abs(np.diag(G) - 1.0)) < 1e-10
+
+
+def test_gram_schmidt_mirrors_follow_the_operator_and_the_block(engine):
+    """rb_off_gram_schmidt caches X z_k per block.  Replacing the matrix in the SAME operator slot, or
+    overwriting mirrored columns with rb_off_spmm, must invalidate that cache (generation counter / gs_n reset);
+    every step is compared with the host-path GramSchmidt on the current data."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(11)
+    Nh = 3000
+    X1 = (sp.diags([-1.0, 2.5, -1.0], [-1, 0, 1], shape=(Nh, Nh))).tocsr()
+    X2 = (sp.diags([-0.5, 4.0, -0.5], [-1, 0, 1], shape=(Nh, Nh)) + sp.diags([0.3, 0.3], [-7, 7], shape=(Nh, Nh))).tocsr()
+    ws = offline.OfflineWorkspace(engine)
+    ws.set_operator("X", X1)
+    ws.new_block("Z", Nh, 16)
+    basis = []
+    gs1 = offline.GramSchmidt(engine, X1)
+    for k in range(4):
+        v = rng.standard_normal(Nh)
+        z, _ = ws.gram_schmidt("Z", "X", v)
+        zh = gs1.apply(v, np.stack(basis, axis=1) if basis else None)
+        assert np.max(np.abs(z - zh)) <= 1e-12 * np.max(np.abs(zh))
+        basis.append(z)
+    # (1) a NEW matrix registered under the same name / slot: the mirrors X z_k are stale
+    ws.set_operator("X", X2)
+    v = rng.standard_normal(Nh)
+    z, _ = ws.gram_schmidt("Z", "X", v, append=False)
+    zh = offline.GramSchmidt(engine, X2).apply(v, np.stack(basis, axis=1))
+    assert np.max(np.abs(z - zh)) <= 1e-12 * np.max(np.abs(zh))
+    # (2) rb_off_spmm overwrites mirrored columns 1..2 of the block
+    ws.new_block("S", Nh, 4)
+    ws.append("S", rng.standard_normal((Nh, 2)))
+    ws.set_operator("A", X1)
+    ws.spmm("A", "S", (0, 2), "Z", 1)
+    Znow = ws.read("Z")
+    z, _ = ws.gram_schmidt("Z", "X", v, append=False)
+    zh = offline.GramSchmidt(engine, X2).apply(v, Znow)
+    assert np.max(np.abs(z - zh)) <= 1e-12 * np.max(np.abs(zh))
