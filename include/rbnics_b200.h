@@ -200,6 +200,14 @@ int rb_off_spmm(rb_ctx* ctx, int csrA, int blkS, int s0, int n, int blkY, int y0
  * appends the result to the block (RBReduction.update_basis_matrix, rb_reduction.py:130-142).                       */
 int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, double* norm_out);
 
+/* Resident POD (rbnics/backends/basic/proper_orthogonal_decomposition_base.py:39-92): modes Z[:, z0:z0+n] =
+ * S[:, s0:s0+ns] V (V: ns x n row-major on the host; dolfin/wrapping/functions_list_mul.py:26-36), their squared
+ * X-norms z_j^T X z_j from the DIAGONAL only (:80-87; csrX < 0: identity; dof rows [row_begin, row_end), summed over the
+ * ranks when rb_set_allreduce is set), and the column scaling z_j *= scale[j].                                        */
+int rb_off_lincomb(rb_ctx* ctx, int blkS, int s0, int ns, const double* V, int n, int blkZ, int z0);
+int rb_off_column_norms2(rb_ctx* ctx, int blkZ, int z0, int n, int csrX, int64_t row_begin, int64_t row_end, double* out);
+int rb_off_scale_columns(rb_ctx* ctx, int blkZ, int z0, int n, const double* scale);
+
 /* ---- multi-GPU offline path: dof rows partitioned over the ranks ---------------------------------
  * The reference runs these products under PETSc's row partition: every VecDot is an MPI all-reduce
  * (rbnics/backends/dolfin/wrapping/vector_mul.py:8-9; N^2 of them per Gram matrix, one per old basis function in

@@ -1156,7 +1156,8 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool vali
 template <int NTC>
 __global__ void __launch_bounds__(LC_THREADS, 2) rb_lincomb_kernel(const double* __restrict__ S, int lds, int ns,
                                                                    const double* __restrict__ V, int ldv, int n,
-                                                                   double* __restrict__ Z, long long Nh, int col0) {
+                                                                   double* __restrict__ Z, int ldz, long long Nh,
+                                                                   int col0) {
   extern __shared__ __align__(16) double lc_smem[];
   double(*As)[LC_BM * LC_APITCH] = reinterpret_cast<double(*)[LC_BM * LC_APITCH]>(lc_smem);
   double(*Bs)[LC_KC * LC_BPITCH] = reinterpret_cast<double(*)[LC_KC * LC_BPITCH]>(lc_smem + LC_NST * LC_BM * LC_APITCH);
@@ -1220,8 +1221,8 @@ __global__ void __launch_bounds__(LC_THREADS, 2) rb_lincomb_kernel(const double*
 #pragma unroll
     for (int nt = 0; nt < NTC; ++nt) {
       const int c = n0 + nt * 8 + q4 * 2;
-      if (c < n) Z[r * n + c] = acc[mt][nt][0];
-      if (c + 1 < n) Z[r * n + c + 1] = acc[mt][nt][1];
+      if (c < n) Z[r * ldz + c] = acc[mt][nt][0];
+      if (c + 1 < n) Z[r * ldz + c + 1] = acc[mt][nt][1];
     }
   }
 }
@@ -1229,12 +1230,30 @@ __global__ void __launch_bounds__(LC_THREADS, 2) rb_lincomb_kernel(const double*
 // ny column tiles of 32 starting at column col0 of V / Z
 template <int NTC>
 static cudaError_t lincomb_launch(cudaStream_t st, size_t smem, const double* dS, int lds, int ns, const double* dV,
-                                  int ldv, int n, double* dZ, long long Nh, int ny, int col0) {
+                                  int ldv, int n, double* dZ, int ldz, long long Nh, int ny, int col0) {
   cudaError_t e = cudaFuncSetAttribute(rb_lincomb_kernel<NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)((Nh + LC_BM - 1) / LC_BM), ny);
-  rb_lincomb_kernel<NTC><<<grid, LC_THREADS, smem, st>>>(dS, lds, ns, dV, ldv, n, dZ, Nh, col0);
+  rb_lincomb_kernel<NTC><<<grid, LC_THREADS, smem, st>>>(dS, lds, ns, dV, ldv, n, dZ, ldz, Nh, col0);
   return cudaGetLastError();
+}
+
+// Z (pitch ldz) = S (Nh x Ns, pitch lds, 16-byte aligned rows) * V (Ns x n, even pitch ldv); all on the device
+static int lincomb_device(rb_ctx* ctx, long long Nh, int Ns, int n, const double* pS, int lds, const double* pV, int ldv,
+                          double* pZ, int ldz) {
+  cudaStream_t st = ctx->stream;
+  const size_t smem = (size_t)LC_NST * (LC_BM * LC_APITCH + LC_KC * LC_BPITCH) * sizeof(double);
+  // full 32-column tiles in one launch, the narrower last tile with the 8-column tile count it needs
+  const int nfull = n / LC_BN, rem = n % LC_BN;
+  if (nfull > 0) RB_CUDA(lincomb_launch<4>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, nfull, 0));
+  if (rem > 0) {
+    const int c0 = nfull * LC_BN, ntc = (rem + 7) / 8;
+    RB_CUDA(ntc == 1   ? lincomb_launch<1>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, 1, c0)
+            : ntc == 2 ? lincomb_launch<2>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, 1, c0)
+            : ntc == 3 ? lincomb_launch<3>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, 1, c0)
+                       : lincomb_launch<4>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, 1, c0));
+  }
+  return RB_OK;
 }
 
 extern "C" int rb_lincomb(rb_ctx* ctx, int64_t Nh, int Ns, int n, const double* S, const double* V, double* Z) {
@@ -1247,20 +1266,8 @@ extern "C" int rb_lincomb(rb_ctx* ctx, int64_t Nh, int Ns, int n, const double* 
   if (int rc = upload_cols(ctx, S, Nh, Ns, dS, &lds)) return rc;
   if (int rc = upload_cols(ctx, V, Ns, n, dV, &ldv)) return rc;
   RB_CUDA(dZ.alloc((size_t)Nh * n * sizeof(double)));
-  const size_t smem = (size_t)LC_NST * (LC_BM * LC_APITCH + LC_KC * LC_BPITCH) * sizeof(double);
   RB_CUDA(cudaEventRecord(ctx->ev[4], st));
-  // full 32-column tiles in one launch, the narrower last tile with the 8-column tile count it needs
-  const int nfull = n / LC_BN, rem = n % LC_BN;
-  const double *pS = dS.as<double>(), *pV = dV.as<double>();
-  double* pZ = dZ.as<double>();
-  if (nfull > 0) RB_CUDA(lincomb_launch<4>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, Nh, nfull, 0));
-  if (rem > 0) {
-    const int c0 = nfull * LC_BN, ntc = (rem + 7) / 8;
-    RB_CUDA(ntc == 1   ? lincomb_launch<1>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, Nh, 1, c0)
-            : ntc == 2 ? lincomb_launch<2>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, Nh, 1, c0)
-            : ntc == 3 ? lincomb_launch<3>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, Nh, 1, c0)
-                       : lincomb_launch<4>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, Nh, 1, c0));
-  }
+  if (int rc = lincomb_device(ctx, Nh, Ns, n, dS.as<double>(), lds, dV.as<double>(), ldv, dZ.as<double>(), n)) return rc;
   RB_CUDA(cudaEventRecord(ctx->ev[5], st));
   RB_CUDA(cudaMemcpyAsync(Z, dZ.p, (size_t)Nh * n * sizeof(double), cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaStreamSynchronize(st));
@@ -1268,7 +1275,7 @@ extern "C" int rb_lincomb(rb_ctx* ctx, int64_t Nh, int Ns, int n, const double* 
   cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]);
   ctx->last_ms[0] = a;
   ctx->last_ms[4] = a;
-  ctx->last_launches = (nfull > 0) + (rem > 0);
+  ctx->last_launches = (n / LC_BN > 0) + (n % LC_BN > 0);
   return RB_OK;
 }
 
@@ -1723,4 +1730,150 @@ extern "C" int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, i
   rb_off_blk_t* Z = off_blk(ctx, blkZ);
   if (!Z) RB_FAIL(RB_ERR_ARG, "rb_off_gram_schmidt: empty slot");
   return rb_off_gram_schmidt_rows(ctx, blkZ, csrX, z, append, 0, Z->Nh, norm_out);
+}
+
+// =====================================================================================================================
+// Resident POD helpers: modes Z = S V, their X-norms from the DIAGONAL only, column scaling
+// (rbnics/backends/basic/proper_orthogonal_decomposition_base.py:77-92, dolfin/wrapping/functions_list_mul.py:26-36)
+// =====================================================================================================================
+constexpr int CD_BLOCKS = 592;
+
+// partial[block][c] = sum over the block's rows of Z[r, c] * Y[r, c]  (n <= 128 columns, lanes over columns)
+__global__ void __launch_bounds__(256) rb_coldot_partial_kernel(const double* __restrict__ Z, int ldz,
+                                                                const double* __restrict__ Y, int ldy, int n,
+                                                                long long row_begin, long long row_end,
+                                                                double* __restrict__ partial) {
+  __shared__ double sh[8][128];
+  const int lane = threadIdx.x & 31, rr = threadIdx.x >> 5;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long r = row_begin + blockIdx.x * 8LL + rr; r < row_end; r += 8LL * CD_BLOCKS) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int c = lane + 32 * t;
+      if (c < n) acc[t] = fma(Z[r * ldz + c], Y[r * ldy + c], acc[t]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) sh[rr][lane + 32 * t] = acc[t];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    double s = 0.0;
+    for (int k = 0; k < 8; ++k) s += sh[k][threadIdx.x];  // fixed order: deterministic
+    if ((int)threadIdx.x < n) partial[(long long)blockIdx.x * 128 + threadIdx.x] = s;
+  }
+}
+
+__global__ void rb_coldot_final_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  const int c = threadIdx.x;
+  if (c >= n) return;
+  double s = 0.0;
+  for (int b = 0; b < CD_BLOCKS; ++b) s += partial[(long long)b * 128 + c];
+  out[c] = s;
+}
+
+__global__ void rb_scale_cols_kernel(double* __restrict__ Z, int ldz, int n, long long Nh, const double* __restrict__ sc) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= Nh * n) return;
+  const long long r = t / n;
+  const int c = (int)(t % n);
+  Z[r * ldz + c] *= sc[c];
+}
+
+extern "C" int rb_off_lincomb(rb_ctx* ctx, int blkS, int s0, int ns, const double* V, int n, int blkZ, int z0) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  rb_off_blk_t* S = off_blk(ctx, blkS);
+  rb_off_blk_t* Z = off_blk(ctx, blkZ);
+  if (!S || !Z || !V) RB_FAIL(RB_ERR_ARG, "rb_off_lincomb: empty slot");
+  if (S->Nh != Z->Nh) RB_FAIL(RB_ERR_ARG, "rb_off_lincomb: inconsistent number of dofs");
+  if (s0 < 0 || ns <= 0 || s0 + ns > S->n || n <= 0 || z0 < 0 || z0 + n > Z->cap || S == Z)
+    RB_FAIL(RB_ERR_ARG, "rb_off_lincomb: column range outside the block");
+  if (s0 & 1) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_off_lincomb: the first source column must be even (16-byte aligned rows)");
+  cudaStream_t st = ctx->stream;
+  DevBuf dV;
+  int ldv = n;
+  if (int rc = upload_cols(ctx, V, ns, n, dV, &ldv)) return rc;
+  RB_CUDA(cudaEventRecord(ctx->ev[4], st));
+  if (int rc = lincomb_device(ctx, S->Nh, ns, n, S->d + s0, S->ld, dV.as<double>(), ldv, Z->d + z0, Z->ld)) return rc;
+  RB_CUDA(cudaEventRecord(ctx->ev[5], st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  float a = 0;
+  cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]);
+  ctx->last_ms[0] = a;
+  ctx->last_ms[4] = a;
+  ctx->last_launches = (n / LC_BN > 0) + (n % LC_BN > 0);
+  if (Z->n < z0 + n) Z->n = z0 + n;
+  if (z0 < Z->gs_n) Z->gs_n = z0;
+  return RB_OK;
+}
+
+extern "C" int rb_off_column_norms2(rb_ctx* ctx, int blkZ, int z0, int n, int csrX, int64_t row_begin, int64_t row_end,
+                                    double* out) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  rb_off_blk_t* Z = off_blk(ctx, blkZ);
+  rb_off_csr_t* X = csrX >= 0 ? off_csr(ctx, csrX) : nullptr;
+  if (!Z || !out || (csrX >= 0 && !X)) RB_FAIL(RB_ERR_ARG, "rb_off_column_norms2: empty slot");
+  if (z0 < 0 || n <= 0 || n > 128 || z0 + n > Z->n) RB_FAIL(RB_ERR_ARG, "rb_off_column_norms2: bad column range");
+  const long long Nh = Z->Nh;
+  if (row_begin < 0 || row_end > Nh || row_begin > row_end) RB_FAIL(RB_ERR_ARG, "rb_off_column_norms2: bad row range");
+  cudaStream_t st = ctx->stream;
+  PoolBuf Ybuf(ctx, 0), part(ctx, 1), dOut(ctx, 2);
+  RB_CUDA(part.alloc((size_t)CD_BLOCKS * 128 * sizeof(double)));
+  RB_CUDA(dOut.alloc(128 * sizeof(double)));
+  const double* Y = Z->d + z0;
+  int ldy = Z->ld;
+  RB_CUDA(cudaEventRecord(ctx->ev[4], st));
+  if (X) {
+    RB_CUDA(Ybuf.alloc((size_t)Nh * n * sizeof(double)));
+    const long long nrows = row_end - row_begin;
+    if (nrows > 0) {
+      if (n <= 32) {
+        rb_spmm_narrow_kernel<<<(unsigned)((nrows * n + 255) / 256), 256, 0, st>>>(X->ip, X->ix, X->dt, Z->d + z0, Z->ld, n,
+                                                                                  Ybuf.as<double>(), n, row_begin, row_end);
+      } else {
+        const int nchunk = (n + 127) / 128;
+        rb_spmm_kernel<<<(unsigned)((nrows * nchunk * 32 + 255) / 256), 256, 0, st>>>(
+            X->ip, X->ix, X->dt, Z->d + z0, Z->ld, n, Ybuf.as<double>(), n, row_begin, row_end);
+      }
+      RB_CUDA(cudaGetLastError());
+    }
+    Y = Ybuf.as<double>();
+    ldy = n;
+  }
+  rb_coldot_partial_kernel<<<CD_BLOCKS, 256, 0, st>>>(Z->d + z0, Z->ld, Y, ldy, n, row_begin, row_end, part.as<double>());
+  rb_coldot_final_kernel<<<1, 128, 0, st>>>(part.as<double>(), n, dOut.as<double>());
+  RB_CUDA(cudaGetLastError());
+  RB_CUDA(cudaEventRecord(ctx->ev[5], st));
+  if (ctx->allreduce) {
+    RB_CUDA(cudaStreamSynchronize(st));
+    if (ctx->allreduce(ctx->allreduce_user, dOut.as<double>(), n))
+      RB_FAIL(RB_ERR_CUDA, "rb_off_column_norms2: the all-reduce callback failed");
+  }
+  RB_CUDA(cudaMemcpyAsync(out, dOut.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  float a = 0;
+  cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]);
+  ctx->last_ms[0] = a;
+  ctx->last_ms[4] = a;
+  ctx->last_launches = X ? 3 : 2;
+  return RB_OK;
+}
+
+extern "C" int rb_off_scale_columns(rb_ctx* ctx, int blkZ, int z0, int n, const double* scale) {
+  if (!ctx) return RB_ERR_ARG;
+  RB_CUDA(cudaSetDevice(ctx->device));
+  rb_off_blk_t* Z = off_blk(ctx, blkZ);
+  if (!Z || !scale) RB_FAIL(RB_ERR_ARG, "rb_off_scale_columns: empty slot");
+  if (z0 < 0 || n <= 0 || z0 + n > Z->n) RB_FAIL(RB_ERR_ARG, "rb_off_scale_columns: bad column range");
+  cudaStream_t st = ctx->stream;
+  PoolBuf dSc(ctx, 2);
+  RB_CUDA(dSc.alloc((size_t)n * sizeof(double)));
+  RB_CUDA(cudaMemcpyAsync(dSc.p, scale, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  rb_scale_cols_kernel<<<(unsigned)((Z->Nh * n + 255) / 256), 256, 0, st>>>(Z->d + z0, Z->ld, n, Z->Nh, dSc.as<double>());
+  RB_CUDA(cudaGetLastError());
+  RB_CUDA(cudaStreamSynchronize(st));
+  if (z0 < Z->gs_n) Z->gs_n = z0;
+  ctx->last_launches = 1;
+  return RB_OK;
 }

@@ -283,6 +283,39 @@ class OfflineWorkspace:
             self.dist.allreduce_sum_(Cm)
         return Cm
 
+    def lincomb(self, S, V, Z, col0=0, cols=None):
+        """Z[:, col0:col0+n] = S[:, cols] V on resident blocks (V: host, ns x n): S * eigenvectors of the POD."""
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        if V.ndim == 1:
+            V = np.ascontiguousarray(V[:, None])
+        s0, s1 = cols if cols is not None else (0, self.ncols(S))
+        assert V.shape[0] == s1 - s0
+        e = self.engine
+        e._check(e._lib.rb_off_lincomb(e._h, self._blk[S], int(s0), int(s1 - s0), L.dptr(V), int(V.shape[1]),
+                                       self._blk[Z], int(col0)))
+
+    def column_norms2(self, Z, X=None, cols=None):
+        """[z_j^T X z_j for the columns j of the block]: the diagonal of Z^T X Z without the off-diagonal work."""
+        c0, c1 = cols if cols is not None else (0, self.ncols(Z))
+        out = np.empty(c1 - c0)
+        rb, re = _dist_range(self.Nh, self.dist)
+        e = self.engine
+        self._device_allreduce = install_device_allreduce(e, self.dist)
+        for a in range(c0, c1, 128):
+            n = min(128, c1 - a)
+            part = np.empty(n)
+            e._check(e._lib.rb_off_column_norms2(e._h, self._blk[Z], int(a), int(n), self._csr[X] if X is not None else -1,
+                                                 rb, re, L.dptr(part)))
+            out[a - c0:a - c0 + n] = part
+        if self.dist is not None and self.dist.size > 1 and not self._device_allreduce:
+            self.dist.allreduce_sum_(out)
+        return out
+
+    def scale_columns(self, Z, scale, col0=0):
+        scale = np.ascontiguousarray(scale, dtype=np.float64)
+        e = self.engine
+        e._check(e._lib.rb_off_scale_columns(e._h, self._blk[Z], int(col0), int(scale.shape[0]), L.dptr(scale)))
+
     def gram_schmidt(self, Z, X, new_function, append=True):
         """Orthonormalise ``new_function`` against the columns of block Z (X inner product); optionally append it.
         With more than one rank the dof rows are partitioned like the Gram products: every projection coefficient is
@@ -300,3 +333,55 @@ class OfflineWorkspace:
             e._check(e._lib.rb_off_gram_schmidt(e._h, self._blk[Z], self._csr[X] if X is not None else -1, L.dptr(z),
                                                 1 if append else 0, C.byref(norm)))
         return z, norm.value
+
+
+class ResidentProperOrthogonalDecomposition:
+    """POD by the method of snapshots on DEVICE-RESIDENT snapshots (rbnics/backends/basic/
+    proper_orthogonal_decomposition_base.py:39-92; interface of rbnics/backends/abstract/
+    proper_orthogonal_decomposition.py:11-44).  Snapshots are appended to a block of the workspace as they are produced
+    (each crosses PCIe once); ``apply`` is ONE Gram matrix S^T X S, the host eigen-decomposition of the small matrix
+    (scipy.linalg.eigh, the reference's own call, rbnics/backends/online/numpy/eigen_solver.py:36-56), ONE tall-skinny
+    product for the modes, their X-norms from the diagonal only and a column scaling -- nothing of size Nh x Ns goes back
+    to the host unless the caller reads the basis."""
+
+    def __init__(self, workspace, inner_product, Nh, capacity, snapshots="pod_snapshots", basis="pod_basis"):
+        self.ws = workspace
+        self.X = inner_product          # operator name in the workspace, or None for the Euclidean product
+        self.snapshots, self.basis = snapshots, basis
+        self.Nh, self.capacity = int(Nh), int(capacity)
+        self.clear()
+
+    def clear(self):
+        self.ws.new_block(self.snapshots, self.Nh, self.capacity)
+        self.eigenvalues = []
+        self.retained_energy = []
+
+    def store_snapshot(self, snapshot, weight=None):
+        s = np.asarray(snapshot, dtype=np.float64)
+        self.ws.append(self.snapshots, s if weight is None else s * weight)
+
+    def apply(self, Nmax, tol, read_basis=True):
+        """-> (eigenvalues[:N], eigenvectors, basis (Nh x N array, or the block name if not read_basis), N)."""
+        ws = self.ws
+        Ns = ws.ncols(self.snapshots)
+        correlation = ws.gram(self.snapshots, self.X)
+        eigs, eigv = scipy.linalg.eigh(correlation)
+        idx = eigs.argsort()[::-1]
+        eigs, eigv = eigs[idx], eigv[:, idx]
+        Nmax = min(Nmax, Ns)
+        self.eigenvalues = [float(e) for e in eigs]
+        abs_e = np.abs(eigs)
+        total = abs_e.sum()
+        self.retained_energy = list(np.cumsum(abs_e) / total) if total > 0.0 else [1.0] * Ns
+        N = 0
+        for n in range(Nmax):
+            N = n + 1
+            if tol > 0.0 and self.retained_energy[n] > 1.0 - tol:
+                break
+        V = np.ascontiguousarray(eigv[:, :N])
+        ws.new_block(self.basis, self.Nh, max(N, 2))
+        ws.lincomb(self.snapshots, V, self.basis)
+        norms2 = ws.column_norms2(self.basis, self.X)          # b^T X b of every mode (:80-87), diagonal only
+        ws.scale_columns(self.basis, np.array([1.0 / sqrt(v) if v > 0.0 else 1.0 for v in norms2]))
+        Z = ws.read(self.basis) if read_basis else self.basis
+        return self.eigenvalues[:N], [eigv[:, n].copy() for n in range(N)], Z, N

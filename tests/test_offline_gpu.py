@@ -339,3 +339,37 @@ def test_gram_schmidt_mirrors_follow_the_operator_and_the_block(engine):
     z, _ = ws.gram_schmidt("Z", "X", v, append=False)
     zh = offline.GramSchmidt(engine, X2).apply(v, Znow)
     assert np.max(np.abs(z - zh)) <= 1e-12 * np.max(np.abs(zh))
+
+
+def test_resident_pod_equals_host_path_and_golden(engine):
+    """ResidentProperOrthogonalDecomposition (snapshots resident, one Gram, modes by one product, norms from the
+    diagonal) gives the eigenvalues / modes of the upload-every-call class and of the reference's loop (golden)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_offline.npz"))
+    Nh = int(g["Nh"])
+    X = sp.csr_matrix((g["X_data"], g["X_indices"], g["X_indptr"]), shape=(Nh, Nh))
+    S = g["S"]
+    Ns = S.shape[1]
+    ws = offline.OfflineWorkspace(engine)
+    ws.set_operator("X", X)
+    pod = offline.ResidentProperOrthogonalDecomposition(ws, "X", Nh, Ns + 3)
+    host = offline.ProperOrthogonalDecomposition(engine, X)
+    for k in range(Ns):
+        pod.store_snapshot(S[:, k])
+        host.store_snapshot(S[:, k])
+    e1, v1, Z1, N1 = pod.apply(Ns, 1e-10)
+    e2, v2, Z2, N2 = host.apply(Ns, 1e-10)
+    assert N1 == N2 == int(g["pod_N"])
+    lam = g["pod_eigenvalues"]
+    assert np.max(np.abs(np.array(pod.eigenvalues) - lam)) <= 1e-10 * lam[0]       # north_star tolerance
+    for k in range(min(N1, 3)):       # well-separated leading modes, up to sign
+        ref = g["pod_basis"][:, k]
+        sgn = np.sign(Z1[:, k] @ (X @ ref))
+        assert np.max(np.abs(sgn * Z1[:, k] - ref)) <= 1e-6 * np.max(np.abs(ref))
+    for k in range(N1):               # same eigenvectors -> same modes as the host-path class
+        sgn2 = np.sign(Z1[:, k] @ (X @ Z2[:, k]))
+        assert np.max(np.abs(sgn2 * Z1[:, k] - Z2[:, k])) <= 1e-9 * np.max(np.abs(Z2[:, k]))
+    n2 = ws.column_norms2("pod_basis", "X")
+    assert np.max(np.abs(n2 - 1.0)) <= 1e-12
+    Gs = np.sum(S * S, axis=0)
+    assert np.max(np.abs(ws.column_norms2("pod_snapshots", None) - Gs)) <= 1e-12 * np.max(Gs)
