@@ -104,6 +104,14 @@ int rb_sweep(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta, int n_bc,
  * delta_out: B, eps2_out: B x (K+1), u_out: B x (K+1) x N (any may be NULL).                                      */
 int rb_sweep_parabolic(rb_ctx* ctx, int Qm, int K, double dt, const double* weights, double* max_val,
                        int64_t* max_idx, double* delta_out, double* eps2_out, double* u_out);
+/* The same with a non-homogeneous initial condition: U0 (B x N, row-major, may be NULL = zero) holds the reduced initial
+ * condition of every parameter (rbnics/problems/base/time_dependent_reduced_problem.py:277-302 and the projection of
+ * rbnics/backends/online/numpy/time_stepping.py:104-112), init_err2 (B, may be NULL = zero) its squared error estimate
+ * get_initial_error_estimate_squared(), which is the bound at t0 (abstract_parabolic_rb_reduced_problem.py:41-44; no
+ * division by beta) and enters the time quadrature with weights[0].                                                 */
+int rb_sweep_parabolic_ic(rb_ctx* ctx, int Qm, int K, double dt, const double* weights, const double* U0,
+                          const double* init_err2, double* max_val, int64_t* max_idx, double* delta_out,
+                          double* eps2_out, double* u_out);
 
 /* ---- output functional of the solutions of the last sweep (testing-set sweeps of error_analysis / speedup_analysis,
  * rbnics/reduction_methods/base/rb_reduction.py:312-390):  out[p] = u_p^T ( sum_q ThetaS[p][q] * S[q] ),

@@ -431,8 +431,8 @@ def residual_norm_squared_stokes(u, theta, E, N):
 # Parabolic problems: POD-Greedy sweep
 # ----------------------------------------------------------------------------------------------------------------------
 
-def parabolic_solve(theta_m, theta_a, theta_f, M_q, A_q, f_q, N, dt, K):
-    """Linear implicit Euler from a zero initial condition, K steps.
+def parabolic_solve(theta_m, theta_a, theta_f, M_q, A_q, f_q, N, dt, K, u0=None):
+    """Linear implicit Euler from the initial condition u0 (zero if None), K steps.
 
     rbnics/problems/parabolic/abstract_parabolic_reduced_problem.py:17-36 (residual = M udot + A u - f,
     jacobian = M * coef + A) driven by rbnics/backends/online/numpy/time_stepping.py:104-112 (lhs = jacobian(1/dt),
@@ -442,7 +442,7 @@ def parabolic_solve(theta_m, theta_a, theta_f, M_q, A_q, f_q, N, dt, K):
     A = np.array(product_order1(theta_a, [a[:N, :N] for a in A_q]))
     f = np.array(product_order1(theta_f, [v[:N] for v in f_q]))
     zero = np.zeros(N)
-    u_prev = np.zeros(N)
+    u_prev = np.zeros(N) if u0 is None else np.array(u0, dtype=np.float64)
     sols, dots = [u_prev.copy()], [np.zeros(N)]
     for _ in range(K):
         minus_prev_over_dt = u_prev.copy()
@@ -467,7 +467,7 @@ def parabolic_residual_norm_squared(u, udot, theta_m, theta_a, theta_f, G_ff, G_
     return float(elliptic + 2.0 * np.dot(udot, mf) + 2.0 * np.dot(udot, ma @ u) + np.dot(udot, mm @ udot))
 
 
-def parabolic_estimate_error(eps2_over_time, beta, dt):
+def parabolic_estimate_error(eps2_over_time, beta, dt, initial_error_estimate_squared=0.0):
     """Error bound over time (0 at t0 for a homogeneous initial condition, sqrt(|eps2|/beta) afterwards) and its time
     quadrature sqrt(simpson(bound^2, dx=dt)).
 
@@ -475,11 +475,11 @@ def parabolic_estimate_error(eps2_over_time, beta, dt):
     rbnics/reduction_methods/base/time_dependent_rb_reduction.py:280-288,
     rbnics/backends/common/time_quadrature.py:22-29 (scipy.integrate.simpson)."""
     from scipy.integrate import simpson
-    bound = [0.0] + [sqrt(abs(e) / beta) for e in eps2_over_time[1:]]
+    bound = [sqrt(abs(initial_error_estimate_squared))] + [sqrt(abs(e) / beta) for e in eps2_over_time[1:]]
     return sqrt(simpson([v ** 2 for v in bound], dx=dt)), bound
 
 
-def parabolic_sweep_loop(Theta_m, Theta_a, Theta_f, beta, M_q, A_q, f_q, G, N, dt, K):
+def parabolic_sweep_loop(Theta_m, Theta_a, Theta_f, beta, M_q, A_q, f_q, G, N, dt, K, U0=None, init_err2=None):
     """The reference's POD-Greedy closure over a training set (serial).  G = dict of the six Gram storages
     ("ff", "af", "aa", "mf", "ma", "mm").  Returns (delta[B], argmax, eps2[B][K+1], U[B][K+1][N])."""
     B = Theta_a.shape[0]
@@ -490,11 +490,12 @@ def parabolic_sweep_loop(Theta_m, Theta_a, Theta_f, beta, M_q, A_q, f_q, G, N, d
         tm = tuple(float(x) for x in Theta_m[p])
         ta = tuple(float(x) for x in Theta_a[p])
         tf = tuple(float(x) for x in Theta_f[p])
-        sols, dots = parabolic_solve(tm, ta, tf, M_q, A_q, f_q, N, dt, K)
+        sols, dots = parabolic_solve(tm, ta, tf, M_q, A_q, f_q, N, dt, K, None if U0 is None else U0[p])
         for k in range(1, K + 1):
             eps2_all[p, k] = parabolic_residual_norm_squared(sols[k], dots[k], tm, ta, tf, G["ff"], G["af"], G["aa"],
                                                              G["mf"], G["ma"], G["mm"], N)
-        deltas[p], _ = parabolic_estimate_error(eps2_all[p], float(beta[p]), dt)
+        deltas[p], _ = parabolic_estimate_error(eps2_all[p], float(beta[p]), dt,
+                                                0.0 if init_err2 is None else float(init_err2[p]))
         U_all[p] = sols
     return deltas, argmax_first(deltas), eps2_all, U_all
 

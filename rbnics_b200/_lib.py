@@ -37,6 +37,8 @@ SIGNATURES = {
                                       C.c_int]),
     "rb_sweep_parabolic": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, c_double_p, c_double_p, c_int64_p,
                                      c_double_p, c_double_p, c_double_p]),
+    "rb_sweep_parabolic_ic": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, c_double_p, c_double_p, c_double_p,
+                                        c_double_p, c_int64_p, c_double_p, c_double_p, c_double_p]),
     "rb_compute_outputs": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]),
     "rb_supremizers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int64, c_double_p, c_double_p,
                                  c_double_p]),

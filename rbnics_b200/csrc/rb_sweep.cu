@@ -1208,7 +1208,15 @@ static int launch_estimator(rb_ctx* ctx, const double* Uvec, int ldu, int vecN, 
 // chunk size of the assembly scratch and its (re)allocation
 int rb_lu_mw_quantum(int N);
 static int prepare_assembly(rb_ctx* ctx, long long B, long long* chunk_out, size_t* asm_smem_out) {
+  // one wave of the assembly GEMM (148 x 128 parameters = 1.5 GB of assembled matrices at N = 100); small systems take
+  // as many parameters as fit the same budget, so that the per-chunk launches (5 per time step in the parabolic sweep)
+  // stay large
   long long chunk = (long long)ctx->sm_count * ASM_BM;
+  {
+    const long long budget = 1536LL << 20;
+    const long long fit = budget / ((long long)ctx->EP * (long long)sizeof(double));
+    if (fit > chunk) chunk = fit / chunk * chunk;
+  }
   if (const char* e = getenv("RB_LU_CHUNK")) {  // tuning knob; anything that is not a positive count is ignored
     const long long v = atoll(e);
     if (v > 0) chunk = v;
@@ -1435,8 +1443,29 @@ __global__ void __launch_bounds__(256) rb_parabolic_finalize_kernel(const double
 int rb_launch_lu_rhs(rb_ctx* ctx, int64_t count, const double* Ab, const double* theta, const double* thetaBC,
                      const double* rhs_in, double* u, int ldu);
 
+// UV[p] = [u0[p] | 0]; acc[p] = w0 * |e0[p]|  (non-homogeneous initial condition)
+__global__ void rb_parabolic_init_kernel(const double* __restrict__ u0, const double* __restrict__ e0, double w0,
+                                         double* __restrict__ UV, int ldu, int N, long long n, double* __restrict__ acc,
+                                         double* __restrict__ u_hist, long long hist_pitch) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n * N) return;
+  const long long p = t / N;
+  const int i = (int)(t % N);
+  const double v = u0 ? u0[p * N + i] : 0.0;
+  UV[p * ldu + i] = v;
+  UV[p * ldu + N + i] = 0.0;
+  if (u_hist) u_hist[p * hist_pitch + i] = v;
+  if (i == 0) acc[p] = e0 ? w0 * fabs(e0[p]) : 0.0;
+}
+
 extern "C" int rb_sweep_parabolic(rb_ctx* ctx, int Qm, int K, double dt, const double* weights, double* max_val,
                                   int64_t* max_idx, double* delta_out, double* eps2_out, double* u_out) {
+  return rb_sweep_parabolic_ic(ctx, Qm, K, dt, weights, nullptr, nullptr, max_val, max_idx, delta_out, eps2_out, u_out);
+}
+
+extern "C" int rb_sweep_parabolic_ic(rb_ctx* ctx, int Qm, int K, double dt, const double* weights, const double* U0,
+                                     const double* init_err2, double* max_val, int64_t* max_idx, double* delta_out,
+                                     double* eps2_out, double* u_out) {
   if (!ctx) return RB_ERR_ARG;
   RB_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->have_system || !ctx->have_est || !ctx->have_train)
@@ -1466,9 +1495,10 @@ extern "C" int rb_sweep_parabolic(rb_ctx* ctx, int Qm, int K, double dt, const d
     ctx->blk_cap = fin_blocks;
   }
   // chunk-sized work arrays: [u | udot], rhs, new solution; optional histories (device side, whole training set)
-  double *dUV = nullptr, *dRhs = nullptr, *dUnew = nullptr, *dHistE = nullptr, *dHistU = nullptr;
+  double *dUV = nullptr, *dRhs = nullptr, *dUnew = nullptr, *dHistE = nullptr, *dHistU = nullptr, *dU0 = nullptr,
+         *dE0 = nullptr;
   auto free_all = [&]() {
-    for (double* q : {dUV, dRhs, dUnew, dHistE, dHistU})
+    for (double* q : {dUV, dRhs, dUnew, dHistE, dHistU, dU0, dE0})
       if (q) cudaFree(q);
   };
 #define RB_PB(call)                                                                                  \
@@ -1487,7 +1517,14 @@ extern "C" int rb_sweep_parabolic(rb_ctx* ctx, int Qm, int K, double dt, const d
   if (u_out) RB_PB(cudaMalloc(&dHistU, (size_t)B * (K + 1) * N * sizeof(double)));
   if (dHistE) RB_PB(cudaMemsetAsync(dHistE, 0, (size_t)B * (K + 1) * sizeof(double), st));
   if (dHistU) RB_PB(cudaMemsetAsync(dHistU, 0, (size_t)B * (K + 1) * N * sizeof(double), st));
-  RB_PB(cudaMemsetAsync(ctx->dEps2, 0, (size_t)B * sizeof(double), st));  // accumulator of w_k bound_k^2
+  if (U0) {  // reduced initial condition of every parameter (time_dependent_reduced_problem.py:277-302 + projection)
+    RB_PB(cudaMalloc(&dU0, (size_t)B * N * sizeof(double)));
+    RB_PB(cudaMemcpyAsync(dU0, U0, (size_t)B * N * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  if (init_err2) {  // get_initial_error_estimate_squared(): the bound at t0 (abstract_parabolic_rb_reduced_problem.py:41-44)
+    RB_PB(cudaMalloc(&dE0, (size_t)B * sizeof(double)));
+    RB_PB(cudaMemcpyAsync(dE0, init_err2, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
   int launches = 0;
   RB_PB(cudaEventRecord(ctx->ev[0], st));
   for (long long c0 = 0; c0 < B; c0 += chunk) {
@@ -1497,7 +1534,11 @@ extern "C" int rb_sweep_parabolic(rb_ctx* ctx, int Qm, int K, double dt, const d
       return rc;
     }
     ++launches;
-    RB_PB(cudaMemsetAsync(dUV, 0, (size_t)n * 2 * N * sizeof(double), st));  // zero initial condition
+    rb_parabolic_init_kernel<<<(unsigned)((n * N + 255) / 256), 256, 0, st>>>(
+        dU0 ? dU0 + c0 * N : nullptr, dE0 ? dE0 + c0 : nullptr, weights[0], dUV, 2 * N, N, n, ctx->dEps2 + c0,
+        dHistU ? dHistU + c0 * (K + 1) * N : nullptr, (long long)(K + 1) * N);
+    RB_PB(cudaGetLastError());
+    ++launches;
     const double* th = ctx->dTheta + c0 * ctx->QT;
     for (int k = 1; k <= K; ++k) {
       rb_parabolic_rhs_kernel<<<(unsigned)((n + 3) / 4), 128, 4 * N * sizeof(double), st>>>(

@@ -87,7 +87,10 @@ class ParabolicSweep:
         self.weights = np.ascontiguousarray(simpson_weights(self.K, self.dt))
 
     def sweep(self, Theta_m, Theta_a, Theta_f, beta, ThetaBC=None, index_offset=0, index_stride=1, want_delta=False,
-              want_eps2=False, want_u=False):
+              want_eps2=False, want_u=False, U0=None, initial_error_estimate_squared=None):
+        """``U0`` (B x N): reduced initial condition of every parameter (None: homogeneous);
+        ``initial_error_estimate_squared`` (B): the squared bound at t0 (None: zero).  Both are cheap host-side batched
+        products of theta_ic with the reduced initial-condition vectors."""
         Theta = np.ascontiguousarray(np.concatenate([Theta_m, Theta_a, Theta_f], axis=1), dtype=np.float64)
         eng = self.engine
         eng.set_training_set(Theta, beta, ThetaBC, index_offset=index_offset, index_stride=index_stride)
@@ -96,6 +99,14 @@ class ParabolicSweep:
         delta = np.empty(B) if want_delta else None
         eps2 = np.empty((B, self.K + 1)) if want_eps2 else None
         u = np.empty((B, self.K + 1, self.N)) if want_u else None
-        eng._check(eng._lib.rb_sweep_parabolic(eng._h, self.Qm, self.K, self.dt, L.dptr(self.weights), C.byref(mv),
-                                               C.byref(mi), L.dptr(delta), L.dptr(eps2), L.dptr(u)))
+        if U0 is not None:
+            U0 = np.ascontiguousarray(U0, dtype=np.float64)
+            assert U0.shape == (B, self.N)
+        e0 = None
+        if initial_error_estimate_squared is not None:
+            e0 = np.ascontiguousarray(initial_error_estimate_squared, dtype=np.float64)
+            assert e0.shape == (B,)
+        eng._check(eng._lib.rb_sweep_parabolic_ic(eng._h, self.Qm, self.K, self.dt, L.dptr(self.weights), L.dptr(U0),
+                                                  L.dptr(e0), C.byref(mv), C.byref(mi), L.dptr(delta), L.dptr(eps2),
+                                                  L.dptr(u)))
         return {"max": mv.value, "argmax": mi.value, "delta": delta, "eps2": eps2, "u": u}

@@ -66,3 +66,34 @@ def test_cuda_parabolic_sweep_matches_reference(engine):
     assert np.max(np.abs(r["delta"] - G["delta"]) / G["delta"]) <= 1e-10
     assert r["argmax"] == int(np.argmax(G["delta"]))
     assert abs(r["max"] - G["delta"].max()) <= 1e-10 * G["delta"].max()
+
+
+@pytest.mark.gpu
+def test_cuda_parabolic_sweep_with_initial_condition(engine):
+    """Non-homogeneous initial condition (SURVEY.md 8f row 2 / VERDICT r1): u^0 of every parameter and the squared
+    error estimate at t0 enter the sweep; compared with the loop oracle started from the same u^0
+    (rbnics/backends/online/numpy/time_stepping.py:104-112, abstract_parabolic_rb_reduced_problem.py:29-46)."""
+    from rbnics_b200.parabolic import ParabolicSweep
+    E = {("f", "f"): G["E_f_f"], ("a", "f"): G["E_a_f"], ("a", "a"): G["E_a_a"], ("m", "f"): G["E_m_f"],
+         ("m", "a"): G["E_m_a"], ("m", "m"): G["E_m_m"]}
+    B = G["Theta_m"].shape[0]
+    rng = np.random.default_rng(4)
+    U0 = 0.3 * rng.standard_normal((B, N))
+    e0 = rng.uniform(0.0, 0.2, B)
+    Gd = {"ff": [[float(x) for x in row] for row in G["E_f_f"]],
+          "af": [[v for v in row] for row in G["E_a_f"]], "aa": [[v for v in row] for row in G["E_a_a"]],
+          "mf": [[v for v in row] for row in G["E_m_f"]], "ma": [[v for v in row] for row in G["E_m_a"]],
+          "mm": [[v for v in row] for row in G["E_m_m"]]}
+    d, i, eps2, U = O.parabolic_sweep_loop(G["Theta_m"], G["Theta_a"], G["Theta_f"], G["beta"], list(G["M"]), list(G["A"]),
+                                           list(G["F"]), Gd, N, DT, K, U0=U0, init_err2=e0)
+    sw = ParabolicSweep(engine, G["M"], G["A"], G["F"], E, dt=DT, K=K)
+    r = sw.sweep(G["Theta_m"], G["Theta_a"], G["Theta_f"], G["beta"], want_delta=True, want_eps2=True, want_u=True,
+                 U0=U0, initial_error_estimate_squared=e0)
+    assert np.array_equal(r["u"][:, 0], U0)
+    assert np.max(np.abs(r["u"] - U)) <= 1e-10 * np.max(np.abs(U))
+    scale = np.max(np.abs(eps2), axis=1, keepdims=True)
+    assert np.max(np.abs(r["eps2"][:, 1:] - eps2[:, 1:]) / scale) <= 1e-10
+    assert np.max(np.abs(r["delta"] - d) / d) <= 1e-10
+    assert r["argmax"] == i
+    zero = sw.sweep(G["Theta_m"], G["Theta_a"], G["Theta_f"], G["beta"], want_delta=True)   # and the default is unchanged
+    assert np.max(np.abs(zero["delta"] - G["delta"]) / G["delta"]) <= 1e-10
