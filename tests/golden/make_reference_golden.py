@@ -37,7 +37,7 @@ def main():
     for name, case in CASES.items():
         out = os.path.join(HERE, "reference_real_sweep_%s.npz" % name)
         subprocess.run([sys.executable, RUN, "sweep", "numpy"] + [str(x) for x in case] + [out], check=True)
-    for case in ("tutorial01", "stress3", "config2"):
+    for case in ("tutorial01", "stress3", "config2", "tutorial01_mesh", "tutorial02_mesh"):
         out = os.path.join(HERE, "reference_real_greedy_%s.npz" % case)
         subprocess.run([sys.executable, RUN, "greedy", "numpy", case, "0", out], check=True)
     sdir = os.path.join(HERE, "storage_real")

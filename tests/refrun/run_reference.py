@@ -30,6 +30,11 @@ GREEDY_CASES = {
     "stress3": dict(n=14, nblocks=3, nloads=1, compliant=True, a_range=(0.1, 10.0), ntrain=100, Nmax=20, tol=2e-7, seed=1),
     # shapes of tutorials/02_elastic_block: Q_a = 9, Q_f = 3, 11 parameters (8 stiffness in [1, 100] + 3 loads), non-compliant
     "config2": dict(n=18, nblocks=9, nloads=3, compliant=False, a_range=(1.0, 100.0), ntrain=200, Nmax=20, tol=1e-12, seed=2),
+    # the reference's OWN tutorial meshes (tests/golden/mesh_*.npz) with the P1 assembler of tests/truth_problems.py
+    "tutorial01_mesh": dict(truth="ThermalBlockTutorialMesh", nblocks=2, nloads=1, compliant=True, a_range=(0.1, 10.0),
+                            ntrain=100, Nmax=4, tol=1e-5, seed=0),
+    "tutorial02_mesh": dict(truth="ElasticBlockTutorialMesh", nblocks=9, nloads=3, compliant=False, a_range=(1.0, 100.0),
+                            ntrain=200, Nmax=20, tol=1e-12, seed=3),
 }
 
 
@@ -146,6 +151,7 @@ def main():
     if mode == "greedy":
         case, plugin, outfile = sys.argv[3], int(sys.argv[4]), sys.argv[5]
         sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import truth_problems
         from truth_problems import ThermalBlock
         from oracle import reference_truth as T
         cfg = GREEDY_CASES[case]
@@ -158,7 +164,10 @@ def main():
                 sys.path.append(integ)
             from rbnics_b200_plugin.sweep import B200Sweep
             decorator = B200Sweep()
-        tb = ThermalBlock(n=cfg["n"], nblocks=cfg["nblocks"], nloads=cfg["nloads"])
+        if "truth" in cfg:
+            tb = getattr(truth_problems, cfg["truth"])()
+        else:
+            tb = ThermalBlock(n=cfg["n"], nblocks=cfg["nblocks"], nloads=cfg["nloads"])
         problem = T.make_thermal_block_problem(tb, compliant=cfg["compliant"], decorator=decorator)
         mu_range = [cfg["a_range"]] * (cfg["nblocks"] - 1) + [(-1.0, 1.0)] * cfg["nloads"]
         import contextlib

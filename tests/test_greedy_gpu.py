@@ -105,6 +105,12 @@ REAL_CASES = {   # the configurations of tests/refrun/run_reference.py:GREEDY_CA
     "tutorial01": dict(n=12, nblocks=2, nloads=1, compliant=True, a_range=(0.1, 10.0), Nmax=4, tol=1e-5),
     "stress3": dict(n=14, nblocks=3, nloads=1, compliant=True, a_range=(0.1, 10.0), Nmax=20, tol=2e-7),
     "config2": dict(n=18, nblocks=9, nloads=3, compliant=False, a_range=(1.0, 100.0), Nmax=20, tol=1e-12),
+    # the reference's own tutorial meshes (tutorials/01_thermal_block/data/thermal_block.xml: 304 vertices;
+    # tutorials/02_elastic_block/data/elastic_block.xml: 1346 vertices, vector P1) with the numpy P1 assembler
+    "tutorial01_mesh": dict(truth="ThermalBlockTutorialMesh", nblocks=2, nloads=1, compliant=True, a_range=(0.1, 10.0),
+                            Nmax=4, tol=1e-5),
+    "tutorial02_mesh": dict(truth="ElasticBlockTutorialMesh", nblocks=9, nloads=3, compliant=False, a_range=(1.0, 100.0),
+                            Nmax=20, tol=1e-12),
 }
 
 
@@ -124,7 +130,12 @@ def test_greedy_sequence_identical_to_the_real_reference(engine, case, resident)
     cfg = REAL_CASES[case]
     g = np.load(os.path.join(GOLD, f"reference_real_greedy_{case}.npz"))
     mu_range = [cfg["a_range"]] * (cfg["nblocks"] - 1) + [(-1.0, 1.0)] * cfg["nloads"]
-    tp = ThermalBlock(n=cfg["n"], nblocks=cfg["nblocks"], nloads=cfg["nloads"], mu_range=mu_range)
+    if "truth" in cfg:
+        import truth_problems
+        tp = getattr(truth_problems, cfg["truth"])()
+        assert tp.mu_range == mu_range
+    else:
+        tp = ThermalBlock(n=cfg["n"], nblocks=cfg["nblocks"], nloads=cfg["nloads"], mu_range=mu_range)
     train = [tuple(mu) for mu in g["training_set"]]
     kind = L.RB_EST_SQRT_OF_EPS2_OVER_BETA if cfg["compliant"] else L.RB_EST_SQRT_EPS2_OVER_BETA
     run = ReducedBasisGreedy(engine, tp, train, Nmax=cfg["Nmax"], tol=cfg["tol"], estimator_kind=kind,

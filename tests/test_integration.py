@@ -99,7 +99,7 @@ def test_real_reference_greedy_reproduces_the_committed_fixture(tmp_path):
 @pytest.mark.gpu
 @needs_reference
 @pytest.mark.parametrize("case,backend", [("tutorial01", "numpy"), ("tutorial01", "b200"), ("stress3", "numpy"),
-                                          ("config2", "numpy")])
+                                          ("config2", "numpy"), ("tutorial01_mesh", "numpy")])
 def test_reference_offline_loop_with_the_b200_greedy_override(tmp_path, case, backend):
     """@B200Sweep() on the problem: RBniCS' own offline loop (truth solves, Gram-Schmidt, projections, Riesz products
     -- all the reference's code) with every `training_set.max(closure)` replaced by one batched sweep on the GPU selects
