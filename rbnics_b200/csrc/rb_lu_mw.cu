@@ -42,7 +42,8 @@ template <int NT, int NW>
 struct MwSmem {
   using C = MwCfg<NT, NW>;
   double ring[2][C::SLOT];
-  double P[C::NP8][8];                  // the panel, row-major: gather of pivot rows, transpose into the pivot phase
+  double P[C::NP8][10];                 // the panel, row-major (pitch 10: conflict-free LDS.128 of one row per lane):
+                                        // gather of pivot rows, transpose into the pivot phase
   double Ub[8][8];                      // U_qp of the record being applied / the pivot rows of the panel being factored
   double slot[2][NW][10];               // pivot candidates of the warps: row entries t+1..7, 1/pivot, rhs entry
   unsigned long long keys[2][NW];
@@ -286,17 +287,19 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
       }
       // ---- apply the records q < p
       for (int q = 0; q < p; ++q) {
-        // dump the panel: the rows pivoted in panel q are final here
-#pragma unroll
-        for (int i = 0; i < TPW; ++i) {
-          const int tr = w + NW * i;
-          if (tr < NT) *reinterpret_cast<double2*>(&sm.P[8 * tr + g][2 * q4]) = make_double2(c[i][0], c[i][1]);
-        }
-        mw_sync<NTH>();  // (A) the dump is visible; everybody is done with record q - 1 (and, for q = 0, the panel of A)
-        if (q + 1 < p) fill((q + 1) & 1, Lrec + (long long)(q + 1) * C::REC, sm.recsz[q + 1], keep);
+        // dump the tile rows that hold the pivot rows of panel q (they are final here); the mask travels in the record
         wait_slot(q & 1);
         const double* rq = sm.ring[q & 1];
         const int* prq = reinterpret_cast<const int*>(rq + 64);
+        {
+          const unsigned dm = (unsigned)prq[9] >> w;
+#pragma unroll
+          for (int i = 0; i < TPW; ++i)
+            if ((dm >> (NW * i)) & 1u)  // uniform
+              *reinterpret_cast<double2*>(&sm.P[8 * (w + NW * i) + g][2 * q4]) = make_double2(c[i][0], c[i][1]);
+        }
+        mw_sync<NTH>();  // (A) the dump is visible; everybody is done with record q - 1 (and, for q = 0, the panel of A)
+        if (q + 1 < p) fill((q + 1) & 1, Lrec + (long long)(q + 1) * C::REC, sm.recsz[q + 1], keep);
         if (w == q % NW) {
           // U_qp = L_qq^-1 X on the tensor pipe (the inverse of the 8x8 unit-lower block travels in the record)
           const double2 la = *reinterpret_cast<const double2*>(rq + 2 * lane);
@@ -395,6 +398,13 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
 #pragma unroll
           for (int t = 0; t < 8; ++t) mw_st1_keep(dst + (t * 4 + (tid & 3)) * 2 + (tid >> 2), x[t], keep);
           reinterpret_cast<int*>(dst + 64)[tid] = sm.pivrow[c0 + tid];
+        }
+        if (tid == 9 % NTH) {  // tile rows that hold the pivot rows of this panel: the only ones later panels must dump
+          unsigned dm = 0u;
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (t < nst) dm |= 1u << (sm.pivrow[c0 + t] >> 3);
+          reinterpret_cast<int*>(dst + 64)[9] = (int)dm;
         }
         if (tid == 8 % NTH) {
           reinterpret_cast<int*>(dst + 64)[8] = (int)live_tr;
