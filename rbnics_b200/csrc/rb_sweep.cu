@@ -1252,10 +1252,23 @@ static int launch_assembly(rb_ctx* ctx, long long c0, long long n, size_t asm_sm
   aa.Ql = ctx->Ql;
   aa.QlP = ctx->QlP;
   aa.EP = ctx->EP;
-  // row blocks x entry-tile splits: 2 resident CTAs per SM, ~2 waves
+  // row blocks x entry-tile splits: 2 resident CTAs per SM.  The split is the one in [2 waves .. 4 waves] that wastes the
+  // least of its last wave (146 row blocks x 5 splits = 730 CTAs on 296 slots ran 3 waves for 2.47 waves of work)
   const unsigned nrb_asm = (unsigned)((n + ASM_BM - 1) / ASM_BM);
-  unsigned esplit = (unsigned)std::max<long long>(1, (4LL * ctx->sm_count + nrb_asm - 1) / nrb_asm);
-  esplit = std::min<unsigned>(esplit, (unsigned)(ctx->EP / ASM_BE));
+  const unsigned slots = 2u * (unsigned)ctx->sm_count;
+  const unsigned max_split = (unsigned)(ctx->EP / ASM_BE);
+  unsigned esplit = 1;
+  double best_eff = 0.0;
+  for (unsigned e = 1; e <= max_split && (unsigned long long)e * nrb_asm <= 4ull * slots + nrb_asm; ++e) {
+    const unsigned long long total = (unsigned long long)e * nrb_asm;
+    const unsigned long long waves = (total + slots - 1) / slots;
+    double eff = (double)total / (double)(waves * slots);
+    if (total < slots) eff *= 0.5;  // less than one wave: not enough CTAs to hide the tile loads
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      esplit = e;
+    }
+  }
   dim3 grid(esplit, nrb_asm);
   rb_assemble_kernel<<<grid, 256, asm_smem, ctx->stream>>>(aa);
   RB_CUDA(cudaGetLastError());
