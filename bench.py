@@ -416,9 +416,13 @@ def run_b200_arm(args):
             dist.barrier()
 
     def step_resident():
+        if dist is not None:   # the collective reads the engine's device-resident (max, argmax, #non-finite) directly
+            eng.sweep_resident(raise_on_singular=False)
+            v, i, bad = dist.maxloc_device(eng)
+            if bad:
+                raise RuntimeError("non-finite error estimators in the bench sweep")
+            return v, i
         r = eng.sweep_resident()
-        if dist is not None:
-            return dist.maxloc(r["max"], r["argmax"])
         return r["max"], r["argmax"]
 
     def step_e2e():

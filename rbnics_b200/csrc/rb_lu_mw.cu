@@ -182,6 +182,15 @@ __device__ __forceinline__ void mw_pivot_step(double (&pv)[MwCfg<NT, NW>::RPL][8
   }
 }
 
+#ifdef RB_MW_PROFILE
+// per-phase cycle counters of thread 0 of every CTA, summed into rb_mw_prof[0..16) (instrumented build only:
+// tools/lu_phase_probe.py; the table is in DESIGN.md 4.2)
+__device__ unsigned long long rb_mw_prof[16];
+#define MW_ACC(slot, since) do { const long long n__ = clock64(); if (tid == 0) pacc[slot] += n__ - (since); (since) = n__; } while (0)
+#else
+#define MW_ACC(slot, since) do { } while (0)
+#endif
+
 template <int NT, int NW, int OCC>
 __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, double* __restrict__ scratch,
                                                                  unsigned long long* __restrict__ next_sys) {
@@ -202,6 +211,10 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
     mbar_fence_init();
   }
   mw_sync<NTH>();
+#ifdef RB_MW_PROFILE
+  long long pacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tp = clock64();
+#endif
   unsigned phase = 0u;  // bit s: parity of the next completion of ring slot s (uniform)
   const uint64_t keep = mw_policy_keep(), stream = mw_policy_stream();
   auto fill = [&](int slot, const double* src, int bytes, uint64_t policy) {  // one thread, one instruction per transfer
@@ -265,9 +278,12 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
                                         ((bal & 0xff0000u) ? 4u : 0u) | ((bal & 0xff000000u) ? 8u : 0u);
       }
       // ---- the staged panel of the assembled matrix into accumulator tiles, the first record on its way
+      MW_ACC(0, tp);  // rhs / live mask / loop head
       mw_sync<NTH>();  // the record of the previous panel is complete (and fenced)
       if (p > 0) fill(0, Lrec, sm.recsz[0], keep);
+      MW_ACC(1, tp);  // barrier at the panel top
       wait_slot(1);
+      MW_ACC(2, tp);  // wait for the staged panel of A
       double c[TPW][2];
       {
         const double* As = sm.ring[1];
@@ -285,10 +301,12 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
           c[i][1] = v.y;
         }
       }
+      MW_ACC(3, tp);  // panel tiles into registers
       // ---- apply the records q < p
       for (int q = 0; q < p; ++q) {
         // dump the tile rows that hold the pivot rows of panel q (they are final here); the mask travels in the record
         wait_slot(q & 1);
+        MW_ACC(4, tp);  // wait for record q
         const double* rq = sm.ring[q & 1];
         const int* prq = reinterpret_cast<const int*>(rq + 64);
         {
@@ -298,8 +316,10 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
             if ((dm >> (NW * i)) & 1u)  // uniform
               *reinterpret_cast<double2*>(&sm.P[8 * (w + NW * i) + g][2 * q4]) = make_double2(c[i][0], c[i][1]);
         }
+        MW_ACC(5, tp);  // dump
         mw_sync<NTH>();  // (A) the dump is visible; everybody is done with record q - 1 (and, for q = 0, the panel of A)
         if (q + 1 < p) fill((q + 1) & 1, Lrec + (long long)(q + 1) * C::REC, sm.recsz[q + 1], keep);
+        MW_ACC(6, tp);  // barrier A + issue of the next fill
         if (w == q % NW) {
           // U_qp = L_qq^-1 X on the tensor pipe (the inverse of the 8x8 unit-lower block travels in the record)
           const double2 la = *reinterpret_cast<const double2*>(rq + 2 * lane);
@@ -311,7 +331,9 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
           // U block (q, p) -> packed store straight from the accumulator layout (read once, at the very end)
           mw_st2_keep(Ust + ((long long)(p * (p + 1) / 2 + q)) * 64 + 8 * g + 2 * q4, u0, u1, keep);
         }
+        MW_ACC(7, tp);  // U_qp (computing warp) / nothing (the other)
         mw_sync<NTH>();  // (B) U_qp is visible; P may be overwritten
+        MW_ACC(8, tp);  // barrier B
         const double b0 = sm.Ub[q4][g], b1 = sm.Ub[4 + q4][g];
         unsigned lv = (unsigned)prq[8];  // tile rows with non-zero multipliers (packed in this order)
         const double* af = rq + 72 + 2 * lane + 64 * __popc(lv & ((1u << w) - 1u));
@@ -326,6 +348,7 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
           af += 64 * __popc(lv & ((1u << NW) - 1u));
           lv >>= NW;
         }
+        MW_ACC(9, tp);  // tile updates with record q
       }
       // ---- transpose into the pivot phase
 #pragma unroll
@@ -351,6 +374,7 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
         }
       }
       double* udiag = Ust + ((long long)(p * (p + 1) / 2 + p)) * 64;
+      MW_ACC(10, tp);  // transpose into rows
       mw_pivot_step<0, NT, NW>(pv, b, deadm, tst, sm, udiag, keep, c0, tid, lane, w);
       if (nst > 1) mw_pivot_step<1, NT, NW>(pv, b, deadm, tst, sm, udiag, keep, c0, tid, lane, w);
       if (nst > 2) mw_pivot_step<2, NT, NW>(pv, b, deadm, tst, sm, udiag, keep, c0, tid, lane, w);
@@ -359,6 +383,7 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
       if (nst > 5) mw_pivot_step<5, NT, NW>(pv, b, deadm, tst, sm, udiag, keep, c0, tid, lane, w);
       if (nst > 6) mw_pivot_step<6, NT, NW>(pv, b, deadm, tst, sm, udiag, keep, c0, tid, lane, w);
       if (nst > 7) mw_pivot_step<7, NT, NW>(pv, b, deadm, tst, sm, udiag, keep, c0, tid, lane, w);
+      MW_ACC(11, tp);  // the 8 pivot steps
       mw_sync<NTH>();  // Ub (multipliers of the pivot rows), pivrow are complete
 
       // ---- the record of this panel (not needed after the last one)
@@ -411,7 +436,9 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
           sm.recsz[p] = (72 + 64 * __popc(live_tr)) * 8;
         }
       }
+      MW_ACC(12, tp);  // publish (record, L_qq^-1)
       mw_fence_async();  // this thread's record / U stores before the bulk copies issued after the next barrier
+      MW_ACC(13, tp);  // proxy fence
     }
 
     // ---- back-substitution U x = y by panels in reverse; ys is overwritten with the solution.
@@ -467,8 +494,24 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
       const int k = tid + NTH * j;
       if (k < N) args.U[sys * (long long)args.ldu + k] = sm.ys[k];
     }
+    MW_ACC(14, tp);  // back-substitution + store
   }
+#ifdef RB_MW_PROFILE
+  if (tid == 0)
+    for (int k = 0; k < 16; ++k) atomicAdd(&rb_mw_prof[k], (unsigned long long)pacc[k]);
+#endif
 }
+
+#ifdef RB_MW_PROFILE
+extern "C" int rb_mw_profile_read(unsigned long long* out16, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out16, rb_mw_prof, sizeof(unsigned long long) * 16);
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[16] = {0};
+    e = cudaMemcpyToSymbol(rb_mw_prof, z, sizeof(z));
+  }
+  return (int)e;
+}
+#endif
 
 // Warps per system and systems in flight per SM (env RB_MW_NW = 1 | 2 | 4 selects the A/B variants in builds with
 // -DRB_AB_VARIANTS; the default is 2 warps).
