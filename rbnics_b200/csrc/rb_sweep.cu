@@ -932,7 +932,14 @@ extern "C" int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_c
       for (int r = 0; r < nfull; ++r) {
         const int w = std::min(RW, L - RW * r);
         const int base = new_tile(members[i], (RW * r) / 4, c);
-        for (size_t j = i; j < std::min(members.size(), i + GRP); ++j) put_cols(base, RW * (int)(j - i), members[j], RW * r, w);
+        // A warp (wn) multiplies two of the four 16-column ranges of a tile, and row block b only meets column blocks
+        // j <= b: with the blocks of a full group placed as [j0, j3 | j1, j2] both warps become busy one row block
+        // earlier than with [j0, j1 | j2, j3] (the CTA advances at the pace of its busiest warp)
+        static const bool est_perm = !(getenv("RB_EST_PERM") && atoi(getenv("RB_EST_PERM")) == 0);
+        const bool full_group = (GRP == 4 && i + GRP <= members.size() && est_perm);
+        static const int perm4[4] = {0, 2, 3, 1};
+        for (size_t j = i; j < std::min(members.size(), i + GRP); ++j)
+          put_cols(base, RW * (full_group ? perm4[j - i] : (int)(j - i)), members[j], RW * r, w);
       }
     }
     if (leftover)
