@@ -735,8 +735,13 @@ extern "C" int rb_ctx_create(int device, rb_ctx** out) {
     delete ctx;
     return RB_ERR_CUDA;
   }
-  for (int i = 0; i < 6; ++i) cudaEventCreate(&ctx->ev[i]);
-  if (cudaMalloc(&ctx->dResult, sizeof(MaxLoc)) != cudaSuccess) {
+  bool ok = true;
+  for (int i = 0; i < 6; ++i) ok = ok && cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->dResult, sizeof(MaxLoc)) == cudaSuccess;
+  if (!ok) {  // release what was created so far
+    for (int i = 0; i < 6; ++i)
+      if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RB_ERR_CUDA;
   }
@@ -813,7 +818,7 @@ extern "C" int rb_set_system(rb_ctx* ctx, int N, int Ql, int Qr, const double* A
     if (int rc = dev_realloc(ctx, &ctx->dAq, (size_t)ctx->QlP * ctx->EP)) return rc;
     if (int rc = dev_realloc(ctx, &ctx->dF, (size_t)std::max(Qr, 1) * NP)) return rc;
     if (int rc = dev_realloc(ctx, &ctx->dBcRows, (size_t)std::max(n_bc, 1))) return rc;
-    double* dA = nullptr;
+    double* dA = nullptr;  // (freed on every path below)
     RB_CUDA(cudaMalloc(&dA, (size_t)Ql * N * N * sizeof(double)));
     cudaError_t e = cudaMemcpyAsync(dA, A, (size_t)Ql * N * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
