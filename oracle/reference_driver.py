@@ -162,6 +162,72 @@ def elliptic_reduced_problem(A, F, Gff, Gaf, Gaa, compliant=False):
     return rp
 
 
+def _block_tensor(arr, sizes):
+    """Matrix / vector of the reference with COMPONENT-DICTIONARY sizes (Stokes: u, s, p) around a block-embedded array."""
+    from rbnics.backends.online import OnlineMatrix, OnlineVector
+    from rbnics.utils.io import OnlineSizeDict
+    arr = np.asarray(arr, dtype=np.float64)
+    if arr.ndim == 0:
+        return float(arr)
+
+    def N():
+        d = OnlineSizeDict()
+        for c, n in sizes:
+            d[c] = n
+        return d
+
+    t = OnlineMatrix(N(), N()) if arr.ndim == 2 else OnlineVector(N())
+    t.content[:] = arr
+    return t
+
+
+def stokes_reduced_problem(op, E, n):
+    """The reference's StokesRBReducedProblem (components u, s, p with n basis functions each) filled with
+    block-embedded reduced operators op[term] (Q x 3n x 3n / Q x 3n) and error-estimation storages E[(t1, t2)].
+    mu = (theta_a..., theta_b..., theta_bt..., theta_f..., theta_g..., beta)."""
+    from rbnics.backends.online import OnlineAffineExpansionStorage
+    from rbnics.problems.stokes import StokesRBReducedProblem
+    from rbnics.utils.io import OnlineSizeDict
+    terms = ["a", "b", "bt", "f", "g"]
+    Q = {t: int(np.asarray(op[t]).shape[0]) for t in terms}
+    Truth = make_truth_problem_class()
+    off, sl = 0, {}
+    for t in terms:
+        sl[t] = slice(off, off + Q[t])
+        off += Q[t]
+    tp = Truth(terms + ["bt_restricted"], {"a": 2, "b": 2, "bt": 2, "f": 1, "g": 1, "bt_restricted": 2},
+               dict(Q, bt_restricted=Q["bt"]), components=("u", "s", "p"),
+               theta_of_mu=lambda term, mu: tuple(mu[sl[term]]), beta_of_mu=lambda mu: mu[-1])
+    tp.set_mu_range([(0.0, 1.0)] * (off + 1))
+    rp = StokesRBReducedProblem(tp)
+    sizes = (("u", n), ("s", n), ("p", n))
+
+    def sd(v):
+        d = OnlineSizeDict()
+        for c, _ in sizes:
+            d[c] = v
+        return d
+
+    rp.N, rp.N_bc = sd(n), sd(0)
+    rp.dirichlet_bc = {c: False for c, _ in sizes}
+    rp.dirichlet_bc_are_homogeneous = {c: False for c, _ in sizes}
+    rp.Q = dict(Q)
+    for t in terms:
+        arr = np.asarray(op[t], dtype=np.float64)
+        st = OnlineAffineExpansionStorage(arr.shape[0])
+        for q in range(arr.shape[0]):
+            st[q] = _block_tensor(arr[q], sizes)
+        rp.operator[t] = st
+    for (t1, t2), arr in E.items():
+        arr = np.asarray(arr, dtype=np.float64)
+        st = OnlineAffineExpansionStorage(arr.shape[0], arr.shape[1])
+        for i in range(arr.shape[0]):
+            for j in range(arr.shape[1]):
+                st[i, j] = _block_tensor(arr[i, j], sizes)
+        rp.error_estimation_operator[t1, t2] = st
+    return rp
+
+
 def training_set(Theta):
     """The reference's ParameterSpaceSubset holding the rows of Theta as tuples of Python floats."""
     from rbnics.sampling import ParameterSpaceSubset

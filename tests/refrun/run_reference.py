@@ -4,6 +4,8 @@ backend of RBniCS is chosen at import time, so every backend gets its own interp
 
     python tests/refrun/run_reference.py names   <backend>           -> JSON: exported names, type modules, dispatch tables
     python tests/refrun/run_reference.py sweep   <backend> <N> <Qa> <Qf> <B> <seed> <compliant> <out.npz>
+    python tests/refrun/run_reference.py stokes  <backend> <case> <out.npz>   StokesRBReducedProblem (components u, s, p:
+                 component-dictionary slicing, 9 error-estimation term pairs) on the operators of reference_stokes_<case>.npz
     python tests/refrun/run_reference.py storage <backend> <directory>   -> writes storages with the reference's own save()
     python tests/refrun/run_reference.py greedy  <backend> <case> <plugin 0|1> <out.npz>
                  the reference's complete offline stage, ReducedBasis(problem).offline(), on a dense FEniCS-free truth
@@ -93,6 +95,36 @@ def main():
                  delta=np.array(col["delta"]), u=np.array(col["u"]), max=float(mx), argmax=int(am),
                  backend=online.OnlineMatrix.__module__)
         print(json.dumps({"max": float(mx), "argmax": int(am), "backend": online.OnlineMatrix.__module__}))
+        return
+
+    if mode == "stokes":
+        case, outfile = sys.argv[3], sys.argv[4]
+        g = np.load(os.path.join(ROOT, "tests", "golden", "reference_stokes_%s.npz" % case))
+        assert int(g["n_bc"]) == 0
+        pairs = [("f", "f"), ("g", "g"), ("a", "f"), ("bt", "f"), ("b", "g"), ("a", "a"), ("a", "bt"), ("bt", "bt"), ("b", "b")]
+        R.disable_reduced_solution_cache()
+        rp = R.stokes_reduced_problem({t: g["op_" + t] for t in ("a", "b", "bt", "f", "g")},
+                                      {(t1, t2): g["E_%s_%s" % (t1, t2)] for (t1, t2) in pairs}, int(g["n"]))
+        Theta = np.concatenate([g["theta_" + t] for t in ("a", "b", "bt", "f", "g")] + [g["beta"][:, None]], axis=1)
+        col = {}
+        ts = R.training_set(Theta)
+        mx, am = R.greedy_sweep(rp, ts, col)
+        out = {"max": float(mx), "argmax": int(am), "backend": online.OnlineMatrix.__module__}
+        if len(sys.argv) > 5 and sys.argv[5] == "plugin":
+            # the Stokes family of the _greedy override (integration/rbnics_b200_plugin/sweep.py) on the same reduced problem:
+            # ONE batched sweep instead of the per-parameter closure
+            import types
+            integ = os.path.join(ROOT, "integration")
+            if integ not in sys.path:
+                sys.path.append(integ)
+            from rbnics_b200_plugin.sweep import GreedySweep
+            gs = GreedySweep(types.SimpleNamespace(truth_problem=rp.truth_problem, training_set=ts))
+            v, i = gs.max(rp)
+            out["plugin_max"], out["plugin_argmax"] = float(v), int(i)
+            gs.close()
+        np.savez(outfile, u=np.array(col["u"]), delta=np.array(col["delta"]), max=float(mx), argmax=int(am),
+                 backend=online.OnlineMatrix.__module__)
+        print(json.dumps(out))
         return
 
     if mode == "storage":

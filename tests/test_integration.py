@@ -113,3 +113,31 @@ def test_reference_offline_loop_with_the_b200_greedy_override(tmp_path, case, ba
     assert np.all(np.abs(est - ref) <= 1e-6 * ref + 1e-9 * ref[0])
     h = np.load(tmp_path / "plugin.npz")
     assert np.max(np.abs(h["A"] - g["A"])) <= 1e-10 * np.max(np.abs(g["A"]))
+
+
+@needs_reference
+def test_real_stokes_reduced_problem_reproduces_the_executed_source_fixture(tmp_path):
+    """The reference's StokesRBReducedProblem (components u, s, p: component-dictionary slicing, block solve, 9 term pairs)
+    run from the real package gives the fixture that round 1 produced by executing the reference's source: bit-identical."""
+    g = np.load(os.path.join(HERE, "golden", "reference_stokes_n5.npz"))
+    out = tmp_path / "stokes.npz"
+    d = _run("stokes", "numpy", "n5", out)
+    h = np.load(out)
+    assert np.array_equal(h["u"], g["U"]) and np.array_equal(h["delta"], g["delta"])
+    assert d["argmax"] == int(np.argmax(g["delta"]))
+
+
+@pytest.mark.gpu
+@needs_reference
+def test_stokes_reduced_problem_on_the_b200_backend_and_plugin_sweep(tmp_path):
+    """Same class with `online backend = b200`: the reference's own block slicing feeds rb_affine_combine / rb_solve_dense /
+    rb_bilinear; and the Stokes family of the `_greedy` override returns the same (max, argmax) from ONE batched sweep."""
+    g = np.load(os.path.join(HERE, "golden", "reference_stokes_n5.npz"))
+    out = tmp_path / "stokes_b200.npz"
+    d = _run("stokes", "b200", "n5", out, "plugin")
+    assert d["backend"] == "rbnics.backends.online.b200.matrix"
+    h = np.load(out)
+    assert np.max(np.abs(h["u"] - g["U"])) <= 1e-10 * np.max(np.abs(g["U"]))
+    assert np.max(np.abs(h["delta"] - g["delta"]) / g["delta"]) <= 1e-10
+    assert d["argmax"] == int(np.argmax(g["delta"])) == d["plugin_argmax"]
+    assert abs(d["plugin_max"] - float(g["delta"].max())) <= 1e-10 * float(g["delta"].max())
