@@ -228,6 +228,58 @@ def stokes_reduced_problem(op, E, n):
     return rp
 
 
+def parabolic_reduced_problem(M, A, F, E, dt, K):
+    """The reference's ParabolicCoerciveRBReducedProblem (implicit Euler through its numpy TimeStepping, per-step error
+    estimator with the m-terms) with homogeneous initial condition, final time K dt.
+    mu = (theta_m..., theta_a..., theta_f..., beta)."""
+    from rbnics.backends.online import OnlineAffineExpansionStorage
+    from rbnics.problems.parabolic import ParabolicCoerciveRBReducedProblem
+    M, A, F = np.asarray(M), np.asarray(A), np.asarray(F)
+    Qm, Qa, Qf, N = M.shape[0], A.shape[0], F.shape[0], A.shape[1]
+    sl = {"m": slice(0, Qm), "a": slice(Qm, Qm + Qa), "f": slice(Qm + Qa, Qm + Qa + Qf)}
+    Truth = make_truth_problem_class()
+    tp = Truth(["m", "a", "f"], {"m": 2, "a": 2, "f": 1}, {"m": Qm, "a": Qa, "f": Qf},
+               theta_of_mu=lambda term, mu: tuple(mu[sl[term]]), beta_of_mu=lambda mu: mu[-1])
+    tp.t, tp.t0, tp.dt, tp.T = 0., 0., float(dt), K * float(dt)
+    tp._time_stepping_parameters = {}
+    tp.set_time = lambda t: setattr(tp, "t", t)
+    tp.set_initial_time = lambda t0: setattr(tp, "t0", t0)
+    tp.set_time_step_size = lambda d: setattr(tp, "dt", d)
+    tp.set_final_time = lambda T: setattr(tp, "T", T)
+    tp.set_mu_range([(0.0, 1.0)] * (Qm + Qa + Qf + 1))
+    rp = ParabolicCoerciveRBReducedProblem(tp)
+    rp.N, rp.N_bc = N, 0
+    rp.dirichlet_bc, rp.dirichlet_bc_are_homogeneous = False, False
+    rp.initial_condition, rp.initial_condition_is_homogeneous = False, True
+    rp.Q = {"m": Qm, "a": Qa, "f": Qf}
+    for t, arr in (("m", M), ("a", A), ("f", F)):
+        rp.operator[t] = _storage_of(OnlineAffineExpansionStorage, arr, 1)
+    for (t1, t2), arr in E.items():
+        rp.error_estimation_operator[t1, t2] = _storage_of(OnlineAffineExpansionStorage, np.asarray(arr), 2)
+    rp._init_time_series("online")
+    return rp
+
+
+def pod_greedy_sweep(reduced_problem, ts, collect=None):
+    """`training_set.max(solve_and_estimate_error)` with the closure of the POD-Greedy `_greedy`
+    (rbnics/reduction_methods/base/time_dependent_rb_reduction.py:280-288): time quadrature of the squared error bound."""
+    from math import sqrt
+    from rbnics.backends import TimeQuadrature
+
+    def solve_and_estimate_error(mu):
+        reduced_problem.set_mu(mu)
+        reduced_problem.solve()
+        error_estimator_over_time = reduced_problem.estimate_error()
+        error_estimator_squared_over_time = [v**2 for v in error_estimator_over_time]
+        time_quadrature = TimeQuadrature((0., reduced_problem.truth_problem.T), error_estimator_squared_over_time)
+        error_estimator = sqrt(time_quadrature.integrate())
+        if collect is not None:
+            collect.setdefault("delta", []).append(float(error_estimator))
+        return error_estimator
+
+    return ts.max(solve_and_estimate_error)
+
+
 def training_set(Theta):
     """The reference's ParameterSpaceSubset holding the rows of Theta as tuples of Python floats."""
     from rbnics.sampling import ParameterSpaceSubset

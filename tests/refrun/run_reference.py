@@ -6,6 +6,8 @@ backend of RBniCS is chosen at import time, so every backend gets its own interp
     python tests/refrun/run_reference.py sweep   <backend> <N> <Qa> <Qf> <B> <seed> <compliant> <out.npz>
     python tests/refrun/run_reference.py stokes  <backend> <case> <out.npz>   StokesRBReducedProblem (components u, s, p:
                  component-dictionary slicing, 9 error-estimation term pairs) on the operators of reference_stokes_<case>.npz
+    python tests/refrun/run_reference.py parabolic <backend> <out.npz> [plugin]   ParabolicCoerciveRBReducedProblem + the
+                 POD-Greedy closure on the operators of reference_parabolic.npz
     python tests/refrun/run_reference.py storage <backend> <directory>   -> writes storages with the reference's own save()
     python tests/refrun/run_reference.py greedy  <backend> <case> <plugin 0|1> <out.npz>
                  the reference's complete offline stage, ReducedBasis(problem).offline(), on a dense FEniCS-free truth
@@ -124,6 +126,32 @@ def main():
             gs.close()
         np.savez(outfile, u=np.array(col["u"]), delta=np.array(col["delta"]), max=float(mx), argmax=int(am),
                  backend=online.OnlineMatrix.__module__)
+        print(json.dumps(out))
+        return
+
+    if mode == "parabolic":
+        outfile = sys.argv[3]
+        g = np.load(os.path.join(ROOT, "tests", "golden", "reference_parabolic.npz"))
+        pairs = [("f", "f"), ("a", "f"), ("a", "a"), ("m", "f"), ("m", "a"), ("m", "m")]
+        # (the RAM cache stays on: the reference's time-dependent monitor re-reads what it has just stored in it)
+        rp = R.parabolic_reduced_problem(g["M"], g["A"], g["F"], {(a, b): g["E_%s_%s" % (a, b)] for (a, b) in pairs},
+                                         float(g["dt"]), int(g["K"]))
+        Theta = np.concatenate([g["Theta_m"], g["Theta_a"], g["Theta_f"], g["beta"][:, None]], axis=1)
+        ts = R.training_set(Theta)
+        col = {}
+        mx, am = R.pod_greedy_sweep(rp, ts, col)
+        out = {"max": float(mx), "argmax": int(am), "backend": online.OnlineMatrix.__module__}
+        if len(sys.argv) > 4 and sys.argv[4] == "plugin":
+            import types
+            integ = os.path.join(ROOT, "integration")
+            if integ not in sys.path:
+                sys.path.append(integ)
+            from rbnics_b200_plugin.sweep import GreedySweep
+            gs = GreedySweep(types.SimpleNamespace(truth_problem=rp.truth_problem, training_set=ts))
+            v, i = gs.max(rp)
+            out["plugin_max"], out["plugin_argmax"] = float(v), int(i)
+            gs.close()
+        np.savez(outfile, delta=np.array(col["delta"]), max=float(mx), argmax=int(am))
         print(json.dumps(out))
         return
 

@@ -141,3 +141,26 @@ def test_stokes_reduced_problem_on_the_b200_backend_and_plugin_sweep(tmp_path):
     assert np.max(np.abs(h["delta"] - g["delta"]) / g["delta"]) <= 1e-10
     assert d["argmax"] == int(np.argmax(g["delta"])) == d["plugin_argmax"]
     assert abs(d["plugin_max"] - float(g["delta"].max())) <= 1e-10 * float(g["delta"].max())
+
+
+@needs_reference
+def test_real_parabolic_reduced_problem_reproduces_the_executed_source_fixture(tmp_path):
+    """ParabolicCoerciveRBReducedProblem of the real package (its numpy TimeStepping, per-step estimator with the m-terms,
+    TimeQuadrature) against the round-1 fixture produced by executing the reference's source."""
+    g = np.load(os.path.join(HERE, "golden", "reference_parabolic.npz"))
+    out = tmp_path / "par.npz"
+    d = _run("parabolic", "numpy", out)
+    h = np.load(out)
+    assert np.max(np.abs(h["delta"] - g["delta"]) / g["delta"]) <= 1e-14
+    assert d["argmax"] == int(np.argmax(g["delta"]))
+
+
+@pytest.mark.gpu
+@needs_reference
+def test_parabolic_family_of_the_plugin_sweep(tmp_path):
+    """The POD-Greedy family of the `_greedy` override on the reference's own parabolic reduced problem: one batched sweep
+    (K implicit-Euler steps, estimator per step, Simpson weights) == training_set.max of the reference's closure."""
+    g = np.load(os.path.join(HERE, "golden", "reference_parabolic.npz"))
+    d = _run("parabolic", "numpy", tmp_path / "par.npz", "plugin")
+    assert d["plugin_argmax"] == d["argmax"] == int(np.argmax(g["delta"]))
+    assert abs(d["plugin_max"] - d["max"]) <= 1e-10 * d["max"]
