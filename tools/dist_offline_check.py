@@ -26,6 +26,7 @@ from rbnics_b200.sweep import DistributedMaxLoc  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nh", type=int, default=250_000)
+    ap.add_argument("--bench", action="store_true", help="also time the partitioned products at N_h = 10^6")
     args = ap.parse_args()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = DistributedMaxLoc(local_rank)
@@ -78,6 +79,54 @@ def main():
            max_rel_diff_vs_single_gpu=worst, max_abs_deviation_from_orthonormal=orth,
            wall_ms_per_step_partitioned=1e3 * t_d / 24, wall_ms_per_step_single=1e3 * t_1 / 24)
     assert worst <= 1e-10 and orth <= 1e-10, (worst, orth)
+
+    # ---- timing at N_h = 10^6 (kernel ms from CUDA events on the engine's stream, max over ranks; the all-reduce is outside
+    #      the events, its wall time is reported separately)
+    if args.bench:
+        import ctypes as C
+
+        def kernel_ms():
+            ms = (C.c_float * 5)()
+            n = C.c_int()
+            eng._lib.rb_last_timings(eng._h, ms, C.byref(n))
+            return float(ms[4])
+
+        side2 = 1000
+        Nb = side2 * side2
+        T2 = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(side2, side2))
+        I2 = sp.identity(side2)
+        Xb = (sp.kron(T2, I2) + sp.kron(I2, T2) + 0.5 * sp.identity(Nb)).tocsr()
+        wsb = offline.OfflineWorkspace(eng, dist=dist)
+        wsb.set_operator("X", Xb)
+        for Ns in (61, 400):
+            Sb = np.ascontiguousarray(np.random.default_rng(Ns).standard_normal((Nb, Ns)))
+            wsb.new_block("Sb", Nb, Ns)
+            wsb.append("Sb", Sb)
+            best_k, best_w = None, None
+            for _ in range(3):
+                dist.barrier()
+                t0 = time.perf_counter()
+                wsb.gram("Sb", "X")
+                w = dist.max_float(time.perf_counter() - t0)
+                k = dist.max_float(kernel_ms())
+                best_k = k if best_k is None else min(best_k, k)
+                best_w = w if best_w is None else min(best_w, w)
+            report("bench: row-partitioned resident Gram S^T X S", Nh_bench=Nb, Ns=Ns, kernel_ms_max_over_ranks=best_k,
+                   wall_ms_with_allreduce_and_d2h=1e3 * best_w)
+            del Sb
+        wsb.new_block("Zb", Nb, 101)
+        wsb.append("Zb", np.ascontiguousarray(np.random.default_rng(1).standard_normal((Nb, 100))))
+        zb = np.random.default_rng(2).standard_normal(Nb)
+        wsb.gram_schmidt("Zb", "X", zb, append=False)
+        best = None
+        for _ in range(3):
+            dist.barrier()
+            t0 = time.perf_counter()
+            wsb.gram_schmidt("Zb", "X", zb, append=False)
+            w = dist.max_float(time.perf_counter() - t0)
+            best = w if best is None else min(best, w)
+        report("bench: row-partitioned Gram-Schmidt step, N = 100 (100 all-reduces of 4.7 KB)", Nh_bench=Nb,
+               wall_ms=1e3 * best)
 
     # ---- a whole greedy run: sharded sweep + partitioned resident offline stage == single-GPU run
     from truth_problems import ThermalBlock
