@@ -86,6 +86,11 @@ struct rb_ctx {
   int* dBlkSrc = nullptr;           // [nblk]
   int* dColScale = nullptr;         // [n_ctile*EST_BN]
   int* dColSrc = nullptr;           // [n_ctile*EST_BN]
+  // small quadratic forms (Kz <= 64) also keep the dense G and the z map: fused parabolic sweep (rb_parabolic.cu)
+  double* dGdense = nullptr;        // [Kz][Kz] or null
+  int* dZsrc = nullptr;             // [Kz] index into V
+  int* dZscale = nullptr;           // [Kz] theta column or -1
+  double* dWeights = nullptr; int weights_cap = 0;  // time-quadrature weights of the parabolic sweep
 
   // training set
   bool have_train = false;

@@ -42,7 +42,8 @@ template <int NT, int NW>
 struct MwSmem {
   using C = MwCfg<NT, NW>;
   double ring[2][C::SLOT];
-  double P[C::NP8][10];                 // the panel, row-major (pitch 10: conflict-free LDS.128 of one row per lane):
+  double P[C::NP8 * 8];                 // the panel, row-major, 16-byte chunks XOR-swizzled with bits 1-2 of the row
+                                        // (mw_pidx: conflict-free LDS.128 of one row per lane without padding):
                                         // gather of pivot rows, transpose into the pivot phase
   double Ub[8][8];                      // U_qp of the record being applied / the pivot rows of the panel being factored
   double slot[2][NW][10];               // pivot candidates of the warps: row entries t+1..7, 1/pivot, rhs entry
@@ -55,6 +56,11 @@ struct MwSmem {
   long long nextsys;                    // the system this CTA works on after the current one (dynamic schedule)
   unsigned livew[2][4];                 // nibble n: tile rows 4n..4n+3 that still held a live row before this panel
 };
+
+// index of entry (row, col) of the swizzled panel buffer MwSmem::P
+__device__ __forceinline__ int mw_pidx(int row, int col) {
+  return row * 8 + ((((col >> 1) ^ (row >> 1)) & 3) << 1) + (col & 1);
+}
 
 template <int NTH>
 __device__ __forceinline__ void mw_sync() {
@@ -114,6 +120,7 @@ __device__ __forceinline__ void mw_pivot_step(double (&pv)[MwCfg<NT, NW>::RPL][8
   // the lane's own candidate among its RPL rows (strict compare: the lower row wins ties)
   unsigned long long key = 0ull;
   int jb = 0;
+  double cand = 1.0;
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
     const unsigned long long kj =
@@ -121,8 +128,12 @@ __device__ __forceinline__ void mw_pivot_step(double (&pv)[MwCfg<NT, NW>::RPL][8
     if (kj > key) {
       key = kj;
       jb = j;
+      cand = pv[j][T];
     }
   }
+  // every lane inverts its own candidate while the two reductions are in flight (same issue slots as one lane doing it
+  // afterwards, but off the dependent chain of the step)
+  const double cand_rinv = mw_rcp(cand);
   // arg-max of the 64-bit key over the warp, lowest row on ties (idamax): REDUX.MAX on the high word, then on
   // {low word without its 8 lowest bits, 128 - row}; candidates that differ only below 2^-44 relative count as equal.
   const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
@@ -137,7 +148,7 @@ __device__ __forceinline__ void mw_pivot_step(double (&pv)[MwCfg<NT, NW>::RPL][8
       if (j == jb) {
 #pragma unroll
         for (int c = T + 1; c < 8; ++c) s[c - 1] = pv[j][c];
-        s[8] = mw_rcp(pv[j][T]);
+        s[8] = cand_rinv;
         s[9] = b[j];
       }
     }
@@ -314,7 +325,7 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
 #pragma unroll
           for (int i = 0; i < TPW; ++i)
             if ((dm >> (NW * i)) & 1u)  // uniform
-              *reinterpret_cast<double2*>(&sm.P[8 * (w + NW * i) + g][2 * q4]) = make_double2(c[i][0], c[i][1]);
+              *reinterpret_cast<double2*>(&sm.P[mw_pidx(8 * (w + NW * i) + g, 2 * q4)]) = make_double2(c[i][0], c[i][1]);
         }
         MW_ACC(5, tp);  // dump
         mw_sync<NTH>();  // (A) the dump is visible; everybody is done with record q - 1 (and, for q = 0, the panel of A)
@@ -323,7 +334,7 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
         if (w == q % NW) {
           // U_qp = L_qq^-1 X on the tensor pipe (the inverse of the 8x8 unit-lower block travels in the record)
           const double2 la = *reinterpret_cast<const double2*>(rq + 2 * lane);
-          const double xb0 = sm.P[prq[q4]][g], xb1 = sm.P[prq[4 + q4]][g];
+          const double xb0 = sm.P[mw_pidx(prq[q4], g)], xb1 = sm.P[mw_pidx(prq[4 + q4], g)];
           double u0 = 0.0, u1 = 0.0;
           dmma884(u0, u1, la.x, xb0);
           dmma884(u0, u1, la.y, xb1);
@@ -354,7 +365,7 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
 #pragma unroll
       for (int i = 0; i < TPW; ++i) {
         const int tr = w + NW * i;
-        if (tr < NT) *reinterpret_cast<double2*>(&sm.P[8 * tr + g][2 * q4]) = make_double2(c[i][0], c[i][1]);
+        if (tr < NT) *reinterpret_cast<double2*>(&sm.P[mw_pidx(8 * tr + g, 2 * q4)]) = make_double2(c[i][0], c[i][1]);
       }
       mw_sync<NTH>();  // everybody is done with the last record: both ring slots are free
       // the next panel of the assembled matrix streams into ring slot 1 while this one is factored
@@ -368,7 +379,7 @@ __global__ void __launch_bounds__(32 * NW, OCC) rb_lu_mw_kernel(LuArgs args, dou
 #pragma unroll
         for (int cc = 0; cc < 8; cc += 2) {
           double2 v = make_double2(0.0, 0.0);
-          if (!((deadm >> j) & 1u)) v = *reinterpret_cast<const double2*>(&sm.P[tid + NTH * j][cc]);
+          if (!((deadm >> j) & 1u)) v = *reinterpret_cast<const double2*>(&sm.P[mw_pidx(tid + NTH * j, cc)]);
           pv[j][cc] = v.x;
           pv[j][cc + 1] = v.y;
         }

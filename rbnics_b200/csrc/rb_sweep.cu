@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "rb_common.cuh"
+#include "rb_parabolic.cuh"
 
 // =====================================================================================================================
 // Packing kernels (run once per greedy iteration, when the reduced operators change)
@@ -758,7 +759,7 @@ extern "C" void rb_ctx_destroy(rb_ctx* ctx) {
                   ctx->dTileCls,  ctx->dBlkCls,  ctx->dTileCb,
                   ctx->dTheta,    ctx->dThetaBC, ctx->dBeta,    ctx->dAb,      ctx->dU,       ctx->dPart,
                   ctx->dDelta,    ctx->dEps2,    ctx->dBlkVal,  ctx->dBlkIdx,  ctx->dResult,  ctx->dSplitBegin,
-                  ctx->dLuScratch};
+                  ctx->dLuScratch, ctx->dGdense,  ctx->dZsrc,    ctx->dZscale,  ctx->dWeights};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int t = 0; t < RB_OFF_SLOTS; ++t) {
@@ -1084,7 +1085,29 @@ extern "C" int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_c
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // tab is a local vector
-  cudaFree(dG);
+  // the fused parabolic sweep multiplies with the dense G itself
+  if (ctx->dGdense) cudaFree(ctx->dGdense);
+  if (ctx->dZsrc) cudaFree(ctx->dZsrc);
+  if (ctx->dZscale) cudaFree(ctx->dZscale);
+  ctx->dGdense = nullptr;
+  ctx->dZsrc = ctx->dZscale = nullptr;
+  if (e == cudaSuccess && Kz <= 64) {
+    std::vector<int> zsrc(Kz), zscale(Kz);
+    for (int b = 0; b < nblk; ++b)
+      for (int t = 0; t < blk_len[b]; ++t) {
+        zsrc[ubegin[b] + t] = blk_src_off[b] + t;
+        zscale[ubegin[b] + t] = scale_norm[b];
+      }
+    e = cudaMalloc(&ctx->dZsrc, Kz * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->dZscale, Kz * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->dZsrc, zsrc.data(), Kz * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->dZscale, zscale.data(), Kz * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      ctx->dGdense = dG;
+      dG = nullptr;
+    }
+  }
+  if (dG) cudaFree(dG);
   if (dTab) cudaFree(dTab);
   if (e != cudaSuccess) RB_FAIL(RB_ERR_CUDA, std::string("rb_set_estimator: ") + cudaGetErrorString(e));
   RB_CUDA(cudaFuncSetAttribute(rb_estimator_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1276,8 +1299,8 @@ static int launch_assembly(rb_ctx* ctx, long long c0, long long n, size_t asm_sm
     const unsigned long long waves = (total + slots - 1) / slots;
     double eff = (double)total / (double)(waves * slots);
     if (total < slots) eff *= 0.5;  // less than one wave: not enough CTAs to hide the tile loads
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
+    if (eff > best_eff - 1e-9) {  // ties: the finer split (shorter CTAs, smoother tail)
+      best_eff = std::max(eff, best_eff);
       esplit = e;
     }
   }
@@ -1503,11 +1526,18 @@ extern "C" int rb_sweep_parabolic_ic(rb_ctx* ctx, int Qm, int K, double dt, cons
   if (ctx->est_vecN != 2 * N) RB_FAIL(RB_ERR_STATE, "rb_sweep_parabolic: set the estimator with solution_len = 2 N");
   const long long B = ctx->B;
   cudaStream_t st = ctx->stream;
-  long long chunk = 0;
+  // small systems (NP <= 32, Kz <= 64: tutorial 06) run the whole time loop of a parameter in one kernel; everything
+  // else goes through the per-step launches below (RB_PARABOLIC_FUSED=0 forces them: tests compare the two)
+  const int VP = roundup(ctx->LV + 1, 2);
+  const bool allow_fused = !(getenv("RB_PARABOLIC_FUSED") && atoi(getenv("RB_PARABOLIC_FUSED")) == 0);
+  const bool fused = allow_fused && ctx->dGdense && rb_parabolic_fused_supported(ctx->NP, ctx->Kz, Qm, VP);
+  long long chunk = B;
   size_t asm_smem = 0;
-  if (int rc = prepare_assembly(ctx, B, &chunk, &asm_smem)) return rc;
   int nsplit = 1;
-  if (int rc = prepare_estimator_splits(ctx, chunk, &nsplit)) return rc;
+  if (!fused) {
+    if (int rc = prepare_assembly(ctx, B, &chunk, &asm_smem)) return rc;
+    if (int rc = prepare_estimator_splits(ctx, chunk, &nsplit)) return rc;
+  }
   if (B > ctx->delta_cap) {
     if (int rc = dev_realloc(ctx, &ctx->dDelta, (size_t)B)) return rc;
     if (int rc = dev_realloc(ctx, &ctx->dEps2, (size_t)B)) return rc;
@@ -1535,9 +1565,11 @@ extern "C" int rb_sweep_parabolic_ic(rb_ctx* ctx, int Qm, int K, double dt, cons
       return RB_ERR_CUDA;                                                                            \
     }                                                                                                \
   } while (0)
-  RB_PB(cudaMalloc(&dUV, (size_t)chunk * 2 * N * sizeof(double)));
-  RB_PB(cudaMalloc(&dRhs, (size_t)chunk * N * sizeof(double)));
-  RB_PB(cudaMalloc(&dUnew, (size_t)chunk * N * sizeof(double)));
+  if (!fused) {
+    RB_PB(cudaMalloc(&dUV, (size_t)chunk * 2 * N * sizeof(double)));
+    RB_PB(cudaMalloc(&dRhs, (size_t)chunk * N * sizeof(double)));
+    RB_PB(cudaMalloc(&dUnew, (size_t)chunk * N * sizeof(double)));
+  }
   if (eps2_out) RB_PB(cudaMalloc(&dHistE, (size_t)B * (K + 1) * sizeof(double)));
   if (u_out) RB_PB(cudaMalloc(&dHistU, (size_t)B * (K + 1) * N * sizeof(double)));
   if (dHistE) RB_PB(cudaMemsetAsync(dHistE, 0, (size_t)B * (K + 1) * sizeof(double), st));
@@ -1551,8 +1583,56 @@ extern "C" int rb_sweep_parabolic_ic(rb_ctx* ctx, int Qm, int K, double dt, cons
     RB_PB(cudaMemcpyAsync(dE0, init_err2, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
   }
   int launches = 0;
+  if (fused) {
+    if (K + 1 > ctx->weights_cap) {
+      if (ctx->dWeights) cudaFree(ctx->dWeights);
+      ctx->dWeights = nullptr;
+      ctx->weights_cap = 0;
+      RB_PB(cudaMalloc(&ctx->dWeights, (size_t)(K + 1) * sizeof(double)));
+      ctx->weights_cap = K + 1;
+    }
+    RB_PB(cudaMemcpyAsync(ctx->dWeights, weights, (size_t)(K + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
   RB_PB(cudaEventRecord(ctx->ev[0], st));
-  for (long long c0 = 0; c0 < B; c0 += chunk) {
+  if (fused) {
+    PbArgs pa;
+    pa.theta = ctx->dTheta;
+    pa.thetaBC = ctx->n_bc ? ctx->dThetaBC : nullptr;
+    pa.beta = ctx->dBeta;
+    pa.Aq = ctx->dAq;
+    pa.F = ctx->dF;
+    pa.bc_rows = ctx->dBcRows;
+    pa.G = ctx->dGdense;
+    pa.zsrc = ctx->dZsrc;
+    pa.zscale = ctx->dZscale;
+    pa.weights = ctx->dWeights;
+    pa.U0 = dU0;
+    pa.E0 = dE0;
+    pa.acc_out = ctx->dEps2;
+    pa.eps2_hist = dHistE;
+    pa.u_hist = dHistU;
+    pa.n = B;
+    pa.N = N;
+    pa.EP = ctx->EP;
+    pa.QT = ctx->QT;
+    pa.Ql = ctx->Ql;
+    pa.Qr = ctx->Qr;
+    pa.Qm = Qm;
+    pa.n_bc = ctx->n_bc;
+    pa.K = K;
+    pa.Kz = ctx->Kz;
+    pa.v_off = ctx->v_off;
+    pa.v_len = ctx->v_len;
+    pa.VP = VP;
+    pa.inv_dt = 1.0 / dt;
+    if (int e = rb_parabolic_fused_launch(pa, ctx->NP, st)) {
+      free_all();
+      ctx->err = std::string("rb_parabolic_fused_kernel: ") + cudaGetErrorString((cudaError_t)e);
+      return RB_ERR_CUDA;
+    }
+    ++launches;
+  }
+  for (long long c0 = 0; c0 < B && !fused; c0 += chunk) {
     const long long n = std::min(chunk, B - c0);
     if (int rc = launch_assembly(ctx, c0, n, asm_smem)) {
       free_all();
