@@ -54,7 +54,7 @@ def main():
     beta = Ta.min(axis=1)
     eng = SweepEngine(0)
     sw = ParabolicSweep(eng, M, A, F, E, dt=dt, K=K)
-    for _ in range(2):
+    for _ in range(4):
         t0 = time.perf_counter()
         r = sw.sweep(Tm, Ta, Tf, beta, want_delta=True)
         wall = time.perf_counter() - t0
@@ -89,8 +89,11 @@ def main():
                       "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64, "unit": "TFLOP/s",
                                    "frac": achieved / fp64, "algorithmic_flops_per_param": flops,
                                    "algorithmic_bytes_per_param": bytes_,
-                                   "note": "small systems (N = 20): the K x 5 launches per chunk work on matrices that "
-                                           "live in L2; the bound that matters is launch / latency, not the FP64 pipe"},
+                                   "note": "one kernel per sweep (rb_parabolic.cu): factors, rhs operator and z rows stay in "
+                                           "shared memory for all K steps; HBM traffic is the theta rows only.  The 2N "
+                                           "dependent shuffle + FMA links of the two triangular solves of every step "
+                                           "run on the FP64 pipe, only the residual norm (z^T G z) on DMMA, so the DMMA "
+                                           "peak is an upper bound the solve part cannot reach"},
                       "cpu_baseline": {"value": ns / cpu * cores, "unit": "params/s", "cores": cores, "kind": "port",
                                        "sample": f"{ns} parameters on one core ({cpu:.1f} s), loop-faithful oracle "
                                                  "(oracle/rb_oracle.py parabolic_sweep_loop), scaled by the core count "

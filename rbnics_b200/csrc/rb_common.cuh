@@ -87,7 +87,7 @@ struct rb_ctx {
   int* dColScale = nullptr;         // [n_ctile*EST_BN]
   int* dColSrc = nullptr;           // [n_ctile*EST_BN]
   // small quadratic forms (Kz <= 64) also keep the dense G and the z map: fused parabolic sweep (rb_parabolic.cu)
-  double* dGdense = nullptr;        // [Kz][Kz] or null
+  double* dGdense = nullptr;        // G as DMMA B fragments, zero padded to 64 x 64 (rb_parabolic_pack_g), or null
   int* dZsrc = nullptr;             // [Kz] index into V
   int* dZscale = nullptr;           // [Kz] theta column or -1
   double* dWeights = nullptr; int weights_cap = 0;  // time-quadrature weights of the parabolic sweep
@@ -98,6 +98,12 @@ struct rb_ctx {
   int QT = 0, n_bc_train = 0;
   int64_t idx_off = 0, idx_stride = 1;
   double *dTheta = nullptr, *dThetaBC = nullptr, *dBeta = nullptr;
+  // pipelined upload of rb_sweep (host buffers in): Theta rows arrive in pieces on copy_stream, the chunk loop of the
+  // sweep waits for the piece it is about to read; up_pieces == 0: everything is resident
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> up_ev;
+  long long up_piece = 0;
+  int up_pieces = 0;
 
   // work buffers
   double* dAb = nullptr; int64_t ab_cap = 0;       // assembled matrices of one chunk [chunk][EP]

@@ -21,18 +21,32 @@ namespace {
 constexpr int PB_WARPS = 8;
 constexpr int PB_ZP = 68;  // pitch of a z row (64 + 4: conflict-free A-fragment loads)
 
+// shared-memory carve-up (doubles)
+struct PbLayout {
+  int ms, rs, zs, vs, es, total;
+  __host__ __device__ PbLayout(int NP, int Qm, int VP) {
+    ms = 0;                                  // [Qm][NP (col j)][NP (row i)]   M_q / dt
+    rs = ms + Qm * NP * NP;                  // [8][NP (col j)][NP (row i)]    L\U of the 8 parameters, rows in place
+    zs = rs + PB_WARPS * NP * NP;            // [2][8][PB_ZP]                  z rows (double buffered over the steps)
+    vs = zs + 2 * PB_WARPS * PB_ZP;          // [8][VP]                        [u (NP) | udot (NP) | theta slice | 1]
+    es = vs + PB_WARPS * VP;                 // [2][8 (tile)][8 (parameter)]   partial residual norms
+    total = es + 2 * 8 * 8;
+  }
+};
+
 template <int NP>
-__global__ void __launch_bounds__(32 * PB_WARPS, (NP <= 20 ? 2 : 1)) rb_parabolic_fused_kernel(PbArgs a) {
+__global__ void __launch_bounds__(32 * PB_WARPS, 3) rb_parabolic_fused_kernel(PbArgs a) {
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) double pbs[];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int g = lane >> 2, q4 = lane & 3;
   const int N = a.N;
-  const int VP = a.VP;  // pitch of a V row: [u (N) | udot (N) | theta slice | 1 | 0 ...]
-  double* Ms = pbs;                                      // [Qm][NP (col j)][NP (row i)]
-  double* Zs = Ms + a.Qm * NP * NP;                      // [2][8][PB_ZP]
-  double* Vs = Zs + 2 * PB_WARPS * PB_ZP;                // [8][VP]
-  double* Es = Vs + PB_WARPS * VP;                       // [2][8 (tile)][8 (parameter)]
+  const PbLayout lay(NP, a.Qm, a.VP);
+  double* Ms = pbs + lay.ms;
+  double* R = pbs + lay.rs + w * NP * NP;  // entry (row i, col j) at j * NP + i
+  double* Zs = pbs + lay.zs;
+  double* V = pbs + lay.vs + w * a.VP;
+  double* Es = pbs + lay.es;
 
   for (int t = tid; t < a.Qm * NP * NP; t += 32 * PB_WARPS) {
     const int q = t / (NP * NP), r = t % (NP * NP);
@@ -40,89 +54,72 @@ __global__ void __launch_bounds__(32 * PB_WARPS, (NP <= 20 ? 2 : 1)) rb_paraboli
   }
   for (int t = tid; t < 2 * PB_WARPS * PB_ZP; t += 32 * PB_WARPS) Zs[t] = 0.0;
 
-  // B fragments of column tile w of G: entry (k = 4 ks + q4, n = 8 w + g), zero outside Kz
-  double Bf[16];
-#pragma unroll
-  for (int ks = 0; ks < 16; ++ks) {
-    const int k = 4 * ks + q4, n = 8 * w + g;
-    Bf[ks] = (k < a.Kz && n < a.Kz) ? __ldg(a.G + (long long)k * a.Kz + n) : 0.0;
-  }
-
   const long long p = (long long)blockIdx.x * PB_WARPS + w;
   const bool live = p < a.n;
   const long long pc = live ? p : a.n - 1;  // idle warps of the last CTA shadow a valid parameter (they share barriers)
   const double* th = a.theta + pc * a.QT;
+  const bool inrow = lane < NP;
 
   // ---- row `lane` of M/dt + A(mu), f(mu); lifting and padding rows are unit rows
-  double row[NP];
   double f = 0.0;
   bool isbc = false;
   {
-    const bool in = lane < N;
-#pragma unroll
-    for (int j = 0; j < NP; ++j) row[j] = 0.0;
-    if (in) {
-      for (int q = 0; q < a.Ql; ++q) {
-        const double tq = __ldg(th + q);
-        const double* Aq = a.Aq + (long long)q * a.EP + lane;
-#pragma unroll
-        for (int j = 0; j < NP; ++j) row[j] = fma(tq, __ldg(Aq + j * NP), row[j]);
-      }
-      for (int q = 0; q < a.Qr; ++q) f = fma(__ldg(th + a.Ql + q), __ldg(a.F + q * NP + lane), f);
-    }
-    bool unit = !in;
+    bool unit = lane >= N;
     for (int t = 0; t < a.n_bc; ++t)
       if (__ldg(a.bc_rows + t) == lane) {
         unit = isbc = true;
         f = __ldg(a.thetaBC + pc * a.n_bc + t);
       }
-    if (unit) {
+    if (inrow) {
+      if (unit) {
 #pragma unroll
-      for (int j = 0; j < NP; ++j) row[j] = (j == lane) ? 1.0 : 0.0;
-      if (!isbc) f = 0.0;
+        for (int j = 0; j < NP; ++j) R[j * NP + lane] = (j == lane) ? 1.0 : 0.0;
+      } else {
+#pragma unroll 4
+        for (int j = 0; j < NP; ++j) {
+          double v = 0.0;
+          for (int q = 0; q < a.Ql; ++q) v = fma(__ldg(th + q), __ldg(a.Aq + (long long)q * a.EP + j * NP + lane), v);
+          R[j * NP + lane] = v;
+        }
+        for (int q = 0; q < a.Qr; ++q) f = fma(__ldg(th + a.Ql + q), __ldg(a.F + q * NP + lane), f);
+      }
     }
   }
+  __syncwarp();
 
-  // ---- PA = LU, implicit partial pivoting (largest |a|, lowest row on ties: LAPACK idamax)
-  bool done = lane >= NP;
-  int piv_of = 0;     // lane t: the row that became pivot t
-  double rinv = 0.0;  // reciprocal pivot of this row
-#pragma unroll
+  // ---- PA = LU in place, implicit partial pivoting (largest |a|, lowest row on ties: LAPACK idamax); rows never move
+  bool done = !inrow;
+  int myrow = 0;      // lane t: the row that became pivot t
+  double rinv = 0.0;  // lane t: reciprocal of pivot t
   for (int t = 0; t < NP; ++t) {
-    const double at = row[t];
+    const double at = inrow ? R[t * NP + lane] : 0.0;
     const unsigned long long key = done ? 0ull : ((unsigned long long)__double_as_longlong(fabs(at)) + 1ull);
-    const double ri = 1.0 / at;  // speculative: only the winner's is used
     const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
     const unsigned mhi = __reduce_max_sync(FULL, hi);
     const unsigned lo2 = (hi == mhi) ? lo : 0u;
     const unsigned mlo = __reduce_max_sync(FULL, lo2);
     const unsigned ball = __ballot_sync(FULL, hi == mhi && lo == mlo && !done);
-    const int wl = ball ? (__ffs(ball) - 1) : t;  // no live row left cannot happen (NP rows, NP steps)
-    const double rv = __shfl_sync(FULL, ri, wl);
-    const bool iwin = lane == wl;
-    const double l = at * rv;
-#pragma unroll
-    for (int j = t + 1; j < NP; ++j) {
-      const double pj = __shfl_sync(FULL, row[j], wl);
-      if (!done && !iwin) row[j] = fma(-l, pj, row[j]);
+    const int wl = ball ? (__ffs(ball) - 1) : t;  // (NP live rows for NP steps: there always is a candidate)
+    const double rv = 1.0 / R[t * NP + wl];
+    if (lane == t) {
+      myrow = wl;
+      rinv = rv;
     }
-    if (!done && !iwin) row[t] = l;
-    if (iwin) {
+    if (lane == wl) {
       done = true;
-      rinv = ri;
+    } else if (!done) {
+      const double l = at * rv;
+      R[t * NP + lane] = l;
+      for (int j = t + 1; j < NP; ++j) R[j * NP + lane] = fma(-l, R[j * NP + wl], R[j * NP + lane]);
     }
-    if (lane == t) piv_of = wl;
+    __syncwarp();
   }
-  // rows into pivot order: lane s <- row piv_of(s).  From here on lane s holds L[s][0..s) | U[s][s..NP)
-#pragma unroll
-  for (int j = 0; j < NP; ++j) row[j] = __shfl_sync(FULL, row[j], piv_of);
-  rinv = __shfl_sync(FULL, rinv, piv_of);
-  f = __shfl_sync(FULL, f, piv_of);
-  isbc = __shfl_sync(FULL, (int)isbc, piv_of) != 0;
-  const int myrow = piv_of;  // original row of this lane's equation (rhs assembly)
+  // from here on lane s works on equation myrow(s): pivot-order space without moving a row
+  f = __shfl_sync(FULL, f, myrow);
+  isbc = __shfl_sync(FULL, (int)isbc, myrow) != 0;
+  const double* Rr = R + myrow;  // Rr[t * NP] = L[s][t] (t < s) | U[s][t] (t >= s)
 
-  // ---- z map of this lane: entries lane and lane + 32
-  double* V = Vs + w * VP;
+  // ---- z map of this lane (entries lane and lane + 32), remapped to V = [u (NP) | udot (NP) | theta slice | 1]
   int zsrc[2];
   double zsc[2];
 #pragma unroll
@@ -131,18 +128,18 @@ __global__ void __launch_bounds__(32 * PB_WARPS, (NP <= 20 ? 2 : 1)) rb_paraboli
     zsrc[h] = 0;
     zsc[h] = 0.0;
     if (k < a.Kz) {
-      zsrc[h] = __ldg(a.zsrc + k);
+      const int src = __ldg(a.zsrc + k);
+      zsrc[h] = src < N ? src : (src < 2 * N ? NP + (src - N) : 2 * NP + (src - 2 * N));
       const int sc = __ldg(a.zscale + k);
       zsc[h] = sc < 0 ? 1.0 : __ldg(th + sc);
     }
   }
-  // V = [u^0 | 0 | theta slice | 1 | 0 ...]
   double uprev = 0.0;
   if (lane < N && a.U0) uprev = a.U0[pc * N + lane];
-  for (int t = lane; t < VP; t += 32) {
+  for (int t = lane; t < a.VP; t += 32) {
     double v = 0.0;
-    if (t >= 2 * N && t < 2 * N + a.v_len) v = __ldg(th + a.v_off + (t - 2 * N));
-    if (t == 2 * N + a.v_len) v = 1.0;
+    if (t >= 2 * NP && t < 2 * NP + a.v_len) v = __ldg(th + a.v_off + (t - 2 * NP));
+    if (t == 2 * NP + a.v_len) v = 1.0;
     V[t] = v;
   }
   __syncwarp();
@@ -152,43 +149,45 @@ __global__ void __launch_bounds__(32 * PB_WARPS, (NP <= 20 ? 2 : 1)) rb_paraboli
   double* eh = (live && a.eps2_hist) ? a.eps2_hist + p * (a.K + 1) : nullptr;
   double* uh = (live && a.u_hist) ? a.u_hist + p * (long long)(a.K + 1) * N : nullptr;
   if (uh && lane < N) uh[lane] = uprev;
+  const bool rhs_m = !isbc && myrow < N && inrow;
+  const double* Gf = a.Gfrag + w * 32 + lane;  // B fragments of column tile w: k-step ks at Gf[ks * 256] (L1 resident)
   __syncthreads();  // Ms, the zero padding of Zs
 
   for (int k = 1; k <= a.K; ++k) {
     const int buf = k & 1;
-    // ---- rhs of equation `myrow`: f + sum_q theta_q (M_q/dt u^{k-1})  (lifting rows: theta_bc)
+    // ---- rhs of equation myrow: f + sum_q theta_q (M_q/dt u^{k-1})  (lifting rows: theta_bc)
     double y = f;
-    if (!isbc && myrow < N) {
+    if (rhs_m) {
       for (int q = 0; q < a.Qm; ++q) {
         const double* Mq = Ms + q * NP * NP + myrow;
         double s = 0.0;
 #pragma unroll
         for (int j = 0; j < NP; j += 2) {
-          const double2 u2 = *reinterpret_cast<const double2*>(V + j);  // entries >= N meet zero columns of M_q
-          s = fma(Mq[j * NP], (j < N) ? u2.x : 0.0, s);
-          if (j + 1 < NP) s = fma(Mq[(j + 1) * NP], (j + 1 < N) ? u2.y : 0.0, s);
+          const double2 u2 = *reinterpret_cast<const double2*>(V + j);  // V[N..NP) stays zero
+          s = fma(Mq[j * NP], u2.x, s);
+          s = fma(Mq[(j + 1) * NP], u2.y, s);
         }
         y = fma(__ldg(th + q), s, y);
       }
     }
-    // ---- L y' = y, U x = y' in pivot order
+    // ---- L y' = y, U x = y' in pivot order: one shuffle per column, the factors stream from shared memory
 #pragma unroll
     for (int t = 0; t < NP - 1; ++t) {
       const double yt = __shfl_sync(FULL, y, t);
-      if (lane > t) y = fma(-row[t], yt, y);
+      if (lane > t) y = fma(-Rr[t * NP], yt, y);
     }
     double x = 0.0;
 #pragma unroll
     for (int t = NP - 1; t >= 0; --t) {
       const double xt = __shfl_sync(FULL, y * rinv, t);
       if (lane == t) x = xt;
-      if (lane < t) y = fma(-row[t], xt, y);
+      if (lane < t) y = fma(-Rr[t * NP], xt, y);
     }
     // ---- V = [u^k | (u^k - u^{k-1}) / dt | ...], z
     __syncwarp();
     if (lane < N) {
       V[lane] = x;
-      V[N + lane] = (x - uprev) * a.inv_dt;
+      V[NP + lane] = (x - uprev) * a.inv_dt;
       if (uh) uh[(long long)k * N + lane] = x;
     }
     uprev = x;
@@ -203,8 +202,8 @@ __global__ void __launch_bounds__(32 * PB_WARPS, (NP <= 20 ? 2 : 1)) rb_paraboli
       double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
 #pragma unroll
       for (int ks = 0; ks < 16; ks += 2) {
-        dmma884(c0, c1, Zg[4 * ks + q4], Bf[ks]);
-        dmma884(d0, d1, Zg[4 * ks + 4 + q4], Bf[ks + 1]);
+        dmma884(c0, c1, Zg[4 * ks + q4], __ldg(Gf + ks * 256));
+        dmma884(d0, d1, Zg[4 * ks + 4 + q4], __ldg(Gf + ks * 256 + 256));
       }
       const double2 zz = *reinterpret_cast<const double2*>(Zg + 8 * w + 2 * q4);
       double part = fma(c0 + d0, zz.x, (c1 + d1) * zz.y);
@@ -228,7 +227,7 @@ template <int NP>
 int pb_launch(const PbArgs& a, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rb_parabolic_fused_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(rb_parabolic_fused_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -240,12 +239,20 @@ int pb_launch(const PbArgs& a, size_t smem, cudaStream_t st) {
 }  // namespace
 
 bool rb_parabolic_fused_supported(int NP, int Kz, int Qm, int VP) {
-  if (NP < 4 || NP > 32 || NP % 4 != 0 || Kz > 64 || Kz <= 0) return false;
-  return rb_parabolic_fused_smem(NP, Qm, VP) <= 100 * 1024;
+  if (NP < 4 || NP > 32 || NP % 4 != 0 || Kz > 64 || Kz <= 0 || VP % 2 != 0) return false;
+  return rb_parabolic_fused_smem(NP, Qm, VP) <= 160 * 1024;
 }
 
-size_t rb_parabolic_fused_smem(int NP, int Qm, int VP) {
-  return sizeof(double) * ((size_t)Qm * NP * NP + 2 * PB_WARPS * PB_ZP + (size_t)PB_WARPS * VP + 2 * 8 * 8);
+size_t rb_parabolic_fused_smem(int NP, int Qm, int VP) { return sizeof(double) * (size_t)PbLayout(NP, Qm, VP).total; }
+
+// B fragments of G for DMMA m8n8k4, zero padded to 64 x 64: [ks (16)][column tile (8)][lane (32)]
+void rb_parabolic_pack_g(const double* G, int Kz, double* out4096) {
+  for (int ks = 0; ks < 16; ++ks)
+    for (int w = 0; w < 8; ++w)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int k = 4 * ks + (lane & 3), n = 8 * w + (lane >> 2);
+        out4096[(ks * 8 + w) * 32 + lane] = (k < Kz && n < Kz) ? G[(size_t)k * Kz + n] : 0.0;
+      }
 }
 
 int rb_parabolic_fused_launch(const PbArgs& a, int NP, cudaStream_t st) {

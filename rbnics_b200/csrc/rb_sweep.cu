@@ -771,6 +771,8 @@ extern "C" void rb_ctx_destroy(rb_ctx* ctx) {
     if (p) cudaFree(p);
   for (int i = 0; i < 6; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (cudaEvent_t e : ctx->up_ev) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1102,12 +1104,14 @@ extern "C" int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_c
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dZscale, Kz * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(ctx->dZsrc, zsrc.data(), Kz * sizeof(int), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(ctx->dZscale, zscale.data(), Kz * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->dGdense, 4096 * sizeof(double));
     if (e == cudaSuccess) {
-      ctx->dGdense = dG;
-      dG = nullptr;
+      std::vector<double> frag(4096);
+      rb_parabolic_pack_g(G, Kz, frag.data());
+      e = cudaMemcpy(ctx->dGdense, frag.data(), 4096 * sizeof(double), cudaMemcpyHostToDevice);
     }
   }
-  if (dG) cudaFree(dG);
+  cudaFree(dG);
   if (dTab) cudaFree(dTab);
   if (e != cudaSuccess) RB_FAIL(RB_ERR_CUDA, std::string("rb_set_estimator: ") + cudaGetErrorString(e));
   RB_CUDA(cudaFuncSetAttribute(rb_estimator_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1118,9 +1122,12 @@ extern "C" int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_c
   return RB_OK;
 }
 
-extern "C" int rb_set_training_set(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta, int n_bc,
-                                   const double* ThetaBC, const double* beta, int64_t index_offset,
-                                   int64_t index_stride) {
+// pieces == false: everything is resident when the call returns.  pieces == true (rb_sweep): beta / theta_bc first, then
+// the Theta rows in pieces on the copy stream with one event per piece; the caller's buffers must stay valid until the
+// sweep that follows has returned (rb_sweep synchronises both streams before it does).
+static int set_training_set_impl(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta, int n_bc,
+                                 const double* ThetaBC, const double* beta, int64_t index_offset, int64_t index_stride,
+                                 bool pieces) {
   if (!ctx) return RB_ERR_ARG;
   RB_CUDA(cudaSetDevice(ctx->device));
   if (B <= 0 || n_theta <= 0 || !Theta || !beta || n_bc < 0 || (n_bc > 0 && !ThetaBC) || index_stride <= 0)
@@ -1136,13 +1143,53 @@ extern "C" int rb_set_training_set(rb_ctx* ctx, int64_t B, int n_theta, const do
   ctx->n_bc_train = n_bc;
   ctx->idx_off = index_offset;
   ctx->idx_stride = index_stride;
-  RB_CUDA(cudaMemcpyAsync(ctx->dTheta, Theta, (size_t)B * n_theta * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  if (n_bc)
-    RB_CUDA(cudaMemcpyAsync(ctx->dThetaBC, ThetaBC, (size_t)B * n_bc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  RB_CUDA(cudaMemcpyAsync(ctx->dBeta, beta, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  RB_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->up_pieces = 0;
+  ctx->have_train = false;
+  if (!pieces) {
+    RB_CUDA(cudaMemcpyAsync(ctx->dTheta, Theta, (size_t)B * n_theta * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_bc)
+      RB_CUDA(cudaMemcpyAsync(ctx->dThetaBC, ThetaBC, (size_t)B * n_bc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(cudaMemcpyAsync(ctx->dBeta, beta, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->have_train = true;
+    return RB_OK;
+  }
+  if (!ctx->copy_stream) RB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  // ~16 MB per piece: long enough for full PCIe rate, short enough that the first chunk of the sweep starts at once
+  const long long piece = std::max<long long>(1024, (16ll << 20) / ((long long)n_theta * 8));
+  const int np = (int)((B + piece - 1) / piece);
+  while ((int)ctx->up_ev.size() < np) {
+    cudaEvent_t e;
+    RB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->up_ev.push_back(e);
+  }
+  cudaStream_t cs = ctx->copy_stream;
+  if (n_bc) RB_CUDA(cudaMemcpyAsync(ctx->dThetaBC, ThetaBC, (size_t)B * n_bc * sizeof(double), cudaMemcpyHostToDevice, cs));
+  RB_CUDA(cudaMemcpyAsync(ctx->dBeta, beta, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, cs));
+  for (int i = 0; i < np; ++i) {
+    const long long r0 = i * piece, r1 = std::min<long long>(B, r0 + piece);
+    RB_CUDA(cudaMemcpyAsync(ctx->dTheta + r0 * n_theta, Theta + r0 * n_theta, (size_t)(r1 - r0) * n_theta * sizeof(double),
+                            cudaMemcpyHostToDevice, cs));
+    RB_CUDA(cudaEventRecord(ctx->up_ev[i], cs));
+  }
+  ctx->up_piece = piece;
+  ctx->up_pieces = np;
   ctx->have_train = true;
   return RB_OK;
+}
+
+// the compute stream waits until the Theta rows [0, row_end) (and beta / theta_bc) have arrived
+static int wait_uploaded(rb_ctx* ctx, long long row_end) {
+  if (ctx->up_pieces <= 0) return RB_OK;
+  const int idx = (int)std::min<long long>(ctx->up_pieces - 1, (row_end - 1) / ctx->up_piece);
+  RB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->up_ev[idx], 0));
+  return RB_OK;
+}
+
+extern "C" int rb_set_training_set(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta, int n_bc,
+                                   const double* ThetaBC, const double* beta, int64_t index_offset,
+                                   int64_t index_stride) {
+  return set_training_set_impl(ctx, B, n_theta, Theta, n_bc, ThetaBC, beta, index_offset, index_stride, false);
 }
 
 // choose the number of column splits so that units = row-blocks x splits fill the SMs evenly
@@ -1353,6 +1400,7 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     if (int rc = prepare_assembly(ctx, B, &chunk, &asm_smem)) return rc;
     for (long long c0 = 0; c0 < B; c0 += chunk) {
       const long long n = std::min(chunk, B - c0);
+      if (int rc = wait_uploaded(ctx, c0 + n)) return rc;
       if (int rc = launch_assembly(ctx, c0, n, asm_smem)) return rc;
       ++launches;
       if (int rc = rb_launch_lu(ctx, n, ctx->dAb, ctx->dTheta + c0 * ctx->QT,
@@ -1362,6 +1410,7 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     }
   }
   RB_CUDA(cudaEventRecord(ctx->ev[1], st));
+  if (int rc = wait_uploaded(ctx, B)) return rc;
   if (int rc = launch_estimator(ctx, ctx->dU, ctx->ldu, N, ctx->dTheta, B, nsplit)) return rc;
   ++launches;
   RB_CUDA(cudaEventRecord(ctx->ev[2], st));
@@ -1528,7 +1577,7 @@ extern "C" int rb_sweep_parabolic_ic(rb_ctx* ctx, int Qm, int K, double dt, cons
   cudaStream_t st = ctx->stream;
   // small systems (NP <= 32, Kz <= 64: tutorial 06) run the whole time loop of a parameter in one kernel; everything
   // else goes through the per-step launches below (RB_PARABOLIC_FUSED=0 forces them: tests compare the two)
-  const int VP = roundup(ctx->LV + 1, 2);
+  const int VP = roundup(2 * ctx->NP + ctx->v_len + 2, 2);  // [u (NP) | udot (NP) | theta slice | 1 | 0]
   const bool allow_fused = !(getenv("RB_PARABOLIC_FUSED") && atoi(getenv("RB_PARABOLIC_FUSED")) == 0);
   const bool fused = allow_fused && ctx->dGdense && rb_parabolic_fused_supported(ctx->NP, ctx->Kz, Qm, VP);
   long long chunk = B;
@@ -1602,7 +1651,7 @@ extern "C" int rb_sweep_parabolic_ic(rb_ctx* ctx, int Qm, int K, double dt, cons
     pa.Aq = ctx->dAq;
     pa.F = ctx->dF;
     pa.bc_rows = ctx->dBcRows;
-    pa.G = ctx->dGdense;
+    pa.Gfrag = ctx->dGdense;
     pa.zsrc = ctx->dZsrc;
     pa.zscale = ctx->dZscale;
     pa.weights = ctx->dWeights;
@@ -1701,8 +1750,14 @@ extern "C" int rb_sweep_parabolic_ic(rb_ctx* ctx, int Qm, int K, double dt, cons
 extern "C" int rb_sweep(rb_ctx* ctx, int64_t B, int n_theta, const double* Theta, int n_bc, const double* ThetaBC,
                         const double* beta, int64_t index_offset, int64_t index_stride, int estimator_kind,
                         double* max_val, int64_t* max_idx, double* delta_out, double* u_out, double* eps2_out) {
-  if (int rc = rb_set_training_set(ctx, B, n_theta, Theta, n_bc, ThetaBC, beta, index_offset, index_stride)) return rc;
-  return rb_sweep_resident(ctx, estimator_kind, max_val, max_idx, delta_out, u_out, eps2_out);
+  // host buffers in: the upload of the Theta rows overlaps the assembly + LU of the chunks that are already there
+  int rc = set_training_set_impl(ctx, B, n_theta, Theta, n_bc, ThetaBC, beta, index_offset, index_stride, true);
+  if (rc == RB_OK) rc = rb_sweep_resident(ctx, estimator_kind, max_val, max_idx, delta_out, u_out, eps2_out);
+  if (ctx && ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);  // also on error paths: the caller's buffers are free again
+    ctx->up_pieces = 0;
+  }
+  return rc;
 }
 
 // out[p] = sum_q ThetaS[p][q] * (S[q] . u_p): one warp per parameter
