@@ -1290,12 +1290,12 @@ static int launch_estimator(rb_ctx* ctx, const double* Uvec, int ldu, int vecN, 
 // chunk size of the assembly scratch and its (re)allocation
 int rb_lu_mw_quantum(int N);
 static int prepare_assembly(rb_ctx* ctx, long long B, long long* chunk_out, size_t* asm_smem_out) {
-  // one wave of the assembly GEMM (148 x 128 parameters = 1.5 GB of assembled matrices at N = 100); small systems take
-  // as many parameters as fit the same budget, so that the per-chunk launches (5 per time step in the parabolic sweep)
-  // stay large
+  // at least one wave of the assembly GEMM (148 x 128 parameters), and as many parameters as fit 6 GB of assembled
+  // matrices (69,264 at N = 100): every LU launch ends with a tail of one system time (~0.15 ms) in which the SMs run
+  // dry, so fewer, longer launches pay (1.5 GB chunks: 157.1 ms per 10^6 parameters, 6 GB: 153.8, 12 GB: 153.7)
   long long chunk = (long long)ctx->sm_count * ASM_BM;
   {
-    const long long budget = 1536LL << 20;
+    const long long budget = 6144LL << 20;
     const long long fit = budget / ((long long)ctx->EP * (long long)sizeof(double));
     if (fit > chunk) chunk = fit / chunk * chunk;
   }

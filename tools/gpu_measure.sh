@@ -17,9 +17,9 @@ timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 -
 # full captures of the hot kernels at the bench launch configuration (first launch after the warm-up sweeps)
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_estimator_kernel -s 3 -c 1 \
     -o $OUT/${TAG}_estimator_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_est.log 2>&1
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_lu_mw_kernel -s 160 -c 1 \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_lu_mw_kernel -s 40 -c 1 \
     -o $OUT/${TAG}_lu_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_lu.log 2>&1
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_assemble_kernel -s 160 -c 1 \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_assemble_kernel -s 40 -c 1 \
     -o $OUT/${TAG}_asm_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_asm.log 2>&1
 # offline basis linear algebra: kernel times + launch list + full captures of the two Gram kernels
 timeout -s KILL 600 python bench_offline.py > $OUT/${TAG}_offline_kernels.jsonl 2> $OUT/${TAG}_offline.err || tail -5 $OUT/${TAG}_offline.err
@@ -30,4 +30,11 @@ timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k re
     -o $OUT/${TAG}_gram_fused_full -f python tools/gram_probe.py 61 > $OUT/${TAG}_ncu_fused.log 2>&1
 timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:rb_tsmm2_kernel -c 1 \
     -o $OUT/${TAG}_tsmm2_full -f python tools/gram_probe.py 400 > $OUT/${TAG}_ncu_tsmm2.log 2>&1
+# POD-Greedy (parabolic) sweep: bench line, launch list, full capture of the fused kernel
+timeout -s KILL 300 python bench_parabolic.py > $OUT/${TAG}_parabolic_sweep.json 2> $OUT/${TAG}_parabolic.err || tail -5 $OUT/${TAG}_parabolic.err
+cut -c1-400 $OUT/${TAG}_parabolic_sweep.json
+timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $OUT/${TAG}_parabolic_launches.csv \
+    python bench_parabolic.py --cpu-sample 4 > $OUT/${TAG}_ncu_parabolic.log 2>&1
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:rb_parabolic_fused -s 1 -c 1 \
+    -o $OUT/${TAG}_parabolic_full -f python bench_parabolic.py --cpu-sample 4 > $OUT/${TAG}_ncu_parabolic_full.log 2>&1
 ls -la $OUT | tail -12
