@@ -86,8 +86,8 @@ struct rb_ctx {
   int* dBlkSrc = nullptr;           // [nblk]
   int* dColScale = nullptr;         // [n_ctile*EST_BN]
   int* dColSrc = nullptr;           // [n_ctile*EST_BN]
-  // small quadratic forms (Kz <= 64) also keep the dense G and the z map: fused parabolic sweep (rb_parabolic.cu)
-  double* dGdense = nullptr;        // G as DMMA B fragments, zero padded to 64 x 64 (rb_parabolic_pack_g), or null
+  // small quadratic forms (Kz <= 128) also keep the dense G and the z map: fused parabolic sweep (rb_parabolic.cu)
+  double* dGdense = nullptr;        // G as DMMA B fragments, zero padded to 64 x 64 or 128 x 128 (rb_parabolic_pack_g), or null
   int* dZsrc = nullptr;             // [Kz] index into V
   int* dZscale = nullptr;           // [Kz] theta column or -1
   double* dWeights = nullptr; int weights_cap = 0;  // time-quadrature weights of the parabolic sweep

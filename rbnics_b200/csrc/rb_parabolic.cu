@@ -12,36 +12,38 @@
 // column and no dynamic register index.  The residual norm of a step is eps2 = z^T G z, z = scale (.) V[src]
 // (rb_set_estimator_ex); the 8 parameters of a CTA form the M = 8 dimension of DMMA m8n8k4: warp w multiplies column tile
 // w of G (B fragments constant for the whole kernel: registers) with the z rows of all 8 parameters (shared memory).
-// Served sizes: NP <= 32, Kz <= 64; anything else takes the multi-launch path of rb_sweep.cu.
+// Served sizes: NP <= 32, Kz <= 128 (z rows padded to ZH = 2 or 4 chunks of 32 entries); anything else takes the
+// multi-launch path of rb_sweep.cu.
 #include "rb_common.cuh"
 #include "rb_parabolic.cuh"
 
 namespace {
 
 constexpr int PB_WARPS = 8;
-constexpr int PB_ZP = 68;  // pitch of a z row (64 + 4: conflict-free A-fragment loads)
+__host__ __device__ constexpr int pb_zp(int ZH) { return 32 * ZH + 4; }  // pitch of a z row (+ 4: conflict-free A-fragment loads)
 
 // shared-memory carve-up (doubles)
 struct PbLayout {
   int ms, rs, zs, vs, es, total;
-  __host__ __device__ PbLayout(int NP, int Qm, int VP) {
+  __host__ __device__ PbLayout(int NP, int Qm, int VP, int ZH) {
     ms = 0;                                  // [Qm][NP (col j)][NP (row i)]   M_q / dt
     rs = ms + Qm * NP * NP;                  // [8][NP (col j)][NP (row i)]    L\U of the 8 parameters, rows in place
-    zs = rs + PB_WARPS * NP * NP;            // [2][8][PB_ZP]                  z rows (double buffered over the steps)
-    vs = zs + 2 * PB_WARPS * PB_ZP;          // [8][VP]                        [u (NP) | udot (NP) | theta slice | 1]
+    zs = rs + PB_WARPS * NP * NP;            // [2][8][pb_zp(ZH)]              z rows (double buffered over the steps)
+    vs = zs + 2 * PB_WARPS * pb_zp(ZH);      // [8][VP]                        [u (NP) | udot (NP) | theta slice | 1]
     es = vs + PB_WARPS * VP;                 // [2][8 (tile)][8 (parameter)]   partial residual norms
     total = es + 2 * 8 * 8;
   }
 };
 
-template <int NP>
-__global__ void __launch_bounds__(32 * PB_WARPS, 3) rb_parabolic_fused_kernel(PbArgs a) {
+template <int NP, int ZH>
+__global__ void __launch_bounds__(32 * PB_WARPS, (ZH == 2 ? 3 : 2)) rb_parabolic_fused_kernel(PbArgs a) {
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr int PB_ZP = pb_zp(ZH), KS = 8 * ZH, TPW = ZH / 2;  // k-steps of the z^T G z product, column tiles per warp
   extern __shared__ __align__(16) double pbs[];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int g = lane >> 2, q4 = lane & 3;
   const int N = a.N;
-  const PbLayout lay(NP, a.Qm, a.VP);
+  const PbLayout lay(NP, a.Qm, a.VP, ZH);
   double* Ms = pbs + lay.ms;
   double* R = pbs + lay.rs + w * NP * NP;  // entry (row i, col j) at j * NP + i
   double* Zs = pbs + lay.zs;
@@ -119,11 +121,11 @@ __global__ void __launch_bounds__(32 * PB_WARPS, 3) rb_parabolic_fused_kernel(Pb
   isbc = __shfl_sync(FULL, (int)isbc, myrow) != 0;
   const double* Rr = R + myrow;  // Rr[t * NP] = L[s][t] (t < s) | U[s][t] (t >= s)
 
-  // ---- z map of this lane (entries lane and lane + 32), remapped to V = [u (NP) | udot (NP) | theta slice | 1]
-  int zsrc[2];
-  double zsc[2];
+  // ---- z map of this lane (entries lane + 32 h), remapped to V = [u (NP) | udot (NP) | theta slice | 1]
+  int zsrc[ZH];
+  double zsc[ZH];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < ZH; ++h) {
     const int k = lane + 32 * h;
     zsrc[h] = 0;
     zsc[h] = 0.0;
@@ -150,7 +152,8 @@ __global__ void __launch_bounds__(32 * PB_WARPS, 3) rb_parabolic_fused_kernel(Pb
   double* uh = (live && a.u_hist) ? a.u_hist + p * (long long)(a.K + 1) * N : nullptr;
   if (uh && lane < N) uh[lane] = uprev;
   const bool rhs_m = !isbc && myrow < N && inrow;
-  const double* Gf = a.Gfrag + w * 32 + lane;  // B fragments of column tile w: k-step ks at Gf[ks * 256] (L1 resident)
+  // B fragments of column tile nt: k-step ks at Gfrag[(nt * KS + ks) * 32 + lane] (constant: L1 / L2 resident)
+  const double* Gf = a.Gfrag + (long long)w * KS * 32 + lane;
   __syncthreads();  // Ms, the zero padding of Zs
 
   for (int k = 1; k <= a.K; ++k) {
@@ -193,20 +196,30 @@ __global__ void __launch_bounds__(32 * PB_WARPS, 3) rb_parabolic_fused_kernel(Pb
     uprev = x;
     __syncwarp();
     double* Z = Zs + (buf * PB_WARPS + w) * PB_ZP;
-    Z[lane] = zsc[0] * V[zsrc[0]];
-    Z[lane + 32] = zsc[1] * V[zsrc[1]];
+#pragma unroll
+    for (int h = 0; h < ZH; ++h) Z[lane + 32 * h] = zsc[h] * V[zsrc[h]];
     __syncthreads();
-    // ---- W = Z G (8 parameters x column tile w), e = rowsum(W (.) Z)
+    // ---- W = Z G (8 parameters x the column tiles w, w + 8, ... of this warp), e = rowsum(W (.) Z)
     {
       const double* Zg = Zs + (buf * PB_WARPS + g) * PB_ZP;
-      double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+      double c[TPW][2][2];
 #pragma unroll
-      for (int ks = 0; ks < 16; ks += 2) {
-        dmma884(c0, c1, Zg[4 * ks + q4], __ldg(Gf + ks * 256));
-        dmma884(d0, d1, Zg[4 * ks + 4 + q4], __ldg(Gf + ks * 256 + 256));
+      for (int t = 0; t < TPW; ++t) c[t][0][0] = c[t][0][1] = c[t][1][0] = c[t][1][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < KS; ks += 2) {
+        const double a0 = Zg[4 * ks + q4], a1 = Zg[4 * ks + 4 + q4];
+#pragma unroll
+        for (int t = 0; t < TPW; ++t) {
+          dmma884(c[t][0][0], c[t][0][1], a0, __ldg(Gf + (t * 8 * KS + ks) * 32));
+          dmma884(c[t][1][0], c[t][1][1], a1, __ldg(Gf + (t * 8 * KS + ks + 1) * 32));
+        }
       }
-      const double2 zz = *reinterpret_cast<const double2*>(Zg + 8 * w + 2 * q4);
-      double part = fma(c0 + d0, zz.x, (c1 + d1) * zz.y);
+      double part = 0.0;
+#pragma unroll
+      for (int t = 0; t < TPW; ++t) {
+        const double2 zz = *reinterpret_cast<const double2*>(Zg + 8 * (w + 8 * t) + 2 * q4);
+        part += fma(c[t][0][0] + c[t][1][0], zz.x, (c[t][0][1] + c[t][1][1]) * zz.y);
+      }
       part += __shfl_xor_sync(FULL, part, 1);
       part += __shfl_xor_sync(FULL, part, 2);
       if (q4 == 0) Es[(buf * 8 + w) * 8 + g] = part;
@@ -223,43 +236,53 @@ __global__ void __launch_bounds__(32 * PB_WARPS, 3) rb_parabolic_fused_kernel(Pb
   if (live && lane == 0) a.acc_out[p] = acc;
 }
 
-template <int NP>
+template <int NP, int ZH>
 int pb_launch(const PbArgs& a, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rb_parabolic_fused_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(rb_parabolic_fused_kernel<NP, ZH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const unsigned grid = (unsigned)((a.n + PB_WARPS - 1) / PB_WARPS);
-  rb_parabolic_fused_kernel<NP><<<grid, 32 * PB_WARPS, smem, st>>>(a);
+  rb_parabolic_fused_kernel<NP, ZH><<<grid, 32 * PB_WARPS, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
 
 }  // namespace
 
+int rb_parabolic_zh(int Kz) { return Kz <= 64 ? 2 : 4; }
+
 bool rb_parabolic_fused_supported(int NP, int Kz, int Qm, int VP) {
-  if (NP < 4 || NP > 32 || NP % 4 != 0 || Kz > 64 || Kz <= 0 || VP % 2 != 0) return false;
-  return rb_parabolic_fused_smem(NP, Qm, VP) <= 160 * 1024;
+  if (NP < 4 || NP > 32 || NP % 4 != 0 || Kz > 128 || Kz <= 0 || VP % 2 != 0) return false;
+  return rb_parabolic_fused_smem(NP, Kz, Qm, VP) <= 160 * 1024;
 }
 
-size_t rb_parabolic_fused_smem(int NP, int Qm, int VP) { return sizeof(double) * (size_t)PbLayout(NP, Qm, VP).total; }
+size_t rb_parabolic_fused_smem(int NP, int Kz, int Qm, int VP) {
+  return sizeof(double) * (size_t)PbLayout(NP, Qm, VP, rb_parabolic_zh(Kz)).total;
+}
 
-// B fragments of G for DMMA m8n8k4, zero padded to 64 x 64: [ks (16)][column tile (8)][lane (32)]
-void rb_parabolic_pack_g(const double* G, int Kz, double* out4096) {
-  for (int ks = 0; ks < 16; ++ks)
-    for (int w = 0; w < 8; ++w)
+// B fragments of G for DMMA m8n8k4, zero padded to 32 ZH x 32 ZH: [column tile (4 ZH)][k-step (8 ZH)][lane (32)]
+size_t rb_parabolic_pack_g_doubles(int Kz) {
+  const int ZH = rb_parabolic_zh(Kz);
+  return (size_t)(4 * ZH) * (8 * ZH) * 32;
+}
+void rb_parabolic_pack_g(const double* G, int Kz, double* out) {
+  const int ZH = rb_parabolic_zh(Kz), KS = 8 * ZH, NTL = 4 * ZH;
+  for (int nt = 0; nt < NTL; ++nt)
+    for (int ks = 0; ks < KS; ++ks)
       for (int lane = 0; lane < 32; ++lane) {
-        const int k = 4 * ks + (lane & 3), n = 8 * w + (lane >> 2);
-        out4096[(ks * 8 + w) * 32 + lane] = (k < Kz && n < Kz) ? G[(size_t)k * Kz + n] : 0.0;
+        const int k = 4 * ks + (lane & 3), n = 8 * nt + (lane >> 2);
+        out[((size_t)nt * KS + ks) * 32 + lane] = (k < Kz && n < Kz) ? G[(size_t)k * Kz + n] : 0.0;
       }
 }
 
 int rb_parabolic_fused_launch(const PbArgs& a, int NP, cudaStream_t st) {
-  const size_t smem = rb_parabolic_fused_smem(NP, a.Qm, a.VP);
+  const size_t smem = rb_parabolic_fused_smem(NP, a.Kz, a.Qm, a.VP);
+  const int ZH = rb_parabolic_zh(a.Kz);
   switch (NP) {
 #define RB_PB_CASE(n) \
-  case n: return pb_launch<n>(a, smem, st);
+  case n: return ZH == 2 ? pb_launch<n, 2>(a, smem, st) : pb_launch<n, 4>(a, smem, st);
     RB_PB_CASE(4) RB_PB_CASE(8) RB_PB_CASE(12) RB_PB_CASE(16) RB_PB_CASE(20) RB_PB_CASE(24) RB_PB_CASE(28) RB_PB_CASE(32)
 #undef RB_PB_CASE
     default: return (int)cudaErrorInvalidValue;

@@ -10,7 +10,7 @@ struct PbArgs {
   const double* Aq;       // [Ql][EP]: entry (i, j) of term q at q*EP + j*NP + i
   const double* F;        // [Qr][NP]
   const int* bc_rows;     // [n_bc]
-  const double* Gfrag;    // [16][8][32] the quadratic form of the estimator as DMMA B fragments (rb_parabolic_pack_g)
+  const double* Gfrag;    // the quadratic form of the estimator as DMMA B fragments (rb_parabolic_pack_g)
   const int* zsrc;        // [Kz] index into V = [u | udot | theta slice | 1]
   const int* zscale;      // [Kz] theta column that scales the entry, or -1
   const double* weights;  // [K+1] time-quadrature weights (device)
@@ -25,6 +25,7 @@ struct PbArgs {
 };
 
 bool rb_parabolic_fused_supported(int NP, int Kz, int Qm, int VP);
-size_t rb_parabolic_fused_smem(int NP, int Qm, int VP);
+size_t rb_parabolic_fused_smem(int NP, int Kz, int Qm, int VP);
 int rb_parabolic_fused_launch(const PbArgs& a, int NP, cudaStream_t st);
-void rb_parabolic_pack_g(const double* G, int Kz, double* out4096);
+size_t rb_parabolic_pack_g_doubles(int Kz);
+void rb_parabolic_pack_g(const double* G, int Kz, double* out);

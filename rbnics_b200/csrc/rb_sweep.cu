@@ -1093,7 +1093,7 @@ extern "C" int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_c
   if (ctx->dZscale) cudaFree(ctx->dZscale);
   ctx->dGdense = nullptr;
   ctx->dZsrc = ctx->dZscale = nullptr;
-  if (e == cudaSuccess && Kz <= 64) {
+  if (e == cudaSuccess && Kz <= 128) {
     std::vector<int> zsrc(Kz), zscale(Kz);
     for (int b = 0; b < nblk; ++b)
       for (int t = 0; t < blk_len[b]; ++t) {
@@ -1104,11 +1104,12 @@ extern "C" int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_c
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dZscale, Kz * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(ctx->dZsrc, zsrc.data(), Kz * sizeof(int), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(ctx->dZscale, zscale.data(), Kz * sizeof(int), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->dGdense, 4096 * sizeof(double));
+    const size_t nfrag = rb_parabolic_pack_g_doubles(Kz);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->dGdense, nfrag * sizeof(double));
     if (e == cudaSuccess) {
-      std::vector<double> frag(4096);
+      std::vector<double> frag(nfrag);
       rb_parabolic_pack_g(G, Kz, frag.data());
-      e = cudaMemcpy(ctx->dGdense, frag.data(), 4096 * sizeof(double), cudaMemcpyHostToDevice);
+      e = cudaMemcpy(ctx->dGdense, frag.data(), nfrag * sizeof(double), cudaMemcpyHostToDevice);
     }
   }
   cudaFree(dG);
@@ -1575,7 +1576,7 @@ extern "C" int rb_sweep_parabolic_ic(rb_ctx* ctx, int Qm, int K, double dt, cons
   if (ctx->est_vecN != 2 * N) RB_FAIL(RB_ERR_STATE, "rb_sweep_parabolic: set the estimator with solution_len = 2 N");
   const long long B = ctx->B;
   cudaStream_t st = ctx->stream;
-  // small systems (NP <= 32, Kz <= 64: tutorial 06) run the whole time loop of a parameter in one kernel; everything
+  // small systems (NP <= 32, Kz <= 128: tutorial 06) run the whole time loop of a parameter in one kernel; everything
   // else goes through the per-step launches below (RB_PARABOLIC_FUSED=0 forces them: tests compare the two)
   const int VP = roundup(2 * ctx->NP + ctx->v_len + 2, 2);  // [u (NP) | udot (NP) | theta slice | 1 | 0]
   const bool allow_fused = !(getenv("RB_PARABOLIC_FUSED") && atoi(getenv("RB_PARABOLIC_FUSED")) == 0);

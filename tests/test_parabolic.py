@@ -55,7 +55,7 @@ def test_parabolic_quadratic_form_and_simpson_weights_match_reference():
 
 @pytest.fixture(params=["fused", "per_step_launches"])
 def path(request, monkeypatch):
-    """Both device paths of rb_sweep_parabolic: the one-kernel time loop (rb_parabolic.cu; NP <= 32, Kz <= 64) and the
+    """Both device paths of rb_sweep_parabolic: the one-kernel time loop (rb_parabolic.cu; NP <= 32, Kz <= 128) and the
     per-step launches that serve every other size."""
     monkeypatch.setenv("RB_PARABOLIC_FUSED", "1" if request.param == "fused" else "0")
     return request.param
@@ -144,10 +144,11 @@ def _storages(E):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("N,Qm,Qa,Qf,B", [(3, 1, 2, 1, 5), (7, 2, 2, 3, 17), (16, 1, 2, 1, 8), (20, 1, 2, 1, 33),
-                                          (21, 1, 2, 1, 9), (30, 1, 1, 1, 12), (32, 1, 2, 1, 6)])
+                                          (21, 1, 2, 1, 9), (30, 1, 1, 1, 12), (20, 1, 3, 1, 19), (24, 2, 3, 2, 10),
+                                          (32, 1, 2, 1, 6), (32, 2, 2, 1, 7)])
 def test_cuda_parabolic_sweep_sizes(engine, path, N, Qm, Qa, Qf, B):
-    """Every register-array instantiation of the fused kernel (NP = 4 ... 32), partial last CTAs, and sizes that only
-    the per-step path serves (N = 32 with Kz = 97), against the loop oracle."""
+    """Every instantiation of the fused kernel (NP = 4 ... 32; z rows of 64 and of 128 entries: Kz = 81, 97, 122),
+    partial last CTAs, and a size that only the per-step path serves (N = 32 with Kz = 129), against the loop oracle."""
     from rbnics_b200.parabolic import ParabolicSweep
     K, dt = 9, 0.07
     M, A, F, E, Tm, Ta, Tf, beta = _random_parabolic(N, Qm, Qa, Qf, B, seed=N)
