@@ -231,6 +231,11 @@ int rb_set_allreduce(rb_ctx* ctx, rb_allreduce_fn fn, void* user);
  * is returned complete on every rank.                                                                             */
 int rb_off_gram_schmidt_rows(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, int64_t row_begin,
                              int64_t row_end, double* norm_out);
+/* The same with the first `first_col` columns of the block left out of the projection: lifting functions of
+ * non-homogeneous Dirichlet conditions stay in the basis but are not orthogonalised against --
+ * GS.apply(new, basis_functions[N_bc:]), rbnics/reduction_methods/base/rb_reduction.py:125-139.                     */
+int rb_off_gram_schmidt_from(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, int first_col, int64_t row_begin,
+                             int64_t row_end, double* norm_out);
 
 #ifdef __cplusplus
 }

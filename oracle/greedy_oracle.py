@@ -17,17 +17,23 @@ def greedy_offline(tp, training_set, Nmax, tol, kind="sqrt_eps2_over_beta", vect
     Theta_a = tp.compute_theta("a", mus)
     Theta_f = tp.compute_theta("f", mus)
     beta = tp.get_stability_factor_lower_bound(mus)
-    Z = np.zeros((Nh, 0))
+    # non-homogeneous Dirichlet conditions: the lifting functions are the first N_bc basis functions
+    # (rbnics/problems/base/parametrized_reduced_differential_problem.py:283-299; N counts the others, :329)
+    liftings = getattr(tp, "dirichlet_bc_liftings", None)
+    Z = np.zeros((Nh, 0)) if liftings is None else np.array(liftings, dtype=np.float64)
+    N_bc = Z.shape[1]
+    Theta_bc = tp.compute_theta("dirichlet_bc", mus) if N_bc else None
     selected, estimators, all_deltas = [], [], []
 
     def sweep(N):
         A_q, f_q = O.build_reduced_operators(Z, tp.operators_a, tp.operators_f)
         G_ff, G_af, G_aa, _, _ = O.build_error_estimation_operators(Z, X, tp.operators_a, tp.operators_f, tp.riesz_solve)
         if vectorised:
-            A, F, Gff, Gaf, Gaa = O.stack_operators(A_q, f_q, G_ff, G_af, G_aa, N)
-            d, U, i, v = O.sweep_batched(Theta_a, Theta_f, beta, A, F, Gff, Gaf, Gaa, kind=kind)
+            A, F, Gff, Gaf, Gaa = O.stack_operators(A_q, f_q, G_ff, G_af, G_aa, N + N_bc)
+            d, U, i, v = O.sweep_batched(Theta_a, Theta_f, beta, A, F, Gff, Gaf, Gaa, Theta_bc=Theta_bc, kind=kind)
         else:
-            d, U, i, v = O.sweep_loop(Theta_a, Theta_f, beta, A_q, f_q, G_ff, G_af, G_aa, N, kind=kind)
+            d, U, i, v = O.sweep_loop(Theta_a, Theta_f, beta, A_q, f_q, G_ff, G_af, G_aa, N + N_bc, Theta_bc=Theta_bc,
+                                      kind=kind)
         return d, i, v
 
     d, i, v = sweep(0)
@@ -36,8 +42,12 @@ def greedy_offline(tp, training_set, Nmax, tol, kind="sqrt_eps2_over_beta", vect
     all_deltas.append(d)
     N = 0
     while N < Nmax and estimators[-1] / estimators[0] >= tol:
-        snapshot = tp.solve(training_set[selected[-1]])
-        z = O.gram_schmidt(snapshot, Z, X)
+        mu = training_set[selected[-1]]
+        snapshot = tp.solve(mu)
+        if N_bc:  # postprocess_snapshot (differential_problem_reduction_method.py:73-108); GS against the basis
+            # functions after the liftings only (rb_reduction.py:125-139)
+            snapshot = snapshot - Z[:, :N_bc] @ tp.compute_theta("dirichlet_bc", [mu])[0]
+        z = O.gram_schmidt(snapshot, Z[:, N_bc:], X)
         Z = np.concatenate([Z, z[:, None]], axis=1)
         N += 1
         d, i, v = sweep(N)

@@ -80,6 +80,8 @@ SIGNATURES = {
     "rb_off_scale_columns": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "rb_off_gram_schmidt_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int64, C.c_int64,
                                            c_double_p]),
+    "rb_off_gram_schmidt_from": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int, C.c_int64,
+                                           C.c_int64, c_double_p]),
 }
 
 # int (*rb_allreduce_fn)(void* user, double* device_buffer, int64_t count)

@@ -1619,11 +1619,19 @@ extern "C" int rb_set_allreduce(rb_ctx* ctx, rb_allreduce_fn fn, void* user) {
 
 extern "C" int rb_off_gram_schmidt_rows(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, int64_t row_begin,
                                         int64_t row_end, double* norm_out) {
+  return rb_off_gram_schmidt_from(ctx, blkZ, csrX, z, append, 0, row_begin, row_end, norm_out);
+}
+
+// first_col > 0: the first columns of the block are not projected out -- lifting functions of non-homogeneous Dirichlet
+// conditions, GS.apply(new, basis_functions[N_bc:]) in rbnics/reduction_methods/base/rb_reduction.py:125-139
+extern "C" int rb_off_gram_schmidt_from(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, int first_col,
+                                        int64_t row_begin, int64_t row_end, double* norm_out) {
   if (!ctx) return RB_ERR_ARG;
   RB_CUDA(cudaSetDevice(ctx->device));
   rb_off_blk_t* Z = off_blk(ctx, blkZ);
   rb_off_csr_t* X = csrX >= 0 ? off_csr(ctx, csrX) : nullptr;
   if (!Z || !z || (csrX >= 0 && !X)) RB_FAIL(RB_ERR_ARG, "rb_off_gram_schmidt: empty slot");
+  if (first_col < 0 || first_col > Z->n) RB_FAIL(RB_ERR_ARG, "rb_off_gram_schmidt: first column outside the block");
   if (append && Z->n + 1 > Z->cap) RB_FAIL(RB_ERR_ARG, "rb_off_gram_schmidt: block capacity exceeded");
   cudaStream_t st = ctx->stream;
   const long long Nh = Z->Nh;
@@ -1677,18 +1685,19 @@ extern "C" int rb_off_gram_schmidt_rows(rb_ctx* ctx, int blkZ, int csrX, double*
   // next kernel reads them, so every rank subtracts the same d_k.
   double* part[2] = {dPart.as<double>(), dPart.as<double>() + GS_BLOCKS};
   double* zr = dz.as<double>() + rb;
-  if (Z->n > 0) {
-    rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(zr, 1, xz + rb, 1, nrows, part[0]);
+  if (Z->n > first_col) {
+    rb_dot_partial_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(zr, 1, xz + (size_t)first_col * Nh + rb, 1, nrows, part[0]);
     ++launches;
     if (int rc = reduce(part[0], GS_BLOCKS)) return rc;
   }
-  for (int k = 0; k < Z->n; ++k) {
-    rb_gs_step_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(part[k & 1], Z->zt + (size_t)k * Nh + rb, zr,
+  for (int k = first_col; k < Z->n; ++k) {
+    const int b = (k - first_col) & 1;
+    rb_gs_step_kernel<<<GS_BLOCKS, GS_THREADS, 0, st>>>(part[b], Z->zt + (size_t)k * Nh + rb, zr,
                                                        k + 1 < Z->n ? xz + (size_t)(k + 1) * Nh + rb : nullptr, nrows,
-                                                       part[(k + 1) & 1]);
+                                                       part[b ^ 1]);
     ++launches;
     if (k + 1 < Z->n)
-      if (int rc = reduce(part[(k + 1) & 1], GS_BLOCKS)) return rc;
+      if (int rc = reduce(part[b ^ 1], GS_BLOCKS)) return rc;
   }
   RB_CUDA(cudaGetLastError());
   if (partitioned) {  // gather the rows the other ranks projected: sum of the zero-padded pieces

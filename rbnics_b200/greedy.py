@@ -14,6 +14,14 @@ as an object with
     inner_product : scipy.sparse X                             solve(mu) -> Nh-vector (truth solution)
     riesz_solve(rhs) -> X^-1 rhs (homogeneous Dirichlet)       compute_theta(term, mus) -> (B x Q) array, vectorised
     get_stability_factor_lower_bound(mus) -> (B,) array
+
+Non-homogeneous Dirichlet conditions (optional): ``dirichlet_bc_liftings`` = (Nh x N_bc) array of lifting functions,
+one per term of ``compute_theta("dirichlet_bc", mus)`` -> (B x N_bc).  As in the reference they are the first N_bc
+basis functions (parametrized_reduced_differential_problem.py:283-299), their rows of the reduced system are lifting
+rows with right-hand side theta_bc (backends/online/basic/wrapping/DirichletBC.py:37-56), a snapshot is stripped of
+``liftings @ theta_bc(mu)`` before it enters the basis (differential_problem_reduction_method.py:73-108) and
+Gram-Schmidt runs against ``basis_functions[N_bc:]`` only (rb_reduction.py:125-139).  ``self.N`` counts ALL basis
+functions here (the reference's ``N + N_bc``); ``Nmax`` bounds ``self.N - self.N_bc`` like the reference's ``N``.
 """
 from __future__ import annotations
 
@@ -50,7 +58,10 @@ class ReducedBasisGreedy:
         mus = np.asarray(self.training_set, dtype=np.float64)
         Theta = np.concatenate([tp.compute_theta("a", mus), tp.compute_theta("f", mus)], axis=1)
         beta = tp.get_stability_factor_lower_bound(mus)
-        self._sweep = TrainingSetSweep(engine, Theta, beta, dist=dist)
+        liftings = getattr(tp, "dirichlet_bc_liftings", None)
+        self.N_bc = 0 if liftings is None else int(np.asarray(liftings).shape[1])
+        ThetaBC = tp.compute_theta("dirichlet_bc", mus) if self.N_bc else None
+        self._sweep = TrainingSetSweep(engine, Theta, beta, ThetaBC=ThetaBC, dist=dist)
         # reduced problem state
         self.N = 0
         self.basis_functions = np.zeros((self.Nh, 0))
@@ -72,11 +83,11 @@ class ReducedBasisGreedy:
                 self._a_symmetric.append(sym)
                 if not sym:   # z^T A_q Z_j = (A_q^T z) . Z_j: the transposed operator gives the new ROW as a mat-vec too
                     ws.set_operator(f"A{q}T", A.T.tocsr())
-            ws.new_block("Z", self.Nh, Nmax + 1)
+            ws.new_block("Z", self.Nh, Nmax + 1 + self.N_bc)
             ws.new_block("YA", self.Nh, 2 * self.Qa)   # [A_q z_new | A_q^T z_new] for all q, side by side
             ws.new_block("F", self.Nh, self.Qf)
             ws.append("F", np.stack([np.asarray(f, dtype=np.float64) for f in tp.operators_f], axis=1))
-            ws.new_block("R", self.Nh, self.Qa * (Nmax + 1) + self.Qf)   # Riesz representers: r_f first, then (n, q)
+            ws.new_block("R", self.Nh, self.Qa * (Nmax + 1 + self.N_bc) + self.Qf)   # Riesz representers: r_f, then (n, q)
             self.ws = ws
         self.greedy_selected_parameters = []
         self.greedy_selected_indices = []
@@ -137,7 +148,8 @@ class ReducedBasisGreedy:
             Z = self.basis_functions
             self.operator_a = offline.project_matrices(self.engine, Z, tp.operators_a)
             self.operator_f = offline.project_vectors(self.engine, Z, tp.operators_f)
-        self.engine.set_system(self.operator_a, self.operator_f)
+        # the liftings are the first N_bc basis functions: their rows are lifting rows (DirichletBC.py:37-56)
+        self.engine.set_system(self.operator_a, self.operator_f, bc_rows=list(range(min(self.N_bc, self.N))) or None)
 
     # -- reduced_problem.build_error_estimation_operators() ------------------------------------------------------
     def build_error_estimation_operators(self):
@@ -219,23 +231,45 @@ class ReducedBasisGreedy:
         self.greedy_error_estimators.append(error_estimator_max)
         return (error_estimator_max, error_estimator_max / self.greedy_error_estimators[0])
 
+    def postprocess_snapshot(self, snapshot):
+        """Remove the non-homogeneous Dirichlet part (differential_problem_reduction_method.py:73-108)."""
+        if self.N_bc == 0:
+            return snapshot
+        theta_bc = self.truth_problem.compute_theta("dirichlet_bc", [self.mu])[0]
+        return snapshot - self.basis_functions[:, :self.N_bc] @ theta_bc
+
     def update_basis_matrix(self, snapshot):
         if self.resident:
-            new_basis_function, _ = self.ws.gram_schmidt("Z", "X", snapshot, append=True)
+            new_basis_function, _ = self.ws.gram_schmidt("Z", "X", snapshot, append=True, first_col=self.N_bc)
         else:
-            new_basis_function = self.GS.apply(snapshot, self.basis_functions)
+            new_basis_function = self.GS.apply(snapshot, self.basis_functions[:, self.N_bc:])
         self.basis_functions = np.concatenate([self.basis_functions, new_basis_function[:, None]], axis=1)
         self.N += 1
 
+    def _init_lifting_functions(self):
+        """The lifting functions enter the basis as they are (no orthonormalisation), one at a time so that the
+        incremental operator updates see them like any other new basis function."""
+        liftings = np.asarray(self.truth_problem.dirichlet_bc_liftings, dtype=np.float64)
+        for k in range(self.N_bc):
+            if self.resident:
+                self.ws.append("Z", liftings[:, k])
+            self.basis_functions = np.concatenate([self.basis_functions, liftings[:, k:k + 1]], axis=1)
+            self.N += 1
+            if k + 1 < self.N_bc:   # (the last one is followed by the builds of offline())
+                self.build_reduced_operators()
+                self.build_error_estimation_operators()
+
     # -- RBReduction._offline ------------------------------------------------------------------------------------
     def offline(self):
+        if self.N_bc and self.N == 0:
+            self._init_lifting_functions()
         self.build_reduced_operators()
         self.build_error_estimation_operators()
         (absolute, relative) = self.greedy()
         if self.verbose:
             print("initial maximum absolute error estimator over training set =", absolute)
-        while self.N < self.Nmax and relative >= self.tol:
-            snapshot = self.truth_problem.solve(self.mu)
+        while self.N - self.N_bc < self.Nmax and relative >= self.tol:
+            snapshot = self.postprocess_snapshot(self.truth_problem.solve(self.mu))
             self.update_basis_matrix(snapshot)
             self.build_reduced_operators()
             self.build_error_estimation_operators()

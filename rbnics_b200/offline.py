@@ -316,8 +316,9 @@ class OfflineWorkspace:
         e = self.engine
         e._check(e._lib.rb_off_scale_columns(e._h, self._blk[Z], int(col0), int(scale.shape[0]), L.dptr(scale)))
 
-    def gram_schmidt(self, Z, X, new_function, append=True):
-        """Orthonormalise ``new_function`` against the columns of block Z (X inner product); optionally append it.
+    def gram_schmidt(self, Z, X, new_function, append=True, first_col=0):
+        """Orthonormalise ``new_function`` against the columns ``first_col:`` of block Z (X inner product); optionally
+        append it.  ``first_col = N_bc`` leaves the lifting functions out (rb_reduction.py:125-139).
         With more than one rank the dof rows are partitioned like the Gram products: every projection coefficient is
         one all-reduce (rbnics/backends/basic/gram_schmidt.py:29-33 under PETSc's row partition: one VecDot each), the
         order of the reference's modified Gram-Schmidt is kept."""
@@ -325,13 +326,9 @@ class OfflineWorkspace:
         norm = C.c_double()
         e = self.engine
         self._device_allreduce = install_device_allreduce(e, self.dist)
-        if self._device_allreduce:
-            rb, re = _dist_range(self.Nh, self.dist)
-            e._check(e._lib.rb_off_gram_schmidt_rows(e._h, self._blk[Z], self._csr[X] if X is not None else -1,
-                                                     L.dptr(z), 1 if append else 0, rb, re, C.byref(norm)))
-        else:
-            e._check(e._lib.rb_off_gram_schmidt(e._h, self._blk[Z], self._csr[X] if X is not None else -1, L.dptr(z),
-                                                1 if append else 0, C.byref(norm)))
+        rb, re = _dist_range(self.Nh, self.dist) if self._device_allreduce else (0, self.Nh)
+        e._check(e._lib.rb_off_gram_schmidt_from(e._h, self._blk[Z], self._csr[X] if X is not None else -1, L.dptr(z),
+                                                 1 if append else 0, int(first_col), rb, re, C.byref(norm)))
         return z, norm.value
 
 

@@ -7,7 +7,7 @@ import pytest
 from oracle import greedy_oracle
 from rbnics_b200 import _lib as L
 from rbnics_b200.greedy import ReducedBasisGreedy
-from truth_problems import ThermalBlock
+from truth_problems import ThermalBlock, ThermalBlockNonHomogeneousDirichlet
 
 pytestmark = pytest.mark.gpu
 
@@ -37,6 +37,28 @@ def test_greedy_thermal_block_stress_variant(engine):
     run = ReducedBasisGreedy(engine, tp, train, Nmax=8, tol=1e-4).offline()
     ref = greedy_oracle.greedy_offline(tp, train, Nmax=8, tol=1e-4, vectorised=True)
     _compare(run, ref, 1e-5)
+
+
+@pytest.mark.parametrize("mode", ["host", "full_recomputation", "resident"])
+def test_greedy_with_lifting_functions(engine, mode):
+    """Non-homogeneous Dirichlet data (N_bc = 2 lifting functions): liftings first in the basis, lifting rows in the
+    reduced solve (DirichletBC.py:37-56), snapshots stripped of their Dirichlet part
+    (differential_problem_reduction_method.py:73-108), Gram-Schmidt against basis_functions[N_bc:] only
+    (rb_reduction.py:125-139) -- against the CPU restatement of the same loop."""
+    tp = ThermalBlockNonHomogeneousDirichlet()
+    train = tp.sample_training_set(150, seed=3)
+    ref = greedy_oracle.greedy_offline(tp, train, Nmax=5, tol=1e-6, vectorised=True)
+    run = ReducedBasisGreedy(engine, tp, train, Nmax=5, tol=1e-6, incremental=(mode != "full_recomputation"),
+                             resident=(mode == "resident")).offline()
+    assert run.N_bc == 2 and run.N - run.N_bc == len(run.greedy_selected_indices) - 1 >= 4
+    _compare(run, ref, 1e-6)
+    Z, Zr = run.basis_functions, ref["Z"]
+    assert np.array_equal(Z[:, :2], tp.dirichlet_bc_liftings)
+    assert np.max(np.abs(Z - Zr)) <= 1e-8 * np.max(np.abs(Zr))
+    # the reduced-basis functions vanish on the Dirichlet part and are X-orthonormal among themselves
+    assert np.max(np.abs(Z[tp.dirichlet, 2:])) <= 1e-12
+    gram = Z[:, 2:].T @ (tp.inner_product @ Z[:, 2:])
+    assert np.max(np.abs(gram - np.eye(gram.shape[0]))) <= 1e-10
 
 
 def test_incremental_offline_updates_equal_full_recomputation(engine):

@@ -211,6 +211,75 @@ class ThermalBlockTutorialMesh(_AffineTruth):
         raise ValueError(term)
 
 
+class ThermalBlockNonHomogeneousDirichlet:
+    """The thermal block of tutorial 01 on its own mesh with NON-homogeneous Dirichlet data: u = mu_2 on Gamma_3 (top)
+    and u = mu_3 on Gamma_1 (bottom), flux mu_1 on Gamma_2 (sides) -- the situation of the reference's lifting
+    machinery (tutorials 03/04: one lifting function per theta_bc term, parametrized_reduced_differential_problem.py:
+    283-299).  All vertices are dofs; the operators are assembled WITHOUT boundary conditions (as DOLFIN's affine
+    terms are), the inner product and the Riesz solves carry the homogeneous condition (identity rows/columns on the
+    Dirichlet vertices), `solve` imposes the parametrised values, and the lifting functions are the discrete harmonic
+    extensions of the indicator of each Dirichlet part at theta_a = (1, 1)."""
+    nblocks, nloads = 2, 1
+
+    def __init__(self):
+        m = P1Mesh("thermal_block")
+        self.mesh = m
+        self.Nh = m.nv
+        self.operators_a = [m.stiffness(m.cell_markers == 1).tocsr(), m.stiffness(m.cell_markers == 2).tocsr()]
+        self.operators_f = [m.boundary_load(2)]
+        top = m.vertices_on(3)
+        bottom = np.setdiff1d(m.vertices_on(1), top)
+        self.dirichlet_parts = [top, bottom]
+        self.dirichlet = np.concatenate(self.dirichlet_parts)
+        self.free = np.setdiff1d(np.arange(m.nv), self.dirichlet)
+        K = (self.operators_a[0] + self.operators_a[1]).tolil()
+        K[self.dirichlet, :] = 0.0
+        K[:, self.dirichlet] = 0.0
+        K[self.dirichlet, self.dirichlet] = 1.0
+        self.inner_product = K.tocsr()
+        self._lu = spla.splu(self.inner_product.tocsc())
+        self.mu_range = [(0.1, 10.0), (-1.0, 1.0), (0.5, 2.0), (-0.5, 0.5)]
+        ones = (1.0, 1.0)
+        self.dirichlet_bc_liftings = np.stack(
+            [self._solve_with_values(ones, np.zeros(m.nv), [(part, 1.0)]) for part in self.dirichlet_parts], axis=1)
+
+    def compute_theta(self, term, mus):
+        mus = np.atleast_2d(np.asarray(mus, dtype=np.float64))
+        if term == "a":
+            return np.stack([mus[:, 0], np.ones(mus.shape[0])], axis=1)
+        if term == "f":
+            return mus[:, 1:2].copy()
+        if term == "dirichlet_bc":
+            return mus[:, 2:4].copy()
+        raise ValueError(term)
+
+    def get_stability_factor_lower_bound(self, mus):
+        return self.compute_theta("a", mus).min(axis=1)
+
+    def _solve_with_values(self, theta_a, f, values):
+        A = sum(t * Aq for t, Aq in zip(theta_a, self.operators_a)).tocsr()
+        u = np.zeros(self.Nh)
+        for part, v in values:
+            u[part] = v
+        rhs = (f - A @ u)[self.free]
+        u[self.free] = spla.spsolve(A[self.free][:, self.free].tocsc(), rhs)
+        return u
+
+    def solve(self, mu):
+        tha = self.compute_theta("a", [mu])[0]
+        thf = self.compute_theta("f", [mu])[0]
+        thbc = self.compute_theta("dirichlet_bc", [mu])[0]
+        f = sum(t * fq for t, fq in zip(thf, self.operators_f))
+        return self._solve_with_values(tha, f, list(zip(self.dirichlet_parts, thbc)))
+
+    def riesz_solve(self, rhs):
+        r = np.array(rhs, dtype=np.float64)
+        r[self.dirichlet] = 0.0          # the residual is a functional on the functions that vanish on the Dirichlet part
+        return self._lu.solve(r)
+
+    sample_training_set = ThermalBlock.sample_training_set
+
+
 class ElasticBlockTutorialMesh(_AffineTruth):
     """tutorials/02_elastic_block/tutorial_elastic_block.ipynb:170-262,301-313: vector P1 on data/elastic_block.xml
     (1346 vertices, 2692 dofs), a_q = int_{Omega_q} 2 lambda_2 sym grad u : sym grad v + lambda_1 div u div v
