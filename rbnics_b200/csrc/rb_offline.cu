@@ -17,6 +17,8 @@
 // Z = S V kernel built on 160 small row copies per stage measured 2x SLOWER than the cp.async one below (kept).
 #include <algorithm>
 
+#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no link against libcuda)
+
 #include "rb_common.cuh"
 
 constexpr int TS_TM = 64, TS_TN = 64, TS_KC = 32, TS_THREADS = 128, TS_STAGES = 3;
@@ -196,11 +198,20 @@ __global__ void __launch_bounds__(TS_THREADS) rb_tsmm_kernel(const double* __res
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int T2_KC = 32, T2_NST = 3;
 
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
 template <int TM>
 __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
     rb_tsmm2_kernel(const double* __restrict__ S, int lds, int ns, const double* __restrict__ Y, int ldy, int ns2,
                     long long row_begin, long long row_end, long long rows_per_split, double* __restrict__ ws, int ldw,
-                    int sym) {
+                    int sym, int use_tmap, const __grid_constant__ CUtensorMap tmS,
+                    const __grid_constant__ CUtensorMap tmY) {
   constexpr int WM = TM / 32, P = TM + 4;
   if (sym && blockIdx.y < blockIdx.x) return;  // C == C^T: tiles below the diagonal are mirrored by the reduction
   extern __shared__ __align__(128) unsigned char t2_smem[];
@@ -243,6 +254,17 @@ __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
 
   auto issue = [&](int st, int c) {  // executed by one whole warp: lane l brings row l of the chunk
     const long long r0 = rs + (long long)c * T2_KC;
+    if (use_tmap) {
+      // 2-D tensor maps (box = 32 rows x (TM + 4) columns): ONE TMA instruction per operand and stage.  The box is 4
+      // columns wider than the tile on purpose -- its dense rows in shared memory are then exactly the padded pitch the
+      // fragment loads want; columns past the operand and rows past row_end are filled with zeros by the TMA unit.
+      if (lane == 0) {
+        mbar_arrive_expect_tx(full + st, 2u * (uint32_t)(T2_KC * P * 8));
+        tma_load_2d(As + st * T2_KC * P, &tmS, i0, (int)r0, full + st);
+        tma_load_2d(Bs + st * T2_KC * P, &tmY, j0, (int)r0, full + st);
+      }
+      return;
+    }
     const int nrows = (int)min((long long)T2_KC, re - r0);
     double* as = As + (st * T2_KC + lane) * P;
     double* bs = Bs + (st * T2_KC + lane) * P;
@@ -350,7 +372,8 @@ template <int TM>
 __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
     rb_tsmm2_bal_kernel(const double* __restrict__ S, int lds, int ns, const double* __restrict__ Y, int ldy, int ns2,
                         long long row_begin, long long row_end, long long rows_per_split, double* __restrict__ ws,
-                        int ldw, int contig) {
+                        int ldw, int contig, int use_tmap, const __grid_constant__ CUtensorMap tmS,
+                        const __grid_constant__ CUtensorMap tmY) {
   constexpr int WM = TM / 32, P = TM + 4;
   // contig: both operands start at column 0 of rows no longer than a stage row, so the 32 rows of a chunk are ONE piece
   // of memory per operand -- one bulk copy each instead of 64 per-lane copies (~40 clk apiece on the refilling warp,
@@ -384,6 +407,14 @@ __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
 
   auto issue = [&](int st, int c) {  // executed by one whole warp: lane l brings row l of the chunk
     const long long r0 = rs + (long long)c * T2_KC;
+    if (!contig && use_tmap) {  // column sub-range of a wider block: one 2-D TMA box per operand (see rb_tsmm2_kernel)
+      if (lane == 0) {
+        mbar_arrive_expect_tx(full + st, 2u * (uint32_t)(T2_KC * P * 8));
+        tma_load_2d(As + st * T2_KC * P, &tmS, 0, (int)r0, full + st);
+        tma_load_2d(Bs + st * T2_KC * P, &tmY, 0, (int)r0, full + st);
+      }
+      return;
+    }
     const int nrows = (int)min((long long)T2_KC, re - r0);
     double* as = As + st * T2_KC * P + lane * PA;
     double* bs = Bs + st * T2_KC * P + lane * PB;
@@ -486,7 +517,7 @@ __global__ void __launch_bounds__(FG_THREADS, 1)
     rb_gram_fused_kernel(const double* __restrict__ S, int lds, int ns, const double* __restrict__ S2, int ld2, int ns2,
                          int reuse, const long long* __restrict__ ip, const int* __restrict__ ix,
                          const double* __restrict__ dt, long long row_begin, long long row_end,
-                         double* __restrict__ ws, int ldw) {
+                         double* __restrict__ ws, int ldw, int use_tmap, const __grid_constant__ CUtensorMap tmS) {
   extern __shared__ __align__(128) unsigned char fg_smem[];
   double* As = reinterpret_cast<double*>(fg_smem);               // [NST][KC][P]
   double* Bs = As + FG_NST * FG_KC * FG_P;                       // [NST][KC][P]
@@ -594,7 +625,12 @@ __global__ void __launch_bounds__(FG_THREADS, 1)
     if (n > 0) mbar_wait(empty + st, (uint32_t)(n - 1) & 1u);
     const long long r0 = rs + (long long)c * CS;
     const int nrows = (int)min((long long)FG_KC, re - r0);
-    if (u == 0) {
+    if (u == 0 && use_tmap) {  // the chunk's S rows as ONE 2-D TMA box (16 rows x FG_P columns, zero filled outside)
+      if (lane == 0) {
+        mbar_arrive_expect_tx(fullA + st, (uint32_t)(FG_KC * FG_P * 8));
+        tma_load_2d(As + st * FG_KC * FG_P, &tmS, 0, (int)r0, fullA + st);
+      }
+    } else if (u == 0) {
       double* as = As + (st * FG_KC + lane) * FG_P;
       if (lane < FG_KC && lane >= nrows) {  // rows past the end count as zeros
         for (int c2 = 0; c2 < 64; ++c2) as[c2] = 0.0;
@@ -834,6 +870,31 @@ int csr_is_symmetric(rb_ctx* ctx, long long Nh, const long long* dIp, const int*
   return RB_OK;
 }
 
+// row-major [rows][ld] doubles seen from `ptr` as a 2-D tensor of `cols` x `rows`; box = box_cols x box_rows
+typedef CUresult (*rb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool make_tensor_map(CUtensorMap* map, const double* ptr, long long cols, long long rows, long long ld, int box_cols,
+                     int box_rows = T2_KC) {
+  static const rb_encode_tiled_fn encode = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (rb_encode_tiled_fn)f;
+  }();
+  if (!encode || cols <= 0 || rows <= 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+
 // Fused path of gram_device for ns, ns2 <= 64 with an operator: one kernel + the split reduction.
 int gram_fused_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, int lds, const double* dS2, int ld2,
                       const long long* dIndptr, const int* dIndices, const double* dData, long long rb, long long re,
@@ -852,9 +913,13 @@ int gram_fused_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* 
   RB_CUDA(cudaEventRecord(ctx->ev[4], st));
   // in-chunk rows of S2 are read from the staged A operand only if that holds all the columns S2 needs
   const int reuse = (dS == dS2 && lds == ld2 && ((ns2 + 1) & ~1) <= ((ns + 1) & ~1)) ? 1 : 0;
+  static const int no_tmap = getenv("RB_TSMM_TMAP") && atoi(getenv("RB_TSMM_TMAP")) == 0;
+  CUtensorMap tmS;
+  memset(&tmS, 0, sizeof(tmS));
+  const int use_tmap = !no_tmap && re > 0 && make_tensor_map(&tmS, dS, (ns + 1) & ~1, re, lds, FG_P, FG_KC);
   rb_gram_fused_kernel<<<(unsigned)nsplit, FG_THREADS, smem, st>>>(dS, lds, ns, dS2, ld2, ns2, reuse, dIndptr,
                                                                               dIndices, dData, rb, re,
-                                                                              ws.as<double>(), ldw);
+                                                                              ws.as<double>(), ldw, use_tmap, tmS);
   RB_CUDA(cudaGetLastError());
   rb_split_reduce_kernel<<<(ns * ns2 + 63) / 64, 256, 0, st>>>(ws.as<double>(), ldw, (int)(FG_NKG * nsplit), ns, ns2,
                                                                dC.as<double>(), 0);
@@ -1028,19 +1093,29 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
   dim3 grid(ti, tj, (unsigned)nsplit);
   if (!v2)
     rb_tsmm_kernel<<<grid, TS_THREADS, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw);
-  else if (bal && TM == 64)
-    rb_tsmm2_bal_kernel<64><<<dim3((unsigned)nsplit), 128, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps,
-                                                                      ws.as<double>(), ldw,
-                                                                      (s_at0 && y_at0 && lds <= TM + 4 && ldy <= TM + 4) ? 1 : 0);
-  else if (bal)
-    rb_tsmm2_bal_kernel<128><<<dim3((unsigned)nsplit), 512, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps,
-                                                                       ws.as<double>(), ldw,
-                                                                       (s_at0 && y_at0 && lds <= TM + 4 && ldy <= TM + 4) ? 1 : 0);
-  else if (TM == 64)
-    rb_tsmm2_kernel<64><<<grid, 128, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw, 0);
-  else
-    rb_tsmm2_kernel<128><<<grid, 512, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw,
-                                                  sym ? 1 : 0);
+  else {
+    // operands as 2-D tensor maps (RB_TSMM_TMAP=0: one 1-D bulk copy per row instead, for A/B runs); a single tile
+    // whose operands are whole rows takes one contiguous bulk copy per operand and stage instead
+    static const int no_tmap = getenv("RB_TSMM_TMAP") && atoi(getenv("RB_TSMM_TMAP")) == 0;
+    const int contig = (bal && s_at0 && y_at0 && lds <= TM + 4 && ldy <= TM + 4) ? 1 : 0;
+    CUtensorMap tmS, tmY;
+    memset(&tmS, 0, sizeof(tmS));
+    memset(&tmY, 0, sizeof(tmY));
+    const int use_tmap = !no_tmap && !contig && re > 0 && make_tensor_map(&tmS, dS, (ns + 1) & ~1, re, lds, TM + 4) &&
+                         make_tensor_map(&tmY, dY, (ns2 + 1) & ~1, re, ldy, TM + 4);
+    if (bal && TM == 64)
+      rb_tsmm2_bal_kernel<64><<<dim3((unsigned)nsplit), 128, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps,
+                                                                        ws.as<double>(), ldw, contig, use_tmap, tmS, tmY);
+    else if (bal)
+      rb_tsmm2_bal_kernel<128><<<dim3((unsigned)nsplit), 512, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps,
+                                                                         ws.as<double>(), ldw, contig, use_tmap, tmS, tmY);
+    else if (TM == 64)
+      rb_tsmm2_kernel<64><<<grid, 128, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw, 0,
+                                                   use_tmap, tmS, tmY);
+    else
+      rb_tsmm2_kernel<128><<<grid, 512, smem, st>>>(dS, lds, ns, dY, ldy, ns2, rb, re, rps, ws.as<double>(), ldw,
+                                                    sym ? 1 : 0, use_tmap, tmS, tmY);
+  }
   RB_CUDA(cudaGetLastError());
   rb_split_reduce_kernel<<<(ns * ns2 + 63) / 64, 256, 0, st>>>(ws.as<double>(), ldw, (int)nsplit, ns, ns2,
                                                                dC.as<double>(), sym ? TM : 0);
