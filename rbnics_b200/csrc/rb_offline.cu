@@ -206,6 +206,46 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
       : "memory");
 }
 
+// One 32-row chunk of a warp's MT x NT sub-tiles (8 x 8 each); every (MT, NT) is its own fully unrolled instantiation,
+// chosen once per warp, so there are no predicates inside the DMMA stream.
+template <int MT, int NT>
+__device__ __forceinline__ void t2_chunk(double (&acc)[4][4][2], const double* __restrict__ as,
+                                         const double* __restrict__ bs, int PA, int PB) {
+#pragma unroll
+  for (int ks = 0; ks < T2_KC / 4; ++ks) {
+    double af[MT], bf[NT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) af[mt] = as[4 * ks * PA + mt * 8];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) bf[nt] = bs[4 * ks * PB + nt * 8];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+  }
+}
+
+template <int MT>
+__device__ __forceinline__ void t2_chunk_nt(int nt_w, double (&acc)[4][4][2], const double* as, const double* bs, int PA,
+                                            int PB) {
+  switch (nt_w) {
+    case 1: t2_chunk<MT, 1>(acc, as, bs, PA, PB); break;
+    case 2: t2_chunk<MT, 2>(acc, as, bs, PA, PB); break;
+    case 3: t2_chunk<MT, 3>(acc, as, bs, PA, PB); break;
+    default: t2_chunk<MT, 4>(acc, as, bs, PA, PB); break;
+  }
+}
+
+__device__ __forceinline__ void t2_chunk_dispatch(int mt_w, int nt_w, double (&acc)[4][4][2], const double* as,
+                                                  const double* bs, int PA, int PB) {
+  switch (mt_w) {
+    case 1: t2_chunk_nt<1>(nt_w, acc, as, bs, PA, PB); break;
+    case 2: t2_chunk_nt<2>(nt_w, acc, as, bs, PA, PB); break;
+    case 3: t2_chunk_nt<3>(nt_w, acc, as, bs, PA, PB); break;
+    default: t2_chunk_nt<4>(nt_w, acc, as, bs, PA, PB); break;
+  }
+}
+
 template <int TM>
 __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
     rb_tsmm2_kernel(const double* __restrict__ S, int lds, int ns, const double* __restrict__ Y, int ldy, int ns2,
@@ -220,8 +260,8 @@ __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
   uint64_t* full = reinterpret_cast<uint64_t*>(Bs + T2_NST * T2_KC * P);
   int* cnt = reinterpret_cast<int*>(full + T2_NST);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp / WM, wn = (warp + wm) % WM;  // rotated so that a single active row or column of warps still
-                                                    // spreads over the four SM sub-partitions
+  int wm = warp / WM, wn = (warp + wm) % WM;  // rotated so that a single active row or column of warps still
+                                              // spreads over the four SM sub-partitions
   // rows of the tile grid are TM wide (the last one narrower); its columns deal the ceil(ns2/32) warp columns out
   // evenly (4,3,3,3 rather than 4,4,4,1), which keeps am*an a multiple of 4 in most tiles -- a CTA takes as long as
   // its busiest SM sub-partition.  The symmetric variant needs the same cut in both directions.
@@ -240,7 +280,20 @@ __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
   const long long rs = row_begin + split * rows_per_split;
   const long long re = min(row_end, rs + rows_per_split);
   const int nchunks = (int)((re - rs + T2_KC - 1) / T2_KC);
-  const int nactive = am * an;
+  // a diagonal tile of a symmetric product needs its warp tiles on and above the diagonal only (the reduction mirrors at
+  // warp-tile granularity): they are dealt to warps 0, 1, 2, ... row by row, so that the 10 tiles of a full 4 x 4 tile
+  // load the four SM sub-partitions 3, 3, 2, 2 instead of 4, 3, 2, 1
+  const bool diag = sym && blockIdx.x == blockIdx.y;
+  if (diag) {
+    int k = warp;
+    wm = 0;
+    while (wm < am && k >= an - wm) {
+      k -= an - wm;
+      ++wm;
+    }
+    wn = wm + k;
+  }
+  const int nactive = diag ? an * (an + 1) / 2 : am * an;
   const int wa = min(am * 32, ((ns + 1) & ~1) - i0), wb = min(an * 32, ((ns2 + 1) & ~1) - j0);  // columns copied per row
   if (tid == 0) {
     for (int s = 0; s < T2_NST; ++s) {
@@ -290,24 +343,14 @@ __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
     for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
   const int g = lane >> 2, q4 = lane & 3;
   const int aoff = q4 * P + wm * 32 + g, boff = q4 * P + wn * 32 + g;
+  // 8-column sub-tiles of this warp that hold columns of the product (the last warp row / column of the grid may be
+  // partly outside: 400 columns = 12 full warp columns + one of two sub-tiles)
+  const int mt_w = min(4, (ns - (i0 + wm * 32) + 7) / 8), nt_w = min(4, (ns2 - (j0 + wn * 32) + 7) / 8);
   int st = 0;
   uint32_t phase = 0;
   for (int c = 0; c < nchunks; ++c) {
     mbar_wait(full + st, phase);
-    const double* as = As + st * T2_KC * P + aoff;
-    const double* bs = Bs + st * T2_KC * P + boff;
-#pragma unroll
-    for (int ks = 0; ks < T2_KC / 4; ++ks) {
-      double af[4], bf[4];
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt) af[mt] = as[4 * ks * P + mt * 8];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) bf[nt] = bs[4 * ks * P + nt * 8];
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
-    }
+    t2_chunk_dispatch(mt_w, nt_w, acc, As + st * T2_KC * P + aoff, Bs + st * T2_KC * P + boff, P, P);
     __syncwarp();
     int old = 0;
     if (lane == 0) old = atomicAdd(&cnt[st], 1);
@@ -328,7 +371,8 @@ __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int j = j0 + wn * 32 + nt * 8 + q4 * 2;
-      *reinterpret_cast<double2*>(w + (long long)i * ldw + j) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      if (mt < mt_w && nt < nt_w)
+        *reinterpret_cast<double2*>(w + (long long)i * ldw + j) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
     }
   }
 }
@@ -340,34 +384,6 @@ __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
 // warp column likewise; the k loop of every (rows, columns) count is its own fully unrolled instantiation, chosen
 // once per warp, so there are no predicates inside the DMMA stream.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int MT, int NT>
-__device__ __forceinline__ void t2_chunk(double (&acc)[4][4][2], const double* __restrict__ as,
-                                         const double* __restrict__ bs, int PA, int PB) {
-#pragma unroll
-  for (int ks = 0; ks < T2_KC / 4; ++ks) {
-    double af[MT], bf[NT];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) af[mt] = as[4 * ks * PA + mt * 8];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) bf[nt] = bs[4 * ks * PB + nt * 8];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
-  }
-}
-
-template <int MT>
-__device__ __forceinline__ void t2_chunk_nt(int nt_w, double (&acc)[4][4][2], const double* as, const double* bs, int PA,
-                                            int PB) {
-  switch (nt_w) {
-    case 1: t2_chunk<MT, 1>(acc, as, bs, PA, PB); break;
-    case 2: t2_chunk<MT, 2>(acc, as, bs, PA, PB); break;
-    case 3: t2_chunk<MT, 3>(acc, as, bs, PA, PB); break;
-    default: t2_chunk<MT, 4>(acc, as, bs, PA, PB); break;
-  }
-}
-
 template <int TM>
 __global__ void __launch_bounds__(32 * (TM / 32) * (TM / 32), TM == 64 ? 2 : 1)
     rb_tsmm2_bal_kernel(const double* __restrict__ S, int lds, int ns, const double* __restrict__ Y, int ldy, int ns2,
@@ -742,7 +758,7 @@ __global__ void __launch_bounds__(256) rb_split_reduce_kernel(const double* __re
   double s = 0.0;
   if (e < ns * ns2) {
     int i = e / ns2, j = e % ns2;
-    if (sym_tm && j / sym_tm < i / sym_tm) {  // tile below the diagonal: take the mirrored entry
+    if (sym_tm && j / sym_tm < i / sym_tm) {  // (warp) tile below the diagonal: take the mirrored entry
       const int t = i;
       i = j;
       j = t;
@@ -1118,7 +1134,7 @@ int gram_device(rb_ctx* ctx, long long Nh, int ns, int ns2, const double* dS, in
   }
   RB_CUDA(cudaGetLastError());
   rb_split_reduce_kernel<<<(ns * ns2 + 63) / 64, 256, 0, st>>>(ws.as<double>(), ldw, (int)nsplit, ns, ns2,
-                                                               dC.as<double>(), sym ? TM : 0);
+                                                               dC.as<double>(), sym ? 32 : 0);
   RB_CUDA(cudaGetLastError());
   RB_CUDA(cudaEventRecord(ctx->ev[0], st));
   if (ctx->allreduce) {  // sum of the ranks' partials, in place in HBM
