@@ -52,6 +52,16 @@ def main():
     C1 = offline.gram(eng, S, X)                      # single-GPU product of the same inputs (hook switched off)
     err = dist.max_float(float(np.max(np.abs(Cd - C1)) / np.max(np.abs(C1))))
     report("row-partitioned resident Gram, NCCL all-reduce in HBM", Ns=40, max_rel_diff_vs_single_gpu=err)
+    # several CTA tiles: symmetric tiles mirrored at warp-tile granularity per rank, THEN summed over the ranks
+    S2 = np.ascontiguousarray(rng.standard_normal((Nh, 200)))
+    ws_d.new_block("S200", Nh, 200)
+    ws_d.append("S200", S2)
+    Cd = ws_d.gram("S200", "X")
+    C1 = offline.gram(eng, S2, X)
+    err = dist.max_float(float(np.max(np.abs(Cd - C1)) / np.max(np.abs(C1))))
+    sym = dist.max_float(float(np.max(np.abs(Cd - Cd.T)) / np.max(np.abs(Cd))))
+    report("row-partitioned resident Gram, several tiles (tensor-map TMA, mirrored upper triangle)", Ns=200,
+           max_rel_diff_vs_single_gpu=err, max_rel_asymmetry=sym)
     assert err <= 1e-12, err
 
     # ---- Gram-Schmidt: 24 vectors orthonormalised one after the other, partitioned vs single GPU
