@@ -192,7 +192,12 @@ int rb_gram_schmidt(rb_ctx* ctx, int64_t Nh, int n, const double* Zb, const int6
  * cross PCIe.  Blocks are dof-major: Nh rows, up to `capacity` columns.                                            */
 int rb_off_csr(rb_ctx* ctx, int slot, int64_t Nh, const int64_t* indptr, const int32_t* indices, const double* data);
 int rb_off_block(rb_ctx* ctx, int slot, int64_t Nh, int capacity);             /* (re)create an empty block            */
-int rb_off_append(rb_ctx* ctx, int slot, int n, const double* cols);           /* cols: Nh x n row-major on the host   */
+int rb_off_append(rb_ctx* ctx, int slot, int n, const double* cols);
+/* The same for a rank of the dof-row partitioned offline path: only the rows [row_lo, row_hi) of `cols` (still the
+ * address of the FULL Nh x n array) are transferred -- the rank's own rows plus the halo its operator rows reference
+ * (PETSc keeps exactly those ghost entries for MatMult / VecDot on the local rows of the dolfin backend);
+ * the other rows of the new columns are zero on this device.                                                          */
+int rb_off_append_rows(rb_ctx* ctx, int slot, int n, const double* cols, int64_t row_lo, int64_t row_hi);           /* cols: Nh x n row-major on the host   */
 int rb_off_size(rb_ctx* ctx, int slot, int64_t* Nh, int* ncols);
 int rb_off_read(rb_ctx* ctx, int slot, int c0, int n, double* out);            /* out: Nh x n row-major                */
 /* C (ns x ns2, host) = S[:, s0:s0+ns]^T X S2[:, t0:t0+ns2] over the dof rows [row_begin, row_end); csrX < 0: identity

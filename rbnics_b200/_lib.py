@@ -68,6 +68,7 @@ SIGNATURES = {
     "rb_off_csr": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_int64_p, c_int32_p, c_double_p]),
     "rb_off_block": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int]),
     "rb_off_append": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p]),
+    "rb_off_append_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int64, C.c_int64]),
     "rb_off_size": (C.c_int, [C.c_void_p, C.c_int, c_int64_p, c_int_p]),
     "rb_off_read": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "rb_off_spmm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

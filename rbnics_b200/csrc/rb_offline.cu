@@ -1601,19 +1601,52 @@ __global__ void rb_off_gather_kernel(const double* __restrict__ src, int cap, in
   dst[t] = src[(t / n) * cap + c0 + (t % n)];
 }
 
+// columns c0 .. c0+n of the rows outside [lo, hi) := 0
+__global__ void rb_off_zero_rows_outside_kernel(double* __restrict__ d, int ld, int c0, int n, long long Nh, long long lo,
+                                                long long hi) {
+  const long long outside = Nh - (hi - lo);
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= outside * n) return;
+  long long r = t / n;
+  const int c = (int)(t % n);
+  if (r >= lo) r += hi - lo;
+  d[r * ld + c0 + c] = 0.0;
+}
+
 extern "C" int rb_off_append(rb_ctx* ctx, int slot, int n, const double* cols) {
+  if (!ctx) return RB_ERR_ARG;
+  rb_off_blk_t* b = off_blk(ctx, slot);
+  if (!b) RB_FAIL(RB_ERR_ARG, "rb_off_append: empty slot");
+  return rb_off_append_rows(ctx, slot, n, cols, 0, b->Nh);
+}
+
+// Only the dof rows [row_lo, row_hi) of the new columns cross PCIe (a rank's own rows plus the rows its operator rows
+// reference); the others are zero-filled on the device and must not be read by this rank's products.
+extern "C" int rb_off_append_rows(rb_ctx* ctx, int slot, int n, const double* cols, int64_t row_lo, int64_t row_hi) {
   if (!ctx) return RB_ERR_ARG;
   RB_CUDA(cudaSetDevice(ctx->device));
   rb_off_blk_t* b = off_blk(ctx, slot);
   if (!b || n <= 0 || !cols) RB_FAIL(RB_ERR_ARG, "rb_off_append: bad arguments");
   if (b->n + n > b->cap) RB_FAIL(RB_ERR_ARG, "rb_off_append: block capacity exceeded");
-  DevBuf tmp;
-  RB_CUDA(tmp.alloc((size_t)b->Nh * n * sizeof(double)));
-  RB_CUDA(cudaMemcpyAsync(tmp.p, cols, (size_t)b->Nh * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  rb_off_scatter_kernel<<<(unsigned)((b->Nh * n + 255) / 256), 256, 0, ctx->stream>>>(tmp.as<double>(), n, b->d, b->ld,
-                                                                                     b->n, b->Nh);
-  RB_CUDA(cudaGetLastError());
-  RB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (row_lo < 0 || row_hi > b->Nh || row_lo > row_hi) RB_FAIL(RB_ERR_ARG, "rb_off_append_rows: bad row range");
+  const long long rows = row_hi - row_lo;
+  if (rows > 0) {
+    DevBuf tmp;
+    RB_CUDA(tmp.alloc((size_t)rows * n * sizeof(double)));
+    RB_CUDA(cudaMemcpyAsync(tmp.p, cols + row_lo * n, (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice,
+                            ctx->stream));
+    rb_off_scatter_kernel<<<(unsigned)((rows * n + 255) / 256), 256, 0, ctx->stream>>>(
+        tmp.as<double>(), n, b->d + row_lo * b->ld, b->ld, b->n, rows);
+    RB_CUDA(cudaGetLastError());
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));  // tmp is freed on return
+  }
+  if (rows < b->Nh) {
+    const long long outside = (b->Nh - rows) * n;
+    rb_off_zero_rows_outside_kernel<<<(unsigned)((outside + 255) / 256), 256, 0, ctx->stream>>>(b->d, b->ld, b->n, n, b->Nh,
+                                                                                              row_lo, row_hi);
+    RB_CUDA(cudaGetLastError());
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   b->n += n;
   return RB_OK;
 }

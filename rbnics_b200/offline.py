@@ -214,13 +214,49 @@ class OfflineWorkspace:
 
     SLOTS = 128
 
-    def __init__(self, engine, dist=None):
+    def __init__(self, engine, dist=None, row_local=True):
         self.engine = engine
         self.dist = dist
         self._csr = {}
         self._blk = {}
         self.Nh = None
         self._device_allreduce = install_device_allreduce(engine, dist)
+        # dof-row partition: a rank uploads only the rows its products read -- its own rows and the rows the operator
+        # rows it owns reference (the ghost entries PETSc keeps); HBM keeps the full-size arrays, PCIe carries 1/size
+        self.row_local = bool(row_local) and dist is not None and dist.size > 1
+        self._halo = {}     # operator name -> (lo, hi): rows referenced by the rank's operator rows
+        self._valid = {}    # block name -> (lo, hi): rows of the block that hold data on this rank
+
+    def _operator_halo(self, X):
+        rb, re = _dist_range(X.shape[0], self.dist)
+        if re <= rb:
+            return rb, rb
+        X = X.tocsr()
+        idx = X.indices[X.indptr[rb]:X.indptr[re]]
+        if idx.size == 0:
+            return rb, re
+        return min(rb, int(idx.min())), max(re, int(idx.max()) + 1)
+
+    def upload_range(self):
+        """Rows a new block column must hold on this rank: own rows + halo of every operator registered so far."""
+        lo, hi = _dist_range(self.Nh, self.dist)
+        for (a, b) in self._halo.values():
+            lo, hi = min(lo, a), max(hi, b)
+        return lo, hi
+
+    def _narrow(self, block, rows):
+        a, b = self._valid.get(block, (0, self.Nh))
+        self._valid[block] = (max(a, rows[0]), min(b, rows[1]))
+
+    def _require(self, block, operator=None):
+        """A product over the rank's rows needs them (and, under an operator, its halo) to hold data."""
+        if not self.row_local:
+            return
+        need = self._halo[operator] if operator is not None else _dist_range(self.Nh, self.dist)
+        have = self._valid.get(block, (0, self.Nh))
+        if need[0] < have[0] or need[1] > have[1]:
+            raise RuntimeError(f"OfflineWorkspace: block {block!r} holds rows {have} on this rank but {need} are "
+                               f"needed (register the operators before appending to the block)")
 
     def _slot(self, table, name):
         if name not in table:
@@ -235,6 +271,8 @@ class OfflineWorkspace:
         e._check(e._lib.rb_off_csr(e._h, self._slot(self._csr, name), X.shape[0], ip.ctypes.data_as(L.c_int64_p),
                                    ix.ctypes.data_as(L.c_int32_p), L.dptr(dt)))
         self.Nh = X.shape[0]
+        if self.row_local:
+            self._halo[name] = self._operator_halo(X)
 
     def new_block(self, name, Nh, capacity):
         e = self.engine
@@ -253,20 +291,35 @@ class OfflineWorkspace:
             cols = cols[:, None]
         cols = np.ascontiguousarray(cols)
         e = self.engine
-        e._check(e._lib.rb_off_append(e._h, self._blk[name], cols.shape[1], L.dptr(cols)))
+        if self.row_local:
+            lo, hi = self.upload_range()
+            e._check(e._lib.rb_off_append_rows(e._h, self._blk[name], cols.shape[1], L.dptr(cols), lo, hi))
+            self._narrow(name, (lo, hi))
+        else:
+            e._check(e._lib.rb_off_append(e._h, self._blk[name], cols.shape[1], L.dptr(cols)))
 
     def read(self, name, c0=0, n=None):
+        """Columns of a block on the host, complete on every rank (row-local blocks: the ranks' own rows are summed)."""
         n = self.ncols(name) - c0 if n is None else n
         out = np.empty((self.Nh, n))
         e = self.engine
         e._check(e._lib.rb_off_read(e._h, self._blk[name], int(c0), int(n), L.dptr(out)))
+        if self.row_local and self._valid.get(name, (0, self.Nh)) != (0, self.Nh):
+            self._require(name)
+            rb, re = _dist_range(self.Nh, self.dist)
+            out[:rb] = 0.0
+            out[re:] = 0.0
+            self.dist.allreduce_sum_(out)
         return out
 
     def spmm(self, A, S, cols, Y, col0):
         """Y[:, col0:col0+n] = A * S[:, cols[0]:cols[1]] on resident operands (operator and block names)."""
         e = self.engine
+        self._require(S, A)
         e._check(e._lib.rb_off_spmm(e._h, self._csr[A], self._blk[S], int(cols[0]), int(cols[1] - cols[0]),
                                     self._blk[Y], int(col0)))
+        if self.row_local and self._valid.get(S, (0, self.Nh)) != (0, self.Nh):
+            self._narrow(Y, _dist_range(self.Nh, self.dist))   # Y = A S is right where S held the rows A referenced
 
     def gram(self, S, X=None, S2=None, cols=None, cols2=None):
         """C = S[:, cols]^T X S2[:, cols2]; S, S2 block names, X operator name or None (identity); cols = (begin, end)."""
@@ -276,6 +329,8 @@ class OfflineWorkspace:
         Cm = np.empty((s1 - s0, t1 - t0))
         rb, re = _dist_range(self.Nh, self.dist)
         e = self.engine
+        self._require(S)
+        self._require(S2, X)
         self._device_allreduce = install_device_allreduce(e, self.dist)
         e._check(e._lib.rb_off_gram(e._h, self._blk[S], int(s0), int(s1 - s0), self._csr[X] if X is not None else -1,
                                     self._blk[S2], int(t0), int(t1 - t0), rb, re, L.dptr(Cm)))
@@ -293,6 +348,8 @@ class OfflineWorkspace:
         e = self.engine
         e._check(e._lib.rb_off_lincomb(e._h, self._blk[S], int(s0), int(s1 - s0), L.dptr(V), int(V.shape[1]),
                                        self._blk[Z], int(col0)))
+        if self.row_local:
+            self._narrow(Z, self._valid.get(S, (0, self.Nh)))
 
     def column_norms2(self, Z, X=None, cols=None):
         """[z_j^T X z_j for the columns j of the block]: the diagonal of Z^T X Z without the off-diagonal work."""
@@ -300,6 +357,7 @@ class OfflineWorkspace:
         out = np.empty(c1 - c0)
         rb, re = _dist_range(self.Nh, self.dist)
         e = self.engine
+        self._require(Z, X)
         self._device_allreduce = install_device_allreduce(e, self.dist)
         for a in range(c0, c1, 128):
             n = min(128, c1 - a)
@@ -327,6 +385,10 @@ class OfflineWorkspace:
         e = self.engine
         self._device_allreduce = install_device_allreduce(e, self.dist)
         rb, re = _dist_range(self.Nh, self.dist) if self._device_allreduce else (0, self.Nh)
+        if self._device_allreduce:
+            self._require(Z, X)
+        elif self.row_local and self._valid.get(Z, (0, self.Nh)) != (0, self.Nh):
+            raise RuntimeError("OfflineWorkspace.gram_schmidt: a row-local block needs the device all-reduce (NCCL)")
         e._check(e._lib.rb_off_gram_schmidt_from(e._h, self._blk[Z], self._csr[X] if X is not None else -1, L.dptr(z),
                                                  1 if append else 0, int(first_col), rb, re, C.byref(norm)))
         return z, norm.value

@@ -373,3 +373,62 @@ def test_resident_pod_equals_host_path_and_golden(engine):
     assert np.max(np.abs(n2 - 1.0)) <= 1e-12
     Gs = np.sum(S * S, axis=0)
     assert np.max(np.abs(ws.column_norms2("pod_snapshots", None) - Gs)) <= 1e-12 * np.max(Gs)
+
+
+class _EmulatedRank:
+    """One rank of a dof-row partition without a process group: the test sums the ranks' partials itself."""
+    backend = "emulated"
+
+    def __init__(self, rank, size):
+        self.rank, self.size = rank, size
+
+    def allreduce_sum_(self, a):
+        return a
+
+
+def test_row_local_uploads_of_a_partitioned_workspace():
+    """SURVEY.md 8e row 2 / VERDICT r1 item 7: a rank uploads only its own dof rows plus the rows its operator rows
+    reference (rb_off_append_rows); the partials over the ranks' rows still sum to the full products, Y = A S is right on
+    the own rows, `read` reassembles the block, and a product whose halo was not uploaded fails loudly."""
+    from rbnics_b200.engine import SweepEngine
+    side = 60
+    Nh, Ns, size = side * side, 37, 3
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(side, side))
+    I = sp.identity(side)
+    X = (sp.kron(T, I) + sp.kron(I, T) + 0.5 * sp.identity(Nh)).tocsr()          # 5-point stencil: halo of `side` rows
+    A = (X + sp.diags([0.3], [2], shape=(Nh, Nh))).tocsr()                       # unsymmetric, halo side / side + ...
+    rng = np.random.default_rng(11)
+    S = rng.standard_normal((Nh, Ns))
+    C_full, CI_full, CA_full = S.T @ (X @ S), S.T @ S, S.T @ (A @ S)
+    C_sum, CI_sum, CA_sum, S_sum = 0.0, 0.0, 0.0, 0.0
+    for rank in range(size):
+        eng = SweepEngine(0)
+        try:
+            ws = offline.OfflineWorkspace(eng, dist=_EmulatedRank(rank, size))
+            assert ws.row_local
+            ws.set_operator("X", X)
+            ws.set_operator("A", A)
+            ws.new_block("S", Nh, Ns)
+            ws.new_block("Y", Nh, Ns)
+            ws.append("S", S)
+            rb, re = offline.row_range(Nh, rank, size)
+            lo, hi = ws.upload_range()
+            assert (lo, hi) == (max(0, rb - side), min(Nh, re + side)) and hi - lo < Nh
+            C_sum = C_sum + ws.gram("S", "X")
+            CI_sum = CI_sum + ws.gram("S")
+            ws.spmm("A", "S", (0, Ns), "Y", 0)
+            CA_sum = CA_sum + ws.gram("S", None, "Y")
+            with pytest.raises(RuntimeError, match="are needed"):
+                ws.gram("S", "X", "Y")                       # X Y would need halo rows of Y = A S, which are not there
+            S_sum = S_sum + ws.read("S")                     # own rows, zeros elsewhere (the all-reduce is emulated)
+            wide = (X + sp.diags([1e-3], [3 * side], shape=(Nh, Nh))).tocsr()
+            ws.set_operator("W", wide)
+            if rank < size - 1:
+                with pytest.raises(RuntimeError, match="register the operators before"):
+                    ws.gram("S", "W")
+        finally:
+            eng.close()
+    assert np.max(np.abs(C_sum - C_full)) <= 1e-12 * np.max(np.abs(C_full))
+    assert np.max(np.abs(CI_sum - CI_full)) <= 1e-12 * np.max(np.abs(CI_full))
+    assert np.max(np.abs(CA_sum - CA_full)) <= 1e-12 * np.max(np.abs(CA_full))
+    assert np.array_equal(S_sum, S)
