@@ -905,8 +905,13 @@ bool make_tensor_map(CUtensorMap* map, const double* ptr, long long cols, long l
   const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
+  static const int promo = getenv("RB_TMAP_L2PROMO") ? atoi(getenv("RB_TMAP_L2PROMO")) : 3;
+  const CUtensorMapL2promotion l2 = promo == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                    : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                    : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                 : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), dims, strides, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
