@@ -1399,8 +1399,11 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
     long long chunk = 0;
     size_t asm_smem = 0;
     if (int rc = prepare_assembly(ctx, B, &chunk, &asm_smem)) return rc;
-    for (long long c0 = 0; c0 < B; c0 += chunk) {
-      const long long n = std::min(chunk, B - c0);
+    // while the Theta rows are still arriving (rb_sweep from host buffers) the first chunk is a short one, so that the
+    // solve starts after ~8 MB of the upload instead of after a whole 6 GB chunk's worth of rows
+    const long long first = ctx->up_pieces > 0 ? std::min(chunk, std::max<long long>(1, chunk / 4)) : chunk;
+    for (long long c0 = 0, n = 0; c0 < B; c0 += n) {
+      n = std::min(c0 == 0 ? first : chunk, B - c0);
       if (int rc = wait_uploaded(ctx, c0 + n)) return rc;
       if (int rc = launch_assembly(ctx, c0, n, asm_smem)) return rc;
       ++launches;
