@@ -218,6 +218,9 @@ int rb_off_gram_schmidt(rb_ctx* ctx, int blkZ, int csrX, double* z, int append, 
  * X-norms z_j^T X z_j from the DIAGONAL only (:80-87; csrX < 0: identity; dof rows [row_begin, row_end), summed over the
  * ranks when rb_set_allreduce is set), and the column scaling z_j *= scale[j].                                        */
 int rb_off_lincomb(rb_ctx* ctx, int blkS, int s0, int ns, const double* V, int n, int blkZ, int z0);
+/* accumulate != 0: Z[:, z0:z0+n] += S[:, s0:s0+ns] V on existing columns of Z -- `snapshot - basis_functions *
+ * projected_snapshot_N` of the POD-Greedy orthogonalisation (time_dependent_rb_reduction.py:178-189) on resident data */
+int rb_off_lincomb_add(rb_ctx* ctx, int blkS, int s0, int ns, const double* V, int n, int blkZ, int z0, int accumulate);
 int rb_off_column_norms2(rb_ctx* ctx, int blkZ, int z0, int n, int csrX, int64_t row_begin, int64_t row_end, double* out);
 int rb_off_scale_columns(rb_ctx* ctx, int blkZ, int z0, int n, const double* scale);
 

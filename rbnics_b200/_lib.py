@@ -77,6 +77,8 @@ SIGNATURES = {
     "rb_off_gram_schmidt": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p]),
     "rb_set_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rb_off_lincomb": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int, C.c_int]),
+    "rb_off_lincomb_add": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_int]),
     "rb_off_column_norms2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, c_double_p]),
     "rb_off_scale_columns": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "rb_off_gram_schmidt_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int64, C.c_int64,

@@ -1253,7 +1253,7 @@ template <int NTC>
 __global__ void __launch_bounds__(LC_THREADS, 2) rb_lincomb_kernel(const double* __restrict__ S, int lds, int ns,
                                                                    const double* __restrict__ V, int ldv, int n,
                                                                    double* __restrict__ Z, int ldz, long long Nh,
-                                                                   int col0) {
+                                                                   int col0, int accumulate) {
   extern __shared__ __align__(16) double lc_smem[];
   double(*As)[LC_BM * LC_APITCH] = reinterpret_cast<double(*)[LC_BM * LC_APITCH]>(lc_smem);
   double(*Bs)[LC_KC * LC_BPITCH] = reinterpret_cast<double(*)[LC_KC * LC_BPITCH]>(lc_smem + LC_NST * LC_BM * LC_APITCH);
@@ -1317,8 +1317,8 @@ __global__ void __launch_bounds__(LC_THREADS, 2) rb_lincomb_kernel(const double*
 #pragma unroll
     for (int nt = 0; nt < NTC; ++nt) {
       const int c = n0 + nt * 8 + q4 * 2;
-      if (c < n) Z[r * ldz + c] = acc[mt][nt][0];
-      if (c + 1 < n) Z[r * ldz + c + 1] = acc[mt][nt][1];
+      if (c < n) Z[r * ldz + c] = accumulate ? Z[r * ldz + c] + acc[mt][nt][0] : acc[mt][nt][0];
+      if (c + 1 < n) Z[r * ldz + c + 1] = accumulate ? Z[r * ldz + c + 1] + acc[mt][nt][1] : acc[mt][nt][1];
     }
   }
 }
@@ -1326,28 +1326,29 @@ __global__ void __launch_bounds__(LC_THREADS, 2) rb_lincomb_kernel(const double*
 // ny column tiles of 32 starting at column col0 of V / Z
 template <int NTC>
 static cudaError_t lincomb_launch(cudaStream_t st, size_t smem, const double* dS, int lds, int ns, const double* dV,
-                                  int ldv, int n, double* dZ, int ldz, long long Nh, int ny, int col0) {
+                                  int ldv, int n, double* dZ, int ldz, long long Nh, int ny, int col0,
+                                  int accumulate) {
   cudaError_t e = cudaFuncSetAttribute(rb_lincomb_kernel<NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)((Nh + LC_BM - 1) / LC_BM), ny);
-  rb_lincomb_kernel<NTC><<<grid, LC_THREADS, smem, st>>>(dS, lds, ns, dV, ldv, n, dZ, ldz, Nh, col0);
+  rb_lincomb_kernel<NTC><<<grid, LC_THREADS, smem, st>>>(dS, lds, ns, dV, ldv, n, dZ, ldz, Nh, col0, accumulate);
   return cudaGetLastError();
 }
 
 // Z (pitch ldz) = S (Nh x Ns, pitch lds, 16-byte aligned rows) * V (Ns x n, even pitch ldv); all on the device
 static int lincomb_device(rb_ctx* ctx, long long Nh, int Ns, int n, const double* pS, int lds, const double* pV, int ldv,
-                          double* pZ, int ldz) {
+                          double* pZ, int ldz, int accumulate = 0) {
   cudaStream_t st = ctx->stream;
   const size_t smem = (size_t)LC_NST * (LC_BM * LC_APITCH + LC_KC * LC_BPITCH) * sizeof(double);
   // full 32-column tiles in one launch, the narrower last tile with the 8-column tile count it needs
   const int nfull = n / LC_BN, rem = n % LC_BN;
-  if (nfull > 0) RB_CUDA(lincomb_launch<4>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, nfull, 0));
+  if (nfull > 0) RB_CUDA(lincomb_launch<4>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, nfull, 0, accumulate));
   if (rem > 0) {
     const int c0 = nfull * LC_BN, ntc = (rem + 7) / 8;
-    RB_CUDA(ntc == 1   ? lincomb_launch<1>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, 1, c0)
-            : ntc == 2 ? lincomb_launch<2>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, 1, c0)
-            : ntc == 3 ? lincomb_launch<3>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, 1, c0)
-                       : lincomb_launch<4>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, 1, c0));
+    RB_CUDA(ntc == 1   ? lincomb_launch<1>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, 1, c0, accumulate)
+            : ntc == 2 ? lincomb_launch<2>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, 1, c0, accumulate)
+            : ntc == 3 ? lincomb_launch<3>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, 1, c0, accumulate)
+                       : lincomb_launch<4>(st, smem, pS, lds, Ns, pV, ldv, n, pZ, ldz, Nh, 1, c0, accumulate));
   }
   return RB_OK;
 }
@@ -1918,6 +1919,13 @@ __global__ void rb_scale_cols_kernel(double* __restrict__ Z, int ldz, int n, lon
 }
 
 extern "C" int rb_off_lincomb(rb_ctx* ctx, int blkS, int s0, int ns, const double* V, int n, int blkZ, int z0) {
+  return rb_off_lincomb_add(ctx, blkS, s0, ns, V, n, blkZ, z0, 0);
+}
+
+// accumulate != 0: Z[:, z0:z0+n] += S[:, s0:s0+ns] V on existing columns -- e.g. snapshot -= basis_functions * projection
+// (rbnics/reduction_methods/base/time_dependent_rb_reduction.py:178-189) without the snapshots leaving the device
+extern "C" int rb_off_lincomb_add(rb_ctx* ctx, int blkS, int s0, int ns, const double* V, int n, int blkZ, int z0,
+                                  int accumulate) {
   if (!ctx) return RB_ERR_ARG;
   RB_CUDA(cudaSetDevice(ctx->device));
   rb_off_blk_t* S = off_blk(ctx, blkS);
@@ -1926,13 +1934,15 @@ extern "C" int rb_off_lincomb(rb_ctx* ctx, int blkS, int s0, int ns, const doubl
   if (S->Nh != Z->Nh) RB_FAIL(RB_ERR_ARG, "rb_off_lincomb: inconsistent number of dofs");
   if (s0 < 0 || ns <= 0 || s0 + ns > S->n || n <= 0 || z0 < 0 || z0 + n > Z->cap || S == Z)
     RB_FAIL(RB_ERR_ARG, "rb_off_lincomb: column range outside the block");
+  if (accumulate && z0 + n > Z->n) RB_FAIL(RB_ERR_ARG, "rb_off_lincomb_add: the target columns do not exist yet");
   if (s0 & 1) RB_FAIL(RB_ERR_UNSUPPORTED, "rb_off_lincomb: the first source column must be even (16-byte aligned rows)");
   cudaStream_t st = ctx->stream;
   DevBuf dV;
   int ldv = n;
   if (int rc = upload_cols(ctx, V, ns, n, dV, &ldv)) return rc;
   RB_CUDA(cudaEventRecord(ctx->ev[4], st));
-  if (int rc = lincomb_device(ctx, S->Nh, ns, n, S->d + s0, S->ld, dV.as<double>(), ldv, Z->d + z0, Z->ld)) return rc;
+  if (int rc = lincomb_device(ctx, S->Nh, ns, n, S->d + s0, S->ld, dV.as<double>(), ldv, Z->d + z0, Z->ld, accumulate))
+    return rc;
   RB_CUDA(cudaEventRecord(ctx->ev[5], st));
   RB_CUDA(cudaStreamSynchronize(st));
   float a = 0;

@@ -338,16 +338,17 @@ class OfflineWorkspace:
             self.dist.allreduce_sum_(Cm)
         return Cm
 
-    def lincomb(self, S, V, Z, col0=0, cols=None):
-        """Z[:, col0:col0+n] = S[:, cols] V on resident blocks (V: host, ns x n): S * eigenvectors of the POD."""
+    def lincomb(self, S, V, Z, col0=0, cols=None, accumulate=False):
+        """Z[:, col0:col0+n] = S[:, cols] V on resident blocks (V: host, ns x n): S * eigenvectors of the POD;
+        ``accumulate=True`` adds to existing columns instead (snapshot -= basis_functions * projection)."""
         V = np.ascontiguousarray(V, dtype=np.float64)
         if V.ndim == 1:
             V = np.ascontiguousarray(V[:, None])
         s0, s1 = cols if cols is not None else (0, self.ncols(S))
         assert V.shape[0] == s1 - s0
         e = self.engine
-        e._check(e._lib.rb_off_lincomb(e._h, self._blk[S], int(s0), int(s1 - s0), L.dptr(V), int(V.shape[1]),
-                                       self._blk[Z], int(col0)))
+        e._check(e._lib.rb_off_lincomb_add(e._h, self._blk[S], int(s0), int(s1 - s0), L.dptr(V), int(V.shape[1]),
+                                           self._blk[Z], int(col0), 1 if accumulate else 0))
         if self.row_local:
             self._narrow(Z, self._valid.get(S, (0, self.Nh)))
 

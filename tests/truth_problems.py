@@ -94,6 +94,36 @@ class ThermalBlock:
         return out
 
 
+class ThermalBlockUnsteady(ThermalBlock):
+    """tutorials/06_thermal_block_unsteady as a FEniCS-free stand-in: the thermal block above with a mass term,
+    m(u, v) = int u v (lumped: identity / (n+1)^2), theta_m = (1,), implicit Euler with step dt up to T = K dt from a
+    homogeneous initial condition (tutorial_thermal_block_unsteady.ipynb: dt = 0.05, T = 3)."""
+
+    def __init__(self, n=12, nblocks=2, nloads=1, dt=0.05, K=60, **kw):
+        ThermalBlock.__init__(self, n=n, nblocks=nblocks, nloads=nloads, **kw)
+        self.operators_m = [(sp.identity(self.Nh) / (n + 1) ** 2).tocsr()]
+        self.dt, self.K = float(dt), int(K)
+
+    def compute_theta(self, term, mus):
+        if term == "m":
+            return np.ones((np.atleast_2d(np.asarray(mus)).shape[0], 1))
+        return ThermalBlock.compute_theta(self, term, mus)
+
+    def solve_over_time(self, mu):
+        """(K+1) x Nh: u^0 = 0, (M/dt + A) u^k = M u^{k-1}/dt + f (time_stepping.py:104-112 at truth level)."""
+        thm = self.compute_theta("m", [mu])[0]
+        tha = self.compute_theta("a", [mu])[0]
+        thf = self.compute_theta("f", [mu])[0]
+        M = sum(t * Mq for t, Mq in zip(thm, self.operators_m))
+        A = sum(t * Aq for t, Aq in zip(tha, self.operators_a))
+        f = sum(t * fq for t, fq in zip(thf, self.operators_f))
+        lu = spla.splu((M / self.dt + A).tocsc())
+        U = np.zeros((self.K + 1, self.Nh))
+        for k in range(1, self.K + 1):
+            U[k] = lu.solve(M @ U[k - 1] / self.dt + f)
+        return U
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # The reference's OWN tutorial meshes (tests/golden/mesh_*.npz, extracted from the DOLFIN XML files by
 # tests/golden/make_mesh_fixtures.py) with a plain-numpy P1 assembler: same geometry, sub-domains, boundary markers,
