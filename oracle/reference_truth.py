@@ -9,7 +9,7 @@ real reference are available as golden data (tests/golden/make_reference_golden.
 How: RBniCS dispatches on argument types, and its numpy online backend is a complete backend for "truth" problems
 whose space is the span of a basis of a higher-level space (two-level reduction).  `DenseSpace(Nh)` is an `int` (so
 `Function(V)`, `Matrix`, `Vector` build Nh-sized numpy containers) that is ALSO an `AbstractFunctionsList` (so
-`BasisFunctionsMatrix(V)`, `GramSchmidt(V, X)` ... accept it as the root space R^Nh).  Three helpers the numpy backend
+`BasisFunctionsMatrix(V)`, `GramSchmidt(V, X)` ... accept it as the root space R^Nh).  The helpers the numpy backend
 leaves unimplemented for this use ("TODO" / missing) are filled in by `install_numpy_truth_backend_helpers()`, restated
 from the dolfin wrappers of the same name; they are outside the hot path of this repository.
 """
@@ -87,6 +87,19 @@ def install_numpy_truth_backend_helpers():
 
     bfm.wrapping.basis_functions_matrix_mul_online_vector = basis_functions_matrix_mul_online_vector
 
+    # (3) S * eigenvector of the POD (proper_orthogonal_decomposition_base.py:80), "TODO" in
+    # rbnics/backends/online/numpy/wrapping/functions_list_mul.py:12-13, restated from the dolfin wrapper
+    # (rbnics/backends/dolfin/wrapping/functions_list_mul.py:26-38): sum_i s_i * v_i in list order
+    import rbnics.backends.online.numpy.functions_list as fl
+
+    def functions_list_mul_online_vector(functions_list, online_vector):
+        output = OnlineFunction(functions_list.space)
+        for (i, fun_i) in enumerate(functions_list):
+            output.vector().content[:] += fun_i.vector().content * online_vector[i]
+        return output
+
+    fl.wrapping.functions_list_mul_online_vector = functions_list_mul_online_vector
+
 
 def ram_cache_only():
     """`[problems] cache = RAM`: the default disk cache of truth solutions would write into the working directory."""
@@ -145,6 +158,75 @@ def make_thermal_block_problem(tb, compliant, theta_f_scale=1.0, decorator=None)
     if decorator is not None:
         DenseThermalBlock = decorator(DenseThermalBlock)
     return DenseThermalBlock(DenseSpace(Nh))
+
+
+def make_unsteady_thermal_block_problem(tb):
+    """The reference's ParabolicCoerciveProblem over `tb` (tests/truth_problems.ThermalBlockUnsteady): terms m, a, f of
+    tutorials/06_thermal_block_unsteady/tutorial_thermal_block_unsteady.ipynb with theta_m = (1,), homogeneous initial
+    condition; time stepping and POD-Greedy are the reference's own (numpy online backend at truth level)."""
+    from rbnics import ParabolicCoerciveProblem
+    from rbnics.backends.online import OnlineMatrix, OnlineVector
+    DenseSpace = make_dense_space_class()
+    Nh, nb, nl = tb.Nh, tb.nblocks, tb.nloads
+
+    def M(a):
+        m = OnlineMatrix(Nh, Nh)
+        m.content[:] = a.toarray() if hasattr(a, "toarray") else a
+        return m
+
+    def V(a):
+        v = OnlineVector(Nh)
+        v.content[:] = a
+        return v
+
+    class DenseThermalBlockUnsteady(ParabolicCoerciveProblem):
+        def __init__(self, V, **kwargs):
+            ParabolicCoerciveProblem.__init__(self, V, **kwargs)
+
+        def name(self):
+            return "DenseThermalBlockUnsteady"
+
+        def compute_theta(self, term):
+            mu = self.mu
+            if term == "m":
+                return (1.,)
+            if term == "a":
+                return tuple(mu[:nb - 1]) + (1.,)
+            if term == "f":
+                return tuple(mu[nb - 1:nb - 1 + nl])
+            raise ValueError("Invalid term for compute_theta().")
+
+        def get_stability_factor_lower_bound(self):
+            return min(self.compute_theta("a"))
+
+        def assemble_operator(self, term):
+            if term == "m":
+                return tuple(M(a) for a in tb.operators_m)
+            if term == "a":
+                return tuple(M(a) for a in tb.operators_a)
+            if term == "f":
+                return tuple(V(f) for f in tb.operators_f)
+            if term in ("inner_product", "projection_inner_product"):
+                return (M(tb.inner_product),)
+            raise ValueError("Invalid term for assemble_operator().")
+
+    problem = DenseThermalBlockUnsteady(DenseSpace(Nh))
+    problem.set_mu_range(tb.mu_range)
+    problem.set_time_step_size(tb.dt)
+    problem.set_final_time(tb.dt * tb.K)
+    return problem
+
+
+def run_pod_greedy_offline(problem, ntrain, Nmax, N1, tol, seed):
+    """ReducedBasis(parabolic problem).offline() with set_Nmax(Nmax, POD_Greedy=N1): the reference's POD-Greedy."""
+    from rbnics import ReducedBasis
+    rm = ReducedBasis(problem)
+    rm.set_Nmax(Nmax, POD_Greedy=N1)
+    rm.set_tolerance(tol, POD_Greedy=0.0)
+    np.random.seed(seed)
+    rm.initialize_training_set(ntrain)
+    rp = rm.offline()
+    return rm, rp
 
 
 def run_offline(problem, mu_range, ntrain, Nmax, tol, seed):

@@ -13,6 +13,9 @@ backend of RBniCS is chosen at import time, so every backend gets its own interp
                  the reference's complete offline stage, ReducedBasis(problem).offline(), on a dense FEniCS-free truth
                  problem (oracle/reference_truth.py); plugin = 1 decorates the problem with @B200Sweep(), so that the
                  reference's own greedy loop calls the batched sweep on the GPU
+    python tests/refrun/run_reference.py pod_greedy numpy <case> <out.npz>
+                 the reference's complete POD-Greedy offline stage of a parabolic problem (BASELINE configs[3]):
+                 ReducedBasis(ParabolicCoerciveProblem).offline() with set_Nmax(Nmax, POD_Greedy=N1)
 """
 import json
 import os
@@ -39,6 +42,13 @@ GREEDY_CASES = {
                             ntrain=100, Nmax=4, tol=1e-5, seed=0),
     "tutorial02_mesh": dict(truth="ElasticBlockTutorialMesh", nblocks=9, nloads=3, compliant=False, a_range=(1.0, 100.0),
                             ntrain=200, Nmax=20, tol=1e-12, seed=3),
+}
+
+
+# real-reference POD-Greedy runs: unsteady thermal block of tests/truth_problems.py (tutorial 06 terms)
+POD_GREEDY_CASES = {
+    "unsteady2": dict(n=10, nblocks=2, nloads=1, dt=0.05, K=20, ntrain=60, Nmax=8, N1=2, tol=1e-6, seed=10),
+    "unsteady3": dict(n=12, nblocks=3, nloads=1, dt=0.05, K=30, ntrain=60, Nmax=9, N1=3, tol=1e-6, seed=12),
 }
 
 
@@ -254,6 +264,36 @@ def main():
         print(json.dumps({"N": int(N), "selected_indices": indices,
                           "error_estimators": [float(x) for x in rm.greedy_error_estimators],
                           "uses_plugin": bool(plugin) and hasattr(rm, "_b200_greedy_sweep")}))
+        return
+    if mode == "pod_greedy":
+        case, outfile = sys.argv[3], sys.argv[4]
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from truth_problems import ThermalBlockUnsteady
+        from oracle import reference_truth as T
+        cfg = POD_GREEDY_CASES[case]
+        T.install_numpy_truth_backend_helpers()
+        T.ram_cache_only()
+        tb = ThermalBlockUnsteady(n=cfg["n"], nblocks=cfg["nblocks"], nloads=cfg["nloads"], dt=cfg["dt"], K=cfg["K"])
+        problem = T.make_unsteady_thermal_block_problem(tb)
+        import contextlib
+        import io
+        log = io.StringIO()
+        with contextlib.redirect_stdout(log):
+            rm, rp = T.run_pod_greedy_offline(problem, cfg["ntrain"], cfg["Nmax"], cfg["N1"], cfg["tol"], cfg["seed"])
+        ts = [tuple(float(x) for x in mu) for mu in rm.training_set]
+        selected = [tuple(float(x) for x in mu) for mu in rm.greedy_selected_parameters]
+        indices = [ts.index(mu) for mu in selected]
+        N = rp.N
+        Qm, Qa, Qf = rp.Q["m"], rp.Q["a"], rp.Q["f"]
+        Mr = np.array([np.asarray(rp.operator["m"][q].content)[:N, :N] for q in range(Qm)])
+        A = np.array([np.asarray(rp.operator["a"][q].content)[:N, :N] for q in range(Qa)])
+        F = np.array([np.asarray(rp.operator["f"][q].content)[:N] for q in range(Qf)])
+        Z = np.array([np.asarray(rp.basis_functions[i].vector().content) for i in range(N)]).T
+        np.savez(outfile, case=case, training_set=np.array(ts), selected_indices=np.array(indices),
+                 error_estimators=np.array([float(x) for x in rm.greedy_error_estimators]), N=N, M=Mr, A=A, F=F, Z=Z,
+                 **{k: np.asarray(v) for k, v in cfg.items()})
+        print(json.dumps({"N": int(N), "selected_indices": indices,
+                          "error_estimators": [float(x) for x in rm.greedy_error_estimators]}))
         return
     raise SystemExit("unknown mode " + mode)
 

@@ -87,6 +87,19 @@ def test_reference_reduced_problem_on_the_b200_backend(tmp_path, case, args):
 
 
 @needs_reference
+def test_real_reference_pod_greedy_reproduces_the_committed_fixture(tmp_path):
+    """The complete POD-Greedy offline stage of the real package (parabolic problem), run again, gives the committed
+    selected indices and estimators."""
+    g = np.load(os.path.join(HERE, "golden", "reference_real_pod_greedy_unsteady2.npz"))
+    out = tmp_path / "again.npz"
+    d = _run("pod_greedy", "numpy", "unsteady2", out)
+    h = np.load(out)
+    assert d["selected_indices"] == [int(i) for i in g["selected_indices"]]
+    assert np.array_equal(g["error_estimators"], h["error_estimators"])
+    assert np.array_equal(g["Z"], h["Z"])
+
+
+@needs_reference
 def test_real_reference_greedy_reproduces_the_committed_fixture(tmp_path):
     """ReducedBasis(problem).offline() of the unmodified reference, run again, gives the committed greedy sequence."""
     g = np.load(os.path.join(HERE, "golden", "reference_real_greedy_tutorial01.npz"))

@@ -59,3 +59,64 @@ def test_cuda_sweep_matches_the_real_reference(engine, case):
     assert abs(res["max"] - float(g["max"])) <= RTOL * float(g["max"])
     assert np.max(np.abs(res["delta"] - g["delta"]) / np.abs(g["delta"])) <= RTOL
     assert np.max(np.abs(res["u"] - g["u"])) <= RTOL * np.max(np.abs(g["u"]))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# POD-Greedy (BASELINE configs[3]): the COMPLETE offline stage of the real package on a parabolic problem,
+# ReducedBasis(ParabolicCoerciveProblem).offline() with set_Nmax(Nmax, POD_Greedy=N1)
+# (tests/golden/reference_real_pod_greedy_<case>.npz, tests/refrun/run_reference.py pod_greedy)
+# ----------------------------------------------------------------------------------------------------------------------
+POD_GREEDY_CASES = ("unsteady2", "unsteady3")
+
+
+def _pod_greedy_case(case):
+    import sys
+    sys.path.insert(0, HERE)
+    from truth_problems import ThermalBlockUnsteady
+    g = dict(np.load(os.path.join(HERE, "golden", f"reference_real_pod_greedy_{case}.npz")))
+    tp = ThermalBlockUnsteady(n=int(g["n"]), nblocks=int(g["nblocks"]), nloads=int(g["nloads"]), dt=float(g["dt"]),
+                              K=int(g["K"]))
+    train = [tuple(float(x) for x in mu) for mu in g["training_set"]]
+    assert train == tp.sample_training_set(int(g["ntrain"]), seed=int(g["seed"]))   # the reference's own sampling
+    return g, tp, train
+
+
+def _same_basis_up_to_signs(Z, Zr, X, tol):
+    cross = Zr.T @ (X @ Z)
+    assert np.max(np.abs(np.abs(np.diag(cross)) - 1.0)) <= tol
+    return np.sign(np.diag(cross))
+
+
+@pytest.mark.parametrize("case", POD_GREEDY_CASES)
+def test_pod_greedy_oracle_matches_the_real_reference(case):
+    """The CPU restatement of the POD-Greedy loop selects the real package's parameters, with its estimators and basis."""
+    from oracle import pod_greedy_oracle
+    g, tp, train = _pod_greedy_case(case)
+    ref = pod_greedy_oracle.pod_greedy_offline(tp, train, Nmax=int(g["Nmax"]), tol=float(g["tol"]), N1=int(g["N1"]))
+    assert ref["selected"] == [int(i) for i in g["selected_indices"]]
+    est, est_ref = np.array(ref["estimators"]), g["error_estimators"]
+    assert np.max(np.abs(est - est_ref)) <= 1e-9 * est_ref[0]
+    assert ref["Z"].shape[1] == int(g["N"])
+    _same_basis_up_to_signs(ref["Z"], g["Z"], tp.inner_product, 1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True])
+@pytest.mark.parametrize("case", POD_GREEDY_CASES)
+def test_cuda_pod_greedy_matches_the_real_reference(engine, case, resident):
+    """rbnics_b200.pod_greedy on the GPU against the real package's complete POD-Greedy offline stage: identical
+    sequence of selected parameters, estimator maxima, basis and reduced operators (POD modes up to their signs)."""
+    from rbnics_b200.pod_greedy import PODGreedyReducedBasis
+    g, tp, train = _pod_greedy_case(case)
+    run = PODGreedyReducedBasis(engine, tp, train, Nmax=int(g["Nmax"]), tol=float(g["tol"]), N1=int(g["N1"]),
+                                resident=resident).offline()
+    assert run.greedy_selected_indices == [int(i) for i in g["selected_indices"]]
+    est, est_ref = np.array(run.greedy_error_estimators), g["error_estimators"]
+    assert np.max(np.abs(est - est_ref)) <= 1e-7 * est_ref[0]
+    assert abs(est[0] - est_ref[0]) <= 1e-12 * est_ref[0]
+    assert run.N == int(g["N"])
+    sgn = _same_basis_up_to_signs(run.basis_functions, g["Z"], tp.inner_product, 1e-6)
+    D = np.outer(sgn, sgn)
+    for ours, theirs in ((run.operator_m, g["M"]), (run.operator_a, g["A"])):
+        assert np.max(np.abs(ours * D[None] - theirs)) <= 1e-6 * np.max(np.abs(theirs))
+    assert np.max(np.abs(run.operator_f * sgn[None] - g["F"])) <= 1e-6 * np.max(np.abs(g["F"]))
