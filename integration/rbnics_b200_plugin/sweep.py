@@ -152,10 +152,12 @@ class GreedySweep(object):
         self._prepare_tables(rp)
         fam, terms, theta, beta = self._tables
         N = _online_size(rp)
-        if _total(N) == 0 and fam != "elliptic":
+        if _total(N) == 0 and fam == "stokes":
             raise NotImplementedError("B200Sweep: empty reduced space for " + fam)
         eng = self.engine
         if fam == "parabolic":
+            if _total(N) == 0:
+                return self._max_parabolic_empty(rp, theta, beta)
             return self._max_parabolic(rp, N, theta, beta)
         key2 = tuple(slice(None, N) for _ in range(2))
         op = {t: _stack(rp.operator[t][key2 if rp.terms_order[t] == 2 else key2[0]]) for t in terms}
@@ -204,6 +206,25 @@ class GreedySweep(object):
                     if rp.dirichlet_bc[c] and not rp.dirichlet_bc_are_homogeneous[c]]
             return np.concatenate(cols, axis=1)
         return batched(tp, ts, lambda: tp.compute_theta("dirichlet_bc"))
+
+    def _max_parabolic_empty(self, rp, theta, beta):
+        """First POD-Greedy iteration (N = 0): no reduced solution yet, the residual is f at every t > t0, so
+        eps2 = theta_f^T G_ff theta_f does not depend on time; one sweep of the empty elliptic system gives
+        sqrt(|eps2| / beta), and the Simpson quadrature of a constant (zero at t0) is the sum of its weights."""
+        from rbnics_b200.parabolic import simpson_weights
+        eng = self.engine
+        Qa, Qf = theta["a"].shape[1], theta["f"].shape[1]
+        eng.set_system(np.zeros((Qa, 0, 0)), np.zeros((Qf, 0)))
+        eng.set_estimator([-1], [0], [Qf], Qa, Qf, _stack(rp.error_estimation_operator["f", "f"]))
+        K = int(round((rp.T - rp.t0) / rp.dt))
+        comm = self.rm.training_set.mpi_comm
+        Theta = np.ascontiguousarray(np.concatenate([theta["a"], theta["f"]], axis=1)[comm.rank::comm.size])
+        r = eng.sweep(Theta, np.ascontiguousarray(beta[comm.rank::comm.size]), kind=L.RB_EST_SQRT_OF_EPS2_OVER_BETA,
+                      index_offset=comm.rank, index_stride=comm.size)
+        v, i = r["max"] * float(np.sqrt(simpson_weights(K, rp.dt)[1:].sum())), r["argmax"]
+        if self.dist is not None:
+            v, i = self.dist.maxloc(v, i)
+        return v, i
 
     def _max_parabolic(self, rp, N, theta, beta):
         """POD-Greedy: one implicit-Euler trajectory per parameter, estimator per step, Simpson quadrature."""

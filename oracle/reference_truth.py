@@ -160,7 +160,7 @@ def make_thermal_block_problem(tb, compliant, theta_f_scale=1.0, decorator=None)
     return DenseThermalBlock(DenseSpace(Nh))
 
 
-def make_unsteady_thermal_block_problem(tb):
+def make_unsteady_thermal_block_problem(tb, decorator=None):
     """The reference's ParabolicCoerciveProblem over `tb` (tests/truth_problems.ThermalBlockUnsteady): terms m, a, f of
     tutorials/06_thermal_block_unsteady/tutorial_thermal_block_unsteady.ipynb with theta_m = (1,), homogeneous initial
     condition; time stepping and POD-Greedy are the reference's own (numpy online backend at truth level)."""
@@ -210,6 +210,8 @@ def make_unsteady_thermal_block_problem(tb):
                 return (M(tb.inner_product),)
             raise ValueError("Invalid term for assemble_operator().")
 
+    if decorator is not None:
+        DenseThermalBlockUnsteady = decorator(DenseThermalBlockUnsteady)
     problem = DenseThermalBlockUnsteady(DenseSpace(Nh))
     problem.set_mu_range(tb.mu_range)
     problem.set_time_step_size(tb.dt)

@@ -13,7 +13,7 @@ backend of RBniCS is chosen at import time, so every backend gets its own interp
                  the reference's complete offline stage, ReducedBasis(problem).offline(), on a dense FEniCS-free truth
                  problem (oracle/reference_truth.py); plugin = 1 decorates the problem with @B200Sweep(), so that the
                  reference's own greedy loop calls the batched sweep on the GPU
-    python tests/refrun/run_reference.py pod_greedy numpy <case> <out.npz>
+    python tests/refrun/run_reference.py pod_greedy <backend> <case> <out.npz> [plugin]
                  the reference's complete POD-Greedy offline stage of a parabolic problem (BASELINE configs[3]):
                  ReducedBasis(ParabolicCoerciveProblem).offline() with set_Nmax(Nmax, POD_Greedy=N1)
 """
@@ -267,14 +267,22 @@ def main():
         return
     if mode == "pod_greedy":
         case, outfile = sys.argv[3], sys.argv[4]
+        plugin = len(sys.argv) > 5 and sys.argv[5] == "plugin"
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from truth_problems import ThermalBlockUnsteady
         from oracle import reference_truth as T
         cfg = POD_GREEDY_CASES[case]
         T.install_numpy_truth_backend_helpers()
         T.ram_cache_only()
+        decorator = None
+        if plugin:   # the reference's own POD-Greedy loop with every training_set.max(closure) on the GPU
+            integ = os.path.join(ROOT, "integration")
+            if integ not in sys.path:
+                sys.path.append(integ)
+            from rbnics_b200_plugin.sweep import B200Sweep
+            decorator = B200Sweep()
         tb = ThermalBlockUnsteady(n=cfg["n"], nblocks=cfg["nblocks"], nloads=cfg["nloads"], dt=cfg["dt"], K=cfg["K"])
-        problem = T.make_unsteady_thermal_block_problem(tb)
+        problem = T.make_unsteady_thermal_block_problem(tb, decorator=decorator)
         import contextlib
         import io
         log = io.StringIO()
@@ -293,7 +301,8 @@ def main():
                  error_estimators=np.array([float(x) for x in rm.greedy_error_estimators]), N=N, M=Mr, A=A, F=F, Z=Z,
                  **{k: np.asarray(v) for k, v in cfg.items()})
         print(json.dumps({"N": int(N), "selected_indices": indices,
-                          "error_estimators": [float(x) for x in rm.greedy_error_estimators]}))
+                          "error_estimators": [float(x) for x in rm.greedy_error_estimators],
+                          "uses_plugin": bool(plugin) and hasattr(rm, "_b200_greedy_sweep")}))
         return
     raise SystemExit("unknown mode " + mode)
 

@@ -177,3 +177,20 @@ def test_parabolic_family_of_the_plugin_sweep(tmp_path):
     d = _run("parabolic", "numpy", tmp_path / "par.npz", "plugin")
     assert d["plugin_argmax"] == d["argmax"] == int(np.argmax(g["delta"]))
     assert abs(d["plugin_max"] - d["max"]) <= 1e-10 * d["max"]
+
+
+@pytest.mark.gpu
+@needs_reference
+@pytest.mark.parametrize("case", ["unsteady2", "unsteady3"])
+def test_reference_pod_greedy_loop_with_the_b200_greedy_override(tmp_path, case):
+    """BASELINE configs[3] inside the reference: RBniCS' own POD-Greedy offline loop (truth time stepping, trajectory POD,
+    projections, Riesz products -- all the reference's code) with the closure of TimeDependentRBReduction._greedy replaced
+    by the fused parabolic sweep on the GPU selects the SAME parameters as the unmodified reference."""
+    g = np.load(os.path.join(HERE, "golden", "reference_real_pod_greedy_%s.npz" % case))
+    d = _run("pod_greedy", "numpy", case, tmp_path / "plugin.npz", "plugin")
+    assert d["uses_plugin"] is True
+    assert d["selected_indices"] == g["selected_indices"].tolist()
+    est, ref = np.array(d["error_estimators"]), g["error_estimators"]
+    assert np.all(np.abs(est - ref) <= 1e-7 * ref[0])
+    h = np.load(tmp_path / "plugin.npz")
+    assert np.array_equal(h["Z"][:, :int(g["N1"])], g["Z"][:, :int(g["N1"])])   # same truth code, same first modes
