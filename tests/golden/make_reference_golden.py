@@ -5,6 +5,8 @@ its own classes produce
 
   tests/golden/reference_real_sweep_<case>.npz   EllipticCoercive[Compliant]RBReducedProblem.solve()/estimate_error()
                                                  over a ParameterSpaceSubset, closure of RBReduction._greedy, max()
+  tests/golden/reference_real_pod_galerkin.npz   the COMPLETE POD-Galerkin offline stage, PODGalerkin(problem).offline():
+                                                 POD eigenvalues, retained energy, basis, reduced operators
   tests/golden/reference_real_pod_greedy_<case>.npz  the COMPLETE POD-Greedy offline stage of a parabolic problem
                                                  (ReducedBasis(ParabolicCoerciveProblem).offline(), POD_Greedy = N1)
   tests/golden/reference_real_greedy_<case>.npz  the COMPLETE offline stage, ReducedBasis(problem).offline(), on a dense
@@ -42,6 +44,8 @@ def main():
     for case in ("tutorial01", "stress3", "config2", "tutorial01_mesh", "tutorial02_mesh"):
         out = os.path.join(HERE, "reference_real_greedy_%s.npz" % case)
         subprocess.run([sys.executable, RUN, "greedy", "numpy", case, "0", out], check=True)
+    subprocess.run([sys.executable, RUN, "pod_galerkin", "numpy", os.path.join(HERE, "reference_real_pod_galerkin.npz")],
+                   check=True)
     for case in ("unsteady2", "unsteady3"):
         out = os.path.join(HERE, "reference_real_pod_greedy_%s.npz" % case)
         subprocess.run([sys.executable, RUN, "pod_greedy", "numpy", case, out], check=True)

@@ -13,6 +13,9 @@ backend of RBniCS is chosen at import time, so every backend gets its own interp
                  the reference's complete offline stage, ReducedBasis(problem).offline(), on a dense FEniCS-free truth
                  problem (oracle/reference_truth.py); plugin = 1 decorates the problem with @B200Sweep(), so that the
                  reference's own greedy loop calls the batched sweep on the GPU
+    python tests/refrun/run_reference.py pod_galerkin numpy <out.npz>
+                 the reference's complete POD-Galerkin offline stage, PODGalerkin(problem).offline(), on the dense
+                 thermal block: snapshots, POD eigenvalues / retained energy, basis, reduced operators
     python tests/refrun/run_reference.py pod_greedy <backend> <case> <out.npz> [plugin]
                  the reference's complete POD-Greedy offline stage of a parabolic problem (BASELINE configs[3]):
                  ReducedBasis(ParabolicCoerciveProblem).offline() with set_Nmax(Nmax, POD_Greedy=N1)
@@ -264,6 +267,39 @@ def main():
         print(json.dumps({"N": int(N), "selected_indices": indices,
                           "error_estimators": [float(x) for x in rm.greedy_error_estimators],
                           "uses_plugin": bool(plugin) and hasattr(rm, "_b200_greedy_sweep")}))
+        return
+    if mode == "pod_galerkin":
+        outfile = sys.argv[3]
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from truth_problems import ThermalBlock
+        from oracle import reference_truth as T
+        from rbnics import PODGalerkin
+        cfg = dict(n=12, nblocks=3, nloads=2, ntrain=30, Nmax=10, tol=1e-9, seed=4)
+        T.install_numpy_truth_backend_helpers()
+        T.ram_cache_only()
+        tb = ThermalBlock(n=cfg["n"], nblocks=cfg["nblocks"], nloads=cfg["nloads"])
+        problem = T.make_thermal_block_problem(tb, compliant=False)
+        problem.set_mu_range(tb.mu_range)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            rm = PODGalerkin(problem)
+            rm.set_Nmax(cfg["Nmax"])
+            rm.set_tolerance(cfg["tol"])
+            np.random.seed(cfg["seed"])
+            rm.initialize_training_set(cfg["ntrain"])
+            rp = rm.offline()
+        ts = [tuple(float(x) for x in mu) for mu in rm.training_set]
+        N = rp.N
+        Qa, Qf = rp.Q["a"], rp.Q["f"]
+        A = np.array([np.asarray(rp.operator["a"][q].content)[:N, :N] for q in range(Qa)])
+        F = np.array([np.asarray(rp.operator["f"][q].content)[:N] for q in range(Qf)])
+        Z = np.array([np.asarray(rp.basis_functions[i].vector().content) for i in range(N)]).T
+        np.savez(outfile, training_set=np.array(ts), N=N, A=A, F=F, Z=Z,
+                 eigenvalues=np.array([float(e) for e in rm.POD.eigenvalues]),
+                 retained_energy=np.array([float(e) for e in rm.POD.retained_energy]),
+                 **{k: np.asarray(v) for k, v in cfg.items()})
+        print(json.dumps({"N": int(N), "eigenvalues": [float(e) for e in rm.POD.eigenvalues][:N]}))
         return
     if mode == "pod_greedy":
         case, outfile = sys.argv[3], sys.argv[4]

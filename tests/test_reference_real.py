@@ -120,3 +120,49 @@ def test_cuda_pod_greedy_matches_the_real_reference(engine, case, resident):
     for ours, theirs in ((run.operator_m, g["M"]), (run.operator_a, g["A"])):
         assert np.max(np.abs(ours * D[None] - theirs)) <= 1e-6 * np.max(np.abs(theirs))
     assert np.max(np.abs(run.operator_f * sgn[None] - g["F"])) <= 1e-6 * np.max(np.abs(g["F"]))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# POD-Galerkin: the COMPLETE offline stage of the real package, PODGalerkin(problem).offline()
+# (tests/golden/reference_real_pod_galerkin.npz, tests/refrun/run_reference.py pod_galerkin)
+# ----------------------------------------------------------------------------------------------------------------------
+def _pod_galerkin_case():
+    import sys
+    sys.path.insert(0, HERE)
+    from truth_problems import ThermalBlock
+    g = dict(np.load(os.path.join(HERE, "golden", "reference_real_pod_galerkin.npz")))
+    tp = ThermalBlock(n=int(g["n"]), nblocks=int(g["nblocks"]), nloads=int(g["nloads"]))
+    train = [tuple(float(x) for x in mu) for mu in g["training_set"]]
+    assert train == tp.sample_training_set(int(g["ntrain"]), seed=int(g["seed"]))
+    return g, tp, train
+
+
+def test_pod_oracle_matches_the_real_reference_pod_galerkin():
+    g, tp, train = _pod_galerkin_case()
+    S = np.stack([tp.solve(mu) for mu in train], axis=1)
+    eigs, _, Z, N, retained = O.pod(S, tp.inner_product, int(g["Nmax"]), float(g["tol"]))
+    lam = g["eigenvalues"]
+    assert N == int(g["N"])
+    assert np.max(np.abs(eigs - lam[:N])) <= 1e-10 * lam[0]          # north_star: 1e-10 relative to the largest
+    assert np.max(np.abs(retained - g["retained_energy"])) <= 1e-10
+    _same_basis_up_to_signs(Z, g["Z"], tp.inner_product, 1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [True, False])
+def test_cuda_pod_galerkin_matches_the_real_reference(engine, resident):
+    """rbnics_b200.pod_galerkin.PODGalerkin on the GPU against PODGalerkin(problem).offline() of the real package: POD
+    eigenvalues within 1e-10 of the largest (north_star), the same number of modes and retained energy, the same basis
+    and reduced operators up to the signs of the modes."""
+    from rbnics_b200.pod_galerkin import PODGalerkin
+    g, tp, train = _pod_galerkin_case()
+    run = PODGalerkin(engine, tp, train, Nmax=int(g["Nmax"]), tol=float(g["tol"]), resident=resident).offline()
+    lam = g["eigenvalues"]
+    assert run.N == int(g["N"])
+    assert np.max(np.abs(np.array(run.POD.eigenvalues) - lam)) <= 1e-10 * lam[0]
+    assert np.max(np.abs(np.array(run.POD.retained_energy) - g["retained_energy"])) <= 1e-10
+    sgn = _same_basis_up_to_signs(run.basis_functions, g["Z"], tp.inner_product, 1e-6)
+    assert np.max(np.abs(run.basis_functions * sgn[None] - g["Z"])) <= 1e-6 * np.max(np.abs(g["Z"]))
+    D = np.outer(sgn, sgn)
+    assert np.max(np.abs(run.operator_a * D[None] - g["A"])) <= 1e-6 * np.max(np.abs(g["A"]))
+    assert np.max(np.abs(run.operator_f * sgn[None] - g["F"])) <= 1e-6 * np.max(np.abs(g["F"]))
