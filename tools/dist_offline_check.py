@@ -151,6 +151,20 @@ def main():
            identical_greedy_sequence=bool(same), selected=run_d.greedy_selected_indices,
            max_rel_diff_reduced_operators=dist.max_float(dA))
     assert same and dA <= 1e-9
+    # ---- POD-Greedy (BASELINE configs[3]): training set of the parabolic sweep sharded over the ranks
+    from rbnics_b200.pod_greedy import PODGreedyReducedBasis
+    from truth_problems import ThermalBlockUnsteady
+    tpu = ThermalBlockUnsteady(n=16, nblocks=2, nloads=1, dt=0.05, K=20)
+    trainu = tpu.sample_training_set(2001, seed=5)
+    pg_d = PODGreedyReducedBasis(eng, tpu, trainu, Nmax=6, tol=1e-8, N1=2, dist=dist).offline()
+    pg_1 = PODGreedyReducedBasis(eng1, tpu, trainu, Nmax=6, tol=1e-8, N1=2).offline()
+    same_pg = pg_d.greedy_selected_indices == pg_1.greedy_selected_indices
+    de = float(np.max(np.abs(np.array(pg_d.greedy_error_estimators) - np.array(pg_1.greedy_error_estimators))
+                      / pg_1.greedy_error_estimators[0]))
+    report("POD-Greedy: parabolic sweep sharded over the ranks", ntrain=2001, N=int(pg_d.N),
+           identical_greedy_sequence=bool(same_pg), selected=pg_d.greedy_selected_indices,
+           max_diff_estimators_rel_to_first=dist.max_float(de))
+    assert same_pg and de <= 1e-12
     eng1.close()
     eng.close()
     dist.close()
