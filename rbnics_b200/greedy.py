@@ -25,6 +25,10 @@ functions here (the reference's ``N + N_bc``); ``Nmax`` bounds ``self.N - self.N
 """
 from __future__ import annotations
 
+import time
+from collections import defaultdict
+from contextlib import contextmanager
+
 import numpy as np
 
 from . import _lib as L
@@ -93,6 +97,15 @@ class ReducedBasisGreedy:
         self.greedy_selected_indices = []
         self.greedy_error_estimators = []
         self.mu = None
+        self.timings = defaultdict(float)   # wall seconds per stage, summed over the iterations (bench_greedy.py)
+
+    @contextmanager
+    def _timed(self, stage):
+        t0 = time.perf_counter()
+        try:
+            yield
+        finally:
+            self.timings[stage] += time.perf_counter() - t0
 
     # -- reduced_problem.build_reduced_operators() ---------------------------------------------------------------
     def build_reduced_operators(self):
@@ -221,7 +234,8 @@ class ReducedBasisGreedy:
 
     # -- RBReduction.greedy / _greedy ----------------------------------------------------------------------------
     def _greedy(self):
-        return self._sweep.max(kind=self.kind)
+        with self._timed("gpu_sweep"):
+            return self._sweep.max(kind=self.kind)
 
     def greedy(self):
         (error_estimator_max, error_estimator_argmax) = self._greedy()
@@ -269,10 +283,14 @@ class ReducedBasisGreedy:
         if self.verbose:
             print("initial maximum absolute error estimator over training set =", absolute)
         while self.N - self.N_bc < self.Nmax and relative >= self.tol:
-            snapshot = self.postprocess_snapshot(self.truth_problem.solve(self.mu))
-            self.update_basis_matrix(snapshot)
-            self.build_reduced_operators()
-            self.build_error_estimation_operators()
+            with self._timed("host_truth_solve"):
+                snapshot = self.postprocess_snapshot(self.truth_problem.solve(self.mu))
+            with self._timed("gpu_gram_schmidt"):
+                self.update_basis_matrix(snapshot)
+            with self._timed("gpu_reduced_operators"):
+                self.build_reduced_operators()
+            with self._timed("riesz_solves_and_gram"):
+                self.build_error_estimation_operators()
             (absolute, relative) = self.greedy()
             if self.verbose:
                 print("N =", self.N, "max estimator", absolute, "relative", relative)
