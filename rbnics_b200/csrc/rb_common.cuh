@@ -50,6 +50,18 @@ struct rb_off_blk_t {
   long long gs_row_begin = -1, gs_row_end = -1;  // dof rows the xzt mirror holds (a rank's partition)
 };
 
+// pair-product form of the estimator (rb_est_pair.cu): the quadratic form as one dense GEMM over factor pairs
+struct rb_pair_t {
+  bool ok = false;                  // the record stream below is valid and rb_estimator_pair_kernel serves the sweeps
+  int n_tile = 0, LVP = 0, SK = 0, nstage = 2, vecN = 0;
+  long long issued_macs = 0;        // multiply-adds per parameter issued on the tensor pipe
+  std::vector<int> h_tile_cost;     // records per column tile
+  double* dStream = nullptr;        // records: B fragments of 4 k rows x 64 columns + the factor columns of the 4 rows
+  long long* dTileOff = nullptr;    // [n_tile] first record of a tile (offset in doubles)
+  int* dTileNrec = nullptr;         // [n_tile]
+  int2* dCol = nullptr;             // [n_tile * 64] factor columns (byte offsets in the V' tile) of every column
+};
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Handle
 // ---------------------------------------------------------------------------------------------------------------------
@@ -91,6 +103,7 @@ struct rb_ctx {
   int* dZsrc = nullptr;             // [Kz] index into V
   int* dZscale = nullptr;           // [Kz] theta column or -1
   double* dWeights = nullptr; int weights_cap = 0;  // time-quadrature weights of the parabolic sweep
+  rb_pair_t pair;
 
   // training set
   bool have_train = false;
@@ -152,6 +165,13 @@ struct rb_ctx {
 // LU launcher (rb_lu.cu): factor + solve `count` systems assembled in Ab ([count][EP], column-major NP x NP each).
 // Theta rows start at theta (already offset to the chunk), U at u.
 int rb_launch_lu(rb_ctx* ctx, int64_t count, const double* Ab, const double* theta, const double* thetaBC, double* u);
+
+// pair-product estimator (rb_est_pair.cu); dG = the dense Kz x Kz form on the device
+int rb_pair_setup(rb_ctx* ctx, int nblk, const int* scale_norm, const int* blk_src_off, const int* blk_len,
+                  const int* cls, const int* ubegin, int v_theta_off, int v_theta_len, int solution_len,
+                  const double* dG, int Kz);
+int rb_pair_launch(rb_ctx* ctx, const double* Uvec, int ldu, const double* theta, long long rows, int nsplit);
+void rb_pair_free(rb_ctx* ctx);
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Device helpers

@@ -1,0 +1,536 @@
+// rb_est_pair.cu -- the error estimator as ONE dense GEMM over factor pairs (sm_100a, FP64 DMMA.8x8x4).
+//
+// rbnics/problems/elliptic/elliptic_rb_reduced_problem.py:35-64 (and the compliant / Stokes / parabolic siblings) evaluate
+//   eps2(mu) = z^T G z,   z = concatenation of blocks  s_b(mu) * V[src_b : src_b + len_b],   V = [u | theta | 1].
+// Blocks that scale the same slice of V form a class.  For a pair of classes (c, c') every term of the quadratic form is
+//   (s_b s_b') * M[(b,b'), (n,m)] * (v_n v'_m):   a product of TWO entries of V' = [u | theta | 1 | 0] on the left, a
+// constant, and a product of two entries of V' on the right.  With both symmetries folded into M (b >= b' and, inside a
+// class pair c == c', n >= m) this is, per class pair, a plain dense GEMM
+//   Y[p, col] = sum_k  A[p, k] M[k, col],   A[p, k] = V'[p, i1(k)] V'[p, i2(k)]        (k: block pairs)
+//   eps2[p]  += sum_col Y[p, col] W[p, col], W[p, col] = V'[p, j1(col)] V'[p, j2(col)]  (col: entry pairs)
+// with NO triangular tiles: the multiply-adds issued are the algorithmic ones (Q_a(Q_a+1)/2 * N(N+1)/2 + ...) plus the
+// padding of K to 4 and of the columns to 64 per class pair (0.14 % at N = 100, Q_a = 50, Q_f = 10; the triangular
+// 16-column tiles of rb_estimator_kernel issue 12 % more than the algorithmic count).  The A operand is never stored:
+// every lane builds its fragment entries from the V' tile in shared memory (4 LDS.128 + 4 DMUL per k-step next to 16
+// DMMAs), the two factor columns of the four k rows of a step travel with the B fragments in the same 1-D bulk copy.
+// The orientation (which pair list is K, which one the columns) is chosen per class pair to minimise the padded work.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "rb_common.cuh"
+
+constexpr int PR_REC_DOUBLES = 4 * EST_BN + 4;  // one k4-step of a 64-column tile: B fragments + 4 x (int, int) offsets
+constexpr int PR_MAXSTAGE = 4;
+constexpr int PR_MAX_TILES = 4096;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// packing: dense G (device) -> record stream
+// ---------------------------------------------------------------------------------------------------------------------
+struct PrDesc {  // one padded row or column of a class-pair matrix
+  int x, y;      // kind 0: blocks (b1, b2); kind 1: entries (n, m)
+  int kind;      // -1: padding
+  int voff1, voff2;  // byte offsets of the two factors' columns in the V' tile (column * 32)
+};
+
+struct PrPackArgs {
+  const double* G;
+  double* out;
+  long long total_rec;
+  const int* rec_tile;   // [total_rec]
+  const int* rec_ks;     // [total_rec] k-step inside the tile's stream
+  const int* tile_row0;  // [n_tile] first row descriptor of the tile's class pair
+  const int* tile_same;  // [n_tile] 1: c == c' (folded in the entry pair as well)
+  const PrDesc* row;     // row descriptors of all class pairs
+  const PrDesc* col;     // [n_tile * 64]
+  const int* ubegin;     // [nblk] dense index of a block's first entry
+  int Kz;
+};
+
+__global__ void rb_pair_pack_kernel(PrPackArgs a) {
+  const long long total = a.total_rec * PR_REC_DOUBLES;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long rec = t / PR_REC_DOUBLES;
+    const int r = (int)(t % PR_REC_DOUBLES);
+    const int tile = a.rec_tile[rec], ks = a.rec_ks[rec];
+    if (r >= 4 * EST_BN) {  // factor offsets of k row 4 ks + (r - 256)
+      const PrDesc d = a.row[a.tile_row0[tile] + 4 * ks + (r - 4 * EST_BN)];
+      reinterpret_cast<int2*>(a.out)[t] = make_int2(d.voff1, d.voff2);
+      continue;
+    }
+    // B-fragment order [wn (2)][pair (2)][lane (32)][e (2)] <- M[row 4 ks + lane % 4][column wn*32 + (2 pair + e)*8 + lane / 4]
+    const int wn = r >> 7, pair = (r >> 6) & 1, lane = (r >> 1) & 31, e = r & 1;
+    const PrDesc dr = a.row[a.tile_row0[tile] + 4 * ks + (lane & 3)];
+    const PrDesc dc = a.col[(long long)tile * EST_BN + wn * 32 + (2 * pair + e) * 8 + (lane >> 2)];
+    double v = 0.0;
+    if (dr.kind >= 0 && dc.kind >= 0) {
+      const PrDesc& db = dr.kind == 0 ? dr : dc;  // the block pair
+      const PrDesc& de = dr.kind == 0 ? dc : dr;  // the entry pair
+      const int b1 = db.x, b2 = db.y, n = de.x, m = de.y;
+      const long long Kz = a.Kz;
+      const long long i = a.ubegin[b1] + n, j = a.ubegin[b2] + m;
+      if (!a.tile_same[tile]) {
+        v = a.G[i * Kz + j] + a.G[j * Kz + i];
+      } else if (b1 == b2) {
+        v = a.G[i * Kz + j];
+        if (n != m) v += a.G[j * Kz + i];
+      } else {
+        v = a.G[i * Kz + j] + a.G[j * Kz + i];
+        if (n != m) {
+          const long long i2 = a.ubegin[b1] + m, j2 = a.ubegin[b2] + n;
+          v += a.G[i2 * Kz + j2] + a.G[j2 * Kz + i2];
+        }
+      }
+    }
+    a.out[t] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------------------
+struct PairArgs {
+  const double* stream;
+  const long long* tile_off;  // [n_tile] offset of the tile's first record, in doubles
+  const int* tile_nrec;       // [n_tile]
+  const int2* col;            // [n_tile * 64] byte offsets of the two factors of a column
+  const int* split_begin;     // [nsplit + 1]
+  const double* U;            // [B][ldu]
+  const double* theta;        // [B][QT]
+  double* partial;            // [nsplit][B]
+  long long B;
+  int vecN, ldu, QT, LVP, nsplit, SK, nstage, n_tile;
+};
+
+__host__ __device__ inline size_t pair_smem_bytes(int nstage, int SK, int LVP, int n_tile) {
+  size_t b = (size_t)nstage * SK * PR_REC_DOUBLES * 8;  // record ring
+  b += PR_MAXSTAGE * 8;                                 // full barriers
+  b += PR_MAXSTAGE * 4;                                 // release counters
+  b += (size_t)EST_BM * 8;                              // cross-warp reduction
+  b += (size_t)EST_BM * LVP * 8;                        // V' tile
+  b += (size_t)n_tile * 12;                             // tile offsets + record counts
+  return b + 16;
+}
+
+struct PrFrag {
+  double2 b[2];       // B fragments of the warp's four 8-column tiles
+  double2 p[2], q[2];  // the two factors of the A entries of the lane's four parameter rows
+};
+
+__device__ __forceinline__ void pr_load_b(PrFrag& f, const double* rec, int boff, int q4, int2& idx) {
+  idx = *reinterpret_cast<const int2*>(rec + 4 * EST_BN + q4);
+  f.b[0] = *reinterpret_cast<const double2*>(rec + boff);
+  f.b[1] = *reinterpret_cast<const double2*>(rec + boff + 64);
+}
+__device__ __forceinline__ void pr_load_a(PrFrag& f, const char* vb0, const char* vb1, int2 idx) {
+  f.p[0] = *reinterpret_cast<const double2*>(vb0 + idx.x);
+  f.p[1] = *reinterpret_cast<const double2*>(vb1 + idx.x);
+  f.q[0] = *reinterpret_cast<const double2*>(vb0 + idx.y);
+  f.q[1] = *reinterpret_cast<const double2*>(vb1 + idx.y);
+}
+template <int HALF>
+__device__ __forceinline__ void pr_mma(double (&T)[4][4][2], const double (&av)[4], const PrFrag& f) {
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    dmma884(T[mt][2 * HALF][0], T[mt][2 * HALF][1], av[mt], f.b[HALF].x);
+    dmma884(T[mt][2 * HALF + 1][0], T[mt][2 * HALF + 1][1], av[mt], f.b[HALF].y);
+  }
+}
+
+// CTA = 128 parameters x a contiguous range of column tiles; 8 warps = 4 (m) x 2 (n), warp tile 32 x 32.
+// V' tile layout: [row quad rq = wm*8 + g][column][slot s]  holding parameter row  wm*32 + g + 8 s: the four rows a lane
+// needs of one column are 32 contiguous bytes.  Lanes with odd g read the upper half first (vb0 / vb1), so that the
+// eight lanes of a quarter warp (g in {2j, 2j+1} x 4 consecutive columns) hit eight different 16-byte bank groups;
+// register j of such a lane then belongs to slot j ^ 2.
+__global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_pair_kernel(PairArgs a) {
+  extern __shared__ __align__(128) unsigned char pr_smem_raw[];
+  const int SK = a.SK, NSTAGE = a.nstage, LVP = a.LVP;
+  const int STAGE_DOUBLES = SK * PR_REC_DOUBLES;
+  double* Gs = reinterpret_cast<double*>(pr_smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(Gs + (size_t)NSTAGE * STAGE_DOUBLES);
+  int* s_cnt = reinterpret_cast<int*>(full_bar + PR_MAXSTAGE);
+  double* red = reinterpret_cast<double*>(s_cnt + PR_MAXSTAGE);
+  double* Vs = red + EST_BM;
+  long long* s_tile_off = reinterpret_cast<long long*>(Vs + (size_t)EST_BM * LVP);
+  int* s_tile_nrec = reinterpret_cast<int*>(s_tile_off + a.n_tile);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int split = blockIdx.x % a.nsplit;
+  const long long rb = blockIdx.x / a.nsplit;
+  const long long p0 = rb * EST_BM;
+  const int ct_begin = a.split_begin[split], ct_end = a.split_begin[split + 1];
+
+  // ---- V' tile: [u | theta | 1 | 0]
+  {
+    const int vecN = a.vecN, QT = a.QT;
+    for (int it = tid; it < 32 * LVP; it += EST_THREADS) {
+      const int rq = it / LVP, c = it - rq * LVP;
+      const int rbase = (rq >> 3) * 32 + (rq & 7);
+      double v[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const long long p = p0 + rbase + 8 * s;
+        double x = 0.0;
+        if (p < a.B) {
+          if (c < vecN)
+            x = a.U[p * a.ldu + c];
+          else if (c < vecN + QT)
+            x = a.theta[p * QT + (c - vecN)];
+          else if (c == vecN + QT)
+            x = 1.0;
+        }
+        v[s] = x;
+      }
+      double2* dst = reinterpret_cast<double2*>(Vs + (size_t)it * 4);
+      dst[0] = make_double2(v[0], v[1]);
+      dst[1] = make_double2(v[2], v[3]);
+    }
+  }
+  for (int t = ct_begin + tid; t < ct_end; t += EST_THREADS) {
+    s_tile_off[t] = a.tile_off[t];
+    s_tile_nrec[t] = a.tile_nrec[t];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < PR_MAXSTAGE; ++s) {
+      mbar_init(full_bar + s, 1);
+      s_cnt[s] = 0;
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // ---- record stream: 1-D bulk copies, a stage holds up to SK records of ONE tile.  Every warp advances the producer
+  // cursor identically; the warp that is last to release a slot issues its refill (no producer warp).
+  int pct = ct_begin, prec = 0;
+  auto p_len = [&]() { return min(SK, s_tile_nrec[pct] - prec); };
+  auto issue_stage = [&](int slot) {  // one thread per stage
+    const uint32_t bytes = (uint32_t)p_len() * (PR_REC_DOUBLES * 8u);
+    mbar_arrive_expect_tx(full_bar + slot, bytes);
+    bulk_g2s(Gs + (size_t)slot * STAGE_DOUBLES, a.stream + s_tile_off[pct] + (long long)prec * PR_REC_DOUBLES, bytes,
+             full_bar + slot);
+  };
+  auto advance_cursor = [&]() {
+    prec += p_len();
+    if (prec == s_tile_nrec[pct]) {
+      ++pct;
+      prec = 0;
+    }
+  };
+  for (int s = 0; s < NSTAGE; ++s)
+    if (pct < ct_end) {
+      if (tid == 0) issue_stage(s);
+      advance_cursor();
+    }
+
+  const int wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, q4 = lane & 3, swz = g & 1;
+  const char* vlane = reinterpret_cast<const char*>(Vs) + (size_t)((wm * 8 + g) * LVP) * 32;
+  const char* vb0 = vlane + swz * 16;
+  const char* vb1 = vlane + (1 - swz) * 16;
+  const int boff = wn * 128 + lane * 2;
+  double rowacc[4] = {0.0, 0.0, 0.0, 0.0};
+
+  if (ct_begin < ct_end) {
+    double T[4][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) T[mt][nt][0] = T[mt][nt][1] = 0.0;
+    int ct = ct_begin;
+    int rem = s_tile_nrec[ct];  // records of the tile not yet consumed, counted in whole stages
+    int stage = 0, kin = 0, nin = min(SK, rem);
+    uint32_t phase = 0;
+    const double* cur = Gs;
+    PrFrag f0, f1;
+    int2 idx;
+    mbar_wait(full_bar, 0);
+    pr_load_b(f0, cur, boff, q4, idx);
+    pr_load_a(f0, vb0, vb1, idx);
+
+    // one record: fragments of the NEXT record are requested before the 16 DMMAs of this one are issued
+    auto step = [&](PrFrag& fc, PrFrag& fn) {
+      const bool last_in_stage = (kin + 1 == nin);
+      const bool last_in_tile = last_in_stage && (rem == nin);
+      const bool have_next = !(last_in_tile && ct + 1 == ct_end);
+      const double* nxt = cur + PR_REC_DOUBLES;
+      int ns = stage;
+      uint32_t nph = phase;
+      if (last_in_stage) {
+        ns = stage + 1;
+        if (ns == NSTAGE) {
+          ns = 0;
+          nph ^= 1u;
+        }
+        nxt = Gs + (size_t)ns * STAGE_DOUBLES;
+        if (have_next) mbar_wait(full_bar + ns, nph);
+      }
+      double av[4];
+      av[0] = fc.p[0].x * fc.q[0].x;
+      av[1] = fc.p[0].y * fc.q[0].y;
+      av[2] = fc.p[1].x * fc.q[1].x;
+      av[3] = fc.p[1].y * fc.q[1].y;
+      if (have_next) pr_load_b(fn, nxt, boff, q4, idx);
+      pr_mma<0>(T, av, fc);
+      if (have_next) pr_load_a(fn, vb0, vb1, idx);
+      pr_mma<1>(T, av, fc);
+      cur = nxt;
+      if (!last_in_stage) {
+        ++kin;
+        return;
+      }
+      // stage consumed: release it; the last warp to do so refills the slot
+      __syncwarp();
+      if (lane == 0) {
+        const int old = atomicAdd(&s_cnt[stage], 1);
+        if (old == EST_WARPS - 1) {
+          s_cnt[stage] = 0;
+          if (pct < ct_end) issue_stage(stage);
+        }
+      }
+      if (pct < ct_end) advance_cursor();
+      rem -= nin;
+      if (last_in_tile) {
+        // epilogue of the column tile: rowacc[p] += sum_c Y[p, c] * W[p, c]
+        const int cbase = ct * EST_BN + wn * 32 + q4 * 2;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int2 jj = __ldg(a.col + cbase + nt * 8 + e);
+            const double2 w0 = *reinterpret_cast<const double2*>(vb0 + jj.x);
+            const double2 w1 = *reinterpret_cast<const double2*>(vb1 + jj.x);
+            const double2 x0 = *reinterpret_cast<const double2*>(vb0 + jj.y);
+            const double2 x1 = *reinterpret_cast<const double2*>(vb1 + jj.y);
+            rowacc[0] = fma(T[0][nt][e], w0.x * x0.x, rowacc[0]);
+            rowacc[1] = fma(T[1][nt][e], w0.y * x0.y, rowacc[1]);
+            rowacc[2] = fma(T[2][nt][e], w1.x * x1.x, rowacc[2]);
+            rowacc[3] = fma(T[3][nt][e], w1.y * x1.y, rowacc[3]);
+            T[0][nt][e] = T[1][nt][e] = T[2][nt][e] = T[3][nt][e] = 0.0;
+          }
+        ++ct;
+        if (ct < ct_end) rem = s_tile_nrec[ct];
+      }
+      stage = ns;
+      phase = nph;
+      kin = 0;
+      nin = min(SK, rem);
+    };
+    while (true) {
+      step(f0, f1);
+      if (ct >= ct_end) break;
+      step(f1, f0);
+      if (ct >= ct_end) break;
+    }
+  }
+
+  // reduce over the quad (columns) and over the two n-warps; register j holds slot j ^ (2 swz)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    rowacc[j] += __shfl_xor_sync(0xffffffffu, rowacc[j], 1);
+    rowacc[j] += __shfl_xor_sync(0xffffffffu, rowacc[j], 2);
+  }
+  if (wn == 1 && q4 == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[wm * 32 + g + 8 * (j ^ (2 * swz))] = rowacc[j];
+  }
+  __syncthreads();
+  if (wn == 0 && q4 == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = wm * 32 + g + 8 * (j ^ (2 * swz));
+      const long long p = p0 + r;
+      if (p < a.B) a.partial[(long long)split * a.B + p] = rowacc[j] + red[r];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------------------------
+void rb_pair_free(rb_ctx* ctx) {
+  rb_pair_t& pr = ctx->pair;
+  if (pr.dStream) cudaFree(pr.dStream);
+  if (pr.dTileOff) cudaFree(pr.dTileOff);
+  if (pr.dTileNrec) cudaFree(pr.dTileNrec);
+  if (pr.dCol) cudaFree(pr.dCol);
+  pr.dStream = nullptr;
+  pr.dTileOff = nullptr;
+  pr.dTileNrec = nullptr;
+  pr.dCol = nullptr;
+  pr.ok = false;
+}
+
+static int roundup_i(int x, int m) { return (x + m - 1) / m * m; }
+
+// Builds the record stream from the dense G on the device (dG, Kz x Kz, row-major).  Returns RB_OK also when this form
+// is not used (RB_EST_KERNEL=fold, or a V' tile that does not fit): ctx->pair.ok tells.
+int rb_pair_setup(rb_ctx* ctx, int nblk, const int* scale_norm, const int* blk_src_off, const int* blk_len,
+                  const int* cls, const int* ubegin, int v_theta_off, int v_theta_len, int solution_len,
+                  const double* dG, int Kz) {
+  rb_pair_free(ctx);
+  rb_pair_t& pr = ctx->pair;
+  if (const char* k = getenv("RB_EST_KERNEL"))
+    if (!strcmp(k, "fold")) return RB_OK;
+  const int QT = ctx->Ql + ctx->Qr;
+  const int vecN = solution_len;
+  const int col_one = vecN + QT, col_zero = vecN + QT + 1;
+  const int LVP = vecN + QT + 2;
+  auto vmap = [&](int vidx) {  // index into V = [u | theta[v_off : v_off + v_len] | 1]  ->  column of V'
+    if (vidx < vecN) return vidx;
+    if (vidx < vecN + v_theta_len) return vecN + v_theta_off + (vidx - vecN);
+    return col_one;
+  };
+  auto smap = [&](int sc) { return sc < 0 ? col_one : vecN + sc; };
+
+  std::vector<int> classes;
+  for (int b = 0; b < nblk; ++b)
+    if (cls[b] == b) classes.push_back(b);
+  std::vector<PrDesc> rows, cols;
+  std::vector<int> tile_row0, tile_same, tile_nrec, rec_tile, rec_ks;
+  std::vector<long long> tile_off;
+  const PrDesc pad = {0, 0, -1, col_zero * 32, col_zero * 32};
+  for (size_t ci = 0; ci < classes.size(); ++ci)
+    for (size_t cj = 0; cj <= ci; ++cj) {
+      const int c1 = classes[ci], c2 = classes[cj];
+      const bool same = (ci == cj);
+      std::vector<int> m1, m2;
+      for (int b = 0; b < nblk; ++b) {
+        if (cls[b] == c1) m1.push_back(b);
+        if (cls[b] == c2) m2.push_back(b);
+      }
+      // the two pair lists: block pairs (scales) and entry pairs (slices of V)
+      std::vector<PrDesc> bp, ep;
+      for (size_t i = 0; i < m1.size(); ++i)
+        for (size_t j = 0; j < (same ? i + 1 : m2.size()); ++j) {
+          const int b1 = m1[i], b2 = m2[j];
+          bp.push_back({b1, b2, 0, smap(scale_norm[b1]) * 32, smap(scale_norm[b2]) * 32});
+        }
+      const int L1 = blk_len[c1], L2 = blk_len[c2];
+      for (int n = 0; n < L1; ++n)
+        for (int m = 0; m < (same ? n + 1 : L2); ++m)
+          ep.push_back({n, m, 1, vmap(blk_src_off[c1] + n) * 32, vmap(blk_src_off[c2] + m) * 32});
+      // orientation: K = the list that gives less padded work
+      const long long cost_bp_k = (long long)roundup_i((int)bp.size(), 4) * roundup_i((int)ep.size(), EST_BN);
+      const long long cost_ep_k = (long long)roundup_i((int)ep.size(), 4) * roundup_i((int)bp.size(), EST_BN);
+      const std::vector<PrDesc>& kl = cost_bp_k <= cost_ep_k ? bp : ep;
+      const std::vector<PrDesc>& cl = cost_bp_k <= cost_ep_k ? ep : bp;
+      const int row0 = (int)rows.size();
+      rows.insert(rows.end(), kl.begin(), kl.end());
+      rows.resize(row0 + roundup_i((int)kl.size(), 4), pad);
+      const int nrec = roundup_i((int)kl.size(), 4) / 4;
+      for (size_t j0 = 0; j0 < cl.size(); j0 += EST_BN) {
+        const int tile = (int)tile_row0.size();
+        tile_row0.push_back(row0);
+        tile_same.push_back(same ? 1 : 0);
+        tile_nrec.push_back(nrec);
+        tile_off.push_back((long long)rec_tile.size() * PR_REC_DOUBLES);
+        for (int j = 0; j < EST_BN; ++j) cols.push_back(j0 + j < cl.size() ? cl[j0 + j] : pad);
+        for (int ks = 0; ks < nrec; ++ks) {
+          rec_tile.push_back(tile);
+          rec_ks.push_back(ks);
+        }
+      }
+    }
+  const int n_tile = (int)tile_row0.size();
+  if (n_tile == 0 || n_tile > PR_MAX_TILES) return RB_OK;
+  const int nstage = 2;
+  int max_nrec = 1;
+  for (int t = 0; t < n_tile; ++t) max_nrec = std::max(max_nrec, tile_nrec[t]);
+  int SK = std::min(16, max_nrec);
+  while (SK > 4 && pair_smem_bytes(nstage, SK, LVP, n_tile) > 227 * 1024) --SK;
+  if (pair_smem_bytes(nstage, SK, LVP, n_tile) > 227 * 1024) return RB_OK;  // V' tile too wide: the folded kernel serves
+
+  const long long total_rec = (long long)rec_tile.size();
+  const size_t stream_doubles = (size_t)total_rec * PR_REC_DOUBLES;
+  cudaError_t e = cudaMalloc(&pr.dStream, stream_doubles * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&pr.dTileOff, n_tile * sizeof(long long));
+  if (e == cudaSuccess) e = cudaMalloc(&pr.dTileNrec, n_tile * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&pr.dCol, (size_t)n_tile * EST_BN * sizeof(int2));
+  PrDesc *dRow = nullptr, *dColDesc = nullptr;
+  int* dTab = nullptr;
+  std::vector<int> tab;  // rec_tile | rec_ks | tile_row0 | tile_same | ubegin
+  const size_t o_rec_ks = rec_tile.size(), o_row0 = o_rec_ks + rec_ks.size(), o_same = o_row0 + n_tile,
+               o_ubegin = o_same + n_tile;
+  tab.insert(tab.end(), rec_tile.begin(), rec_tile.end());
+  tab.insert(tab.end(), rec_ks.begin(), rec_ks.end());
+  tab.insert(tab.end(), tile_row0.begin(), tile_row0.end());
+  tab.insert(tab.end(), tile_same.begin(), tile_same.end());
+  tab.insert(tab.end(), ubegin, ubegin + nblk);
+  std::vector<int2> colv(cols.size());
+  for (size_t i = 0; i < cols.size(); ++i) colv[i] = make_int2(cols[i].voff1, cols[i].voff2);
+  if (e == cudaSuccess) e = cudaMalloc(&dRow, rows.size() * sizeof(PrDesc));
+  if (e == cudaSuccess) e = cudaMalloc(&dColDesc, cols.size() * sizeof(PrDesc));
+  if (e == cudaSuccess) e = cudaMalloc(&dTab, tab.size() * sizeof(int));
+  cudaStream_t st = ctx->stream;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dRow, rows.data(), rows.size() * sizeof(PrDesc), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dColDesc, cols.data(), cols.size() * sizeof(PrDesc), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dTab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pr.dTileOff, tile_off.data(), n_tile * sizeof(long long), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pr.dTileNrec, tile_nrec.data(), n_tile * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pr.dCol, colv.data(), colv.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    PrPackArgs pa;
+    pa.G = dG;
+    pa.out = pr.dStream;
+    pa.total_rec = total_rec;
+    pa.rec_tile = dTab;
+    pa.rec_ks = dTab + o_rec_ks;
+    pa.tile_row0 = dTab + o_row0;
+    pa.tile_same = dTab + o_same;
+    pa.row = dRow;
+    pa.col = dColDesc;
+    pa.ubegin = dTab + o_ubegin;
+    pa.Kz = Kz;
+    const long long nthr = total_rec * PR_REC_DOUBLES;
+    const int blocks = (int)std::min<long long>((nthr + 255) / 256, (long long)ctx->sm_count * 16);
+    rb_pair_pack_kernel<<<blocks, 256, 0, st>>>(pa);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the tables are local vectors
+  if (dRow) cudaFree(dRow);
+  if (dColDesc) cudaFree(dColDesc);
+  if (dTab) cudaFree(dTab);
+  const size_t smem = pair_smem_bytes(nstage, SK, LVP, n_tile);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(rb_estimator_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    rb_pair_free(ctx);
+    RB_FAIL(RB_ERR_CUDA, std::string("rb_set_estimator (pair form): ") + cudaGetErrorString(e));
+  }
+  pr.n_tile = n_tile;
+  pr.LVP = LVP;
+  pr.SK = SK;
+  pr.nstage = nstage;
+  pr.vecN = vecN;
+  pr.issued_macs = total_rec * 4 * EST_BN;
+  pr.h_tile_cost = tile_nrec;
+  pr.ok = true;
+  return RB_OK;
+}
+
+int rb_pair_launch(rb_ctx* ctx, const double* Uvec, int ldu, const double* theta, long long rows, int nsplit) {
+  const rb_pair_t& pr = ctx->pair;
+  PairArgs a;
+  a.stream = pr.dStream;
+  a.tile_off = pr.dTileOff;
+  a.tile_nrec = pr.dTileNrec;
+  a.col = pr.dCol;
+  a.split_begin = ctx->dSplitBegin;
+  a.U = Uvec;
+  a.theta = theta;
+  a.partial = ctx->dPart;
+  a.B = rows;
+  a.vecN = pr.vecN;
+  a.ldu = ldu;
+  a.QT = ctx->QT;
+  a.LVP = pr.LVP;
+  a.nsplit = nsplit;
+  a.SK = pr.SK;
+  a.nstage = pr.nstage;
+  a.n_tile = pr.n_tile;
+  const long long nrb = (rows + EST_BM - 1) / EST_BM;
+  const size_t smem = pair_smem_bytes(pr.nstage, pr.SK, pr.LVP, pr.n_tile);
+  rb_estimator_pair_kernel<<<(unsigned)(nrb * nsplit), EST_THREADS, smem, ctx->stream>>>(a);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}

@@ -762,6 +762,7 @@ extern "C" void rb_ctx_destroy(rb_ctx* ctx) {
                   ctx->dLuScratch, ctx->dGdense,  ctx->dZsrc,    ctx->dZscale,  ctx->dWeights};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  rb_pair_free(ctx);
   for (int t = 0; t < RB_OFF_SLOTS; ++t) {
     for (void* p : {(void*)ctx->off_csr[t].ip, (void*)ctx->off_csr[t].ix, (void*)ctx->off_csr[t].dt, (void*)ctx->off_blk[t].d,
                     (void*)ctx->off_blk[t].zt, (void*)ctx->off_blk[t].xzt})
@@ -1112,9 +1113,14 @@ extern "C" int rb_set_estimator_ex(rb_ctx* ctx, int nblk, const int* blk_scale_c
       e = cudaMemcpy(ctx->dGdense, frag.data(), nfrag * sizeof(double), cudaMemcpyHostToDevice);
     }
   }
+  int pair_rc = RB_OK;
+  if (e == cudaSuccess)
+    pair_rc = rb_pair_setup(ctx, nblk, scale_norm.data(), blk_src_off, blk_len, cls.data(), ubegin.data(), v_theta_off,
+                            v_theta_len, solution_len, dG, Kz);
   cudaFree(dG);
   if (dTab) cudaFree(dTab);
   if (e != cudaSuccess) RB_FAIL(RB_ERR_CUDA, std::string("rb_set_estimator: ") + cudaGetErrorString(e));
+  if (pair_rc != RB_OK) return pair_rc;
   RB_CUDA(cudaFuncSetAttribute(rb_estimator_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #ifdef RB_AB_VARIANTS
   RB_CUDA(cudaFuncSetAttribute(rb_estimator_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1215,7 +1221,9 @@ static int choose_nsplit(long long nrb, int sms, int n_ctile) {
 static int prepare_estimator_splits(rb_ctx* ctx, long long rows, int* nsplit_out) {
   cudaStream_t st = ctx->stream;
   const long long nrb = (rows + EST_BM - 1) / EST_BM;
-  const int nsplit = choose_nsplit(nrb, ctx->sm_count, ctx->n_ctile);
+  const int n_ctile = ctx->pair.ok ? ctx->pair.n_tile : ctx->n_ctile;
+  const std::vector<int>& tile_cost = ctx->pair.ok ? ctx->pair.h_tile_cost : ctx->h_tile_cost;
+  const int nsplit = choose_nsplit(nrb, ctx->sm_count, n_ctile);
   if ((long long)nsplit * rows > ctx->part_cap) {
     if (int rc = dev_realloc(ctx, &ctx->dPart, (size_t)nsplit * rows)) return rc;
     ctx->part_cap = (long long)nsplit * rows;
@@ -1224,17 +1232,17 @@ static int prepare_estimator_splits(rb_ctx* ctx, long long rows, int* nsplit_out
     if (int rc = dev_realloc(ctx, &ctx->dSplitBegin, (size_t)nsplit + 1)) return rc;
     ctx->split_cap = nsplit + 1;
   }
-  std::vector<int> sb(nsplit + 1, ctx->n_ctile);
+  std::vector<int> sb(nsplit + 1, n_ctile);
   long long total = 0;
-  for (int ct = 0; ct < ctx->n_ctile; ++ct) total += ctx->h_tile_cost[ct];
+  for (int ct = 0; ct < n_ctile; ++ct) total += tile_cost[ct];
   long long accum = 0;
   int s = 0;
   sb[0] = 0;
-  for (int ct = 0; ct < ctx->n_ctile && s + 1 < nsplit; ++ct) {
-    accum += ctx->h_tile_cost[ct];
+  for (int ct = 0; ct < n_ctile && s + 1 < nsplit; ++ct) {
+    accum += tile_cost[ct];
     if (accum * nsplit >= total * (s + 1)) sb[++s] = ct + 1;
   }
-  for (int t = s + 1; t <= nsplit; ++t) sb[t] = ctx->n_ctile;
+  for (int t = s + 1; t <= nsplit; ++t) sb[t] = n_ctile;
   RB_CUDA(cudaMemcpyAsync(ctx->dSplitBegin, sb.data(), (nsplit + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
   RB_CUDA(cudaStreamSynchronize(st));  // sb is a stack vector
   *nsplit_out = nsplit;
@@ -1244,6 +1252,7 @@ static int prepare_estimator_splits(rb_ctx* ctx, long long rows, int* nsplit_out
 // one estimator launch over `rows` parameters: V = [Uvec (vecN entries, pitch ldu) | theta[v_off : v_off+v_len] | 1]
 static int launch_estimator(rb_ctx* ctx, const double* Uvec, int ldu, int vecN, const double* theta, long long rows,
                             int nsplit) {
+  if (ctx->pair.ok && vecN == ctx->pair.vecN) return rb_pair_launch(ctx, Uvec, ldu, theta, rows, nsplit);
   EstArgs ea;
   ea.Gp = ctx->dGp;
   ea.tile_off = ctx->dTileOff;
@@ -1903,8 +1912,8 @@ extern "C" int rb_result_device_ptrs(rb_ctx* ctx, void** maxloc16, double** delt
 extern "C" int rb_estimator_work(rb_ctx* ctx, int64_t* issued_macs_per_param, int* n_column_tiles) {
   if (!ctx) return RB_ERR_ARG;
   if (!ctx->have_est) RB_FAIL(RB_ERR_STATE, "rb_estimator_work: no estimator set");
-  if (issued_macs_per_param) *issued_macs_per_param = ctx->est_issued_macs;
-  if (n_column_tiles) *n_column_tiles = ctx->n_ctile;
+  if (issued_macs_per_param) *issued_macs_per_param = ctx->pair.ok ? ctx->pair.issued_macs : ctx->est_issued_macs;
+  if (n_column_tiles) *n_column_tiles = ctx->pair.ok ? ctx->pair.n_tile : ctx->n_ctile;
   return RB_OK;
 }
 
