@@ -9,9 +9,9 @@
 //   Y[p, col] = sum_k  A[p, k] M[k, col],   A[p, k] = V'[p, i1(k)] V'[p, i2(k)]        (k: block pairs)
 //   eps2[p]  += sum_col Y[p, col] W[p, col], W[p, col] = V'[p, j1(col)] V'[p, j2(col)]  (col: entry pairs)
 // with NO triangular tiles: the multiply-adds issued are the algorithmic ones (Q_a(Q_a+1)/2 * N(N+1)/2 + ...) plus the
-// padding of K to 4 and of the columns to 64 per class pair (0.14 % at N = 100, Q_a = 50, Q_f = 10; the triangular
+// padding of K to 4 and of the columns to 64 per class pair (0.25 % at N = 100, Q_a = 50, Q_f = 10; the triangular
 // 16-column tiles of rb_estimator_kernel issue 12 % more than the algorithmic count).  The A operand is never stored:
-// every lane builds its fragment entries from the V' tile in shared memory (4 LDS.128 + 4 DMUL per k-step next to 16
+// every lane builds its fragment entries from the V' tile in shared memory (2 LDS.128 + 2 DMUL per k-step next to 16
 // DMMAs), the two factor columns of the four k rows of a step travel with the B fragments in the same 1-D bulk copy.
 // The orientation (which pair list is K, which one the columns) is chosen per class pair to minimise the padded work.
 #include <algorithm>
@@ -30,7 +30,7 @@ constexpr int PR_MAX_TILES = 4096;
 struct PrDesc {  // one padded row or column of a class-pair matrix
   int x, y;      // kind 0: blocks (b1, b2); kind 1: entries (n, m)
   int kind;      // -1: padding
-  int voff1, voff2;  // byte offsets of the two factors' columns in the V' tile (column * 32)
+  int voff1, voff2;  // byte offsets of the two factors' columns in the V' tile (column * 16)
 };
 
 struct PrPackArgs {
@@ -106,42 +106,48 @@ __host__ __device__ inline size_t pair_smem_bytes(int nstage, int SK, int LVP, i
   size_t b = (size_t)nstage * SK * PR_REC_DOUBLES * 8;  // record ring
   b += PR_MAXSTAGE * 8;                                 // full barriers
   b += PR_MAXSTAGE * 4;                                 // release counters
-  b += (size_t)EST_BM * 8;                              // cross-warp reduction
   b += (size_t)EST_BM * LVP * 8;                        // V' tile
   b += (size_t)n_tile * 12;                             // tile offsets + record counts
   return b + 16;
 }
 
 struct PrFrag {
-  double2 b[2];       // B fragments of the warp's four 8-column tiles
-  double2 p[2], q[2];  // the two factors of the A entries of the lane's four parameter rows
+  double2 b[4];  // B fragments of the eight 8-column tiles
+  double av[2];  // A entries of the lane's two parameter rows (products of the two factors)
+};
+struct PrRaw {
+  double2 p, q;  // the two factors of the A entries
 };
 
-__device__ __forceinline__ void pr_load_b(PrFrag& f, const double* rec, int boff, int q4, int2& idx) {
-  idx = *reinterpret_cast<const int2*>(rec + 4 * EST_BN + q4);
-  f.b[0] = *reinterpret_cast<const double2*>(rec + boff);
-  f.b[1] = *reinterpret_cast<const double2*>(rec + boff + 64);
-}
-__device__ __forceinline__ void pr_load_a(PrFrag& f, const char* vb0, const char* vb1, int2 idx) {
-  f.p[0] = *reinterpret_cast<const double2*>(vb0 + idx.x);
-  f.p[1] = *reinterpret_cast<const double2*>(vb1 + idx.x);
-  f.q[0] = *reinterpret_cast<const double2*>(vb0 + idx.y);
-  f.q[1] = *reinterpret_cast<const double2*>(vb1 + idx.y);
-}
-template <int HALF>
-__device__ __forceinline__ void pr_mma(double (&T)[4][4][2], const double (&av)[4], const PrFrag& f) {
+__device__ __forceinline__ void pr_load_b(PrFrag& f, const double* rec, int lane, int2& idx) {
+  idx = *reinterpret_cast<const int2*>(rec + 4 * EST_BN + (lane & 3));
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) {
-    dmma884(T[mt][2 * HALF][0], T[mt][2 * HALF][1], av[mt], f.b[HALF].x);
-    dmma884(T[mt][2 * HALF + 1][0], T[mt][2 * HALF + 1][1], av[mt], f.b[HALF].y);
+  for (int h = 0; h < 4; ++h) f.b[h] = *reinterpret_cast<const double2*>(rec + 64 * h + 2 * lane);
+}
+__device__ __forceinline__ void pr_load_a(PrRaw& r, const char* vlane, int2 idx) {
+  r.p = *reinterpret_cast<const double2*>(vlane + idx.x);
+  r.q = *reinterpret_cast<const double2*>(vlane + idx.y);
+}
+__device__ __forceinline__ void pr_mul_a(PrFrag& f, const PrRaw& r) {
+  f.av[0] = r.p.x * r.q.x;
+  f.av[1] = r.p.y * r.q.y;
+}
+// DMMAs [4 H, 4 H + 4) of the 16 of one record: 8-column tiles 2 H and 2 H + 1, both row tiles
+template <int H>
+__device__ __forceinline__ void pr_mma(double (&T)[2][8][2], const PrFrag& f) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    dmma884(T[mt][2 * H][0], T[mt][2 * H][1], f.av[mt], f.b[H].x);
+    dmma884(T[mt][2 * H + 1][0], T[mt][2 * H + 1][1], f.av[mt], f.b[H].y);
   }
 }
 
-// CTA = 128 parameters x a contiguous range of column tiles; 8 warps = 4 (m) x 2 (n), warp tile 32 x 32.
-// V' tile layout: [row quad rq = wm*8 + g][column][slot s]  holding parameter row  wm*32 + g + 8 s: the four rows a lane
-// needs of one column are 32 contiguous bytes.  Lanes with odd g read the upper half first (vb0 / vb1), so that the
-// eight lanes of a quarter warp (g in {2j, 2j+1} x 4 consecutive columns) hit eight different 16-byte bank groups;
-// register j of such a lane then belongs to slot j ^ 2.
+// CTA = 128 parameters x a contiguous range of column tiles; 8 warps, each one 16 parameters x all 64 columns of the
+// tile (warp tile 16 x 64): one multiplication builds the A entry of 8 DMMAs -- a DMUL between DMMAs costs far more
+// than its two cycles of the FP64 pipe (measured: 1.7 % of the kernel per DMUL and record), so the warp tile is as
+// wide as the column tile.  V' tile layout: [row pair rq = warp*8 + g][column][slot s] holding parameter row
+// warp*16 + g + 8 s; LVP = 4 mod 8, so the eight lanes of a quarter warp (two g x four consecutive columns) read eight
+// different 16-byte bank groups.
 __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_pair_kernel(PairArgs a) {
   extern __shared__ __align__(128) unsigned char pr_smem_raw[];
   const int SK = a.SK, NSTAGE = a.nstage, LVP = a.LVP;
@@ -149,8 +155,7 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_pair_kernel(PairA
   double* Gs = reinterpret_cast<double*>(pr_smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(Gs + (size_t)NSTAGE * STAGE_DOUBLES);
   int* s_cnt = reinterpret_cast<int*>(full_bar + PR_MAXSTAGE);
-  double* red = reinterpret_cast<double*>(s_cnt + PR_MAXSTAGE);
-  double* Vs = red + EST_BM;
+  double* Vs = reinterpret_cast<double*>(s_cnt + PR_MAXSTAGE);
   long long* s_tile_off = reinterpret_cast<long long*>(Vs + (size_t)EST_BM * LVP);
   int* s_tile_nrec = reinterpret_cast<int*>(s_tile_off + a.n_tile);
 
@@ -160,15 +165,16 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_pair_kernel(PairA
   const long long p0 = rb * EST_BM;
   const int ct_begin = a.split_begin[split], ct_end = a.split_begin[split + 1];
 
-  // ---- V' tile: [u | theta | 1 | 0]
+  // ---- V' tile: [u | theta | 1 | 0 ...]
   {
     const int vecN = a.vecN, QT = a.QT;
-    for (int it = tid; it < 32 * LVP; it += EST_THREADS) {
+#pragma unroll 4
+    for (int it = tid; it < 64 * LVP; it += EST_THREADS) {
       const int rq = it / LVP, c = it - rq * LVP;
-      const int rbase = (rq >> 3) * 32 + (rq & 7);
-      double v[4];
+      const int rbase = (rq >> 3) * 16 + (rq & 7);
+      double v[2];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
+      for (int s = 0; s < 2; ++s) {
         const long long p = p0 + rbase + 8 * s;
         double x = 0.0;
         if (p < a.B) {
@@ -181,9 +187,7 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_pair_kernel(PairA
         }
         v[s] = x;
       }
-      double2* dst = reinterpret_cast<double2*>(Vs + (size_t)it * 4);
-      dst[0] = make_double2(v[0], v[1]);
-      dst[1] = make_double2(v[2], v[3]);
+      *reinterpret_cast<double2*>(Vs + (size_t)it * 2) = make_double2(v[0], v[1]);
     }
   }
   for (int t = ct_begin + tid; t < ct_end; t += EST_THREADS) {
@@ -222,62 +226,63 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_pair_kernel(PairA
       advance_cursor();
     }
 
-  const int wm = warp & 3, wn = warp >> 2;
-  const int g = lane >> 2, q4 = lane & 3, swz = g & 1;
-  const char* vlane = reinterpret_cast<const char*>(Vs) + (size_t)((wm * 8 + g) * LVP) * 32;
-  const char* vb0 = vlane + swz * 16;
-  const char* vb1 = vlane + (1 - swz) * 16;
-  const int boff = wn * 128 + lane * 2;
-  double rowacc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int g = lane >> 2, q4 = lane & 3;
+  const char* vlane = reinterpret_cast<const char*>(Vs) + (size_t)((warp * 8 + g) * LVP) * 16;
+  double rowacc[2] = {0.0, 0.0};
 
   if (ct_begin < ct_end) {
-    double T[4][4][2];
+    double T[2][8][2];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) T[mt][nt][0] = T[mt][nt][1] = 0.0;
+      for (int nt = 0; nt < 8; ++nt) T[mt][nt][0] = T[mt][nt][1] = 0.0;
     int ct = ct_begin;
     int rem = s_tile_nrec[ct];  // records of the tile not yet consumed, counted in whole stages
-    int stage = 0, kin = 0, nin = min(SK, rem);
+    int stage = 0, nin = min(SK, rem);
     uint32_t phase = 0;
     const double* cur = Gs;
     PrFrag f0, f1;
+    PrRaw raw;
     int2 idx;
     mbar_wait(full_bar, 0);
-    pr_load_b(f0, cur, boff, q4, idx);
-    pr_load_a(f0, vb0, vb1, idx);
+    pr_load_b(f0, cur, lane, idx);
+    pr_load_a(raw, vlane, idx);
+    pr_mul_a(f0, raw);
 
-    // one record: fragments of the NEXT record are requested before the 16 DMMAs of this one are issued
-    auto step = [&](PrFrag& fc, PrFrag& fn) {
-      const bool last_in_stage = (kin + 1 == nin);
-      const bool last_in_tile = last_in_stage && (rem == nin);
+    // A record inside a stage: the fragments of the NEXT record are requested (and its A entries multiplied) while the
+    // 16 DMMAs of this one issue; nothing but the loop counter sits between two bursts.
+    auto body = [&](const PrFrag& fc, PrFrag& fn, const double* nxt) {
+      pr_load_b(fn, nxt, lane, idx);
+      pr_mma<0>(T, fc);
+      pr_load_a(raw, vlane, idx);
+      pr_mma<1>(T, fc);
+      pr_mma<2>(T, fc);
+      pr_mul_a(fn, raw);
+      pr_mma<3>(T, fc);
+    };
+    // The last record of a stage: the next one (if any) is the first of the next slot.  Returns false at the end of the
+    // CTA's work.
+    auto stage_end = [&](const PrFrag& fc, PrFrag& fn) -> bool {
+      const bool last_in_tile = (rem == nin);
       const bool have_next = !(last_in_tile && ct + 1 == ct_end);
-      const double* nxt = cur + PR_REC_DOUBLES;
-      int ns = stage;
+      int ns = stage + 1;
       uint32_t nph = phase;
-      if (last_in_stage) {
-        ns = stage + 1;
-        if (ns == NSTAGE) {
-          ns = 0;
-          nph ^= 1u;
-        }
-        nxt = Gs + (size_t)ns * STAGE_DOUBLES;
-        if (have_next) mbar_wait(full_bar + ns, nph);
+      if (ns == NSTAGE) {
+        ns = 0;
+        nph ^= 1u;
       }
-      double av[4];
-      av[0] = fc.p[0].x * fc.q[0].x;
-      av[1] = fc.p[0].y * fc.q[0].y;
-      av[2] = fc.p[1].x * fc.q[1].x;
-      av[3] = fc.p[1].y * fc.q[1].y;
-      if (have_next) pr_load_b(fn, nxt, boff, q4, idx);
-      pr_mma<0>(T, av, fc);
-      if (have_next) pr_load_a(fn, vb0, vb1, idx);
-      pr_mma<1>(T, av, fc);
+      const double* nxt = Gs + (size_t)ns * STAGE_DOUBLES;
+      if (have_next) {
+        mbar_wait(full_bar + ns, nph);
+        pr_load_b(fn, nxt, lane, idx);
+      }
+      pr_mma<0>(T, fc);
+      if (have_next) pr_load_a(raw, vlane, idx);
+      pr_mma<1>(T, fc);
+      pr_mma<2>(T, fc);
+      if (have_next) pr_mul_a(fn, raw);
+      pr_mma<3>(T, fc);
       cur = nxt;
-      if (!last_in_stage) {
-        ++kin;
-        return;
-      }
       // stage consumed: release it; the last warp to do so refills the slot
       __syncwarp();
       if (lane == 0) {
@@ -291,55 +296,55 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_pair_kernel(PairA
       rem -= nin;
       if (last_in_tile) {
         // epilogue of the column tile: rowacc[p] += sum_c Y[p, c] * W[p, c]
-        const int cbase = ct * EST_BN + wn * 32 + q4 * 2;
+        const int cbase = ct * EST_BN + q4 * 2;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int2 jj = __ldg(a.col + cbase + nt * 8 + e);
-            const double2 w0 = *reinterpret_cast<const double2*>(vb0 + jj.x);
-            const double2 w1 = *reinterpret_cast<const double2*>(vb1 + jj.x);
-            const double2 x0 = *reinterpret_cast<const double2*>(vb0 + jj.y);
-            const double2 x1 = *reinterpret_cast<const double2*>(vb1 + jj.y);
-            rowacc[0] = fma(T[0][nt][e], w0.x * x0.x, rowacc[0]);
-            rowacc[1] = fma(T[1][nt][e], w0.y * x0.y, rowacc[1]);
-            rowacc[2] = fma(T[2][nt][e], w1.x * x1.x, rowacc[2]);
-            rowacc[3] = fma(T[3][nt][e], w1.y * x1.y, rowacc[3]);
-            T[0][nt][e] = T[1][nt][e] = T[2][nt][e] = T[3][nt][e] = 0.0;
+            const double2 w = *reinterpret_cast<const double2*>(vlane + jj.x);
+            const double2 x = *reinterpret_cast<const double2*>(vlane + jj.y);
+            rowacc[0] = fma(T[0][nt][e], w.x * x.x, rowacc[0]);
+            rowacc[1] = fma(T[1][nt][e], w.y * x.y, rowacc[1]);
+            T[0][nt][e] = T[1][nt][e] = 0.0;
           }
         ++ct;
         if (ct < ct_end) rem = s_tile_nrec[ct];
       }
       stage = ns;
       phase = nph;
-      kin = 0;
       nin = min(SK, rem);
+      return have_next;
     };
+    // per stage: f0 holds the first record
     while (true) {
-      step(f0, f1);
-      if (ct >= ct_end) break;
-      step(f1, f0);
-      if (ct >= ct_end) break;
+      int i = nin - 1;  // records whose successor lies in the same stage
+      for (; i >= 2; i -= 2) {
+        body(f0, f1, cur + PR_REC_DOUBLES);
+        body(f1, f0, cur + 2 * PR_REC_DOUBLES);
+        cur += 2 * PR_REC_DOUBLES;
+      }
+      if (i == 1) {
+        body(f0, f1, cur + PR_REC_DOUBLES);
+        if (!stage_end(f1, f0)) break;
+      } else {
+        if (!stage_end(f0, f1)) break;
+        f0 = f1;
+      }
     }
   }
 
-  // reduce over the quad (columns) and over the two n-warps; register j holds slot j ^ (2 swz)
+  // every warp owns its 16 parameters: reduce over the quad (columns) and store
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 2; ++j) {
     rowacc[j] += __shfl_xor_sync(0xffffffffu, rowacc[j], 1);
     rowacc[j] += __shfl_xor_sync(0xffffffffu, rowacc[j], 2);
   }
-  if (wn == 1 && q4 == 0) {
+  if (q4 == 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[wm * 32 + g + 8 * (j ^ (2 * swz))] = rowacc[j];
-  }
-  __syncthreads();
-  if (wn == 0 && q4 == 0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = wm * 32 + g + 8 * (j ^ (2 * swz));
-      const long long p = p0 + r;
-      if (p < a.B) a.partial[(long long)split * a.B + p] = rowacc[j] + red[r];
+    for (int j = 0; j < 2; ++j) {
+      const long long p = p0 + warp * 16 + g + 8 * j;
+      if (p < a.B) a.partial[(long long)split * a.B + p] = rowacc[j];
     }
   }
 }
@@ -374,7 +379,8 @@ int rb_pair_setup(rb_ctx* ctx, int nblk, const int* scale_norm, const int* blk_s
   const int QT = ctx->Ql + ctx->Qr;
   const int vecN = solution_len;
   const int col_one = vecN + QT, col_zero = vecN + QT + 1;
-  const int LVP = vecN + QT + 2;
+  int LVP = vecN + QT + 2;  // pitch of the V' tile in columns: 4 mod 8 (bank groups, see the kernel)
+  while (LVP % 8 != 4) ++LVP;
   auto vmap = [&](int vidx) {  // index into V = [u | theta[v_off : v_off + v_len] | 1]  ->  column of V'
     if (vidx < vecN) return vidx;
     if (vidx < vecN + v_theta_len) return vecN + v_theta_off + (vidx - vecN);
@@ -388,7 +394,7 @@ int rb_pair_setup(rb_ctx* ctx, int nblk, const int* scale_norm, const int* blk_s
   std::vector<PrDesc> rows, cols;
   std::vector<int> tile_row0, tile_same, tile_nrec, rec_tile, rec_ks;
   std::vector<long long> tile_off;
-  const PrDesc pad = {0, 0, -1, col_zero * 32, col_zero * 32};
+  const PrDesc pad = {0, 0, -1, col_zero * 16, col_zero * 16};
   for (size_t ci = 0; ci < classes.size(); ++ci)
     for (size_t cj = 0; cj <= ci; ++cj) {
       const int c1 = classes[ci], c2 = classes[cj];
@@ -403,12 +409,12 @@ int rb_pair_setup(rb_ctx* ctx, int nblk, const int* scale_norm, const int* blk_s
       for (size_t i = 0; i < m1.size(); ++i)
         for (size_t j = 0; j < (same ? i + 1 : m2.size()); ++j) {
           const int b1 = m1[i], b2 = m2[j];
-          bp.push_back({b1, b2, 0, smap(scale_norm[b1]) * 32, smap(scale_norm[b2]) * 32});
+          bp.push_back({b1, b2, 0, smap(scale_norm[b1]) * 16, smap(scale_norm[b2]) * 16});
         }
       const int L1 = blk_len[c1], L2 = blk_len[c2];
       for (int n = 0; n < L1; ++n)
         for (int m = 0; m < (same ? n + 1 : L2); ++m)
-          ep.push_back({n, m, 1, vmap(blk_src_off[c1] + n) * 32, vmap(blk_src_off[c2] + m) * 32});
+          ep.push_back({n, m, 1, vmap(blk_src_off[c1] + n) * 16, vmap(blk_src_off[c2] + m) * 16});
       // orientation: K = the list that gives less padded work
       const long long cost_bp_k = (long long)roundup_i((int)bp.size(), 4) * roundup_i((int)ep.size(), EST_BN);
       const long long cost_ep_k = (long long)roundup_i((int)ep.size(), 4) * roundup_i((int)bp.size(), EST_BN);

@@ -55,3 +55,46 @@ def test_random_block_tables(engine, seed):
     eps2 = np.einsum("pk,pk->p", Z @ G, Z)
     scale_ref = np.einsum("pk,pk->p", np.abs(Z) @ np.abs(G), np.abs(Z))   # cancellation-aware tolerance
     assert np.max(np.abs(r["eps2"] - eps2) / scale_ref) <= 1e-12, (N, blocks)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_pair_form_and_folded_kernel_agree(engine, seed, monkeypatch):
+    """The two estimator kernels (rb_estimator_pair_kernel, the default, and the folded rb_estimator_kernel behind
+    RB_EST_KERNEL=fold) evaluate the same quadratic form: same eps2 to rounding, and the pair form issues fewer
+    multiply-adds than the folded one on a table with several blocks per class."""
+    rng = np.random.default_rng(5000 + seed)
+    N, Ql, Qr, v_len, blocks = _case(rng)
+    B = int(rng.integers(100, 700))
+    A = np.stack([np.eye(N) * (2.0 + q) + 0.1 * rng.standard_normal((N, N)) for q in range(Ql)])
+    F = rng.standard_normal((Qr, N))
+    Theta = np.concatenate([rng.uniform(0.5, 2.0, (B, Ql)), rng.uniform(-1, 1, (B, Qr))], axis=1)
+    beta = rng.uniform(0.5, 2.0, B)
+    scale, src, length = [b[0] for b in blocks], [b[1] for b in blocks], [b[2] for b in blocks]
+    Kz = sum(length)
+    G = rng.standard_normal((Kz, Kz))
+    engine.set_system(A, F)
+    engine.set_training_set(Theta, beta)
+    out = {}
+    for kind in ("pair", "fold"):
+        monkeypatch.setenv("RB_EST_KERNEL", kind)
+        engine.set_estimator(scale, src, length, Ql, v_len, G)
+        r = engine.sweep_resident(want_u=True, want_eps2=True, raise_on_singular=False)
+        out[kind] = (r["eps2"].copy(), r["u"].copy(), engine.estimator_work())
+    V = np.concatenate([out["pair"][1], Theta[:, Ql:Ql + v_len], np.ones((B, 1))], axis=1)
+    Z = np.concatenate([(Theta[:, sc:sc + 1] if sc >= 0 else 1.0) * V[:, so:so + ln] for sc, so, ln in blocks], axis=1)
+    scale_ref = np.einsum("pk,pk->p", np.abs(Z) @ np.abs(G), np.abs(Z))
+    assert np.array_equal(out["pair"][1], out["fold"][1])
+    assert np.max(np.abs(out["pair"][0] - out["fold"][0]) / scale_ref) <= 1e-12
+    assert out["pair"][2] != out["fold"][2]       # the two packings really were different kernels
+
+
+def test_pair_form_work_at_benchmark_shape(engine):
+    """N=100, Q_a=50, Q_f=10: the pair form issues the algorithmic multiply-adds plus 0.25 % of padding."""
+    from rbnics_b200 import synthetic
+    N, Qa, Qf = 100, 50, 10
+    prob = synthetic.elliptic_reduced_problem(N, Qa, Qf, seed=0, riesz_rank=64)
+    engine.set_system(prob["A"], prob["F"])
+    engine.set_elliptic_estimator(prob["Gff"], prob["Gaf"], prob["Gaa"])
+    w = engine.estimator_work()
+    algorithmic = Qa * (Qa + 1) // 2 * (N * (N + 1) // 2) + Qa * N * Qf + Qf * (Qf + 1) // 2
+    assert algorithmic <= w["issued_macs_per_param"] <= 1.003 * algorithmic

@@ -15,7 +15,7 @@ timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_launches.log 2>&1
 # full captures of the hot kernels at the bench launch configuration (first launch after the warm-up sweeps)
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_estimator_kernel -s 3 -c 1 \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_estimator_pair_kernel -s 3 -c 1 \
     -o $OUT/${TAG}_estimator_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_est.log 2>&1
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_lu_mw_kernel -s 40 -c 1 \
     -o $OUT/${TAG}_lu_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_lu.log 2>&1
