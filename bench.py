@@ -74,9 +74,15 @@ def flops_per_param(N, Qa, Qf):
             "F_fold": asm + lu + est_fold}
 
 
+def estimator_kernel_name():
+    """The estimator kernel the library runs: the pair-product GEMM unless RB_EST_KERNEL=fold (rb_est_pair.cu)."""
+    return "rb_estimator_kernel" if os.environ.get("RB_EST_KERNEL") == "fold" else "rb_estimator_pair_kernel"
+
+
 def estimator_traffic():
-    """dram__bytes_read + dram__bytes_write of one rb_estimator_kernel launch at the bench configuration, from the
-    newest `ncu --set full` summary under profiles/ (tools/ncu_summary.py full ...); (None, reason) if there is none."""
+    """dram__bytes_read + dram__bytes_write of one launch of the estimator kernel at the bench configuration, from the
+    newest `ncu --set full` summary of THAT kernel under profiles/ (tools/ncu_summary.py full ...); (None, reason) if
+    there is none."""
     import glob
     import re
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_estimator_full.json")),
@@ -85,13 +91,15 @@ def estimator_traffic():
     for f in reversed(files):
         try:
             cap = json.load(open(f))["captures"][0]
+            if estimator_kernel_name() not in cap.get("kernel", ""):
+                continue
             tot = 0.0
             for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(cap[k]["value"]) * unit[cap[k]["unit"]]
             return tot, "profiles/" + os.path.basename(f)
         except Exception:
             continue
-    return None, "no ncu --set full summary of rb_estimator_kernel under profiles/"
+    return None, "no ncu --set full summary of " + estimator_kernel_name() + " under profiles/"
 
 
 def fp64_peak_tflops():
@@ -514,13 +522,14 @@ def run_b200_arm(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "rb_estimator_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
+            "roofline": {"bound": "tensor", "kernel": estimator_kernel_name() + " (FP64 DMMA.8x8x4)", "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src,
                          "peak_source": peak_src, "launch_ms": est_launch_ms,
                          "algorithmic_flops_per_param": fl["estimator_folded"], "params_per_launch": n_local,
                          "note": "algorithmic = minimal multiply-adds of the executed (doubly folded) quadratic form; "
-                                 "the kernel issues these plus the zero padding of its triangular 16-column tiles",
+                                 "the kernel issues these plus padding (pair-product GEMM: K to 4 and columns to 64 per "
+                                 "class pair; folded kernel: its triangular 16-column tiles)",
                          "dmma_issued_tflops": issued, "dmma_issue_frac": issued / peak,
                          "issued_flops_per_param": 2 * work["issued_macs_per_param"]},
             "sweep": {"F_fold_flops_per_param": fl["F_fold"], "F_sym_flops_per_param": fl["F_sym"],

@@ -22,6 +22,7 @@
 
 constexpr int PR_REC_DOUBLES = 4 * EST_BN + 4;  // one k4-step of a 64-column tile: B fragments + 4 x (int, int) offsets
 constexpr int PR_MAXSTAGE = 4;
+constexpr int PR_THREADS = EST_THREADS + 32;  // 8 consumer warps + the producer warp of the record stream
 constexpr int PR_MAX_TILES = 4096;
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -104,8 +105,7 @@ struct PairArgs {
 
 __host__ __device__ inline size_t pair_smem_bytes(int nstage, int SK, int LVP, int n_tile) {
   size_t b = (size_t)nstage * SK * PR_REC_DOUBLES * 8;  // record ring
-  b += PR_MAXSTAGE * 8;                                 // full barriers
-  b += PR_MAXSTAGE * 4;                                 // release counters
+  b += 2 * PR_MAXSTAGE * 8;                             // full + empty barriers
   b += (size_t)EST_BM * LVP * 8;                        // V' tile
   b += (size_t)n_tile * 12;                             // tile offsets + record counts
   return b + 16;
@@ -148,14 +148,14 @@ __device__ __forceinline__ void pr_mma(double (&T)[2][8][2], const PrFrag& f) {
 // wide as the column tile.  V' tile layout: [row pair rq = warp*8 + g][column][slot s] holding parameter row
 // warp*16 + g + 8 s; LVP = 4 mod 8, so the eight lanes of a quarter warp (two g x four consecutive columns) read eight
 // different 16-byte bank groups.
-__global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_pair_kernel(PairArgs a) {
+__global__ void __launch_bounds__(PR_THREADS, 1) rb_estimator_pair_kernel(PairArgs a) {
   extern __shared__ __align__(128) unsigned char pr_smem_raw[];
   const int SK = a.SK, NSTAGE = a.nstage, LVP = a.LVP;
   const int STAGE_DOUBLES = SK * PR_REC_DOUBLES;
   double* Gs = reinterpret_cast<double*>(pr_smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(Gs + (size_t)NSTAGE * STAGE_DOUBLES);
-  int* s_cnt = reinterpret_cast<int*>(full_bar + PR_MAXSTAGE);
-  double* Vs = reinterpret_cast<double*>(s_cnt + PR_MAXSTAGE);
+  uint64_t* empty_bar = full_bar + PR_MAXSTAGE;
+  double* Vs = reinterpret_cast<double*>(empty_bar + PR_MAXSTAGE);
   long long* s_tile_off = reinterpret_cast<long long*>(Vs + (size_t)EST_BM * LVP);
   int* s_tile_nrec = reinterpret_cast<int*>(s_tile_off + a.n_tile);
 
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_pair_kernel(PairA
   {
     const int vecN = a.vecN, QT = a.QT;
 #pragma unroll 4
-    for (int it = tid; it < 64 * LVP; it += EST_THREADS) {
+    for (int it = tid; it < 64 * LVP; it += PR_THREADS) {
       const int rq = it / LVP, c = it - rq * LVP;
       const int rbase = (rq >> 3) * 16 + (rq & 7);
       double v[2];
@@ -190,41 +190,43 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_pair_kernel(PairA
       *reinterpret_cast<double2*>(Vs + (size_t)it * 2) = make_double2(v[0], v[1]);
     }
   }
-  for (int t = ct_begin + tid; t < ct_end; t += EST_THREADS) {
+  for (int t = ct_begin + tid; t < ct_end; t += PR_THREADS) {
     s_tile_off[t] = a.tile_off[t];
     s_tile_nrec[t] = a.tile_nrec[t];
   }
   if (tid == 0) {
     for (int s = 0; s < PR_MAXSTAGE; ++s) {
       mbar_init(full_bar + s, 1);
-      s_cnt[s] = 0;
+      mbar_init(empty_bar + s, EST_WARPS);
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  // ---- record stream: 1-D bulk copies, a stage holds up to SK records of ONE tile.  Every warp advances the producer
-  // cursor identically; the warp that is last to release a slot issues its refill (no producer warp).
-  int pct = ct_begin, prec = 0;
-  auto p_len = [&]() { return min(SK, s_tile_nrec[pct] - prec); };
-  auto issue_stage = [&](int slot) {  // one thread per stage
-    const uint32_t bytes = (uint32_t)p_len() * (PR_REC_DOUBLES * 8u);
-    mbar_arrive_expect_tx(full_bar + slot, bytes);
-    bulk_g2s(Gs + (size_t)slot * STAGE_DOUBLES, a.stream + s_tile_off[pct] + (long long)prec * PR_REC_DOUBLES, bytes,
-             full_bar + slot);
-  };
-  auto advance_cursor = [&]() {
-    prec += p_len();
-    if (prec == s_tile_nrec[pct]) {
-      ++pct;
-      prec = 0;
+  // ---- record stream: 1-D bulk copies, a stage (slot of the ring) holds up to SK records of ONE tile.  Warp 8 is the
+  // producer: one lane walks the CTA's tiles, waits until the eight consumer warps have released a slot (empty
+  // barrier) and refills it; a consumer's stage hand-over is then one arrive and one (normally satisfied) wait.
+  if (warp == EST_WARPS) {
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t eph = 1;  // parity that completes immediately on a fresh barrier: the first NSTAGE fills do not wait
+      for (int t = ct_begin; t < ct_end; ++t) {
+        const int nrec = s_tile_nrec[t];
+        const double* src = a.stream + s_tile_off[t];
+        for (int r = 0; r < nrec; r += SK) {
+          mbar_wait(empty_bar + slot, eph);
+          const uint32_t bytes = (uint32_t)min(SK, nrec - r) * (PR_REC_DOUBLES * 8u);
+          mbar_arrive_expect_tx(full_bar + slot, bytes);
+          bulk_g2s(Gs + (size_t)slot * STAGE_DOUBLES, src + (long long)r * PR_REC_DOUBLES, bytes, full_bar + slot);
+          if (++slot == NSTAGE) {
+            slot = 0;
+            eph ^= 1u;
+          }
+        }
+      }
     }
-  };
-  for (int s = 0; s < NSTAGE; ++s)
-    if (pct < ct_end) {
-      if (tid == 0) issue_stage(s);
-      advance_cursor();
-    }
+    return;
+  }
 
   const int g = lane >> 2, q4 = lane & 3;
   const char* vlane = reinterpret_cast<const char*>(Vs) + (size_t)((warp * 8 + g) * LVP) * 16;
@@ -283,16 +285,9 @@ __global__ void __launch_bounds__(EST_THREADS, 1) rb_estimator_pair_kernel(PairA
       if (have_next) pr_mul_a(fn, raw);
       pr_mma<3>(T, fc);
       cur = nxt;
-      // stage consumed: release it; the last warp to do so refills the slot
+      // stage consumed: release the slot to the producer
       __syncwarp();
-      if (lane == 0) {
-        const int old = atomicAdd(&s_cnt[stage], 1);
-        if (old == EST_WARPS - 1) {
-          s_cnt[stage] = 0;
-          if (pct < ct_end) issue_stage(stage);
-        }
-      }
-      if (pct < ct_end) advance_cursor();
+      if (lane == 0) mbar_arrive(empty_bar + stage);
       rem -= nin;
       if (last_in_tile) {
         // epilogue of the column tile: rowacc[p] += sum_c Y[p, c] * W[p, c]
@@ -439,11 +434,13 @@ int rb_pair_setup(rb_ctx* ctx, int nblk, const int* scale_norm, const int* blk_s
     }
   const int n_tile = (int)tile_row0.size();
   if (n_tile == 0 || n_tile > PR_MAX_TILES) return RB_OK;
-  const int nstage = 2;
+  int nstage = 2;
+  if (const char* k = getenv("RB_PAIR_NSTAGE")) nstage = std::min(PR_MAXSTAGE, std::max(2, atoi(k)));  // tuning knob
   int max_nrec = 1;
   for (int t = 0; t < n_tile; ++t) max_nrec = std::max(max_nrec, tile_nrec[t]);
   int SK = std::min(16, max_nrec);
-  while (SK > 4 && pair_smem_bytes(nstage, SK, LVP, n_tile) > 227 * 1024) --SK;
+  if (const char* k = getenv("RB_PAIR_SK")) SK = std::min(max_nrec, std::max(1, atoi(k)));
+  while (SK > 1 && pair_smem_bytes(nstage, SK, LVP, n_tile) > 227 * 1024) --SK;
   if (pair_smem_bytes(nstage, SK, LVP, n_tile) > 227 * 1024) return RB_OK;  // V' tile too wide: the folded kernel serves
 
   const long long total_rec = (long long)rec_tile.size();
@@ -536,7 +533,7 @@ int rb_pair_launch(rb_ctx* ctx, const double* Uvec, int ldu, const double* theta
   a.n_tile = pr.n_tile;
   const long long nrb = (rows + EST_BM - 1) / EST_BM;
   const size_t smem = pair_smem_bytes(pr.nstage, pr.SK, pr.LVP, pr.n_tile);
-  rb_estimator_pair_kernel<<<(unsigned)(nrb * nsplit), EST_THREADS, smem, ctx->stream>>>(a);
+  rb_estimator_pair_kernel<<<(unsigned)(nrb * nsplit), PR_THREADS, smem, ctx->stream>>>(a);
   RB_CUDA(cudaGetLastError());
   return RB_OK;
 }
