@@ -9,7 +9,7 @@
 //   Y[p, col] = sum_k  A[p, k] M[k, col],   A[p, k] = V'[p, i1(k)] V'[p, i2(k)]        (k: block pairs)
 //   eps2[p]  += sum_col Y[p, col] W[p, col], W[p, col] = V'[p, j1(col)] V'[p, j2(col)]  (col: entry pairs)
 // with NO triangular tiles: the multiply-adds issued are the algorithmic ones (Q_a(Q_a+1)/2 * N(N+1)/2 + ...) plus the
-// padding of K to 4 and of the columns to 64 per class pair (0.25 % at N = 100, Q_a = 50, Q_f = 10; the triangular
+// padding of K to 8 and of the columns to 64 per class pair (0.6 % at N = 100, Q_a = 50, Q_f = 10; the triangular
 // 16-column tiles of rb_estimator_kernel issue 12 % more than the algorithmic count).  The A operand is never stored:
 // every lane builds its fragment entries from the V' tile in shared memory (2 LDS.128 + 2 DMUL per k-step next to 16
 // DMMAs), the two factor columns of the four k rows of a step travel with the B fragments in the same 1-D bulk copy.
@@ -311,21 +311,16 @@ __global__ void __launch_bounds__(PR_THREADS, 1) rb_estimator_pair_kernel(PairAr
       nin = min(SK, rem);
       return have_next;
     };
-    // per stage: f0 holds the first record
+    // per stage: f0 holds the first record; every stage has an even number of records (K is padded to 8 per class pair
+    // and SK is even), so the fragment buffers play the same roles in every stage and no registers move at a hand-over
     while (true) {
-      int i = nin - 1;  // records whose successor lies in the same stage
-      for (; i >= 2; i -= 2) {
+      for (int i = nin - 2; i > 0; i -= 2) {
         body(f0, f1, cur + PR_REC_DOUBLES);
         body(f1, f0, cur + 2 * PR_REC_DOUBLES);
         cur += 2 * PR_REC_DOUBLES;
       }
-      if (i == 1) {
-        body(f0, f1, cur + PR_REC_DOUBLES);
-        if (!stage_end(f1, f0)) break;
-      } else {
-        if (!stage_end(f0, f1)) break;
-        f0 = f1;
-      }
+      body(f0, f1, cur + PR_REC_DOUBLES);
+      if (!stage_end(f1, f0)) break;
     }
   }
 
@@ -411,14 +406,14 @@ int rb_pair_setup(rb_ctx* ctx, int nblk, const int* scale_norm, const int* blk_s
         for (int m = 0; m < (same ? n + 1 : L2); ++m)
           ep.push_back({n, m, 1, vmap(blk_src_off[c1] + n) * 16, vmap(blk_src_off[c2] + m) * 16});
       // orientation: K = the list that gives less padded work
-      const long long cost_bp_k = (long long)roundup_i((int)bp.size(), 4) * roundup_i((int)ep.size(), EST_BN);
-      const long long cost_ep_k = (long long)roundup_i((int)ep.size(), 4) * roundup_i((int)bp.size(), EST_BN);
+      const long long cost_bp_k = (long long)roundup_i((int)bp.size(), 8) * roundup_i((int)ep.size(), EST_BN);
+      const long long cost_ep_k = (long long)roundup_i((int)ep.size(), 8) * roundup_i((int)bp.size(), EST_BN);
       const std::vector<PrDesc>& kl = cost_bp_k <= cost_ep_k ? bp : ep;
       const std::vector<PrDesc>& cl = cost_bp_k <= cost_ep_k ? ep : bp;
       const int row0 = (int)rows.size();
       rows.insert(rows.end(), kl.begin(), kl.end());
-      rows.resize(row0 + roundup_i((int)kl.size(), 4), pad);
-      const int nrec = roundup_i((int)kl.size(), 4) / 4;
+      rows.resize(row0 + roundup_i((int)kl.size(), 8), pad);  // an even number of records (see the kernel's stage loop)
+      const int nrec = roundup_i((int)kl.size(), 8) / 4;
       for (size_t j0 = 0; j0 < cl.size(); j0 += EST_BN) {
         const int tile = (int)tile_row0.size();
         tile_row0.push_back(row0);
@@ -438,9 +433,9 @@ int rb_pair_setup(rb_ctx* ctx, int nblk, const int* scale_norm, const int* blk_s
   if (const char* k = getenv("RB_PAIR_NSTAGE")) nstage = std::min(PR_MAXSTAGE, std::max(2, atoi(k)));  // tuning knob
   int max_nrec = 1;
   for (int t = 0; t < n_tile; ++t) max_nrec = std::max(max_nrec, tile_nrec[t]);
-  int SK = std::min(16, max_nrec);
-  if (const char* k = getenv("RB_PAIR_SK")) SK = std::min(max_nrec, std::max(1, atoi(k)));
-  while (SK > 1 && pair_smem_bytes(nstage, SK, LVP, n_tile) > 227 * 1024) --SK;
+  int SK = std::min(16, max_nrec);  // even, like every tile's record count
+  if (const char* k = getenv("RB_PAIR_SK")) SK = std::min(max_nrec, std::max(2, atoi(k) & ~1));
+  while (SK > 2 && pair_smem_bytes(nstage, SK, LVP, n_tile) > 227 * 1024) SK -= 2;
   if (pair_smem_bytes(nstage, SK, LVP, n_tile) > 227 * 1024) return RB_OK;  // V' tile too wide: the folded kernel serves
 
   const long long total_rec = (long long)rec_tile.size();

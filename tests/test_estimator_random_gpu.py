@@ -89,7 +89,7 @@ def test_pair_form_and_folded_kernel_agree(engine, seed, monkeypatch):
 
 
 def test_pair_form_work_at_benchmark_shape(engine):
-    """N=100, Q_a=50, Q_f=10: the pair form issues the algorithmic multiply-adds plus 0.25 % of padding."""
+    """N=100, Q_a=50, Q_f=10: the pair form issues the algorithmic multiply-adds plus 0.6 % of padding."""
     from rbnics_b200 import synthetic
     N, Qa, Qf = 100, 50, 10
     prob = synthetic.elliptic_reduced_problem(N, Qa, Qf, seed=0, riesz_rank=64)
@@ -97,4 +97,4 @@ def test_pair_form_work_at_benchmark_shape(engine):
     engine.set_elliptic_estimator(prob["Gff"], prob["Gaf"], prob["Gaa"])
     w = engine.estimator_work()
     algorithmic = Qa * (Qa + 1) // 2 * (N * (N + 1) // 2) + Qa * N * Qf + Qf * (Qf + 1) // 2
-    assert algorithmic <= w["issued_macs_per_param"] <= 1.003 * algorithmic
+    assert algorithmic <= w["issued_macs_per_param"] <= 1.007 * algorithmic
