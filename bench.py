@@ -528,7 +528,7 @@ def run_b200_arm(args):
                          "peak_source": peak_src, "launch_ms": est_launch_ms,
                          "algorithmic_flops_per_param": fl["estimator_folded"], "params_per_launch": n_local,
                          "note": "algorithmic = minimal multiply-adds of the executed (doubly folded) quadratic form; "
-                                 "the kernel issues these plus padding (pair-product GEMM: K to 4 and columns to 64 per "
+                                 "the kernel issues these plus padding (pair-product GEMM: K to 8 and columns to 64 per "
                                  "class pair; folded kernel: its triangular 16-column tiles)",
                          "dmma_issued_tflops": issued, "dmma_issue_frac": issued / peak,
                          "issued_flops_per_param": 2 * work["issued_macs_per_param"]},
