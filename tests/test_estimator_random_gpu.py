@@ -98,3 +98,27 @@ def test_pair_form_work_at_benchmark_shape(engine):
     w = engine.estimator_work()
     algorithmic = Qa * (Qa + 1) // 2 * (N * (N + 1) // 2) + Qa * N * Qf + Qf * (Qf + 1) // 2
     assert algorithmic <= w["issued_macs_per_param"] <= 1.007 * algorithmic
+
+
+def test_wide_v_tile_falls_back_to_the_folded_kernel(engine):
+    """N = 160 with 60 theta columns: the V' tile of the pair form (128 x (N + Q + 2) doubles) does not fit in shared
+    memory next to its record ring, so rb_set_estimator keeps the folded kernel; the sweep must still be right."""
+    rng = np.random.default_rng(77)
+    N, Ql, Qr, B = 160, 48, 12, 300
+    A = np.stack([np.eye(N) * (2.0 + q) + 0.05 * rng.standard_normal((N, N)) for q in range(Ql)])
+    F = rng.standard_normal((Qr, N))
+    Theta = np.concatenate([rng.uniform(0.5, 2.0, (B, Ql)), rng.uniform(-1, 1, (B, Qr))], axis=1)
+    beta = rng.uniform(0.5, 2.0, B)
+    blocks = [(q, 0, N) for q in range(3)] + [(-1, N, Qr)]
+    scale, src, length = [b[0] for b in blocks], [b[1] for b in blocks], [b[2] for b in blocks]
+    Kz = sum(length)
+    G = rng.standard_normal((Kz, Kz))
+    engine.set_system(A, F)
+    engine.set_estimator(scale, src, length, Ql, Qr, G)
+    engine.set_training_set(Theta, beta)
+    r = engine.sweep_resident(want_u=True, want_eps2=True, raise_on_singular=False)
+    V = np.concatenate([r["u"], Theta[:, Ql:], np.ones((B, 1))], axis=1)
+    Z = np.concatenate([(Theta[:, sc:sc + 1] if sc >= 0 else 1.0) * V[:, so:so + ln] for sc, so, ln in blocks], axis=1)
+    eps2 = np.einsum("pk,pk->p", Z @ G, Z)
+    scale_ref = np.einsum("pk,pk->p", np.abs(Z) @ np.abs(G), np.abs(Z))
+    assert np.max(np.abs(r["eps2"] - eps2) / scale_ref) <= 1e-12
