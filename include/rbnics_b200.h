@@ -62,7 +62,10 @@ int rb_set_system(rb_ctx* ctx, int N, int Ql, int Qr, const double* A, const dou
  *   scale_b = Theta[blk_scale_col[b]]   (blk_scale_col[b] < 0  ->  scale_b = 1)
  * and G the dense (Kz x Kz, Kz = sum len_b) matrix of Riesz Gram blocks (need not be symmetric: only its symmetric
  * part contributes and the kernel uses G + G^T).  Elliptic: blocks b < Qa = (scale theta_a[b], src 0, len N) and one
- * block (scale 1, src N, len Qf) with v_theta = theta_f;  G = [[Gaa, Gaf], [Gaf^T, Gff]].                           */
+ * block (scale 1, src N, len Qf) with v_theta = theta_f;  G = [[Gaa, Gaf], [Gaf^T, Gff]].
+ * The form is evaluated as one dense GEMM over factor pairs per pair of block classes (rb_est_pair.cu); when its
+ * shared-memory tile of V does not fit (N + Ql + Qr > ~210), or with RB_EST_KERNEL=fold in the environment at this
+ * call, by the folded triangular kernel of rb_sweep.cu.  Both give the same eps2 to rounding.                        */
 int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col, const int* blk_src_off, const int* blk_len,
                      int v_theta_off, int v_theta_len, const double* G);
 
@@ -130,7 +133,7 @@ int rb_supremizers(rb_ctx* ctx, int Ns, int Nu, int Q, const double* W, int64_t 
  * issued by the host layer without a host round trip), and to the per-parameter estimators. */
 int rb_result_device_ptrs(rb_ctx* ctx, void** maxloc16, double** delta);
 /* Work of the estimator kernel per parameter as packed by rb_set_estimator: multiply-adds issued on the tensor pipe
- * (k-step records x 256, zero padding of the triangular tiles included) and number of 64-column tiles. */
+ * (k-step records x 256, padding included) and number of 64-column tiles, of the kernel that serves the sweeps. */
 int rb_estimator_work(rb_ctx* ctx, int64_t* issued_macs_per_param, int* n_column_tiles);
 /* Kernel-only timings (ms, CUDA events on the handle's stream) of the last sweep:
  * [0]=assembly GEMM, [1]=LU solve, [2]=estimator GEMM, [3]=finalize+argmax, [4]=total; launches counted. */
