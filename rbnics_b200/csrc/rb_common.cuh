@@ -78,6 +78,9 @@ struct rb_ctx {
   double* dAq = nullptr;      // [QlP][EP] : A_q transposed/padded: entry (i,j) at j*NP+i
   double* dF = nullptr;       // [Qr][NP]
   int* dBcRows = nullptr;     // [n_bc]
+  double* dAqRec = nullptr;   // A_q once more as DMMA B-fragment records per 64-entry tile (rb_asm_rec.cu)
+  bool asmrec_ok = false;
+  int asmrec_KP = 0, asmrec_nslot = 0;
 
   // estimator
   bool have_est = false;
@@ -172,6 +175,11 @@ int rb_pair_setup(rb_ctx* ctx, int nblk, const int* scale_norm, const int* blk_s
                   const double* dG, int Kz);
 int rb_pair_launch(rb_ctx* ctx, const double* Uvec, int ldu, const double* theta, long long rows, int nsplit);
 void rb_pair_free(rb_ctx* ctx);
+
+// record-fed assembly GEMM (rb_asm_rec.cu)
+int rb_asmrec_setup(rb_ctx* ctx);
+int rb_asmrec_launch(rb_ctx* ctx, const double* theta, long long n);
+void rb_asmrec_free(rb_ctx* ctx);
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Device helpers

@@ -763,6 +763,7 @@ extern "C" void rb_ctx_destroy(rb_ctx* ctx) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   rb_pair_free(ctx);
+  rb_asmrec_free(ctx);
   for (int t = 0; t < RB_OFF_SLOTS; ++t) {
     for (void* p : {(void*)ctx->off_csr[t].ip, (void*)ctx->off_csr[t].ix, (void*)ctx->off_csr[t].dt, (void*)ctx->off_blk[t].d,
                     (void*)ctx->off_blk[t].zt, (void*)ctx->off_blk[t].xzt})
@@ -840,7 +841,7 @@ extern "C" int rb_set_system(rb_ctx* ctx, int N, int Ql, int Qr, const double* A
   }
   ctx->have_system = true;
   ctx->have_est = false;  // the estimator layout depends on N
-  return RB_OK;
+  return rb_asmrec_setup(ctx);
 }
 
 extern "C" int rb_set_estimator(rb_ctx* ctx, int nblk, const int* blk_scale_col, const int* blk_src_off,
@@ -1335,6 +1336,7 @@ static int prepare_assembly(rb_ctx* ctx, long long B, long long* chunk_out, size
 
 // Ab[0..n) = sum_q Theta[c0 + p][q] A_q for the chunk starting at parameter c0
 static int launch_assembly(rb_ctx* ctx, long long c0, long long n, size_t asm_smem) {
+  if (ctx->asmrec_ok) return rb_asmrec_launch(ctx, ctx->dTheta + c0 * ctx->QT, n);
   AsmArgs aa;
   aa.theta = ctx->dTheta + c0 * ctx->QT;
   aa.Aq = ctx->dAq;

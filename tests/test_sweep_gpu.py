@@ -146,3 +146,26 @@ def test_sweep_edge_shapes(engine, N, Qa, Qf, B):
     ref = O.sweep_batched(Theta[:, :Qa], Theta[:, Qa:], beta, prob["A"], prob["F"], prob["Gff"], prob["Gaf"],
                           prob["Gaa"], return_eps2=True)
     _check(res, ref, N)
+
+
+@pytest.mark.parametrize("N,Ql", [(100, 50), (37, 7), (64, 12), (5, 1)])
+def test_record_fed_assembly_equals_the_cp_async_kernel(engine, monkeypatch, N, Ql):
+    """rb_assemble_rec_kernel (producer warp + DMMA B-fragment records, the default) and rb_assemble_kernel
+    (RB_ASM_KERNEL=old at rb_set_system) accumulate the terms in the same order: identical reduced solutions."""
+    rng = np.random.default_rng(N * 100 + Ql)
+    Qr, B = 3, 700
+    A = np.stack([np.eye(N) * (2.0 + q) + 0.1 * rng.standard_normal((N, N)) for q in range(Ql)])
+    F = rng.standard_normal((Qr, N))
+    Theta = np.concatenate([rng.uniform(0.5, 2.0, (B, Ql)), rng.uniform(-1, 1, (B, Qr))], axis=1)
+    beta = rng.uniform(0.5, 2.0, B)
+    G = rng.standard_normal((N + Qr, N + Qr))
+    out = {}
+    for kind in ("new", "old"):
+        monkeypatch.setenv("RB_ASM_KERNEL", kind)
+        engine.set_system(A, F)
+        engine.set_estimator([0, -1], [0, N], [N, Qr], Ql, Qr, G)
+        engine.set_training_set(Theta, beta)
+        out[kind] = engine.sweep_resident(want_u=True, raise_on_singular=False)["u"].copy()
+    assert np.array_equal(out["new"], out["old"])
+    U_ref = np.linalg.solve(np.einsum("pq,qij->pij", Theta[:, :Ql], A), (Theta[:, Ql:] @ F)[:, :, None])[:, :, 0]
+    assert np.max(np.abs(out["new"] - U_ref)) <= 1e-10 * np.max(np.abs(U_ref))

@@ -19,7 +19,7 @@ timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_
     -o $OUT/${TAG}_estimator_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_est.log 2>&1
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_lu_mw_kernel -s 40 -c 1 \
     -o $OUT/${TAG}_lu_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_lu.log 2>&1
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_assemble_kernel -s 40 -c 1 \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:rb_assemble_rec_kernel -s 40 -c 1 \
     -o $OUT/${TAG}_asm_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_asm.log 2>&1
 # offline basis linear algebra: kernel times + launch list + full captures of the two Gram kernels
 timeout -s KILL 600 python bench_offline.py > $OUT/${TAG}_offline_kernels.jsonl 2> $OUT/${TAG}_offline.err || tail -5 $OUT/${TAG}_offline.err
