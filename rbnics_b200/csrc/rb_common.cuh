@@ -60,6 +60,11 @@ struct rb_pair_t {
   long long* dTileOff = nullptr;    // [n_tile] first record of a tile (offset in doubles)
   int* dTileNrec = nullptr;         // [n_tile]
   int2* dCol = nullptr;             // [n_tile * 64] factor columns (byte offsets in the V' tile) of every column
+  // launch plan of the current sweep (prepare_estimator_splits): the row blocks that fill whole waves at the coarse
+  // split, and the remaining ones in a second launch with a finer split (shorter CTAs in the last, partial wave)
+  int bulk_nsplit = 0, tail_nsplit = 0;
+  long long bulk_nrb = 0, tail_nrb = 0;
+  int* dSplitBeginTail = nullptr; int tail_cap = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------

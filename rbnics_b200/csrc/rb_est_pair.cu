@@ -100,6 +100,7 @@ struct PairArgs {
   const double* theta;        // [B][QT]
   double* partial;            // [nsplit][B]
   long long B;
+  long long rb0;  // first row block of this launch
   int vecN, ldu, QT, LVP, nsplit, SK, nstage, n_tile;
 };
 
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) rb_estimator_pair_kernel(PairAr
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int split = blockIdx.x % a.nsplit;
-  const long long rb = blockIdx.x / a.nsplit;
+  const long long rb = a.rb0 + blockIdx.x / a.nsplit;
   const long long p0 = rb * EST_BM;
   const int ct_begin = a.split_begin[split], ct_end = a.split_begin[split + 1];
 
@@ -348,6 +349,9 @@ void rb_pair_free(rb_ctx* ctx) {
   if (pr.dTileOff) cudaFree(pr.dTileOff);
   if (pr.dTileNrec) cudaFree(pr.dTileNrec);
   if (pr.dCol) cudaFree(pr.dCol);
+  if (pr.dSplitBeginTail) cudaFree(pr.dSplitBeginTail);
+  pr.dSplitBeginTail = nullptr;
+  pr.tail_cap = 0;
   pr.dStream = nullptr;
   pr.dTileOff = nullptr;
   pr.dTileNrec = nullptr;
@@ -506,14 +510,15 @@ int rb_pair_setup(rb_ctx* ctx, int nblk, const int* scale_norm, const int* blk_s
   return RB_OK;
 }
 
-int rb_pair_launch(rb_ctx* ctx, const double* Uvec, int ldu, const double* theta, long long rows, int nsplit) {
-  const rb_pair_t& pr = ctx->pair;
+// `nsum` partial sums per parameter are added by the finalize kernel; the launch plan (one launch, or whole waves at
+// the coarse split + the remaining row blocks at a finer one) was made by prepare_estimator_splits
+int rb_pair_launch(rb_ctx* ctx, const double* Uvec, int ldu, const double* theta, long long rows, int nsum) {
+  rb_pair_t& pr = ctx->pair;
   PairArgs a;
   a.stream = pr.dStream;
   a.tile_off = pr.dTileOff;
   a.tile_nrec = pr.dTileNrec;
   a.col = pr.dCol;
-  a.split_begin = ctx->dSplitBegin;
   a.U = Uvec;
   a.theta = theta;
   a.partial = ctx->dPart;
@@ -522,13 +527,25 @@ int rb_pair_launch(rb_ctx* ctx, const double* Uvec, int ldu, const double* theta
   a.ldu = ldu;
   a.QT = ctx->QT;
   a.LVP = pr.LVP;
-  a.nsplit = nsplit;
   a.SK = pr.SK;
   a.nstage = pr.nstage;
   a.n_tile = pr.n_tile;
-  const long long nrb = (rows + EST_BM - 1) / EST_BM;
   const size_t smem = pair_smem_bytes(pr.nstage, pr.SK, pr.LVP, pr.n_tile);
-  rb_estimator_pair_kernel<<<(unsigned)(nrb * nsplit), PR_THREADS, smem, ctx->stream>>>(a);
+  const long long nrb = (rows + EST_BM - 1) / EST_BM;
+  const bool planned = pr.tail_nrb > 0 && nrb == pr.bulk_nrb + pr.tail_nrb;  // (a shorter last chunk: one launch)
+  if (nsum != pr.bulk_nsplit)  // the parts write different numbers of partial sums per parameter: the others are zero
+    RB_CUDA(cudaMemsetAsync(ctx->dPart, 0, (size_t)nsum * rows * sizeof(double), ctx->stream));
+  a.split_begin = ctx->dSplitBegin;
+  a.nsplit = pr.bulk_nsplit;
+  a.rb0 = 0;
+  rb_estimator_pair_kernel<<<(unsigned)((planned ? pr.bulk_nrb : nrb) * pr.bulk_nsplit), PR_THREADS, smem, ctx->stream>>>(a);
   RB_CUDA(cudaGetLastError());
+  if (planned) {
+    a.split_begin = pr.dSplitBeginTail;
+    a.nsplit = pr.tail_nsplit;
+    a.rb0 = pr.bulk_nrb;
+    rb_estimator_pair_kernel<<<(unsigned)(pr.tail_nrb * pr.tail_nsplit), PR_THREADS, smem, ctx->stream>>>(a);
+    RB_CUDA(cudaGetLastError());
+  }
   return RB_OK;
 }

@@ -1225,28 +1225,71 @@ static int prepare_estimator_splits(rb_ctx* ctx, long long rows, int* nsplit_out
   const int n_ctile = ctx->pair.ok ? ctx->pair.n_tile : ctx->n_ctile;
   const std::vector<int>& tile_cost = ctx->pair.ok ? ctx->pair.h_tile_cost : ctx->h_tile_cost;
   const int nsplit = choose_nsplit(nrb, ctx->sm_count, n_ctile);
-  if ((long long)nsplit * rows > ctx->part_cap) {
-    if (int rc = dev_realloc(ctx, &ctx->dPart, (size_t)nsplit * rows)) return rc;
-    ctx->part_cap = (long long)nsplit * rows;
+  // Pair-form kernel, large sweeps: the row blocks that fill whole waves of the SMs run at the coarse split; the
+  // remaining ones go into a second launch with a finer split, so that the last, partial wave consists of short CTAs
+  // (10^6 parameters: 7813 row blocks x 3 splits = 158.4 waves cost 159; 158 waves + 19 row blocks x 7 splits cost 158.5).
+  // Time unit below: one CTA that processes all column tiles of a row block.
+  rb_pair_t& pr = ctx->pair;
+  pr.bulk_nsplit = nsplit;
+  pr.bulk_nrb = nrb;
+  pr.tail_nsplit = 0;
+  pr.tail_nrb = 0;
+  static const bool two_part = !(getenv("RB_EST_TAIL") && atoi(getenv("RB_EST_TAIL")) == 0);
+  if (pr.ok && two_part && rows >= 20000) {
+    const long long sms = ctx->sm_count, units = nrb * nsplit, waves_full = units / sms;
+    if (units % sms != 0 && waves_full >= 40) {  // (measured: no gain at 19 waves, -0.34 % at 158)
+      const long long nrb_bulk = waves_full * sms / nsplit, nrb_tail = nrb - nrb_bulk;
+      int best_s = 1;
+      double best_cost = 1e300;
+      for (int s = 1; s <= 16 && s <= n_ctile; ++s) {
+        const double cost = (double)((nrb_tail * s + sms - 1) / sms) / s * (1.0 + 0.01 * (s - 1));
+        if (cost < best_cost - 1e-12) {
+          best_cost = cost;
+          best_s = s;
+        }
+      }
+      const double t_single = (double)((units + sms - 1) / sms) / nsplit;
+      const double t_plan = (double)waves_full / nsplit + best_cost;
+      if (nrb_tail > 0 && t_plan < 0.997 * t_single) {
+        pr.bulk_nrb = nrb_bulk;
+        pr.tail_nrb = nrb_tail;
+        pr.tail_nsplit = best_s;
+      }
+    }
+  }
+  const int nsum = std::max(nsplit, pr.tail_nsplit);  // partial sums per parameter that the finalize kernel adds
+  if ((long long)nsum * rows > ctx->part_cap) {
+    if (int rc = dev_realloc(ctx, &ctx->dPart, (size_t)nsum * rows)) return rc;
+    ctx->part_cap = (long long)nsum * rows;
   }
   if (nsplit + 1 > ctx->split_cap) {
     if (int rc = dev_realloc(ctx, &ctx->dSplitBegin, (size_t)nsplit + 1)) return rc;
     ctx->split_cap = nsplit + 1;
   }
-  std::vector<int> sb(nsplit + 1, n_ctile);
+  if (pr.tail_nsplit + 1 > pr.tail_cap) {
+    if (int rc = dev_realloc(ctx, &pr.dSplitBeginTail, (size_t)pr.tail_nsplit + 1)) return rc;
+    pr.tail_cap = pr.tail_nsplit + 1;
+  }
   long long total = 0;
   for (int ct = 0; ct < n_ctile; ++ct) total += tile_cost[ct];
-  long long accum = 0;
-  int s = 0;
-  sb[0] = 0;
-  for (int ct = 0; ct < n_ctile && s + 1 < nsplit; ++ct) {
-    accum += tile_cost[ct];
-    if (accum * nsplit >= total * (s + 1)) sb[++s] = ct + 1;
-  }
-  for (int t = s + 1; t <= nsplit; ++t) sb[t] = n_ctile;
+  auto split_table = [&](int ns) {  // contiguous tile ranges balanced by the number of records
+    std::vector<int> sb(ns + 1, n_ctile);
+    long long accum = 0;
+    int s = 0;
+    sb[0] = 0;
+    for (int ct = 0; ct < n_ctile && s + 1 < ns; ++ct) {
+      accum += tile_cost[ct];
+      if (accum * ns >= total * (s + 1)) sb[++s] = ct + 1;
+    }
+    for (int t = s + 1; t <= ns; ++t) sb[t] = n_ctile;
+    return sb;
+  };
+  const std::vector<int> sb = split_table(nsplit), sbt = split_table(std::max(pr.tail_nsplit, 1));
   RB_CUDA(cudaMemcpyAsync(ctx->dSplitBegin, sb.data(), (nsplit + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-  RB_CUDA(cudaStreamSynchronize(st));  // sb is a stack vector
-  *nsplit_out = nsplit;
+  if (pr.tail_nsplit > 0)
+    RB_CUDA(cudaMemcpyAsync(pr.dSplitBeginTail, sbt.data(), (pr.tail_nsplit + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaStreamSynchronize(st));  // the tables are stack vectors
+  *nsplit_out = nsum;
   return RB_OK;
 }
 
@@ -1254,6 +1297,7 @@ static int prepare_estimator_splits(rb_ctx* ctx, long long rows, int* nsplit_out
 static int launch_estimator(rb_ctx* ctx, const double* Uvec, int ldu, int vecN, const double* theta, long long rows,
                             int nsplit) {
   if (ctx->pair.ok && vecN == ctx->pair.vecN) return rb_pair_launch(ctx, Uvec, ldu, theta, rows, nsplit);
+  if (ctx->pair.tail_nrb > 0) RB_FAIL(RB_ERR_STATE, "estimator: two-part launch plan without the pair-form kernel");
   EstArgs ea;
   ea.Gp = ctx->dGp;
   ea.tile_off = ctx->dTileOff;
@@ -1427,7 +1471,7 @@ extern "C" int rb_sweep_resident(rb_ctx* ctx, int estimator_kind, double* max_va
   RB_CUDA(cudaEventRecord(ctx->ev[1], st));
   if (int rc = wait_uploaded(ctx, B)) return rc;
   if (int rc = launch_estimator(ctx, ctx->dU, ctx->ldu, N, ctx->dTheta, B, nsplit)) return rc;
-  ++launches;
+  launches += ctx->pair.tail_nrb > 0 ? 2 : 1;
   RB_CUDA(cudaEventRecord(ctx->ev[2], st));
   {
     long long* blk_nf = ctx->dBlkIdx + fin_blocks;
