@@ -529,7 +529,9 @@ def run_b200_arm(args):
                          "algorithmic_flops_per_param": fl["estimator_folded"], "params_per_launch": n_local,
                          "note": "algorithmic = minimal multiply-adds of the executed (doubly folded) quadratic form; "
                                  "the kernel issues these plus padding (pair-product GEMM: K to 8 and columns to 64 per "
-                                 "class pair; folded kernel: its triangular 16-column tiles)",
+                                 "class pair; folded kernel: its triangular 16-column tiles); launch_ms spans the "
+                                 "estimator launch(es) of one sweep (large sweeps: whole waves + a finer-split launch "
+                                 "for the last row blocks)",
                          "dmma_issued_tflops": issued, "dmma_issue_frac": issued / peak,
                          "issued_flops_per_param": 2 * work["issued_macs_per_param"]},
             "sweep": {"F_fold_flops_per_param": fl["F_fold"], "F_sym_flops_per_param": fl["F_sym"],
